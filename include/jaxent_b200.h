@@ -1,0 +1,198 @@
+/*
+ * jaxent_b200.h -- C ABI of the B200-native BV MaxEnt optimise step.
+ *
+ * Drop-in boundary for the one hot path of alexisiddiqui/JAX-ENT (paths below are relative to
+ * /root/reference/jaxent/src):
+ *
+ *   OptaxOptimizer._step_with_rates   opt/optimiser.py:337-445   (value_and_grad + mask + plateau LR + optax)
+ *   compute_loss                      opt/optimiser.py:608-644
+ *   Simulation.forward / forward_pure models/core.py:131-163,270-307
+ *   frame_average_features            utils/jax_fn.py:15-38
+ *   BV_ForwardPass / BV_uptake_ForwardPass  models/HDX/forward.py:15-76
+ *   apply_sparse_mapping              data/splitting/sparse_map.py:220-235
+ *   hdx_uptake_{eye,mean_centred_eye,sigma}_MSE_loss, hdx_pf_l2_loss, maxent_convexKL_loss,
+ *   model_params_L1/L2_loss           opt/losses.py:1541-1657,1790-1841,17-50,304-322,476-513
+ *
+ * The reference has no FFI of its own (it is pure Python on jax/XLA); these entry points are what
+ * a jax.ffi custom call for the path binds (see INTEGRATION.md and csrc/xla_ffi.cc).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / jax types.  All device buffers are caller owned; the
+ *     library never calls cudaMalloc/cudaFree, never synchronises the host and only enqueues work
+ *     on the stream it is given.
+ *   - every function returns 0 on success or a negative JAXENT_E_* code; jaxent_last_error()
+ *     returns a thread-local message for the last failure.
+ *   - there is no CPU fallback: without a CUDA device the compute entry points fail.
+ */
+#ifndef JAXENT_B200_H_
+#define JAXENT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* jaxent_stream_t; /* cudaStream_t */
+
+#define JAXENT_OK 0
+#define JAXENT_E_INVALID (-1)   /* bad shape / alignment / argument   (reference: ValueError, models/core.py:65-66) */
+#define JAXENT_E_UNSUPPORTED (-2) /* unsupported loss / forward combination (raised at plan build) */
+#define JAXENT_E_CUDA (-3)      /* launch / runtime error             (reference: RuntimeError, opt/run.py:350-353) */
+#define JAXENT_E_WORKSPACE (-4) /* workspace too small */
+
+/* loss slot kinds; one per (loss_function, data_target) pair of run_optimise (opt/run.py:376-406) */
+enum {
+  JAXENT_LOSS_UPTAKE_EYE_MSE = 0,    /* hdx_uptake_eye_MSE_loss               opt/losses.py:1601 */
+  JAXENT_LOSS_UPTAKE_MC_EYE_MSE = 1, /* hdx_uptake_mean_centred_eye_MSE_loss  opt/losses.py:1790 */
+  JAXENT_LOSS_UPTAKE_SIGMA_MSE = 2,  /* hdx_uptake_sigma_MSE_loss             opt/losses.py:1541 */
+  JAXENT_LOSS_PF_L2 = 3,             /* hdx_pf_l2_loss                        opt/losses.py:17   */
+  JAXENT_LOSS_MAXENT_CONVEX_KL = 4,  /* maxent_convexKL_loss                  opt/losses.py:304  */
+  JAXENT_LOSS_PARAMS_L1 = 5,         /* model_params_L1_loss                  opt/losses.py:495  */
+  JAXENT_LOSS_PARAMS_L2 = 6          /* model_params_L2_loss                  opt/losses.py:476  */
+};
+
+#define JAXENT_MAX_SLOTS 6
+
+/* Peptide<-residue map in CSR (rows = peptides) plus its transpose in CSC order (rows = residues),
+ * both on the device.  Same linear map as the reference's dense `sparse_map.todense() @ x`. */
+typedef struct {
+  int32_t n_pep;
+  const int32_t* row_ptr; /* (n_pep+1) */
+  const int32_t* col;     /* (nnz) residue index   */
+  const float* val;       /* (nnz)                 */
+  const int32_t* t_ptr;   /* (R+1)   transpose     */
+  const int32_t* t_row;   /* (nnz) peptide index   */
+  const float* t_val;     /* (nnz)                 */
+  const float* y;         /* uptake kinds: (n_pep, T) row-major [Dataset.y_true (P,T,1)]; PF: (n_pep) */
+  const float* W;         /* sigma kind: (n_pep,n_pep) trace-normalised precision, else NULL */
+} JaxentPeptideMap;
+
+typedef struct {
+  int32_t kind;
+  JaxentPeptideMap train; /* data kinds only */
+  JaxentPeptideMap val;
+  float prior_bc, prior_bh; /* PARAMS_L1/L2 */
+} JaxentLossSlot;
+
+/* Static description of one rank's shard of the problem. */
+typedef struct {
+  int32_t R;            /* residues */
+  int32_t T;            /* time points (uptake mode) */
+  int32_t uptake;       /* 1: BV_uptake_ForwardPass, 0: BV_ForwardPass (log_Pf) */
+  int32_t n_slots;
+  int64_t F;            /* frames held by this rank */
+  int64_t F_total;      /* frames of the whole ensemble (eps = 1e-10 / F_total, opt/losses.py:308) */
+  const float* packed;  /* packed features, jaxent_bv_packed_bytes() bytes, 16-byte aligned */
+  const float* k_ints;  /* (R)  uptake mode */
+  const float* timepoints; /* (T) uptake mode */
+  const float* prior;   /* (F) this rank's slice of the MaxEnt prior frame weights, or NULL */
+  double prior_norm;    /* sum over ALL ranks of (|prior_f| + eps); see jaxent_bv_prior_partial() */
+  JaxentLossSlot slots[JAXENT_MAX_SLOTS];
+} JaxentBvProblem;
+
+/* OptaxOptimizer.__init__ arguments (opt/optimiser.py:68-82) */
+typedef struct {
+  float learning_rate;
+  float initial_learning_rate;
+  int32_t initial_steps;
+  float plateau_denominator;
+  float model_parameters_lr_scale;
+  float clip_value;             /* <= 0: no clipping (clip_value=None) */
+  int32_t optimise_frame_weights;
+  int32_t optimise_model_parameters;
+  double b1, b2, eps;           /* optax.adam defaults 0.9 / 0.999 / 1e-8 (doubles: optax forms 1-b1 in Python floats) */
+} JaxentOptConfig;
+
+/* LossComponents (opt/base.py:61-69) of one step, plus the step's scalars. */
+typedef struct {
+  int32_t step;      /* state.step the loss was evaluated at */
+  int32_t branch;    /* 1 if the plateau rule reduced the LR for the update that led here */
+  float lr;          /* learning rate used by that update */
+  float grad_dot;    /* sum vdot(prev_grads, grads) of that update (opt/optimiser.py:398-401) */
+  float bc, bh;      /* BV parameters the loss was evaluated at */
+  float total_train, total_val;
+  float train[JAXENT_MAX_SLOTS], val[JAXENT_MAX_SLOTS];
+  float scaled_train[JAXENT_MAX_SLOTS], scaled_val[JAXENT_MAX_SLOTS];
+  float grad_bc, grad_bh; /* masked d loss / d bc, bh at this step */
+  int32_t complete;  /* 1 once the MaxEnt term has been folded in */
+  int32_t pad;
+} JaxentLossRecord;
+
+typedef struct JaxentPlan JaxentPlan; /* opaque, host memory */
+
+/* identifiers for jaxent_bv_plan_buffer() */
+enum {
+  JAXENT_BUF_RED = 0,      /* double[4R+4]  per-rank partial sums -> all-reduce(sum) #1 across ranks   */
+  JAXENT_BUF_KLSUM = 1,    /* double[4]     per-rank MaxEnt sums  -> all-reduce(sum) #2 across ranks   */
+  JAXENT_BUF_WEIGHTS = 2,  /* float[F]      softmax(z) of the current step (save_state.params.frame_weights) */
+  JAXENT_BUF_RECORDS = 4,  /* JaxentLossRecord[JAXENT_RECORD_RING]                                      */
+  JAXENT_BUF_LOGPF = 5,    /* float[R]      log_Pf of the current step                                  */
+  JAXENT_BUF_UPTAKE = 6,   /* float[T*R]    uptake (T,R) of the current step (uptake mode)              */
+  JAXENT_BUF_AVG = 7       /* float[2R]     frame-averaged heavy / acceptor contacts                    */
+};
+#define JAXENT_RECORD_RING 4096
+
+const char* jaxent_last_error(void);
+int jaxent_version(void);
+/* sizeof of the ABI structs, for binding self-checks: 0 JaxentBvProblem, 1 JaxentOptConfig, 2 JaxentLossRecord,
+ * 3 JaxentLossSlot, 4 JaxentPeptideMap; -1 for an unknown id */
+int jaxent_abi_sizeof(int which);
+
+/* ---- feature packing (one-off; replaces Input_Features.cast_to_jax, custom_types/features.py:82-89) ---- */
+/* bytes of the packed layout for (R,F): [ceil(F/8)*2 quads][2 arrays][R rows][4 frames] fp32 */
+size_t jaxent_bv_packed_bytes(int32_t R, int64_t F);
+/* heavy / acceptor: (R, F) row-major fp32 on the device with leading dimension ld (>= F). */
+int jaxent_bv_pack_features_f32(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld,
+                                int64_t frame_offset, int64_t F_dst, float* packed, jaxent_stream_t stream);
+
+/* per-rank partial of sum_f (|prior_f| + eps) written to out[0] (device double) */
+int jaxent_bv_prior_partial(const float* prior, int64_t F, double eps, double* out, jaxent_stream_t stream);
+/* max_f z_f written to out[0] (device float); used once for the initial log-sum-exp shift */
+int jaxent_bv_max(const float* z, int64_t F, float* out, jaxent_stream_t stream);
+
+/* ---- plan ---- */
+size_t jaxent_bv_workspace_bytes(const JaxentBvProblem* problem);
+int jaxent_bv_plan_create(const JaxentBvProblem* problem, const JaxentOptConfig* cfg, void* workspace,
+                          size_t workspace_bytes, int32_t device_sm_count, JaxentPlan** plan);
+void jaxent_bv_plan_destroy(JaxentPlan* plan);
+int jaxent_bv_plan_buffer(const JaxentPlan* plan, int32_t which, void** ptr, size_t* bytes);
+
+/* ---- state ----
+ * OptaxOptimizer.initialise (opt/optimiser.py:221-304): z0 are the logits (w_init * F_total), zmax
+ * the max of z0 over ALL ranks, bc/bh the BV parameters, fw/fs the (already normalised)
+ * forward_model_weights / forward_model_scaling.  Zeroes the Adam moments. */
+int jaxent_bv_state_init(JaxentPlan* plan, const float* z0, float zmax, float bc, float bh, const float* fw_host,
+                         const float* fs_host, jaxent_stream_t stream);
+
+/* ---- the step, in the three phases a frame-sharded run interleaves with its two all-reduces ----
+ *   pass   : one streaming pass over the packed features: backward of step k (column sums),
+ *            mask, Adam on the frame logits for both plateau-LR branches, forward of step k+1
+ *            (softmax-weighted row sums).  mode 0 = forward only (used once after state_init).
+ *   reduce : per-CTA partials -> JAXENT_BUF_RED (deterministic order)
+ *            [all-reduce(sum) JAXENT_BUF_RED across ranks here]
+ *   tail   : plateau decision, BV-parameter Adam, ln PF / uptake / peptide map / losses and their
+ *            backward (the R x T tail), MaxEnt per-frame terms -> JAXENT_BUF_KLSUM
+ *            [all-reduce(sum) JAXENT_BUF_KLSUM across ranks here]
+ */
+int jaxent_bv_pass(JaxentPlan* plan, int32_t mode, jaxent_stream_t stream);
+int jaxent_bv_reduce(JaxentPlan* plan, jaxent_stream_t stream);
+int jaxent_bv_tail(JaxentPlan* plan, jaxent_stream_t stream);
+/* folds the (all-reduced) MaxEnt sums into the newest loss record without running a pass */
+int jaxent_bv_finish_record(JaxentPlan* plan, jaxent_stream_t stream);
+
+/* single-rank conveniences: init = pass(0)+reduce+tail ; step = pass(1)+reduce+tail */
+int jaxent_bv_forward_init(JaxentPlan* plan, jaxent_stream_t stream);
+int jaxent_bv_step(JaxentPlan* plan, jaxent_stream_t stream);
+
+/* copy the current optimiser state (chosen plateau branch) to caller buffers; any pointer may be NULL.
+ * z/m/v: float[F] logits and Adam moments; g: float[F] masked d loss / d z of the last completed update;
+ * scalars: float[8] = {step, lr, model_lr, mask_idx, bc, bh, count_frame, count_model} */
+int jaxent_bv_export_state(JaxentPlan* plan, float* z, float* m, float* v, float* g, float* scalars,
+                           jaxent_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAXENT_B200_H_ */

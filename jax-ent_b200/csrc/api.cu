@@ -1,0 +1,466 @@
+// C ABI of libjaxent_b200: plan / workspace management and the step entry points.
+// See include/jaxent_b200.h for the contract and the reference symbols each call replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "jx_internal.cuh"
+
+namespace jx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Layout {
+  size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
+  size_t off_w, off_kappa, off_cc, off_ch, off_logpf, off_uptake, off_avg;
+  size_t off_partials, off_red, off_klpart, off_klsum, off_ctl, off_epoch, off_counter, off_records;
+  size_t total;
+};
+
+constexpr int MAX_PASS_CTAS = 2 * 160;
+constexpr int MAX_TAIL_CTAS = 160;
+
+static Layout make_layout(int R, int T, long long F) {
+  Layout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o = align_up(o + bytes, 256);
+    return r;
+  };
+  const size_t fb = (size_t)F * sizeof(float);
+  for (int s = 0; s < 2; ++s)
+    for (int b = 0; b < 2; ++b) {
+      L.off_z[s][b] = take(fb);
+      L.off_m[s][b] = take(fb);
+      L.off_v[s][b] = take(fb);
+    }
+  L.off_g[0] = take(fb);
+  L.off_g[1] = take(fb);
+  L.off_w = take(fb);
+  L.off_kappa = take(fb);
+  L.off_cc = take((size_t)R * 4);
+  L.off_ch = take((size_t)R * 4);
+  L.off_logpf = take((size_t)R * 4);
+  L.off_uptake = take((size_t)(T > 0 ? T : 1) * R * 4);
+  L.off_avg = take((size_t)2 * R * 4);
+  L.off_partials = take((size_t)MAX_PASS_CTAS * (4 * R + 4) * sizeof(double));
+  L.off_red = take((size_t)(4 * R + 4) * sizeof(double));
+  L.off_klpart = take((size_t)MAX_TAIL_CTAS * KL_N * sizeof(double));
+  L.off_klsum = take(KL_N * sizeof(double));
+  L.off_ctl = take(2 * sizeof(Ctl));
+  L.off_epoch = take(sizeof(unsigned));
+  L.off_counter = take(sizeof(unsigned));
+  L.off_records = take((size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord));
+  L.total = o;
+  return L;
+}
+
+__global__ void state_init_kernel(const float* __restrict__ z0, long long F, StateSets st, Ctl* ctl, Ctl init,
+                                  unsigned* epoch, unsigned* counter, double* klsum, JaxentLossRecord* records) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long f = i0; f < F; f += stride) {
+    st.z[0][0][f] = z0[f];
+    st.m[0][0][f] = 0.f;
+    st.v[0][0][f] = 0.f;
+    st.g[0][f] = 0.f;
+    st.g[1][f] = 0.f;
+  }
+  if (i0 == 0) {
+    ctl[0] = init;
+    ctl[1] = init;
+    *epoch = 0u;
+    *counter = 0u;
+    for (int i = 0; i < KL_N; ++i) klsum[i] = 0.0;
+  }
+  for (long long i = i0; i < (long long)(JAXENT_RECORD_RING * sizeof(JaxentLossRecord) / 4); i += stride)
+    reinterpret_cast<int*>(records)[i] = 0;
+}
+
+__global__ void export_kernel(StateSets st, const Ctl* ctl, const unsigned* epoch, long long F, float* z, float* m,
+                              float* v, float* g, float* scalars) {
+  const unsigned ep = *epoch;
+  const Ctl* c = ctl + (ep & 1u);
+  const int set = ep & 1u, br = c->branch;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long f = i0; f < F; f += stride) {
+    if (z) z[f] = st.z[set][br][f];
+    if (m) m[f] = st.m[set][br][f];
+    if (v) v[f] = st.v[set][br][f];
+    if (g) g[f] = st.g[set][f];
+  }
+  if (i0 == 0 && scalars) {
+    scalars[0] = (float)c->step;
+    scalars[1] = c->lr;
+    scalars[2] = c->model_lr;
+    scalars[3] = (float)c->mask_idx;
+    scalars[4] = c->bc;
+    scalars[5] = c->bh;
+    scalars[6] = (float)c->count_frame;
+    scalars[7] = (float)c->count_model;
+  }
+}
+
+}  // namespace jx
+
+struct JaxentPlan {
+  JaxentBvProblem prob;
+  JaxentOptConfig cfg;
+  jx::Layout lay;
+  unsigned char* ws;
+  jx::StateSets st;
+  int pass_threads, rpt, pass_ctas, stages, tail_ctas, p_max;
+  uint32_t tile_bytes, stage_stride;
+  size_t pass_smem, tail_smem;
+  long long n_tiles;
+  int initialised;
+};
+
+using namespace jx;
+
+static int validate_problem(const JaxentBvProblem* p) {
+  if (!p) { set_error("problem is NULL"); return JAXENT_E_INVALID; }
+  if (p->R <= 0 || p->F <= 0 || p->F_total < p->F) {
+    set_error("invalid shape: R=%d F=%lld F_total=%lld", p->R, (long long)p->F, (long long)p->F_total);
+    return JAXENT_E_INVALID;
+  }
+  if (p->R > 4 * PASS_THREADS_MAX) {
+    set_error("n_residues=%d exceeds the supported maximum %d", p->R, 4 * PASS_THREADS_MAX);
+    return JAXENT_E_UNSUPPORTED;
+  }
+  if (!p->packed || (reinterpret_cast<uintptr_t>(p->packed) & 15u)) {
+    set_error("packed features must be a 16-byte aligned device pointer");
+    return JAXENT_E_INVALID;
+  }
+  if (p->n_slots <= 0 || p->n_slots > JAXENT_MAX_SLOTS) {
+    set_error("n_slots=%d outside 1..%d", p->n_slots, JAXENT_MAX_SLOTS);
+    return JAXENT_E_INVALID;
+  }
+  if (p->uptake && (p->T <= 0 || !p->k_ints || !p->timepoints)) {
+    set_error("uptake mode needs T>0, k_ints and timepoints");
+    return JAXENT_E_INVALID;
+  }
+  int n_kl = 0;
+  for (int i = 0; i < p->n_slots; ++i) {
+    const JaxentLossSlot& s = p->slots[i];
+    switch (s.kind) {
+      case JAXENT_LOSS_UPTAKE_EYE_MSE:
+      case JAXENT_LOSS_UPTAKE_MC_EYE_MSE:
+      case JAXENT_LOSS_UPTAKE_SIGMA_MSE:
+        if (!p->uptake) { set_error("slot %d: uptake loss needs BV_uptake_ForwardPass (uptake=1)", i); return JAXENT_E_UNSUPPORTED; }
+        break;
+      case JAXENT_LOSS_PF_L2:
+        if (p->uptake) { set_error("slot %d: hdx_pf_l2_loss needs BV_ForwardPass (uptake=0)", i); return JAXENT_E_UNSUPPORTED; }
+        break;
+      case JAXENT_LOSS_MAXENT_CONVEX_KL:
+        if (!p->prior || !(p->prior_norm > 0.0)) { set_error("slot %d: maxent_convexKL_loss needs prior and prior_norm", i); return JAXENT_E_INVALID; }
+        if (++n_kl > 1) { set_error("at most one maxent_convexKL_loss slot is supported"); return JAXENT_E_UNSUPPORTED; }
+        break;
+      case JAXENT_LOSS_PARAMS_L1:
+      case JAXENT_LOSS_PARAMS_L2:
+        break;
+      default:
+        set_error("slot %d: unsupported loss kind %d (this path covers the losses of SURVEY.md section 8a)", i, s.kind);
+        return JAXENT_E_UNSUPPORTED;
+    }
+    if (s.kind <= JAXENT_LOSS_PF_L2) {
+      const JaxentPeptideMap* maps[2] = {&s.train, &s.val};
+      for (const JaxentPeptideMap* m : maps) {
+        if (m->n_pep < 0 || (m->n_pep > 0 && (!m->row_ptr || !m->col || !m->val || !m->t_ptr || !m->t_row || !m->t_val || !m->y))) {
+          set_error("slot %d: incomplete peptide map", i);
+          return JAXENT_E_INVALID;
+        }
+        if (s.kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE && m->n_pep > 0 && !m->W) {
+          set_error("slot %d: sigma MSE needs the precision matrix W", i);
+          return JAXENT_E_INVALID;
+        }
+      }
+      if (s.train.n_pep <= 0) { set_error("slot %d: empty training set", i); return JAXENT_E_INVALID; }
+    }
+  }
+  return JAXENT_OK;
+}
+
+extern "C" const char* jaxent_last_error(void) { return g_err; }
+extern "C" int jaxent_version(void) { return 100; }
+extern "C" int jaxent_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(JaxentBvProblem);
+    case 1: return (int)sizeof(JaxentOptConfig);
+    case 2: return (int)sizeof(JaxentLossRecord);
+    case 3: return (int)sizeof(JaxentLossSlot);
+    case 4: return (int)sizeof(JaxentPeptideMap);
+    default: return -1;
+  }
+}
+
+extern "C" size_t jaxent_bv_workspace_bytes(const JaxentBvProblem* p) {
+  if (!p || p->R <= 0 || p->F <= 0) return 0;
+  return make_layout(p->R, p->uptake ? p->T : 0, p->F).total;
+}
+
+extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const JaxentOptConfig* cfg, void* workspace,
+                                     size_t workspace_bytes, int32_t device_sm_count, JaxentPlan** out) {
+  if (!out) { set_error("plan output pointer is NULL"); return JAXENT_E_INVALID; }
+  *out = nullptr;
+  int rc = validate_problem(problem);
+  if (rc) return rc;
+  if (!cfg) { set_error("optimiser config is NULL"); return JAXENT_E_INVALID; }
+  if (!(cfg->plateau_denominator > 0.f) || !(cfg->b1 >= 0.0 && cfg->b1 < 1.0) || !(cfg->b2 >= 0.0 && cfg->b2 < 1.0)) {
+    set_error("invalid optimiser config");
+    return JAXENT_E_INVALID;
+  }
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
+    set_error("workspace must be a 256-byte aligned device pointer");
+    return JAXENT_E_INVALID;
+  }
+  const int R = problem->R, T = problem->uptake ? problem->T : 0;
+  Layout L = make_layout(R, T, problem->F);
+  if (workspace_bytes < L.total) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, L.total);
+    return JAXENT_E_WORKSPACE;
+  }
+  if (device_sm_count <= 0) device_sm_count = 148;
+  if (device_sm_count > 160) device_sm_count = 160;
+
+  JaxentPlan* p = new (std::nothrow) JaxentPlan();
+  if (!p) { set_error("out of host memory"); return JAXENT_E_INVALID; }
+  p->prob = *problem;
+  p->cfg = *cfg;
+  p->lay = L;
+  p->ws = static_cast<unsigned char*>(workspace);
+  for (int s = 0; s < 2; ++s)
+    for (int b = 0; b < 2; ++b) {
+      p->st.z[s][b] = reinterpret_cast<float*>(p->ws + L.off_z[s][b]);
+      p->st.m[s][b] = reinterpret_cast<float*>(p->ws + L.off_m[s][b]);
+      p->st.v[s][b] = reinterpret_cast<float*>(p->ws + L.off_v[s][b]);
+    }
+  p->st.g[0] = reinterpret_cast<float*>(p->ws + L.off_g[0]);
+  p->st.g[1] = reinterpret_cast<float*>(p->ws + L.off_g[1]);
+
+  // pass geometry: one residue row per thread, RPT rows when R > 512
+  p->rpt = (R <= PASS_THREADS_MAX) ? 1 : (R <= 2 * PASS_THREADS_MAX ? 2 : 4);
+  const int rows_per_thread_threads = (R + p->rpt - 1) / p->rpt;
+  p->pass_threads = ((rows_per_thread_threads + 31) / 32) * 32;
+  if (p->pass_threads < 32) p->pass_threads = 32;
+  p->tile_bytes = (uint32_t)(FT * R * 2 * sizeof(float));
+  p->stage_stride = (uint32_t)align_up(p->tile_bytes, 128);
+  const size_t smem_budget = (p->rpt == 1 ? 108 : 216) * 1024;
+  const size_t fixed = MAX_STAGES * 8 + 16 * FT * 4 + 2 * FT * 4 + 128;
+  int stages = (int)((smem_budget - fixed) / p->stage_stride);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) { delete p; set_error("tile of %u bytes does not fit a 2-stage ring", p->tile_bytes); return JAXENT_E_UNSUPPORTED; }
+  p->stages = stages;
+  p->pass_smem = (size_t)stages * p->stage_stride + fixed;
+  p->n_tiles = (problem->F + FT - 1) / FT;
+  const int per_sm = (p->rpt == 1) ? 2 : 1;
+  long long ctas = (long long)device_sm_count * per_sm;
+  if (ctas > p->n_tiles) ctas = p->n_tiles;
+  if (ctas > MAX_PASS_CTAS) ctas = MAX_PASS_CTAS;
+  p->pass_ctas = (int)ctas;
+
+  int p_max = 1;
+  for (int i = 0; i < problem->n_slots; ++i)
+    if (problem->slots[i].kind <= JAXENT_LOSS_PF_L2) {
+      if (problem->slots[i].train.n_pep > p_max) p_max = problem->slots[i].train.n_pep;
+      if (problem->slots[i].val.n_pep > p_max) p_max = problem->slots[i].val.n_pep;
+    }
+  p->p_max = p_max;
+  p->tail_smem = tail_smem_bytes(R, T, p_max);
+  if (p->tail_smem > 200 * 1024) {
+    delete p;
+    set_error("R*T / peptide count too large for the tail kernel (%zu bytes of shared memory)", tail_smem_bytes(R, T, p_max));
+    return JAXENT_E_UNSUPPORTED;
+  }
+  long long tctas = (problem->F + 2047) / 2048;
+  if (tctas > device_sm_count) tctas = device_sm_count;
+  if (tctas < 1) tctas = 1;
+  p->tail_ctas = (int)tctas;
+  p->initialised = 0;
+  *out = p;
+  return JAXENT_OK;
+}
+
+extern "C" void jaxent_bv_plan_destroy(JaxentPlan* plan) { delete plan; }
+
+extern "C" int jaxent_bv_plan_buffer(const JaxentPlan* p, int32_t which, void** ptr, size_t* bytes) {
+  if (!p || !ptr || !bytes) { set_error("plan_buffer: NULL argument"); return JAXENT_E_INVALID; }
+  const int R = p->prob.R, T = p->prob.uptake ? p->prob.T : 0;
+  switch (which) {
+    case JAXENT_BUF_RED: *ptr = p->ws + p->lay.off_red; *bytes = (size_t)(4 * R + 4) * 8; break;
+    case JAXENT_BUF_KLSUM: *ptr = p->ws + p->lay.off_klsum; *bytes = KL_N * 8; break;
+    case JAXENT_BUF_WEIGHTS: *ptr = p->ws + p->lay.off_w; *bytes = (size_t)p->prob.F * 4; break;
+    case JAXENT_BUF_RECORDS: *ptr = p->ws + p->lay.off_records; *bytes = (size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord); break;
+    case JAXENT_BUF_LOGPF: *ptr = p->ws + p->lay.off_logpf; *bytes = (size_t)R * 4; break;
+    case JAXENT_BUF_UPTAKE: *ptr = p->ws + p->lay.off_uptake; *bytes = (size_t)T * R * 4; break;
+    case JAXENT_BUF_AVG: *ptr = p->ws + p->lay.off_avg; *bytes = (size_t)2 * R * 4; break;
+    default: set_error("plan_buffer: unknown buffer id %d", which); return JAXENT_E_INVALID;
+  }
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bv_state_init(JaxentPlan* p, const float* z0, float zmax, float bc, float bh, const float* fw_host,
+                                    const float* fs_host, jaxent_stream_t stream) {
+  if (!p || !z0 || !fw_host || !fs_host) { set_error("state_init: NULL argument"); return JAXENT_E_INVALID; }
+  int rc = configure_kernels();
+  if (rc) return rc;
+  Ctl c;
+  memset(&c, 0, sizeof(c));
+  c.lr = p->cfg.initial_learning_rate;
+  c.model_lr = p->cfg.initial_learning_rate * p->cfg.model_parameters_lr_scale;
+  c.bc = bc;
+  c.bh = bh;
+  c.lse = zmax;
+  c.kl_slot = -1;
+  c.lrA = c.lrB = c.lr;
+  c.mlrA = c.mlrB = c.model_lr;
+  c.mask_frame = 1.f;
+  c.bc1 = c.bc2 = 1.f;
+  for (int i = 0; i < p->prob.n_slots; ++i) {
+    c.fw[i] = fw_host[i];
+    c.fs[i] = fs_host[i];
+    if (p->prob.slots[i].kind == JAXENT_LOSS_MAXENT_CONVEX_KL) {
+      c.kl_slot = i;
+      c.kl_scale = fw_host[i] * fs_host[i];
+    }
+  }
+  Ctl* ctl = reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl);
+  state_init_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(
+      z0, p->prob.F, p->st, ctl, c, reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch),
+      reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter), reinterpret_cast<double*>(p->ws + p->lay.off_klsum),
+      reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("state_init launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  p->initialised = 1;
+  return JAXENT_OK;
+}
+
+static int check_ready(const JaxentPlan* p, const char* what) {
+  if (!p) { set_error("%s: plan is NULL", what); return JAXENT_E_INVALID; }
+  if (!p->initialised) { set_error("%s: jaxent_bv_state_init has not been called", what); return JAXENT_E_INVALID; }
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t stream) {
+  int rc = check_ready(p, "pass");
+  if (rc) return rc;
+  if (mode != 0 && mode != 1) { set_error("pass: mode must be 0 or 1"); return JAXENT_E_INVALID; }
+  PassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = p->prob.packed;
+  a.R = p->prob.R;
+  a.mode = mode;
+  a.stages = p->stages;
+  a.part_n = 4 * p->prob.R + 4;
+  a.tile_bytes = p->tile_bytes;
+  a.stage_stride = p->stage_stride;
+  a.n_tiles = p->n_tiles;
+  a.F = p->prob.F;
+  a.st = p->st;
+  a.w = reinterpret_cast<const float*>(p->ws + p->lay.off_w);
+  a.kappa = reinterpret_cast<const float*>(p->ws + p->lay.off_kappa);
+  a.cc = reinterpret_cast<const float*>(p->ws + p->lay.off_cc);
+  a.ch = reinterpret_cast<const float*>(p->ws + p->lay.off_ch);
+  a.partials = reinterpret_cast<double*>(p->ws + p->lay.off_partials);
+  a.klsum = reinterpret_cast<const double*>(p->ws + p->lay.off_klsum);
+  a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
+  a.epoch = reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch);
+  a.records = reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records);
+  a.b1 = (float)p->cfg.b1;
+  a.b2 = (float)p->cfg.b2;
+  a.om_b1 = (float)(1.0 - p->cfg.b1);
+  a.om_b2 = (float)(1.0 - p->cfg.b2);
+  a.eps = (float)p->cfg.eps;
+  a.clip = p->cfg.clip_value;
+  return launch_pass(a, p->pass_threads, p->rpt, p->pass_ctas, p->pass_smem, (cudaStream_t)stream);
+}
+
+extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t stream) {
+  int rc = check_ready(p, "reduce");
+  if (rc) return rc;
+  ReduceArgs a;
+  a.partials = reinterpret_cast<const double*>(p->ws + p->lay.off_partials);
+  a.red = reinterpret_cast<double*>(p->ws + p->lay.off_red);
+  a.epoch = reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch);
+  a.n_part = p->pass_ctas;
+  a.part_n = 4 * p->prob.R + 4;
+  return launch_reduce(a, (cudaStream_t)stream);
+}
+
+extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
+  int rc = check_ready(p, "tail");
+  if (rc) return rc;
+  TailArgs a;
+  memset(&a, 0, sizeof(a));
+  a.prob = p->prob;
+  a.cfg = p->cfg;
+  a.st = p->st;
+  a.red = reinterpret_cast<const double*>(p->ws + p->lay.off_red);
+  a.ctl = reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl);
+  a.epoch = reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch);
+  a.counter = reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter);
+  a.w = reinterpret_cast<float*>(p->ws + p->lay.off_w);
+  a.kappa = reinterpret_cast<float*>(p->ws + p->lay.off_kappa);
+  a.cc = reinterpret_cast<float*>(p->ws + p->lay.off_cc);
+  a.ch = reinterpret_cast<float*>(p->ws + p->lay.off_ch);
+  a.logpf = reinterpret_cast<float*>(p->ws + p->lay.off_logpf);
+  a.uptake = reinterpret_cast<float*>(p->ws + p->lay.off_uptake);
+  a.avg = reinterpret_cast<float*>(p->ws + p->lay.off_avg);
+  a.klpart = reinterpret_cast<double*>(p->ws + p->lay.off_klpart);
+  a.klsum = reinterpret_cast<double*>(p->ws + p->lay.off_klsum);
+  a.records = reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records);
+  a.p_max = p->p_max;
+  a.eps_kl = (float)(1e-10 / (double)p->prob.F_total);
+  return launch_tail(a, p->tail_ctas, p->tail_smem, (cudaStream_t)stream);
+}
+
+extern "C" int jaxent_bv_finish_record(JaxentPlan* p, jaxent_stream_t stream) {
+  int rc = check_ready(p, "finish_record");
+  if (rc) return rc;
+  return launch_finish_record(reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl),
+                              reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch),
+                              reinterpret_cast<const double*>(p->ws + p->lay.off_klsum),
+                              reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records), p->prob.n_slots,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int jaxent_bv_forward_init(JaxentPlan* p, jaxent_stream_t stream) {
+  int rc = jaxent_bv_pass(p, 0, stream);
+  if (rc) return rc;
+  rc = jaxent_bv_reduce(p, stream);
+  if (rc) return rc;
+  return jaxent_bv_tail(p, stream);
+}
+
+extern "C" int jaxent_bv_step(JaxentPlan* p, jaxent_stream_t stream) {
+  int rc = jaxent_bv_pass(p, 1, stream);
+  if (rc) return rc;
+  rc = jaxent_bv_reduce(p, stream);
+  if (rc) return rc;
+  return jaxent_bv_tail(p, stream);
+}
+
+extern "C" int jaxent_bv_export_state(JaxentPlan* p, float* z, float* m, float* v, float* g, float* scalars,
+                                      jaxent_stream_t stream) {
+  int rc = check_ready(p, "export_state");
+  if (rc) return rc;
+  export_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(p->st, reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl),
+                                                       reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch),
+                                                       p->prob.F, z, m, v, g, scalars);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("export launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}

@@ -1,0 +1,136 @@
+// Internal declarations shared by the CUDA translation units.  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jaxent_b200.h"
+
+namespace jx {
+
+constexpr int FT = 8;           // frames per tile (2 quads of 4 frames)
+constexpr int QT = FT / 4;      // quads per tile
+constexpr int MAX_STAGES = 8;   // bulk-copy ring depth upper bound
+constexpr int PASS_THREADS_MAX = 512;
+constexpr int TAIL_THREADS = 512;
+constexpr int KL_N = 4;         // MaxEnt partial sums: sum w*kappa, sum p(log p - log q), sum(q - p), sum w
+
+// Device-resident control block; two copies, indexed by (epoch & 1).  Written only by the tail
+// kernel (and state_init), read by the pass kernel that follows it.
+struct Ctl {
+  int step;         // number of updates applied to the current parameters (reference state.step)
+  int mask_idx;     // optimizer._current_gradient_mask_idx
+  int branch;       // which plateau branch of state set (epoch & 1) holds the current z/m/v
+  int pending;      // a speculative update (pass mode 1) precedes the next tail
+  int have_prev;    // state.gradients is not None
+  int count_frame;  // optax adam count of the "frame" label
+  int count_model;  // optax adam count of the "model" label
+  int kl_slot;      // index of the MaxEnt slot or -1
+  float lr, model_lr;          // optimizer._current_lr / _current_model_lr
+  float bc, bh;                // BV parameters
+  float mb[2], vb[2];          // Adam moments of (bc, bh)
+  float gb_prev[2], gb[2];     // masked d loss / d (bc,bh): previous and current step
+  // prepared for the pass that follows:
+  float lrA, lrB, mlrA, mlrB;  // speculative learning rates (base, base / plateau_denominator)
+  float mask_frame, mask_model;
+  float bc1, bc2;              // 1 - b1^t, 1 - b2^t of the coming frame Adam update
+  float lse;                   // log-sum-exp shift: exp(z - lse) are the softmax weights
+  float kl_scale;              // fw*fs of the MaxEnt slot
+  float last_dot, last_lr;
+  int last_branch;
+  int rec_idx;                 // ring index of this step's loss record
+  double hbar_data;            // sum_r c_r * log_Pf_r  (= sum_j w_j h_j, data part)
+  float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
+};
+
+struct StateSets {
+  float* z[2][2];
+  float* m[2][2];
+  float* v[2][2];
+  float* g[2];
+};
+
+struct PassArgs {
+  const float* packed;
+  int R;
+  int mode;
+  int stages;
+  int part_n;         // 4R + 4
+  uint32_t tile_bytes;
+  uint32_t stage_stride;
+  long long n_tiles;
+  long long F;
+  StateSets st;
+  const float* w;
+  const float* kappa;
+  const float* cc;
+  const float* ch;
+  double* partials;
+  const double* klsum;
+  const Ctl* ctl;
+  const unsigned* epoch;
+  JaxentLossRecord* records;
+  float b1, b2, om_b1, om_b2, eps, clip;
+};
+
+struct ReduceArgs {
+  const double* partials;
+  double* red;
+  unsigned* epoch;
+  int n_part;
+  int part_n;
+};
+
+struct TailArgs {
+  JaxentBvProblem prob;   // by value: device pointers + dims
+  JaxentOptConfig cfg;
+  StateSets st;
+  const double* red;
+  Ctl* ctl;
+  const unsigned* epoch;
+  unsigned* counter;
+  float* w;
+  float* kappa;
+  float* cc;
+  float* ch;
+  float* logpf;
+  float* uptake;
+  float* avg;
+  double* klpart;
+  double* klsum;
+  JaxentLossRecord* records;
+  int p_max;
+  float eps_kl;   // 1e-10 / F_total
+};
+
+void set_error(const char* fmt, ...);
+
+int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s);
+int launch_reduce(const ReduceArgs& a, cudaStream_t s);
+int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
+int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const double* klsum, JaxentLossRecord* rec, int n_slots,
+                         cudaStream_t s);
+size_t tail_smem_bytes(int R, int T, int p_max);
+int configure_kernels();
+
+__device__ __forceinline__ void finish_record(const Ctl* c, const double* klsum, JaxentLossRecord* records, int n_slots) {
+  JaxentLossRecord* r = records + c->rec_idx;
+  if (c->kl_slot >= 0) {
+    const float kl = (float)(klsum[1] + klsum[2]);
+    r->train[c->kl_slot] = kl;
+    r->val[c->kl_slot] = kl;
+  }
+  float tt = 0.f, tv = 0.f;
+  for (int i = 0; i < n_slots; ++i) {
+    const float st = r->train[i] * c->fw[i] * c->fs[i];
+    const float sv = r->val[i] * c->fw[i] * c->fs[i];
+    r->scaled_train[i] = st;
+    r->scaled_val[i] = sv;
+    tt += st;
+    tv += sv;
+  }
+  r->total_train = tt;
+  r->total_val = tv;
+  r->complete = 1;
+}
+
+}  // namespace jx

@@ -1,0 +1,359 @@
+"""BvEngine: owns the device buffers of one rank's shard and drives the C ABI.
+
+PyTorch is used only as plumbing here (device memory, streams, CUDA graphs, torch.distributed);
+every arithmetic kernel on the path lives in libjaxent_b200.so.  Frame sharding: each rank
+holds a contiguous block of frames; per step there are two small all-reduces (NCCL, sum):
+the (4R+4)-double partial-sum vector after the pass and the 4-double MaxEnt vector after the
+tail (include/jaxent_b200.h, "the step, in the three phases").
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+@dataclass
+class SlotSpec:
+    """One (loss function, data target) pair; dense maps are converted to CSR/CSC on upload."""
+
+    kind: int
+    S_train: Optional[np.ndarray] = None
+    y_train: Optional[np.ndarray] = None
+    S_val: Optional[np.ndarray] = None
+    y_val: Optional[np.ndarray] = None
+    W_train: Optional[np.ndarray] = None
+    W_val: Optional[np.ndarray] = None
+    prior_bc: float = 0.35
+    prior_bh: float = 2.0
+
+
+@dataclass
+class OptSettings:
+    """OptaxOptimizer.__init__ arguments (reference opt/optimiser.py:68-82)."""
+
+    learning_rate: float = 1e-4
+    initial_learning_rate: float = 1.0
+    initial_steps: int = 0
+    plateau_denominator: float = 1.005
+    model_parameters_lr_scale: float = 1.0
+    clip_value: Optional[float] = 1.0
+    optimise_frame_weights: bool = True
+    optimise_model_parameters: bool = False
+    b1: float = 0.9
+    b2: float = 0.999
+    eps: float = 1e-8
+
+    def to_c(self) -> L.OptConfig:
+        return L.OptConfig(
+            self.learning_rate,
+            self.initial_learning_rate,
+            int(self.initial_steps),
+            self.plateau_denominator,
+            self.model_parameters_lr_scale,
+            -1.0 if self.clip_value is None else float(self.clip_value),
+            int(self.optimise_frame_weights),
+            int(self.optimise_model_parameters),
+            self.b1,
+            self.b2,
+            self.eps,
+        )
+
+
+def _csr(S: np.ndarray):
+    S = np.asarray(S, np.float32)
+    rows, cols = np.nonzero(S)
+    order = np.lexsort((cols, rows))
+    rows, cols = rows[order], cols[order]
+    ptr = np.zeros(S.shape[0] + 1, np.int32)
+    np.add.at(ptr, rows + 1, 1)
+    return np.cumsum(ptr).astype(np.int32), cols.astype(np.int32), S[rows, cols].astype(np.float32)
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+class BvEngine:
+    def __init__(
+        self,
+        heavy,
+        acceptor,
+        k_ints,
+        timepoints,
+        slots: Sequence[SlotSpec],
+        uptake: bool,
+        settings: OptSettings,
+        prior=None,
+        device: Optional[torch.device] = None,
+        F_total: Optional[int] = None,
+        group=None,
+    ):
+        if not torch.cuda.is_available():
+            raise RuntimeError("jaxent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.group = group
+        self.sharded = group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+        self.settings = settings
+        self.uptake = bool(uptake)
+        self._keep = []  # device tensors referenced by raw pointer from the plan
+
+        R, F = int(heavy.shape[0]), int(heavy.shape[1])
+        if tuple(acceptor.shape) != (R, F):
+            raise ValueError("Input features have different shapes")  # reference models/core.py:61-62
+        self.R, self.F = R, F
+        self.F_total = int(F_total) if F_total is not None else F
+        self.T = int(np.asarray(timepoints).reshape(-1).shape[0]) if self.uptake else 0
+
+        with torch.cuda.device(self.device):
+            self.packed = self._pack(heavy, acceptor)
+            prob = L.BvProblem()
+            prob.R, prob.T, prob.uptake, prob.n_slots = R, self.T, int(self.uptake), len(slots)
+            prob.F, prob.F_total = F, self.F_total
+            prob.packed = self.packed.data_ptr()
+            if self.uptake:
+                if k_ints is None:
+                    raise ValueError("BV_uptake_ForwardPass needs k_ints")
+                self.k_ints = self._dev(np.asarray(k_ints, np.float32).reshape(-1))
+                self.timepoints = self._dev(np.asarray(timepoints, np.float32).reshape(-1))
+                if self.k_ints.numel() != R:
+                    raise ValueError("k_ints must have one entry per residue")
+                prob.k_ints, prob.timepoints = self.k_ints.data_ptr(), self.timepoints.data_ptr()
+            if len(slots) > L.MAX_SLOTS:
+                raise ValueError(f"at most {L.MAX_SLOTS} loss slots are supported")
+            self.kinds = [int(s.kind) for s in slots]
+            has_kl = L.LOSS_MAXENT_CONVEX_KL in self.kinds
+            if has_kl:
+                if prior is None:
+                    raise ValueError("maxent_convexKL_loss needs the prior frame weights")
+                self.prior = self._dev_f32(prior).reshape(-1)
+                if self.prior.numel() != F:
+                    raise ValueError("prior frame weights must match n_frames")
+                eps = 1e-10 / self.F_total
+                tmp = torch.zeros(1, dtype=torch.float64, device=self.device)
+                L.check(self.lib.jaxent_bv_prior_partial(self.prior.data_ptr(), F, eps, tmp.data_ptr(), _stream_ptr()))
+                if self.sharded:
+                    torch.distributed.all_reduce(tmp, group=self.group)
+                prob.prior = self.prior.data_ptr()
+                prob.prior_norm = float(tmp.item())
+            for i, s in enumerate(slots):
+                prob.slots[i].kind = int(s.kind)
+                prob.slots[i].prior_bc, prob.slots[i].prior_bh = float(s.prior_bc), float(s.prior_bh)
+                if s.kind <= L.LOSS_PF_L2:
+                    self._fill_map(prob.slots[i].train, s.S_train, s.y_train, s.W_train, s.kind)
+                    self._fill_map(prob.slots[i].val, s.S_val, s.y_val, s.W_val, s.kind)
+            self.prob = prob
+            nbytes = self.lib.jaxent_bv_workspace_bytes(C.byref(prob))
+            if nbytes == 0:
+                raise L.JaxentError(L.E_INVALID, "workspace size query failed")
+            self.ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self._ws_off = (-self.ws.data_ptr()) % 256
+            cfg = settings.to_c()
+            plan = C.c_void_p()
+            sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            L.check(
+                self.lib.jaxent_bv_plan_create(
+                    C.byref(prob), C.byref(cfg), self.ws.data_ptr() + self._ws_off, nbytes, sm, C.byref(plan)
+                )
+            )
+            self.plan = plan
+            self.red = self._view(L.BUF_RED, torch.float64)
+            self.klsum = self._view(L.BUF_KLSUM, torch.float64)
+            self.weights = self._view(L.BUF_WEIGHTS, torch.float32)
+            self.log_pf = self._view(L.BUF_LOGPF, torch.float32)
+            self.avg = self._view(L.BUF_AVG, torch.float32)
+            self.uptake_out = self._view(L.BUF_UPTAKE, torch.float32).view(self.T, R) if self.uptake else None
+            self._records = self._view(L.BUF_RECORDS, torch.uint8)
+        self.steps_done = 0
+        self._graph = None
+        self._graph_steps = 0
+        self.launches = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.lib.jaxent_bv_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    def _dev(self, a: np.ndarray) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self._keep.append(t)
+        return t
+
+    def _dev_f32(self, a) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            t = a.to(self.device, torch.float32).contiguous()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, np.float32))).to(self.device)
+        self._keep.append(t)
+        return t
+
+    def _view(self, which: int, dtype) -> torch.Tensor:
+        ptr, nb = C.c_void_p(), C.c_size_t()
+        L.check(self.lib.jaxent_bv_plan_buffer(self.plan, which, C.byref(ptr), C.byref(nb)))
+        off = ptr.value - self.ws.data_ptr()
+        return self.ws[off : off + nb.value].view(dtype)
+
+    def _pack(self, heavy, acceptor) -> torch.Tensor:
+        """(R,F) fp32 -> packed tile layout (csrc/bv_pass.cu pack_kernel); replaces cast_to_jax
+        (reference custom_types/features.py:82-89)."""
+        R, F = int(heavy.shape[0]), int(heavy.shape[1])
+        nbytes = self.lib.jaxent_bv_packed_bytes(R, F)
+        packed = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+        h = self._to_dev_matrix(heavy)
+        a = self._to_dev_matrix(acceptor)
+        L.check(
+            self.lib.jaxent_bv_pack_features_f32(h.data_ptr(), a.data_ptr(), R, F, F, 0, F, packed.data_ptr(), _stream_ptr())
+        )
+        torch.cuda.current_stream().synchronize()
+        del h, a
+        return packed
+
+    def _to_dev_matrix(self, x) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            return x.to(self.device, torch.float32, non_blocking=True).contiguous()
+        x = np.asarray(x)
+        if x.dtype != np.float32 or not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x, np.float32)
+        return torch.from_numpy(x).to(self.device, non_blocking=True)
+
+    def _fill_map(self, m: L.PeptideMap, S, y, W, kind: int) -> None:
+        if S is None or y is None:
+            raise ValueError("data loss slot needs a peptide map and targets for train and val")
+        S = np.asarray(S, np.float32)
+        if S.ndim != 2 or S.shape[1] != self.R:
+            raise ValueError(f"peptide map must be (n_peptides, {self.R})")
+        P = S.shape[0]
+        y = np.asarray(y, np.float32)
+        if kind == L.LOSS_PF_L2:
+            y = y.reshape(-1)
+            if y.shape[0] != P:
+                raise ValueError("y_true must have one entry per peptide")
+        else:
+            y = y.reshape(P, -1)  # Dataset.y_true is (P,T,1) in the reference loader
+            if y.shape[1] != self.T:
+                raise ValueError(f"y_true must be (n_peptides, {self.T})")
+        ptr, col, val = _csr(S)
+        tptr, trow, tval = _csr(S.T)
+        m.n_pep = P
+        m.row_ptr, m.col, m.val = self._dev(ptr).data_ptr(), self._dev(col).data_ptr(), self._dev(val).data_ptr()
+        m.t_ptr, m.t_row, m.t_val = self._dev(tptr).data_ptr(), self._dev(trow).data_ptr(), self._dev(tval).data_ptr()
+        m.y = self._dev(y).data_ptr()
+        if kind == L.LOSS_UPTAKE_SIGMA_MSE:
+            if W is None:
+                raise ValueError("hdx_uptake_sigma_MSE_loss needs Dataset.covariance_matrix")
+            W = np.asarray(W, np.float32)
+            if W.shape != (P, P):
+                raise ValueError("covariance_matrix must be (n_peptides, n_peptides)")
+            m.W = self._dev(W).data_ptr()
+
+    # ------------------------------------------------------------------ state
+    def init_state(self, z0, bc: float, bh: float, fw, fs) -> None:
+        """OptaxOptimizer.initialise (reference opt/optimiser.py:221-304) + the step-0 forward."""
+        with torch.cuda.device(self.device):
+            z0 = self._dev_f32(z0).reshape(-1)
+            if z0.numel() != self.F:
+                raise ValueError("frame_weights must have one entry per frame")
+            zmax = torch.empty(1, dtype=torch.float32, device=self.device)
+            L.check(self.lib.jaxent_bv_max(z0.data_ptr(), self.F, zmax.data_ptr(), _stream_ptr()))
+            if self.sharded:
+                torch.distributed.all_reduce(zmax, op=torch.distributed.ReduceOp.MAX, group=self.group)
+            n = len(self.kinds)
+            fw = np.asarray(fw, np.float32).reshape(-1)
+            fs = np.asarray(fs, np.float32).reshape(-1)
+            if fw.shape[0] != n or fs.shape[0] != n:
+                raise ValueError("forward_model_weights / forward_model_scaling must match the number of losses")
+            fwc = (C.c_float * L.MAX_SLOTS)(*fw.tolist())
+            fsc = (C.c_float * L.MAX_SLOTS)(*fs.tolist())
+            L.check(
+                self.lib.jaxent_bv_state_init(
+                    self.plan, z0.data_ptr(), float(zmax.item()), float(bc), float(bh), fwc, fsc, _stream_ptr()
+                )
+            )
+            self._phase(0)
+            self.steps_done = 0
+            self._graph = None
+
+    def _phase(self, mode: int) -> None:
+        s = _stream_ptr()
+        L.check(self.lib.jaxent_bv_pass(self.plan, mode, s))
+        L.check(self.lib.jaxent_bv_reduce(self.plan, s))
+        if self.sharded:
+            torch.distributed.all_reduce(self.red, group=self.group)
+        L.check(self.lib.jaxent_bv_tail(self.plan, s))
+        if self.sharded:
+            torch.distributed.all_reduce(self.klsum, group=self.group)
+        self.launches += 3
+
+    def step(self, n: int = 1) -> None:
+        """n optimise steps, enqueued on the current stream without host synchronisation."""
+        with torch.cuda.device(self.device):
+            for _ in range(n):
+                self._phase(1)
+            self.steps_done += n
+
+    def capture(self, steps_per_graph: int = 2) -> None:
+        """Capture `steps_per_graph` steps (kernels + collectives) into one CUDA graph."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                launches = self.launches
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(steps_per_graph):
+                        self._phase(1)
+                self.launches = launches
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph, self._graph_steps = g, steps_per_graph
+
+    def step_graph(self, n_graphs: int = 1) -> None:
+        if self._graph is None:
+            raise RuntimeError("capture() has not been called")
+        for _ in range(n_graphs):
+            self._graph.replay()
+        self.steps_done += n_graphs * self._graph_steps
+        self.launches += 3 * n_graphs * self._graph_steps
+
+    def finish_record(self) -> None:
+        L.check(self.lib.jaxent_bv_finish_record(self.plan, _stream_ptr()))
+
+    # ------------------------------------------------------------------ results
+    def records(self, first: int, count: int):
+        """Loss records of steps [first, first+count) as ctypes structs (device -> host copy)."""
+        if count <= 0:
+            return []
+        sz = C.sizeof(L.LossRecord)
+        host = self._records.cpu().numpy()
+        out = []
+        for s in range(first, first + count):
+            i = s % L.RECORD_RING
+            out.append(L.LossRecord.from_buffer_copy(host[i * sz : (i + 1) * sz].tobytes()))
+        return out
+
+    def export_state(self, want=("z", "m", "v", "g")):
+        with torch.cuda.device(self.device):
+            bufs = {k: torch.empty(self.F, dtype=torch.float32, device=self.device) for k in want}
+            sc = torch.empty(8, dtype=torch.float32, device=self.device)
+            ptr = lambda k: bufs[k].data_ptr() if k in bufs else None
+            L.check(
+                self.lib.jaxent_bv_export_state(self.plan, ptr("z"), ptr("m"), ptr("v"), ptr("g"), sc.data_ptr(), _stream_ptr())
+            )
+            s = sc.cpu().numpy()
+        scal = dict(step=int(s[0]), lr=float(s[1]), model_lr=float(s[2]), mask_idx=int(s[3]), bc=float(s[4]), bh=float(s[5]),
+                    count_frame=int(s[6]), count_model=int(s[7]))
+        return bufs, scal
+
+    def algorithmic_bytes_per_step(self) -> int:
+        """8*R*F (features once) + 28*F (z,m,v,prior read; z,m,v written)."""
+        return 8 * self.R * self.F + 28 * self.F
