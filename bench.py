@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the BV MaxEnt optimise step (BASELINE.json metric) on B200.
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA path through the C ABI)
+  torchrun ... bench.py --gpus N ...                        frame-sharded over N GPUs (NCCL)
+  python bench.py --impl reference ...                      the CPU port of the reference path (oracle/)
+
+A "step" is one optimise step (forward + backward + Adam) over the whole ensemble.  Default
+workload: BASELINE config 4, synthetic 1M frames x 500 residues x 8 timepoints (4 GB of fp32
+features, far larger than the 126 MB L2, so no L2 flush is needed between steps); with N GPUs
+the same 1M frames are sharded (strong scaling) with two small NCCL all-reduces per step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg3": dict(F=100_000, R=500, T=8, name="synthetic 100k frames x 500 residues x 8 timepoints (BASELINE config 3)"),
+    "cfg4": dict(F=1_000_000, R=500, T=8, name="synthetic 1M frames x 500 residues x 8 timepoints (BASELINE config 4)"),
+    "cfg1": dict(F=500, R=53, T=3, name="BPTI-shaped 500 frames x 53 residues x 3 timepoints (BASELINE config 1 shape)"),
+    "cfg2": dict(F=1000, R=130, T=1, name="aSyn-shaped 1000 frames x 130 residues (BASELINE config 2 shape)"),
+}
+N_BLOCKS = 8  # features are generated in 8 frame blocks so that shards are identical for N = 1, 2, 4, 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def small_problem(R, T, seed=0):
+    """peptide maps / targets / rates (tiny; shared by all ranks and by the CPU arm)."""
+    from jaxent_b200 import synthetic
+
+    return synthetic.make_ensemble(2048, R, T, seed=seed)
+
+
+def row_hi(R, seed=0):
+    rng = np.random.default_rng(seed)
+    lam = rng.uniform(5, 40, R)
+    mu = rng.uniform(0.1, 1.5, R)
+    return np.rint(2 * lam).astype(np.int64), np.rint(2 * mu).astype(np.int64)
+
+
+def gen_block_torch(R, f0, f1, blk, device, seed=0):
+    """integer contact counts U{0..hi_r} for frames [f0,f1) of block `blk` (seeded per block)."""
+    import torch
+
+    hi_h, hi_a = row_hi(R, seed)
+    g = torch.Generator(device=device)
+    g.manual_seed(1000 * seed + blk)
+    n = f1 - f0
+    hh = torch.tensor(hi_h + 1, device=device, dtype=torch.float32)[:, None]
+    ha = torch.tensor(hi_a + 1, device=device, dtype=torch.float32)[:, None]
+    heavy = torch.floor(torch.rand((R, n), device=device, generator=g) * hh).clamp_(max=255)
+    acc = torch.floor(torch.rand((R, n), device=device, generator=g) * ha).clamp_(max=255)
+    return heavy, acc
+
+
+def gen_features(R, F, rank, world, device, seed=0):
+    """this rank's (R, F/world) shard, assembled from the global frame blocks."""
+    import torch
+
+    edges = [F * b // N_BLOCKS for b in range(N_BLOCKS + 1)]
+    per = N_BLOCKS // world
+    blocks = range(rank * per, (rank + 1) * per)
+    hs, as_ = [], []
+    for b in blocks:
+        h, a = gen_block_torch(R, edges[b], edges[b + 1], b, device, seed)
+        hs.append(h)
+        as_.append(a)
+    lo, hi = edges[rank * per], edges[(rank + 1) * per]
+    if len(hs) == 1:
+        return hs[0], as_[0], lo, hi
+    return torch.cat(hs, 1), torch.cat(as_, 1), lo, hi
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_steps(F, R, T, heavy, acc, small, budget_s, max_steps, warm=1):
+    """times the oracle port (NumPy fp32, multi-threaded BLAS) on the full-size workload."""
+    from oracle import bv_oracle as O
+
+    slots = [O.LossSlot(O.UPTAKE_EYE_MSE, small.S_train, small.y_train, small.S_val, small.y_val),
+             O.LossSlot(O.MAXENT_CONVEX_KL, prior=np.full(F, 1.0 / F, np.float32))]
+    pb = O.Problem(heavy, acc, small.k_ints, small.timepoints, slots, True)
+    fw = O.normalize_masked_loss_scalingweights(np.array([1.0, 1.0]), np.ones(2))
+    par = O.Params(np.full(F, 1.0 / F, np.float32), np.ones(F, np.float32), 0.35, 2.0, fw, np.full(2, 1000.0, np.float32), np.ones(2))
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None)
+    st = O.optimizer_initialise(par, cfg, np.float32)
+    for _ in range(warm):
+        st, _, _ = O.step_with_rates(pb, st, cfg, np.float32)
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_steps and (n < 2 or time.perf_counter() - t0 < budget_s):
+        st, loss, _ = O.step_with_rates(pb, st, cfg, np.float32)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, float(loss)
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def host_features(F, R, seed=0):
+    """full (R,F) fp32 arrays on the host: from the GPU generator when a GPU is there (same data as our arm)."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+            h, a, _, _ = gen_features(R, F, 0, 1, dev, seed)
+            return h.cpu().numpy(), a.cpu().numpy()
+    except Exception:
+        pass
+    from jaxent_b200 import synthetic
+
+    hi_h, hi_a = row_hi(R, seed)
+    return (synthetic.make_counts(R, F, hi_h / 2.0, seed * 7919 + 11, host_threads()),
+            synthetic.make_counts(R, F, hi_a / 2.0, seed * 7919 + 13, host_threads()))
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    F, R, T = wl["F"], wl["R"], wl["T"]
+    small = small_problem(R, T)
+    heavy, acc = host_features(F, R)
+    budget = min(60.0, max(5.0, 0.5 * args.steps))
+    sps, n, dt, loss = cpu_steps(F, R, T, heavy, acc, small, budget_s=budget, max_steps=max(2, args.steps), warm=max(1, min(args.warmup, 2)))
+    cores = host_threads()
+    line = {
+        "impl": "reference",
+        "metric": "optimise steps/sec",
+        "value": sps,
+        "unit": "steps/s",
+        "n_gpus": args.gpus,
+        "steps": n,
+        "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": 1e3 / sps,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "frame_residue_timepoint_per_s": sps * F * R * T,
+        "config": {"workload": wl["name"], "frames": F, "residues": R, "timepoints": T},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} full-size optimise steps of the NumPy fp32 oracle port (oracle/bv_oracle.py), {dt:.1f} s; "
+                                   "the reference's JAX loop itself cannot run here (no jax/optax in the image)"},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "final_loss": loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from jaxent_b200 import _lib as L
+    from jaxent_b200.engine import BvEngine, OptSettings, SlotSpec
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torchrun (one process per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    if N_BLOCKS % world:
+        raise SystemExit("--gpus must divide 8")
+
+    F, R, T = wl["F"], wl["R"], wl["T"]
+    small = small_problem(R, T)
+    heavy, acc, lo, hi = gen_features(R, F, rank, world, dev)
+    Fl = hi - lo
+    slots = [SlotSpec(L.LOSS_UPTAKE_EYE_MSE, small.S_train, small.y_train, small.S_val, small.y_val), SlotSpec(L.LOSS_MAXENT_CONVEX_KL)]
+    settings = OptSettings(learning_rate=1.0, initial_learning_rate=1.0, initial_steps=0, clip_value=None)
+    prior = torch.full((Fl,), 1.0 / F, device=dev)
+    fw, fs = [0.5, 0.5], [1000.0, 1000.0]
+
+    # ---- end-to-end job through the host-facing API: features start in pinned host memory (N=1 only keeps a host copy)
+    e2e = None
+    host_h = host_a = None
+    if world == 1 and not args.no_e2e:
+        host_h = torch.empty((R, F), dtype=torch.float32, pin_memory=True)
+        host_a = torch.empty((R, F), dtype=torch.float32, pin_memory=True)
+        host_h.copy_(heavy)
+        host_a.copy_(acc)
+        torch.cuda.synchronize()
+
+    eng = BvEngine(heavy, acc, small.k_ints, small.timepoints, slots, True, settings, prior=prior, device=dev, F_total=F, group=group)
+    del heavy, acc
+    eng.init_state(torch.ones(Fl, device=dev), 0.35, 2.0, fw, fs)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    eng.step(max(3, args.warmup))
+    barrier()
+
+    # ---- timed region: exactly K steps, eager launches, CUDA events around every pass kernel
+    K = args.steps
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    ev_pass = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launches
+    barrier()
+    e0.record()
+    for k in range(K):
+        a, b = ev_pass[k]
+        a.record()
+        L.check(eng.lib.jaxent_bv_pass(eng.plan, 1, sp))
+        b.record()
+        L.check(eng.lib.jaxent_bv_reduce(eng.plan, sp))
+        if eng.sharded:
+            dist.all_reduce(eng.red, group=group)
+        L.check(eng.lib.jaxent_bv_tail(eng.plan, sp))
+        if eng.sharded:
+            dist.all_reduce(eng.klsum, group=group)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    eng.steps_done += K
+    eng.launches += 3 * K
+    ms_total = e0.elapsed_time(e1)
+    pass_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pass]))
+    t = torch.tensor([ms_total, pass_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, pass_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / K
+    sps = 1e3 / ms_step
+
+    # ---- CUDA-graph replay of the same step (informational)
+    graph_ms = None
+    try:
+        eng.capture(2)
+        eng.step_graph(2)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        eng.step_graph(max(1, K // 2))
+        g1.record()
+        barrier()
+        graph_ms = g0.elapsed_time(g1) / (2 * max(1, K // 2))
+    except Exception as ex:  # pragma: no cover
+        graph_ms = None
+        sys.stderr.write(f"graph replay skipped: {ex}\n")
+
+    eng.finish_record()
+    torch.cuda.synchronize()
+    rec = eng.records(eng.steps_done, 1)[0]
+    wsum = eng.weights.double().sum()
+    if world > 1:
+        dist.all_reduce(wsum)
+    wsum = float(wsum)
+
+    # ---- e2e (N=1): whole job from pinned host buffers through the public engine API, loss read back every step
+    if host_h is not None:
+        del eng
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        import ctypes
+
+        rec_bytes = ctypes.sizeof(L.LossRecord)
+        t0 = time.perf_counter()
+        eng2 = BvEngine(host_h, host_a, small.k_ints, small.timepoints, slots, True, settings, prior=prior, device=dev, F_total=F)
+        eng2.init_state(torch.ones(Fl, device=dev), 0.35, 2.0, fw, fs)
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter() - t0
+        rec_dev = eng2._records
+        pinned_rec = torch.empty(rec_bytes, dtype=torch.uint8, pin_memory=True)
+        t1 = time.perf_counter()
+        last = 0.0
+        for k in range(K):
+            eng2.step(1)
+            i = (k % L.RECORD_RING) * rec_bytes
+            pinned_rec.copy_(rec_dev[i : i + rec_bytes], non_blocking=True)  # loss record of step k (complete)
+            torch.cuda.current_stream().synchronize()
+            last = float(np.frombuffer(pinned_rec.numpy().tobytes(), dtype=np.float32)[6])
+        w_host = eng2.weights.cpu()
+        t_steps = time.perf_counter() - t1
+        job = t_setup + t_steps
+        h2d = (2 * R * F * 4 + Fl * 4 * 2)
+        e2e = {
+            "value": K / job,
+            "unit": "steps/s",
+            "h2d_bytes_per_step": h2d / K,
+            "d2h_bytes_per_step": rec_bytes + Fl * 4 / K,
+            "steady_value": K / t_steps,
+            "setup_s": t_setup,
+            "note": "value = whole K-step job from pinned host features (upload+pack+init inside the timed region, loss record "
+                    "read back and host-synchronised every step, final weights read back); steady_value excludes the one-off upload",
+            "last_loss": last,
+        }
+        del eng2, w_host
+
+    peak, peak_src = peaks()
+    alg_bytes = 8 * R * Fl + 28 * Fl
+    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            if host_h is not None:
+                hh, aa = host_h.numpy(), host_a.numpy()
+            else:
+                hh, aa = host_features(F, R)
+            c_sps, c_n, c_dt, _ = cpu_steps(F, R, T, hh, aa, small, budget_s=15.0, max_steps=50)
+            cpu = {"value": c_sps, "unit": "steps/s", "cores": host_threads(), "kind": "port",
+                   "sample": f"{c_n} full-size optimise steps of the NumPy fp32 oracle port in {c_dt:.1f} s (oracle restatement, not the reference's JAX loop)"}
+        line = {
+            "metric": "optimise steps/sec",
+            "value": sps,
+            "unit": "steps/s",
+            "n_gpus": world,
+            "steps": K,
+            "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "frame_residue_timepoint_per_s": sps * F * R * T,
+            "config": {"workload": wl["name"], "frames": F, "residues": R, "timepoints": T, "frames_per_gpu": Fl,
+                       "parallelism": f"frame-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": f"inputs {8 * R * Fl / 1e9:.2f} GB per GPU per step >> 126 MB L2, no flush needed" if 8 * R * Fl > 4e8 else "inputs fit in L2 (latency-bound config; steps/s only)",
+                       "losses": ["hdx_uptake_eye_MSE_loss", "maxent_convexKL_loss"], "optimizer": "adam lr=1.0, plateau 1.005"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "bv_pass_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": pass_ms, "peak_source": peak_src, "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": 3 * K,
+            "clocks": sampler.result(),
+            "graph_ms_per_step": graph_ms,
+            "check": {"sum_weights": wsum, "final_loss": rec.total_train, "final_step": rec.step},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

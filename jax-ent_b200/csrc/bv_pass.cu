@@ -408,19 +408,24 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX, (RPT == 1) ? 2 : 1) bv_pass_
 
 // ------------------------------------------------------------------------------------------ reduce
 // red[j] = sum_cta partials[cta][j] in CTA order (deterministic); also advances the epoch.
-__global__ void reduce_kernel(const ReduceArgs a) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < a.part_n) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int c = 0;
-    for (; c + 3 < a.n_part; c += 4) {
-      s0 += a.partials[(size_t)(c + 0) * a.part_n + j];
-      s1 += a.partials[(size_t)(c + 1) * a.part_n + j];
-      s2 += a.partials[(size_t)(c + 2) * a.part_n + j];
-      s3 += a.partials[(size_t)(c + 3) * a.part_n + j];
-    }
-    for (; c < a.n_part; ++c) s0 += a.partials[(size_t)c * a.part_n + j];
-    a.red[j] = (s0 + s1) + (s2 + s3);
+__global__ void __launch_bounds__(1024) reduce_kernel(const ReduceArgs a) {
+  // 32 columns x 32 partial-groups per block: every load is independent (latency overlapped) and
+  // the summation order is fixed (group-strided, then groups 0..31) -> bitwise reproducible.
+  __shared__ double sh[32][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  double s = 0.0;
+  if (col < a.part_n) {
+#pragma unroll 4
+    for (int c = grp; c < a.n_part; c += 32) s += a.partials[(size_t)c * a.part_n + col];
+  }
+  sh[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && col < a.part_n) {
+    double t = 0.0;
+#pragma unroll
+    for (int g2 = 0; g2 < 32; ++g2) t += sh[g2][lane];
+    a.red[col] = t;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.epoch = *a.epoch + 1u;
 }
@@ -456,9 +461,8 @@ int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, 
 }
 
 int launch_reduce(const ReduceArgs& a, cudaStream_t s) {
-  const int threads = 128;
-  const int blocks = (a.part_n + threads - 1) / threads;
-  reduce_kernel<<<blocks, threads, 0, s>>>(a);
+  const int blocks = (a.part_n + 31) / 32;
+  reduce_kernel<<<blocks, 1024, 0, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("reduce_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;

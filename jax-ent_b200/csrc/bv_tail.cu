@@ -376,10 +376,13 @@ __global__ void __launch_bounds__(TAIL_THREADS) bv_tail_kernel(const TailArgs a)
         // q = (|w|+eps)/sum(|w|+eps); the denominator is 1 + F*eps = 1 + 1e-10 == 1 in fp32
         const float q = fabsf(w) + eps;
         const float p = (float)(((double)fabsf(pb.prior[f]) + (double)eps) / pnorm);
-        const float G_ = 1.0f - p / q;
+        // p/q and log(p/q) in fp64: differencing two fp32 logs leaves a rounding error that is
+        // identical on every frame of a uniform prior and so does not average out over F
+        const double ratio = (double)p / (double)q;
+        const float G_ = (float)(1.0 - ratio);
         kap = (w > 0.f) ? lam * G_ : 0.f;  // d|w|/dw = sign(w); softmax weights are >= 0
         s0 += (double)w * (double)kap;
-        if (p > 0.f) s1 += (double)p * ((double)logf(p) - (double)logf(q));
+        if (p > 0.f) s1 += (double)p * log(ratio);
         s2 += (double)q - (double)p;
       }
       a.kappa[f] = kap;

@@ -1,0 +1,154 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds/loads, exports every symbol that
+include/jaxent_b200.h declares, its structs match the ctypes mirror, argument validation raises
+the documented errors, and host-side logic (CSR conversion, sizes) is right.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from jaxent_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "jaxent_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(jaxent_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/jaxent_b200.h but not exported"
+        assert name in L.SYMBOLS, f"{name} has no ctypes prototype"
+    assert sorted(L.SYMBOLS) == declared
+    assert lib.jaxent_version() >= 100
+
+
+def test_struct_layouts_match():
+    lib = L.load()
+    for i, st in enumerate((L.BvProblem, L.OptConfig, L.LossRecord, L.LossSlot, L.PeptideMap)):
+        assert lib.jaxent_abi_sizeof(i) == C.sizeof(st)
+    assert lib.jaxent_abi_sizeof(99) == -1
+
+
+def test_packed_and_workspace_sizes():
+    lib = L.load()
+    assert lib.jaxent_bv_packed_bytes(500, 1_000_000) == 8 * 500 * 1_000_000
+    assert lib.jaxent_bv_packed_bytes(53, 500) == 8 * 53 * 504  # frames padded to a multiple of 8
+    assert lib.jaxent_bv_packed_bytes(0, 10) == 0
+    pb = L.BvProblem()
+    pb.R, pb.T, pb.uptake, pb.n_slots, pb.F, pb.F_total = 500, 8, 1, 2, 100_000, 100_000
+    n = lib.jaxent_bv_workspace_bytes(C.byref(pb))
+    assert n > 16 * 4 * 100_000
+    assert n < 64 * 1024 * 1024
+
+
+def _valid_problem():
+    pb = L.BvProblem()
+    pb.R, pb.T, pb.uptake, pb.n_slots, pb.F, pb.F_total = 16, 3, 1, 1, 64, 64
+    pb.packed = 0x1000  # never dereferenced by plan_create
+    pb.k_ints = 0x2000
+    pb.timepoints = 0x3000
+    pb.slots[0].kind = L.LOSS_PARAMS_L2
+    return pb
+
+
+def _create(pb, cfg=None, ws=0x100000, nbytes=1 << 30):
+    lib = L.load()
+    cfg = cfg or L.OptConfig(1.0, 1.0, 0, 1.005, 1.0, -1.0, 1, 0, 0.9, 0.999, 1e-8)
+    plan = C.c_void_p()
+    rc = lib.jaxent_bv_plan_create(C.byref(pb), C.byref(cfg), ws, nbytes, 148, C.byref(plan))
+    return rc, plan, lib.jaxent_last_error().decode()
+
+
+def test_plan_create_validation_errors():
+    lib = L.load()
+    rc, plan, msg = _create(_valid_problem())
+    assert rc == 0 and plan.value
+    lib.jaxent_bv_plan_destroy(plan)
+
+    pb = _valid_problem(); pb.R = 0
+    assert _create(pb)[0] == L.E_INVALID
+    pb = _valid_problem(); pb.packed = 0x1004
+    rc, _, msg = _create(pb); assert rc == L.E_INVALID and "aligned" in msg
+    pb = _valid_problem(); pb.n_slots = 7
+    assert _create(pb)[0] == L.E_INVALID
+    pb = _valid_problem(); pb.slots[0].kind = 42
+    rc, _, msg = _create(pb); assert rc == L.E_UNSUPPORTED and "unsupported loss kind" in msg
+    pb = _valid_problem(); pb.slots[0].kind = L.LOSS_PF_L2  # PF loss on the uptake forward pass
+    assert _create(pb)[0] == L.E_UNSUPPORTED
+    pb = _valid_problem(); pb.uptake = 0; pb.slots[0].kind = L.LOSS_UPTAKE_EYE_MSE
+    assert _create(pb)[0] == L.E_UNSUPPORTED
+    pb = _valid_problem(); pb.slots[0].kind = L.LOSS_MAXENT_CONVEX_KL  # no prior
+    assert _create(pb)[0] == L.E_INVALID
+    pb = _valid_problem(); pb.R = 5000
+    assert _create(pb)[0] == L.E_UNSUPPORTED
+    rc, _, msg = _create(_valid_problem(), nbytes=1024); assert rc == L.E_WORKSPACE and "too small" in msg
+    rc, _, msg = _create(_valid_problem(), ws=0x100010); assert rc == L.E_INVALID
+    bad = L.OptConfig(1.0, 1.0, 0, 0.0, 1.0, -1.0, 1, 0, 0.9, 0.999, 1e-8)
+    assert _create(_valid_problem(), cfg=bad)[0] == L.E_INVALID
+
+
+def test_calls_before_state_init_fail_loudly():
+    lib = L.load()
+    rc, plan, _ = _create(_valid_problem())
+    assert rc == 0
+    assert lib.jaxent_bv_pass(plan, 1, None) == L.E_INVALID
+    assert "state_init" in lib.jaxent_last_error().decode()
+    assert lib.jaxent_bv_step(plan, None) == L.E_INVALID
+    assert lib.jaxent_bv_pass(None, 1, None) == L.E_INVALID
+    with pytest.raises(L.JaxentError):
+        L.check(lib.jaxent_bv_tail(plan, None))
+    lib.jaxent_bv_plan_destroy(plan)
+
+
+def test_pack_argument_validation():
+    lib = L.load()
+    assert lib.jaxent_bv_pack_features_f32(None, None, 4, 8, 8, 0, 8, None, None) == L.E_INVALID
+    assert lib.jaxent_bv_pack_features_f32(0x1000, 0x2000, 4, 8, 4, 0, 8, 0x3000, None) == L.E_INVALID  # ld < F
+    assert lib.jaxent_bv_pack_features_f32(0x1000, 0x2000, 4, 8, 8, 2, 16, 0x3000, None) == L.E_INVALID  # offset % 4
+    assert lib.jaxent_bv_pack_features_f32(0x1000, 0x2000, 4, 8, 8, 0, 8, 0x3004, None) == L.E_INVALID  # alignment
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from jaxent_b200.engine import BvEngine, OptSettings, SlotSpec
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BvEngine(np.zeros((4, 8), np.float32), np.zeros((4, 8), np.float32), None, None,
+                 [SlotSpec(L.LOSS_PARAMS_L2)], False, OptSettings())
+
+
+def test_csr_conversion_round_trip():
+    from jaxent_b200.engine import _csr
+
+    rng = np.random.default_rng(0)
+    S = (rng.random((7, 11)) < 0.3) * rng.random((7, 11))
+    ptr, col, val = _csr(S.astype(np.float32))
+    D = np.zeros_like(S, dtype=np.float32)
+    for p in range(7):
+        D[p, col[ptr[p]:ptr[p + 1]]] = val[ptr[p]:ptr[p + 1]]
+        assert np.all(np.diff(col[ptr[p]:ptr[p + 1]]) > 0)
+    np.testing.assert_array_equal(D, S.astype(np.float32))
+    tptr, trow, tval = _csr(S.T.astype(np.float32))
+    assert tptr[-1] == ptr[-1]
+    ptr0, _, _ = _csr(np.zeros((3, 5), np.float32))  # empty (ragged) map
+    assert list(ptr0) == [0, 0, 0, 0]
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "jax-ent_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn

@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the committed golden fixtures, and -- at BASELINE config-3 size -- against a plain
+torch fp64 autograd restatement of the same op.
+
+Tolerances (BASELINE.json north_star): fp32 loss and gradients within 1e-5 relative per step
+(gradients: max-abs error relative to the max-abs gradient); frame weights within 1e-4 (absolute)
+after 1000 steps.  Per-step checks are teacher-forced: the oracle is evaluated at the state the GPU
+exported, so trajectory divergence of the lr=1 Adam dynamics does not leak into the per-step bound.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import bv_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+STEP_RTOL = 1e-5
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+def _oracle_params(case, z, sc):
+    p = case["params"]
+    return O.Params(np.asarray(z, np.float64), p.frame_mask, sc["bc"], sc["bh"], p.fw, p.fs, p.nlf)
+
+
+def _check_steps(case, cfg, n_steps, check_adam=True):
+    eng = H.make_engine(case, cfg)
+    H.init_engine(eng, case)
+    pb = case["problem"]
+    worst_loss = worst_g = 0.0
+    for k in range(n_steps):
+        pre, sc = eng.export_state(("z", "m", "v"))
+        z, m, v = (pre[x].cpu().numpy() for x in ("z", "m", "v"))
+        eng.step(1)
+        _sync()
+        rec = eng.records(k, 1)[0]
+        post, sc2 = eng.export_state(("z", "g"))
+        assert rec.step == k and rec.complete == 1 and sc2["step"] == k + 1
+        losses, g, aux = O.loss_and_grads(pb, _oracle_params(case, z, sc), np.float64)
+        # loss components and total
+        np.testing.assert_allclose(rec.total_train, losses.total_train_loss, rtol=STEP_RTOL)
+        np.testing.assert_allclose(rec.total_val, losses.total_val_loss, rtol=STEP_RTOL)
+        n = len(pb.slots)
+        np.testing.assert_allclose(np.array(rec.train[:n]), losses.train_losses, rtol=STEP_RTOL, atol=1e-9)
+        np.testing.assert_allclose(np.array(rec.val[:n]), losses.val_losses, rtol=STEP_RTOL, atol=1e-9)
+        # masked gradients
+        mask_model = 1.0 if (cfg.optimise_model_parameters and k >= cfg.initial_steps) else 0.0
+        mask_frame = 1.0 if (cfg.optimise_frame_weights or k < cfg.initial_steps) else 0.0
+        gg = post["g"].cpu().numpy()
+        scale = max(np.abs(g.z).max(), 1e-30)
+        gerr = np.abs(gg - g.z * mask_frame).max() / scale
+        assert gerr < STEP_RTOL, f"step {k}: grad error {gerr:.2e}"
+        np.testing.assert_allclose(rec.grad_bc, g.bc * mask_model, rtol=2 * STEP_RTOL, atol=1e-6 * abs(g.bc))
+        np.testing.assert_allclose(rec.grad_bh, g.bh * mask_model, rtol=2 * STEP_RTOL, atol=1e-6 * abs(g.bh))
+        worst_loss = max(worst_loss, abs(rec.total_train - losses.total_train_loss) / abs(losses.total_train_loss))
+        worst_g = max(worst_g, gerr)
+        if check_adam:
+            # the frame Adam update, restated from the exported moments in fp32 (optax formula)
+            nxt = eng.records(k + 1, 1)[0]  # carries lr / branch of the update that led to step k+1
+            sg = (gg * np.float32(nxt.lr)).astype(np.float32)
+            if cfg.clip_value is not None:
+                sg = np.clip(sg, -np.float32(cfg.clip_value), np.float32(cfg.clip_value))
+            u, _, _, _ = O._adam_update(sg, m, v, sc["count_frame"], cfg, np.float32)
+            np.testing.assert_allclose(post["z"].cpu().numpy(), z + u, rtol=0, atol=2e-6 * max(1.0, np.abs(z).max()))
+            assert nxt.branch == int(nxt.grad_dot < 0 and k > 1)
+    return eng, worst_loss, worst_g
+
+
+@pytest.mark.parametrize(
+    "kind,extra,opt_model,clip",
+    [
+        (O.UPTAKE_EYE_MSE, (), False, None),
+        (O.UPTAKE_MC_EYE_MSE, (O.PARAMS_L1,), True, 1.0),
+        (O.UPTAKE_SIGMA_MSE, (), False, None),
+        (O.PF_L2, (O.PARAMS_L2,), True, None),
+    ],
+)
+def test_step_parity_small(kind, extra, opt_model, clip):
+    case = H.make_case(777, 97, 5 if kind != O.PF_L2 else 1, kind, extra=extra, seed=11, gamma=2.0)
+    cfg = O.OptConfig(learning_rate=1.0, initial_learning_rate=1.0, initial_steps=0, clip_value=clip,
+                      optimise_model_parameters=opt_model)
+    _check_steps(case, cfg, 8)
+
+
+def test_step_parity_initial_steps_and_random_prior():
+    case = H.make_case(1000, 130, 1, O.PF_L2, extra=(O.PARAMS_L2,), seed=3, prior="random")
+    cfg = O.OptConfig(learning_rate=0.1, initial_learning_rate=1.0, initial_steps=3, clip_value=None, optimise_model_parameters=True)
+    eng, _, _ = _check_steps(case, cfg, 7)
+    recs = eng.records(0, 7)
+    assert all(r.grad_bc == 0.0 for r in recs[:3]) and recs[4].grad_bc != 0.0  # model params masked during initial steps
+
+
+def test_bpti_fixture_shape_config1():
+    """BASELINE config 1: the real BPTI BV features (53 x 500), T=3."""
+    d = np.load(os.path.join(GOLD, "bpti_bv_features.npz"))
+    case = H.make_case(500, 53, 3, O.UPTAKE_EYE_MSE, seed=0)
+    case["problem"].heavy = d["heavy"].astype(np.float32)
+    case["problem"].acceptor = d["acceptor"].astype(np.float32)
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None)
+    _check_steps(case, cfg, 6)
+
+
+@pytest.mark.parametrize("F,R", [(5, 3), (8, 32), (9, 33), (1001, 513), (300, 1100)])
+def test_ragged_shapes(F, R):
+    """frames not a multiple of the 8-frame tile, rows not a multiple of a warp, R > 512 (2 and 4 rows/thread)."""
+    case = H.make_case(F, R, 3, O.UPTAKE_EYE_MSE, seed=F + R, n_pep=max(4, R // 3))
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=True)
+    _check_steps(case, cfg, 4)
+
+
+def test_forward_outputs_match_oracle():
+    case = H.make_case(3001, 500, 8, O.UPTAKE_EYE_MSE, seed=1)
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None)
+    eng = H.make_engine(case, cfg)
+    rng = np.random.default_rng(0)
+    case["params"].z = rng.dirichlet(np.full(3001, 0.5)).astype(np.float32)  # non-uniform start
+    H.init_engine(eng, case)
+    _sync()
+    st = O.optimizer_initialise(case["params"], cfg, np.float64)
+    _, npar, out = O.compute_loss(case["problem"], st.params, np.float64)
+    np.testing.assert_allclose(eng.weights.cpu().numpy(), npar.z, rtol=3e-6, atol=1e-12)
+    np.testing.assert_allclose(eng.avg.cpu().numpy()[:500], out["avg_heavy"], rtol=2e-6)
+    np.testing.assert_allclose(eng.avg.cpu().numpy()[500:], out["avg_acceptor"], rtol=2e-6)
+    np.testing.assert_allclose(eng.log_pf.cpu().numpy(), out["log_Pf"], rtol=2e-6)
+    np.testing.assert_allclose(eng.uptake_out.cpu().numpy(), out["uptake"], rtol=1e-5, atol=1e-7)
+    assert abs(float(eng.weights.sum()) - 1.0) < 1e-5
+
+
+def test_frame_weights_frozen_when_not_optimised():
+    case = H.make_case(256, 20, 3, O.UPTAKE_EYE_MSE, seed=5, n_pep=8)
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_frame_weights=False, optimise_model_parameters=True)
+    eng = H.make_engine(case, cfg)
+    H.init_engine(eng, case)
+    z0 = eng.export_state(("z",))[0]["z"].clone()
+    eng.step(5)
+    _sync()
+    bufs, sc = eng.export_state(("z",))
+    assert torch.equal(bufs["z"], z0)
+    assert sc["bc"] != 0.35
+
+
+def test_determinism_and_graph_replay_bitwise():
+    case = H.make_case(4099, 130, 5, O.UPTAKE_EYE_MSE, seed=8)
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=True)
+    outs = []
+    for mode in ("eager", "eager", "graph"):
+        eng = H.make_engine(case, cfg)
+        H.init_engine(eng, case)
+        if mode == "graph":
+            eng.capture(2)
+            eng.step_graph(5)
+        else:
+            eng.step(10)
+        _sync()
+        bufs, sc = eng.export_state()
+        outs.append((bufs["z"].clone(), bufs["m"].clone(), bufs["g"].clone(), sc["bc"], eng.records(9, 1)[0].total_train))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+        assert o[3] == outs[0][3] and o[4] == outs[0][4]
+
+
+def test_weights_after_1000_steps_config1_and_2():
+    """north_star: frame weights within 1e-4 after 1000 steps (vs the fp32 mirror of the reference)."""
+    for F, R, T, kind in ((500, 53, 3, O.UPTAKE_EYE_MSE), (1000, 130, 1, O.PF_L2)):
+        case = H.make_case(F, R, T, kind, seed=21, scaling=100.0)
+        cfg = O.OptConfig(learning_rate=0.05, initial_learning_rate=1.0, initial_steps=2, clip_value=None)
+        eng = H.make_engine(case, cfg)
+        H.init_engine(eng, case)
+        eng.step(1000)
+        _sync()
+        st = O.optimizer_initialise(case["params"], cfg, np.float32)
+        for _ in range(1000):
+            st, loss, w = O.step_with_rates(case["problem"], st, cfg, np.float32)
+        wg = eng.weights.cpu().numpy()
+        assert np.abs(wg - w).max() < 1e-4
+        rec = eng.records(999, 1)[0]
+        np.testing.assert_allclose(rec.total_train, loss, rtol=1e-3)
+        assert abs(wg.sum() - 1) < 1e-5
+
+
+def _torch_reference_step(heavy, acc, k, tp, S, y, z, bc, bh, fw, fs, prior):
+    """Plain torch fp64 restatement of compute_loss + grad for the config-3 size check (runs on the GPU)."""
+    f64 = torch.float64
+    z = z.to(f64).requires_grad_(True)
+    w = torch.softmax(z, 0)
+    a, b = heavy.to(f64) @ w, acc.to(f64) @ w
+    lp = bc * a + bh * b
+    u = 1 - torch.exp(-k.to(f64)[None, :] * tp.to(f64)[:, None] / torch.exp(lp)[None, :])
+    r = S.to(f64) @ u.T - y.to(f64)
+    l0 = 0.5 * (r * r).sum() / (y.shape[0] * y.shape[1])
+    F = z.shape[0]
+    eps = 1e-10 / F
+    sw = w.abs() + eps
+    sw = sw / sw.sum()
+    pw = prior.to(f64).abs() + eps
+    pw = pw / pw.sum()
+    l1 = (pw * (pw.log() - sw.log())).sum() + (sw - pw).sum()
+    tot = l0 * fw[0] * fs[0] + l1 * fw[1] * fs[1]
+    (g,) = torch.autograd.grad(tot, z)
+    return float(tot), g, w.detach()
+
+
+def test_config3_size_against_torch_fp64():
+    """BASELINE config 3 (100k frames x 500 residues x 8 timepoints): loss, gradient and Sum(w)=1 at full size."""
+    from jaxent_b200 import _lib as L
+    from jaxent_b200 import synthetic
+    from jaxent_b200.engine import BvEngine, OptSettings, SlotSpec
+
+    F, R, T = 100_000, 500, 8
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    heavy = torch.randint(0, 40, (R, F), device=dev, generator=gen, dtype=torch.int32).float()
+    acc = torch.randint(0, 3, (R, F), device=dev, generator=gen, dtype=torch.int32).float()
+    small = synthetic.make_ensemble(2048, R, T, seed=0)
+    slots = [SlotSpec(L.LOSS_UPTAKE_EYE_MSE, small.S_train, small.y_train, small.S_val, small.y_val), SlotSpec(L.LOSS_MAXENT_CONVEX_KL)]
+    prior = torch.full((F,), 1.0 / F, device=dev)
+    eng = BvEngine(heavy, acc, small.k_ints, small.timepoints, slots, True, OptSettings(learning_rate=1.0, clip_value=None), prior=prior)
+    fw, fs = [0.5, 0.5], [1000.0, 1000.0]
+    eng.init_state(torch.ones(F, device=dev), 0.35, 2.0, fw, fs)
+    k, tp = torch.tensor(small.k_ints, device=dev), torch.tensor(small.timepoints, device=dev)
+    S, y = torch.tensor(small.S_train, device=dev), torch.tensor(small.y_train, device=dev)
+    for step in range(3):
+        z = eng.export_state(("z",))[0]["z"]
+        eng.step(1)
+        _sync()
+        tot, g, w = _torch_reference_step(heavy, acc, k, tp, S, y, z, 0.35, 2.0, fw, fs, prior)
+        rec = eng.records(step, 1)[0]
+        np.testing.assert_allclose(rec.total_train, tot, rtol=STEP_RTOL)
+        gg = eng.export_state(("g",))[0]["g"].to(torch.float64)
+        assert float((gg - g).abs().max() / g.abs().max()) < STEP_RTOL
+    assert abs(float(eng.weights.double().sum()) - 1.0) < 1e-6
+
+
+def test_errors_surface_as_exceptions():
+    from jaxent_b200 import _lib as L
+    from jaxent_b200.engine import BvEngine, OptSettings, SlotSpec
+
+    z = np.zeros((4, 16), np.float32)
+    with pytest.raises(ValueError, match="prior"):
+        BvEngine(z, z, None, None, [SlotSpec(L.LOSS_MAXENT_CONVEX_KL)], False, OptSettings())
+    with pytest.raises(L.JaxentError, match="uptake loss needs"):
+        S = np.eye(4, dtype=np.float32)
+        BvEngine(z, z, None, None, [SlotSpec(L.LOSS_UPTAKE_EYE_MSE, S, np.zeros((4, 0)), S, np.zeros((4, 0)))], False, OptSettings())
+    with pytest.raises(ValueError, match="different shapes"):
+        BvEngine(z, np.zeros((4, 8), np.float32), None, None, [SlotSpec(L.LOSS_PARAMS_L2)], False, OptSettings())
