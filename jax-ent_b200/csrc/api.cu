@@ -137,8 +137,8 @@ static int validate_problem(const JaxentBvProblem* p) {
     set_error("invalid shape: R=%d F=%lld F_total=%lld", p->R, (long long)p->F, (long long)p->F_total);
     return JAXENT_E_INVALID;
   }
-  if (p->R > 4 * PASS_THREADS_MAX) {
-    set_error("n_residues=%d exceeds the supported maximum %d", p->R, 4 * PASS_THREADS_MAX);
+  if (p->R > 2 * PASS_THREADS_MAX) {
+    set_error("n_residues=%d exceeds the supported maximum %d", p->R, 2 * PASS_THREADS_MAX);
     return JAXENT_E_UNSUPPORTED;
   }
   if (!p->packed || (reinterpret_cast<uintptr_t>(p->packed) & 15u)) {
@@ -252,14 +252,14 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   p->st.g[1] = reinterpret_cast<float*>(p->ws + L.off_g[1]);
 
   // pass geometry: one residue row per thread, RPT rows when R > 512
-  p->rpt = (R <= PASS_THREADS_MAX) ? 1 : (R <= 2 * PASS_THREADS_MAX ? 2 : 4);
+  p->rpt = (R <= PASS_THREADS_MAX) ? 1 : 2;
   const int rows_per_thread_threads = (R + p->rpt - 1) / p->rpt;
   p->pass_threads = ((rows_per_thread_threads + 31) / 32) * 32;
   if (p->pass_threads < 32) p->pass_threads = 32;
   p->tile_bytes = (uint32_t)(FT * R * 2 * sizeof(float));
   p->stage_stride = (uint32_t)align_up(p->tile_bytes, 128);
   const size_t smem_budget = (p->rpt == 1 ? 108 : 216) * 1024;
-  const size_t fixed = MAX_STAGES * 8 + 16 * FT * 4 + 2 * FT * 4 + 128;
+  const size_t fixed = MAX_STAGES * 8 + 2 * 16 * FT * 4 + 2 * 2 * FT * 4 + 128;
   int stages = (int)((smem_budget - fixed) / p->stage_stride);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { delete p; set_error("tile of %u bytes does not fit a 2-stage ring", p->tile_bytes); return JAXENT_E_UNSUPPORTED; }
@@ -385,7 +385,7 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.om_b2 = (float)(1.0 - p->cfg.b2);
   a.eps = (float)p->cfg.eps;
   a.clip = p->cfg.clip_value;
-  return launch_pass(a, p->pass_threads, p->rpt, p->pass_ctas, p->pass_smem, (cudaStream_t)stream);
+  return launch_pass(a, p->pass_threads + 32, p->rpt, p->pass_ctas, p->pass_smem, (cudaStream_t)stream);
 }
 
 extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t stream) {

@@ -117,205 +117,241 @@ __global__ void max_kernel(const float* __restrict__ z, long long F, float* out)
 }
 
 // ------------------------------------------------------------------------------------------ the pass
+// Thread roles: `NTc` consumer threads (one residue row each, RPT rows when R > 512) plus one
+// dedicated "Adam warp" (the last warp).  Software pipeline, one tile deep:
+//
+//   consumers, tile i :  wait TMA -> tile to registers -> phase A(i) -> partials to smem -> bar.arrive PART[i&1]
+//                        bar.sync E[(i-1)&1] -> phase B(i-1) on the previous tile's registers
+//   Adam warp, tile i :  bar.sync PART[i&1] -> refill the ring slot -> Adam(i) -> e'(i) to smem -> bar.arrive E[i&1]
+//
+// so the serial per-frame optimiser chain of tile i runs while the consumers stream tile i+1.
+constexpr int BAR_PART0 = 1, BAR_E0 = 3;  // named barrier ids (0 is __syncthreads)
+constexpr int FLUSH_TILES = 16;           // fp32 tile sums are folded into the fp64 partials every 16 tiles
+
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <int RPT>
-__global__ void __launch_bounds__(PASS_THREADS_MAX, (RPT == 1) ? 2 : 1) bv_pass_kernel(const PassArgs a) {
+struct TileRegs {
+  float4 nc[RPT][QT], nh[RPT][QT];
+};
+
+template <int RPT>
+__device__ __forceinline__ void load_tile(TileRegs<RPT>& d, const unsigned char* stage, uint32_t r16, const uint32_t (&rowoff)[RPT]) {
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const unsigned char* p = stage + rowoff[i];
+    d.nc[i][0] = *reinterpret_cast<const float4*>(p);
+    d.nh[i][0] = *reinterpret_cast<const float4*>(p + r16);
+    d.nc[i][1] = *reinterpret_cast<const float4*>(p + 2 * r16);
+    d.nh[i][1] = *reinterpret_cast<const float4*>(p + 3 * r16);
+  }
+}
+
+// phase A: H partials of this thread's rows, transposing warp reduction, one float per (warp, frame)
+template <int RPT>
+__device__ __forceinline__ void phase_a(const TileRegs<RPT>& d, const float (&cc)[RPT], const float (&ch)[RPT],
+                                        float* s_part_warp, int lane, int jred) {
+  float p[FT];
+#pragma unroll
+  for (int q = 0; q < QT; ++q) {
+    p[4 * q + 0] = fmaf(cc[0], d.nc[0][q].x, ch[0] * d.nh[0][q].x);
+    p[4 * q + 1] = fmaf(cc[0], d.nc[0][q].y, ch[0] * d.nh[0][q].y);
+    p[4 * q + 2] = fmaf(cc[0], d.nc[0][q].z, ch[0] * d.nh[0][q].z);
+    p[4 * q + 3] = fmaf(cc[0], d.nc[0][q].w, ch[0] * d.nh[0][q].w);
+  }
+#pragma unroll
+  for (int i = 1; i < RPT; ++i) {
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+      p[4 * q + 0] = fmaf(cc[i], d.nc[i][q].x, fmaf(ch[i], d.nh[i][q].x, p[4 * q + 0]));
+      p[4 * q + 1] = fmaf(cc[i], d.nc[i][q].y, fmaf(ch[i], d.nh[i][q].y, p[4 * q + 1]));
+      p[4 * q + 2] = fmaf(cc[i], d.nc[i][q].z, fmaf(ch[i], d.nh[i][q].z, p[4 * q + 2]));
+      p[4 * q + 3] = fmaf(cc[i], d.nc[i][q].w, fmaf(ch[i], d.nh[i][q].w, p[4 * q + 3]));
+    }
+  }
+  // 8 values x 32 lanes -> each lane ends with the warp total of frame jred (9 shuffles)
+  const bool hi = lane & 16;
+  float q4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = hi ? p[i] : p[i + 4];
+    const float keep = hi ? p[i + 4] : p[i];
+    q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  const bool b3 = lane & 8;
+  float r2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b3 ? q4[i] : q4[i + 2];
+    const float keep = b3 ? q4[i + 2] : q4[i];
+    r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const bool b2_ = lane & 4;
+  const float send = b2_ ? r2[0] : r2[1];
+  const float keep = b2_ ? r2[1] : r2[0];
+  float s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if ((lane & 3) == 0) s_part_warp[jred] = s;
+}
+
+// phase B: acc[i][k] += sum_f e'_f * N[row_i, f]  (k: A/Nc, A/Nh, B/Nc, B/Nh)
+template <int RPT>
+__device__ __forceinline__ void phase_b(const TileRegs<RPT>& d, const float* s_e, float (&acc)[RPT][4]) {
+  const float4* e4 = reinterpret_cast<const float4*>(s_e);
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    const float4 e0 = e4[2 * br], e1 = e4[2 * br + 1];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      float tc = d.nc[i][0].x * e0.x;
+      tc = fmaf(d.nc[i][0].y, e0.y, tc);
+      tc = fmaf(d.nc[i][0].z, e0.z, tc);
+      tc = fmaf(d.nc[i][0].w, e0.w, tc);
+      tc = fmaf(d.nc[i][1].x, e1.x, tc);
+      tc = fmaf(d.nc[i][1].y, e1.y, tc);
+      tc = fmaf(d.nc[i][1].z, e1.z, tc);
+      tc = fmaf(d.nc[i][1].w, e1.w, tc);
+      float th = d.nh[i][0].x * e0.x;
+      th = fmaf(d.nh[i][0].y, e0.y, th);
+      th = fmaf(d.nh[i][0].z, e0.z, th);
+      th = fmaf(d.nh[i][0].w, e0.w, th);
+      th = fmaf(d.nh[i][1].x, e1.x, th);
+      th = fmaf(d.nh[i][1].y, e1.y, th);
+      th = fmaf(d.nh[i][1].z, e1.z, th);
+      th = fmaf(d.nh[i][1].w, e1.w, th);
+      acc[i][2 * br + 0] += tc;
+      acc[i][2 * br + 1] += th;
+    }
+  }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.R;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  const int NT = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NTc = blockDim.x - 32, NWc = NTc >> 5;  // consumer threads / warps
+  const int nbar = blockDim.x;                        // every named barrier counts all threads
+  const bool is_adam = warp == NWc;
 
   unsigned char* ring = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * a.stage_stride);
-  float* s_part = reinterpret_cast<float*>(bars + MAX_STAGES);  // [16][8]
-  float* s_e = s_part + 16 * FT;                                // [2][8], 16-byte aligned
+  float* s_part = reinterpret_cast<float*>(bars + MAX_STAGES);  // [2][16 warps][8 frames]
+  float* s_e = s_part + 2 * 16 * FT;                            // [2][2 branches][8 frames], 16-byte aligned
 
-  // ---- per-step scalars (uniform) ----
   const unsigned ep = *a.epoch;
   const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
-  const int in_set = ep & 1u, out_set = in_set ^ 1;
-  const int in_br = ctl->branch;
-  const float* __restrict__ zin = a.st.z[in_set][in_br];
-  const float* __restrict__ min_ = a.st.m[in_set][in_br];
-  const float* __restrict__ vin = a.st.v[in_set][in_br];
-  const float* __restrict__ gprev = a.st.g[in_set];
-  float* __restrict__ gout = a.st.g[out_set];
-  float* __restrict__ zA = a.st.z[out_set][0];
-  float* __restrict__ mA = a.st.m[out_set][0];
-  float* __restrict__ vA = a.st.v[out_set][0];
-  float* __restrict__ zB = a.st.z[out_set][1];
-  float* __restrict__ mB = a.st.m[out_set][1];
-  float* __restrict__ vB = a.st.v[out_set][1];
   const int mode = a.mode;
-  const float lse = ctl->lse;
-  const float lrA = ctl->lrA, lrB = ctl->lrB;
-  const float maskf = ctl->mask_frame;
-  const float bc1 = ctl->bc1, bc2 = ctl->bc2;
-  const int have_prev = ctl->have_prev;
-  const float hbar = (float)(ctl->hbar_data + a.klsum[0]);
-  const float b1 = a.b1, b2 = a.b2, om_b1 = a.om_b1, om_b2 = a.om_b2, eps = a.eps, clip = a.clip;
 
-  if (blockIdx.x == 0 && tid == 0 && mode == 1) {
-    // fold the (all-reduced) MaxEnt sums into the loss record of the step being differentiated
-    finish_record(ctl, a.klsum, a.records, JAXENT_MAX_SLOTS);
-  }
-
-  // ---- rows owned by this thread ----
-  float ccr[RPT], chr[RPT];
-  int row[RPT];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    row[i] = tid + i * NT;
-    const bool ok = row[i] < R;
-    ccr[i] = (ok && mode) ? a.cc[row[i]] : 0.f;
-    chr[i] = (ok && mode) ? a.ch[row[i]] : 0.f;
-  }
-
-  // ---- static, deterministic tile partition ----
+  // static, deterministic tile partition
   const long long G = gridDim.x, cta = blockIdx.x;
   const long long t0 = a.n_tiles * cta / G, t1 = a.n_tiles * (cta + 1) / G;
   const int n = (int)(t1 - t0);
   const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
+  double* part = a.partials + (size_t)blockIdx.x * a.part_n;
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
     fence_barrier_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    const int pre = n < a.stages ? n : a.stages;
-    for (int s = 0; s < pre; ++s) {
-      const uint32_t bar = smem_u32(&bars[s]);
-      mbar_expect_tx(bar, a.tile_bytes);
-      bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(t0 + s) * a.tile_bytes, a.tile_bytes, bar);
-    }
-  }
 
-  double accAc[RPT], accAh[RPT], accBc[RPT], accBh[RPT];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) accAc[i] = accAh[i] = accBc[i] = accBh[i] = 0.0;
-  double sumA = 0.0, sumB = 0.0, gdot = 0.0;
-
-  const bool adam_lane = (warp == 0) && (lane < FT);
-  // frame slot of this lane after the transposing warp reduction
-  const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-
-  int slot = 0;
-  uint32_t parity = 0;
-  for (int it = 0; it < n; ++it) {
-    // -- prefetch the per-frame optimiser state of this tile (consumed after barrier B1)
-    const long long f = (t0 + it) * FT + lane;
-    const bool valid = adam_lane && (f < a.F);
-    float z_ = 0.f, m_ = 0.f, v_ = 0.f, w_ = 0.f, k_ = 0.f, gp_ = 0.f;
-    if (valid) {
-      z_ = zin[f];
-      m_ = min_[f];
-      v_ = vin[f];
-      if (mode) {
-        w_ = a.w[f];
-        k_ = a.kappa[f];
-        gp_ = gprev[f];
+  if (is_adam) {
+    // ================================================================== Adam warp
+    if (lane == 0) {
+      const int pre = n < a.stages ? n : a.stages;
+      for (int s = 0; s < pre; ++s) {
+        const uint32_t bar = smem_u32(&bars[s]);
+        mbar_expect_tx(bar, a.tile_bytes);
+        bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(t0 + s) * a.tile_bytes, a.tile_bytes, bar);
       }
+      if (blockIdx.x == 0 && mode == 1) finish_record(ctl, a.klsum, a.records, JAXENT_MAX_SLOTS);
     }
+    const int in_set = ep & 1u, out_set = in_set ^ 1;
+    const int in_br = ctl->branch;
+    const float* __restrict__ zin = a.st.z[in_set][in_br];
+    const float* __restrict__ min_ = a.st.m[in_set][in_br];
+    const float* __restrict__ vin = a.st.v[in_set][in_br];
+    const float* __restrict__ gprev = a.st.g[in_set];
+    float* __restrict__ gout = a.st.g[out_set];
+    float* __restrict__ zA = a.st.z[out_set][0];
+    float* __restrict__ mA = a.st.m[out_set][0];
+    float* __restrict__ vA = a.st.v[out_set][0];
+    float* __restrict__ zB = a.st.z[out_set][1];
+    float* __restrict__ mB = a.st.m[out_set][1];
+    float* __restrict__ vB = a.st.v[out_set][1];
+    const float lse = ctl->lse;
+    const float lrA = ctl->lrA, lrB = ctl->lrB;
+    const float maskf = ctl->mask_frame;
+    const float bc1 = ctl->bc1, bc2 = ctl->bc2;
+    const int have_prev = ctl->have_prev;
+    const float hbar = (float)(ctl->hbar_data + a.klsum[0]);
+    const float b1 = a.b1, b2 = a.b2, om_b1 = a.om_b1, om_b2 = a.om_b2, eps = a.eps, clip = a.clip;
+    const int fj = lane & 7, fk = lane >> 3;  // frame within tile, partial-sum group
+    double sumA = 0.0, sumB = 0.0, gdot = 0.0;
 
-    // -- wait for the tile, move this thread's rows into registers
-    mbar_wait(smem_u32(&bars[slot]), parity);
-    const float4* __restrict__ tile = reinterpret_cast<const float4*>(ring + (size_t)slot * a.stage_stride);
-    float4 nc[RPT][QT], nh[RPT][QT];
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-#pragma unroll
-      for (int q = 0; q < QT; ++q) {
-        if (row[i] < R) {
-          nc[i][q] = tile[(q * 2 + 0) * R + row[i]];
-          nh[i][q] = tile[(q * 2 + 1) * R + row[i]];
-        } else {
-          nc[i][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          nh[i][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int slot = 0;
+    for (int it = 0; it < n; ++it) {
+      const int b = it & 1;
+      const long long f = (t0 + it) * FT + fj;
+      const bool valid = (fk == 0) && (f < a.F);
+      float z_ = 0.f, m_ = 0.f, v_ = 0.f, w_ = 0.f, k_ = 0.f, gp_ = 0.f;
+      if (valid) {  // prefetch before waiting on the consumers
+        z_ = zin[f];
+        m_ = min_[f];
+        v_ = vin[f];
+        if (mode) {
+          w_ = a.w[f];
+          k_ = a.kappa[f];
+          gp_ = gprev[f];
         }
       }
-    }
-
-    // -- phase A: column-sum partials over this thread's rows
-    float p[FT];
-#pragma unroll
-    for (int j = 0; j < FT; ++j) p[j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-#pragma unroll
-      for (int q = 0; q < QT; ++q) {
-        p[4 * q + 0] = fmaf(ccr[i], nc[i][q].x, fmaf(chr[i], nh[i][q].x, p[4 * q + 0]));
-        p[4 * q + 1] = fmaf(ccr[i], nc[i][q].y, fmaf(chr[i], nh[i][q].y, p[4 * q + 1]));
-        p[4 * q + 2] = fmaf(ccr[i], nc[i][q].z, fmaf(chr[i], nh[i][q].z, p[4 * q + 2]));
-        p[4 * q + 3] = fmaf(ccr[i], nc[i][q].w, fmaf(chr[i], nh[i][q].w, p[4 * q + 3]));
+      bar_sync(BAR_PART0 + b, nbar);  // partials(it) visible, every consumer has ring[slot] in registers
+      if (lane == 0 && it + a.stages < n) {
+        const uint32_t bar = smem_u32(&bars[slot]);
+        mbar_expect_tx(bar, a.tile_bytes);
+        bulk_g2s(smem_u32(ring + (size_t)slot * a.stage_stride), gsrc + (size_t)(t0 + it + a.stages) * a.tile_bytes,
+                 a.tile_bytes, bar);
       }
-    }
-    // transposing warp reduction: 8 values x 32 lanes -> lane holds the warp total of frame jred
-    {
-      const bool hi = lane & 16;
-      float q4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float send = hi ? p[i] : p[i + 4];
-        const float keep = hi ? p[i + 4] : p[i];
-        q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
-      const bool b3 = lane & 8;
-      float r2[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float send = b3 ? q4[i] : q4[i + 2];
-        const float keep = b3 ? q4[i + 2] : q4[i];
-        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-      const bool b2_ = lane & 4;
-      const float send = b2_ ? r2[0] : r2[1];
-      const float keep = b2_ ? r2[1] : r2[0];
-      float s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      if ((lane & 3) == 0) s_part[warp * FT + jred] = s;
-    }
-    __syncthreads();  // B1: partials visible; every thread has consumed ring[slot]
-
-    // -- refill the slot just consumed
-    if (tid == 0 && it + a.stages < n) {
-      const uint32_t bar = smem_u32(&bars[slot]);
-      mbar_expect_tx(bar, a.tile_bytes);
-      bulk_g2s(smem_u32(ring + (size_t)slot * a.stage_stride), gsrc + (size_t)(t0 + it + a.stages) * a.tile_bytes,
-               a.tile_bytes, bar);
-    }
-
-    // -- per-frame optimiser update (8 lanes of warp 0)
-    if (adam_lane) {
+      if (++slot == a.stages) slot = 0;
+      // H_f: 4 lanes per frame sum a quarter of the warps each, fixed order
+      float H = 0.f;
+      const float* sp = s_part + b * 16 * FT;
+      for (int wv = fk; wv < NWc; wv += 4) H += sp[wv * FT + fj];
+      H += __shfl_xor_sync(0xffffffffu, H, 8);
+      H += __shfl_xor_sync(0xffffffffu, H, 16);
       float eA = 0.f, eB = 0.f;
       if (valid) {
         if (mode) {
-          float H = 0.f;
-          for (int wv = 0; wv < NW; ++wv) H += s_part[wv * FT + lane];
           const float gf = maskf * (w_ * ((H + k_) - hbar));
           const float gpv = have_prev ? gp_ : gf;
           gdot += (double)(gpv * gf);
           gout[f] = gf;
-          // branch A: base learning rate
-          float sA = gf * lrA;
-          if (clip > 0.f) sA = fminf(fmaxf(sA, -clip), clip);
+          float sA = gf * lrA, sB = gf * lrB;
+          if (clip > 0.f) {
+            sA = fminf(fmaxf(sA, -clip), clip);
+            sB = fminf(fmaxf(sB, -clip), clip);
+          }
           const float m1 = om_b1 * sA + b1 * m_;
-          const float v1 = om_b2 * (sA * sA) + b2 * v_;
-          const float z1 = z_ - (m1 / bc1) / (sqrtf(v1 / bc2) + eps);
-          // branch B: plateau-reduced learning rate
-          float sB = gf * lrB;
-          if (clip > 0.f) sB = fminf(fmaxf(sB, -clip), clip);
           const float m2 = om_b1 * sB + b1 * m_;
+          const float v1 = om_b2 * (sA * sA) + b2 * v_;
           const float v2 = om_b2 * (sB * sB) + b2 * v_;
+          const float z1 = z_ - (m1 / bc1) / (sqrtf(v1 / bc2) + eps);
           const float z2 = z_ - (m2 / bc1) / (sqrtf(v2 / bc2) + eps);
+          eA = expf(z1 - lse);
+          eB = expf(z2 - lse);
           zA[f] = z1;
           mA[f] = m1;
           vA[f] = v1;
           zB[f] = z2;
           mB[f] = m2;
           vB[f] = v2;
-          eA = expf(z1 - lse);
-          eB = expf(z2 - lse);
         } else {
           eA = eB = expf(z_ - lse);
           zA[f] = z_;
@@ -325,73 +361,12 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX, (RPT == 1) ? 2 : 1) bv_pass_
         sumA += (double)eA;
         sumB += (double)eB;
       }
-      s_e[lane] = eA;
-      s_e[FT + lane] = eB;
-    }
-    __syncthreads();  // B2: e'_f visible
-
-    // -- phase B: softmax-weighted row sums for both branches
-    {
-      const float4* e4 = reinterpret_cast<const float4*>(s_e);
-      const float4 ea0 = e4[0], ea1 = e4[1], eb0 = e4[2], eb1 = e4[3];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        float tAc = nc[i][0].x * ea0.x;
-        tAc = fmaf(nc[i][0].y, ea0.y, tAc);
-        tAc = fmaf(nc[i][0].z, ea0.z, tAc);
-        tAc = fmaf(nc[i][0].w, ea0.w, tAc);
-        tAc = fmaf(nc[i][1].x, ea1.x, tAc);
-        tAc = fmaf(nc[i][1].y, ea1.y, tAc);
-        tAc = fmaf(nc[i][1].z, ea1.z, tAc);
-        tAc = fmaf(nc[i][1].w, ea1.w, tAc);
-        float tAh = nh[i][0].x * ea0.x;
-        tAh = fmaf(nh[i][0].y, ea0.y, tAh);
-        tAh = fmaf(nh[i][0].z, ea0.z, tAh);
-        tAh = fmaf(nh[i][0].w, ea0.w, tAh);
-        tAh = fmaf(nh[i][1].x, ea1.x, tAh);
-        tAh = fmaf(nh[i][1].y, ea1.y, tAh);
-        tAh = fmaf(nh[i][1].z, ea1.z, tAh);
-        tAh = fmaf(nh[i][1].w, ea1.w, tAh);
-        float tBc = nc[i][0].x * eb0.x;
-        tBc = fmaf(nc[i][0].y, eb0.y, tBc);
-        tBc = fmaf(nc[i][0].z, eb0.z, tBc);
-        tBc = fmaf(nc[i][0].w, eb0.w, tBc);
-        tBc = fmaf(nc[i][1].x, eb1.x, tBc);
-        tBc = fmaf(nc[i][1].y, eb1.y, tBc);
-        tBc = fmaf(nc[i][1].z, eb1.z, tBc);
-        tBc = fmaf(nc[i][1].w, eb1.w, tBc);
-        float tBh = nh[i][0].x * eb0.x;
-        tBh = fmaf(nh[i][0].y, eb0.y, tBh);
-        tBh = fmaf(nh[i][0].z, eb0.z, tBh);
-        tBh = fmaf(nh[i][0].w, eb0.w, tBh);
-        tBh = fmaf(nh[i][1].x, eb1.x, tBh);
-        tBh = fmaf(nh[i][1].y, eb1.y, tBh);
-        tBh = fmaf(nh[i][1].z, eb1.z, tBh);
-        tBh = fmaf(nh[i][1].w, eb1.w, tBh);
-        accAc[i] += (double)tAc;
-        accAh[i] += (double)tAh;
-        accBc[i] += (double)tBc;
-        accBh[i] += (double)tBh;
+      if (fk == 0) {
+        s_e[b * 2 * FT + fj] = eA;
+        s_e[b * 2 * FT + FT + fj] = eB;
       }
+      bar_arrive(BAR_E0 + b, nbar);  // e'(it) visible to the consumers
     }
-    if (++slot == a.stages) {
-      slot = 0;
-      parity ^= 1u;
-    }
-  }
-
-  // ---- per-CTA partials (fp64), reduced across CTAs by reduce_kernel in a fixed order ----
-  double* part = a.partials + (size_t)blockIdx.x * a.part_n;
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    if (row[i] < R) {
-      part[0 * R + row[i]] = accAc[i];
-      part[1 * R + row[i]] = accAh[i];
-      part[2 * R + row[i]] = accBc[i];
-      part[3 * R + row[i]] = accBh[i];
-    }
-  }
-  if (warp == 0) {
     for (int o = 4; o; o >>= 1) {
       sumA += __shfl_xor_sync(0xffffffffu, sumA, o);
       sumB += __shfl_xor_sync(0xffffffffu, sumB, o);
@@ -403,7 +378,97 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX, (RPT == 1) ? 2 : 1) bv_pass_
       part[4 * R + 2] = gdot;
       part[4 * R + 3] = 0.0;
     }
+    return;
   }
+
+  // ==================================================================== consumers
+  float ccr[RPT], chr[RPT];
+  uint32_t rowoff[RPT];
+  int row[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    row[i] = tid + i * NTc;
+    const bool ok = row[i] < R;
+    const int rc = ok ? row[i] : R - 1;  // clamp: finite data, zero coefficients, result never stored
+    rowoff[i] = (uint32_t)rc * 16u;
+    ccr[i] = (ok && mode) ? a.cc[rc] : 0.f;
+    chr[i] = (ok && mode) ? a.ch[rc] : 0.f;
+    if (ok) {
+      part[0 * R + rc] = 0.0;
+      part[1 * R + rc] = 0.0;
+      part[2 * R + rc] = 0.0;
+      part[3 * R + rc] = 0.0;
+    }
+  }
+  const uint32_t r16 = (uint32_t)R * 16u;
+  const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  float acc[RPT][4];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  auto flush = [&]() {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      if (row[i] < R) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          atomicAdd(&part[k * R + row[i]], (double)acc[i][k]);  // single writer per address: deterministic
+          acc[i][k] = 0.f;
+        }
+      }
+    }
+  };
+
+  int slot = 0;
+  uint32_t parity = 0;
+  auto fetch = [&](TileRegs<RPT>& D) {
+    mbar_wait(smem_u32(&bars[slot]), parity);
+    load_tile<RPT>(D, ring + (size_t)slot * a.stage_stride, r16, rowoff);
+    if (++slot == a.stages) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  };
+  float* spw0 = s_part + warp * FT;
+  float* spw1 = s_part + 16 * FT + warp * FT;
+  const float* se0 = s_e;
+  const float* se1 = s_e + 2 * FT;
+
+  TileRegs<RPT> D0, D1;
+  fetch(D0);
+  phase_a<RPT>(D0, ccr, chr, spw0, lane, jred);
+  bar_arrive(BAR_PART0, nbar);
+  int it = 1, since = 0;
+  while (true) {
+    if (it >= n) {
+      bar_sync(BAR_E0, nbar);
+      phase_b<RPT>(D0, se0, acc);
+      break;
+    }
+    fetch(D1);
+    phase_a<RPT>(D1, ccr, chr, spw1, lane, jred);
+    bar_arrive(BAR_PART0 + 1, nbar);
+    bar_sync(BAR_E0, nbar);
+    phase_b<RPT>(D0, se0, acc);
+    ++it;
+    if (it >= n) {
+      bar_sync(BAR_E0 + 1, nbar);
+      phase_b<RPT>(D1, se1, acc);
+      break;
+    }
+    fetch(D0);
+    phase_a<RPT>(D0, ccr, chr, spw0, lane, jred);
+    bar_arrive(BAR_PART0, nbar);
+    bar_sync(BAR_E0 + 1, nbar);
+    phase_b<RPT>(D1, se1, acc);
+    ++it;
+    since += 2;
+    if (since >= FLUSH_TILES) {
+      flush();
+      since = 0;
+    }
+  }
+  flush();
 }
 
 // ------------------------------------------------------------------------------------------ reduce
@@ -439,12 +504,10 @@ __global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, cons
 // ------------------------------------------------------------------------------------------ launchers
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(bv_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+  e = cudaFuncSetAttribute(bv_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<1>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   e = cudaFuncSetAttribute(bv_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<2>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  e = cudaFuncSetAttribute(bv_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<4>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;
 }
 
@@ -452,7 +515,6 @@ int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, 
   switch (rpt) {
     case 1: bv_pass_kernel<1><<<ctas, threads, smem, s>>>(a); break;
     case 2: bv_pass_kernel<2><<<ctas, threads, smem, s>>>(a); break;
-    case 4: bv_pass_kernel<4><<<ctas, threads, smem, s>>>(a); break;
     default: set_error("unsupported rows-per-thread %d", rpt); return JAXENT_E_UNSUPPORTED;
   }
   cudaError_t e = cudaGetLastError();

@@ -87,7 +87,7 @@ def test_plan_create_validation_errors():
     assert _create(pb)[0] == L.E_UNSUPPORTED
     pb = _valid_problem(); pb.slots[0].kind = L.LOSS_MAXENT_CONVEX_KL  # no prior
     assert _create(pb)[0] == L.E_INVALID
-    pb = _valid_problem(); pb.R = 5000
+    pb = _valid_problem(); pb.R = 1025
     assert _create(pb)[0] == L.E_UNSUPPORTED
     rc, _, msg = _create(_valid_problem(), nbytes=1024); assert rc == L.E_WORKSPACE and "too small" in msg
     rc, _, msg = _create(_valid_problem(), ws=0x100010); assert rc == L.E_INVALID

@@ -108,9 +108,9 @@ def test_bpti_fixture_shape_config1():
     _check_steps(case, cfg, 6)
 
 
-@pytest.mark.parametrize("F,R", [(5, 3), (8, 32), (9, 33), (1001, 513), (300, 1100)])
+@pytest.mark.parametrize("F,R", [(5, 3), (8, 32), (9, 33), (1001, 513), (300, 1000)])
 def test_ragged_shapes(F, R):
-    """frames not a multiple of the 8-frame tile, rows not a multiple of a warp, R > 512 (2 and 4 rows/thread)."""
+    """frames not a multiple of the 8-frame tile, rows not a multiple of a warp, R > 512 (2 rows/thread)."""
     case = H.make_case(F, R, 3, O.UPTAKE_EYE_MSE, seed=F + R, n_pep=max(4, R // 3))
     cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=True)
     _check_steps(case, cfg, 4)
