@@ -59,6 +59,7 @@ enum {
  * both on the device.  Same linear map as the reference's dense `sparse_map.todense() @ x`. */
 typedef struct {
   int32_t n_pep;
+  int32_t nnz;            /* number of stored entries (row_ptr[n_pep]) */
   const int32_t* row_ptr; /* (n_pep+1) */
   const int32_t* col;     /* (nnz) residue index   */
   const float* val;       /* (nnz)                 */

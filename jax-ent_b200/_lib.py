@@ -29,6 +29,7 @@ E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = -1, -2, -3, -4
 class PeptideMap(C.Structure):
     _fields_ = [
         ("n_pep", C.c_int32),
+        ("nnz", C.c_int32),
         ("row_ptr", C.c_void_p),
         ("col", C.c_void_p),
         ("val", C.c_void_p),

@@ -25,13 +25,17 @@ struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
   size_t off_w, off_kappa, off_cc, off_ch, off_logpf, off_uptake, off_avg;
   size_t off_partials, off_red, off_klpart, off_klsum, off_ctl, off_epoch, off_counter, off_records;
+  size_t off_blob[JAXENT_MAX_SLOTS];
+  int blob_words[JAXENT_MAX_SLOTS];
   size_t total;
 };
 
 constexpr int MAX_PASS_CTAS = 2 * 160;
 constexpr int MAX_TAIL_CTAS = 160;
 
-static Layout make_layout(int R, int T, long long F) {
+static Layout make_layout(const JaxentBvProblem* pb) {
+  const int R = pb->R, T = pb->uptake ? pb->T : 0;
+  const long long F = pb->F;
   Layout L;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -63,6 +67,15 @@ static Layout make_layout(int R, int T, long long F) {
   L.off_epoch = take(sizeof(unsigned));
   L.off_counter = take(sizeof(unsigned));
   L.off_records = take((size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord));
+  for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
+    L.off_blob[i] = 0;
+    L.blob_words[i] = 0;
+    if (i < pb->n_slots && pb->slots[i].kind <= JAXENT_LOSS_PF_L2) {
+      const JaxentLossSlot& sl = pb->slots[i];
+      L.blob_words[i] = blob_words(R, T, sl.train.n_pep, sl.train.nnz, sl.val.n_pep, sl.val.nnz);
+      L.off_blob[i] = take((size_t)L.blob_words[i] * 4);
+    }
+  }
   L.total = o;
   return L;
 }
@@ -122,7 +135,7 @@ struct JaxentPlan {
   jx::Layout lay;
   unsigned char* ws;
   jx::StateSets st;
-  int pass_threads, rpt, pass_ctas, stages, tail_ctas, p_max;
+  int pass_threads, rpt, pass_ctas, stages, tail_ctas, p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
   uint32_t tile_bytes, stage_stride;
   size_t pass_smem, tail_smem;
   long long n_tiles;
@@ -179,7 +192,7 @@ static int validate_problem(const JaxentBvProblem* p) {
     if (s.kind <= JAXENT_LOSS_PF_L2) {
       const JaxentPeptideMap* maps[2] = {&s.train, &s.val};
       for (const JaxentPeptideMap* m : maps) {
-        if (m->n_pep < 0 || (m->n_pep > 0 && (!m->row_ptr || !m->col || !m->val || !m->t_ptr || !m->t_row || !m->t_val || !m->y))) {
+        if (m->n_pep < 0 || m->nnz < 0 || (m->n_pep > 0 && (!m->row_ptr || !m->col || !m->val || !m->t_ptr || !m->t_row || !m->t_val || !m->y))) {
           set_error("slot %d: incomplete peptide map", i);
           return JAXENT_E_INVALID;
         }
@@ -209,7 +222,8 @@ extern "C" int jaxent_abi_sizeof(int which) {
 
 extern "C" size_t jaxent_bv_workspace_bytes(const JaxentBvProblem* p) {
   if (!p || p->R <= 0 || p->F <= 0) return 0;
-  return make_layout(p->R, p->uptake ? p->T : 0, p->F).total;
+  if (p->n_slots < 0 || p->n_slots > JAXENT_MAX_SLOTS) return 0;
+  return make_layout(p).total;
 }
 
 extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const JaxentOptConfig* cfg, void* workspace,
@@ -228,7 +242,7 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
     return JAXENT_E_INVALID;
   }
   const int R = problem->R, T = problem->uptake ? problem->T : 0;
-  Layout L = make_layout(R, T, problem->F);
+  Layout L = make_layout(problem);
   if (workspace_bytes < L.total) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, L.total);
     return JAXENT_E_WORKSPACE;
@@ -272,23 +286,30 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   if (ctas > MAX_PASS_CTAS) ctas = MAX_PASS_CTAS;
   p->pass_ctas = (int)ctas;
 
-  int p_max = 1;
+  int p_tr = 1, p_va = 1, nnz_tr = 1, nnz_va = 1;
   for (int i = 0; i < problem->n_slots; ++i)
     if (problem->slots[i].kind <= JAXENT_LOSS_PF_L2) {
-      if (problem->slots[i].train.n_pep > p_max) p_max = problem->slots[i].train.n_pep;
-      if (problem->slots[i].val.n_pep > p_max) p_max = problem->slots[i].val.n_pep;
+      const JaxentLossSlot& sl = problem->slots[i];
+      if (sl.train.n_pep > p_tr) p_tr = sl.train.n_pep;
+      if (sl.val.n_pep > p_va) p_va = sl.val.n_pep;
+      if (sl.train.nnz > nnz_tr) nnz_tr = sl.train.nnz;
+      if (sl.val.nnz > nnz_va) nnz_va = sl.val.nnz;
     }
-  p->p_max = p_max;
-  p->tail_smem = tail_smem_bytes(R, T, p_max);
-  if (p->tail_smem > 200 * 1024) {
+  p->p_max_tr = p_tr;
+  p->p_max_va = p_va;
+  p->nnz_max_tr = nnz_tr;
+  p->nnz_max_va = nnz_va;
+  p->tail_smem = tail_smem_bytes(R, T, p_tr, p_va, nnz_tr, nnz_va);
+  if (p->tail_smem > 220 * 1024) {
+    const size_t need = p->tail_smem;
     delete p;
-    set_error("R*T / peptide count too large for the tail kernel (%zu bytes of shared memory)", tail_smem_bytes(R, T, p_max));
+    set_error("R*T / peptide maps too large for the tail kernel (%zu bytes of shared memory)", need);
     return JAXENT_E_UNSUPPORTED;
   }
-  long long tctas = (problem->F + 2047) / 2048;
-  if (tctas > device_sm_count) tctas = device_sm_count;
-  if (tctas < 1) tctas = 1;
-  p->tail_ctas = (int)tctas;
+  // CTA 0 runs the R x T tail; the per-frame MaxEnt work is spread over the others (one CTA does both when F is small)
+  long long fctas = (problem->F + 4095) / 4096;
+  if (fctas > device_sm_count - 1) fctas = device_sm_count - 1;
+  p->tail_ctas = (fctas <= 1) ? 1 : (int)fctas + 1;
   p->initialised = 0;
   *out = p;
   return JAXENT_OK;
@@ -344,6 +365,13 @@ extern "C" int jaxent_bv_state_init(JaxentPlan* p, const float* z0, float zmax, 
       reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("state_init launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  BlobSet bs;
+  for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
+    bs.words[i] = p->lay.blob_words[i];
+    bs.blob[i] = bs.words[i] ? reinterpret_cast<int*>(p->ws + p->lay.off_blob[i]) : nullptr;
+  }
+  rc = launch_build_blobs(p->prob, bs, (cudaStream_t)stream);
+  if (rc) return rc;
   p->initialised = 1;
   return JAXENT_OK;
 }
@@ -422,7 +450,18 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.klpart = reinterpret_cast<double*>(p->ws + p->lay.off_klpart);
   a.klsum = reinterpret_cast<double*>(p->ws + p->lay.off_klsum);
   a.records = reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records);
-  a.p_max = p->p_max;
+  for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
+    a.blobs.words[i] = p->lay.blob_words[i];
+    a.blobs.blob[i] = a.blobs.words[i] ? reinterpret_cast<int*>(p->ws + p->lay.off_blob[i]) : nullptr;
+  }
+  {
+    const long long fc = (p->tail_ctas == 1) ? 1 : p->tail_ctas - 1;
+    a.frames_per_cta = (p->prob.F + fc - 1) / fc;
+  }
+  a.p_max_tr = p->p_max_tr;
+  a.p_max_va = p->p_max_va;
+  a.nnz_max_tr = p->nnz_max_tr;
+  a.nnz_max_va = p->nnz_max_va;
   a.eps_kl = (float)(1e-10 / (double)p->prob.F_total);
   return launch_tail(a, p->tail_ctas, p->tail_smem, (cudaStream_t)stream);
 }

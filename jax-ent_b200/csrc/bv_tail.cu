@@ -1,373 +1,594 @@
 // The "R x T tail" of the BV MaxEnt optimise step and the per-frame MaxEnt terms, sm_100a.
 //
-// Runs between two streaming passes.  Every CTA resolves the plateau-LR branch from the reduced
-// partial sums; CTA 0 then evaluates
+// Runs between two streaming passes.  CTA 0 evaluates
 //   ln PF = bc*<Nc> + bh*<Nh>                   BV_ForwardPass        models/HDX/forward.py:18-37
 //   uptake = 1 - exp(-k t / PF)                 BV_uptake_ForwardPass models/HDX/forward.py:45-76
 //   pred = S u  (CSR)                           apply_sparse_mapping  data/splitting/sparse_map.py:220-235
 //   MSE / mean-centred MSE / sigma MSE / PF-L2  opt/losses.py:1541-1657,1790-1841,17-50
 //   L1/L2 parameter penalties                   opt/losses.py:476-513
-// and their closed-form backward down to c_r = dL/d lnPF_r, the BV-parameter Adam update
-// (opt/optimiser.py:130-134,416-424) and the control block for the next pass, while all CTAs
-// compute the per-frame MaxEnt terms of maxent_convexKL_loss (opt/losses.py:304-322):
-// softmax weights, dKL/dw and the three KL sums.  Sums are carried in fp64.
+// their closed-form backward down to c_r = dL/d lnPF_r, the plateau decision, the BV-parameter Adam
+// update (opt/optimiser.py:130-134,403-424) and the control block of the next pass; the other CTAs
+// compute the per-frame terms of maxent_convexKL_loss (opt/losses.py:304-322): softmax weights,
+// dKL/dw and the KL sums.  All sums are carried in fp64.
+//
+// This kernel sits on the critical path of every step, so it is organised around latency:
+//  * each data slot's peptide maps, transposes and targets live in ONE contiguous device blob
+//    (gathered once by build_blobs_kernel) whose image is the shared-memory layout, so staging is a
+//    single vectorised copy with every load in flight at once, overlapped with the control-block,
+//    k_int / time-point and partial-sum reads;
+//  * every thread derives the step scalars (branch, BV-parameter Adam, next learning rates, bias
+//    corrections, new log-sum-exp) redundantly from shared memory -- no leader-thread sections;
+//  * the back-projection is parallel over (residue, time point) and the loss sums are reduced once.
 #include <cmath>
 
 #include "jx_internal.cuh"
 
 namespace jx {
 
-__device__ __forceinline__ double warp_sum(double v) {
+// ---- code-size discipline: this kernel runs a long straight-line path once per launch, so its cost is
+// dominated by instruction fetch.  Heavy math lives behind single __noinline__ call sites.
+__device__ __noinline__ double wsum(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __noinline__ double dexp(double x) { return exp(x); }
+__device__ __noinline__ double dlog(double x) { return log(x); }
+__device__ __noinline__ float fpow(float a, float b) { return powf(a, b); }
+// floor(x / d) for 0 <= x < 2^21 with inv = 1/d (exact: the fraction is >= 0.5/d away from an integer)
+__device__ __forceinline__ int fdiv(int x, float inv) { return (int)(((float)x + 0.5f) * inv); }
 
-// deterministic block-wide sum; result valid in all threads.  scratch: >= 33 doubles.
-__device__ double block_sum(double v, double* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    double t = (lane < nw) ? scratch[lane] : 0.0;
-    t = warp_sum(t);
-    if (lane == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
-}
-
-struct TailShared {
-  int d;            // branch chosen for the update that produced the current parameters
-  int pending;
-  double S;         // softmax denominator of the current z relative to the old shift
-  float lse_old;
-  float bc, bh;
-  int off;          // offset of the chosen accumulators inside red
+// step scalars, derived once by warp 0 and broadcast through shared memory
+struct StepScalars {
+  int d;  // plateau branch taken by the update that produced the current parameters
+  int pending, step, mask_idx, cm, cf, have_prev;
+  float lr, mlr, bc, bh, mb0, mb1, vb0, vb1;
+  float lrA, lrB, mlrA, mlrB, mask_frame, mask_model, bc1, bc2, lse_new, lse_old;
+  double S, dot;
 };
 
-// One peptide map (train or val) of one data slot.  Returns the unscaled loss; when `grad`,
-// accumulates dL_total/d lnPF_r into sc[].
-__device__ double map_loss(const JaxentPeptideMap& mp, int kind, int R, int T, bool uptake, const double* sE,
-                           const double* slp, const double* sxe, const float* k_ints, const float* tps, double* sres,
-                           double* sgp, double* smean, double* scratch, bool grad, double scale, double* sc) {
-  const int P = mp.n_pep;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (P <= 0) return 0.0;
-  if (kind == JAXENT_LOSS_PF_L2) {
-    double part = 0.0;
-    for (int p = tid; p < P; p += nt) {
-      double pred = 0.0;
-      for (int j = mp.row_ptr[p]; j < mp.row_ptr[p + 1]; ++j) pred += (double)mp.val[j] * slp[mp.col[j]];
-      const double r = pred - (double)mp.y[p];
-      sres[p] = r;
-      part += r * r;
+// warp 0 only.  Reads the previous control block straight from global memory (one round trip that
+// overlaps the staging done by the other warps); the four powf and two log evaluations run on
+// separate lanes behind single call sites.
+__device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restrict__ old, const double* __restrict__ red,
+                                            int R, const JaxentOptConfig cfg) {
+  const int lane = threadIdx.x & 31;
+  StepScalars s;
+  const double SA = red[4 * R + 0], SB = red[4 * R + 1], gdot = red[4 * R + 2];
+  s.pending = old->pending;
+  s.step = old->step;
+  s.mask_idx = old->mask_idx;
+  s.cm = old->count_model;
+  s.cf = old->count_frame;
+  s.have_prev = old->have_prev;
+  s.lr = old->lr;
+  s.mlr = old->model_lr;
+  s.bc = old->bc;
+  s.bh = old->bh;
+  s.mb0 = old->mb[0];
+  s.mb1 = old->mb[1];
+  s.vb0 = old->vb[0];
+  s.vb1 = old->vb[1];
+  s.lse_old = old->lse;
+  const float g0 = old->gb[0], g1 = old->gb[1];
+  const float gp0 = old->gb_prev[0], gp1 = old->gb_prev[1];
+  const float olrA = old->lrA, olrB = old->lrB, omlrA = old->mlrA, omlrB = old->mlrB;
+  const int cm1 = s.cm + (s.pending ? 1 : 0), cf1 = s.cf + (s.pending ? 1 : 0);
+  // lanes 0..3: b1^cm1, b2^cm1, b1^(cf1+1), b2^(cf1+1);  lanes 4,5: log S_A, log S_B
+  float pw = 0.f;
+  double lg = 0.0;
+  if (lane < 4) pw = fpow((lane & 1) ? (float)cfg.b2 : (float)cfg.b1, (float)(lane < 2 ? cm1 : cf1 + 1));
+  if (lane == 4 || lane == 5) lg = dlog(lane == 4 ? SA : SB);
+  const float pw0 = __shfl_sync(0xffffffffu, pw, 0), pw1 = __shfl_sync(0xffffffffu, pw, 1);
+  const float pw2 = __shfl_sync(0xffffffffu, pw, 2), pw3 = __shfl_sync(0xffffffffu, pw, 3);
+  const double lgA = __shfl_sync(0xffffffffu, lg, 4), lgB = __shfl_sync(0xffffffffu, lg, 5);
+  if (lane != 0) return;
+  s.d = 0;
+  s.dot = 0.0;
+  if (s.pending) {
+    const float p0 = s.have_prev ? gp0 : g0, p1 = s.have_prev ? gp1 : g1;
+    s.dot = gdot + (double)p0 * (double)g0 + (double)p1 * (double)g1;
+    s.d = ((float)s.dot < 0.f && s.step > 1) ? 1 : 0;  // opt/optimiser.py:403
+    s.lr = s.d ? olrB : olrA;
+    s.mlr = s.d ? omlrB : omlrA;
+    // optax adam + keep_params_nonnegative on (bc, bh) with the LR-pre-scaled gradients
+    const float b1 = (float)cfg.b1, b2 = (float)cfg.b2, eps = (float)cfg.eps, clip = cfg.clip_value;
+    const float om_b1 = (float)(1.0 - cfg.b1), om_b2 = (float)(1.0 - cfg.b2);
+    s.cm = cm1;
+    const float c1 = 1.0f - pw0, c2 = 1.0f - pw1;
+    float sg0 = g0 * s.mlr, sg1 = g1 * s.mlr;
+    if (clip > 0.f) {
+      sg0 = fminf(fmaxf(sg0, -clip), clip);
+      sg1 = fminf(fmaxf(sg1, -clip), clip);
     }
-    const double loss = block_sum(part, scratch) / (double)P;
-    if (grad) {
-      const double g = scale * 2.0 / (double)P;
-      for (int r = tid; r < R; r += nt) {
-        double acc = 0.0;
-        for (int j = mp.t_ptr[r]; j < mp.t_ptr[r + 1]; ++j) acc += (double)mp.t_val[j] * sres[mp.t_row[j]];
-        sc[r] += g * acc;
-      }
-    }
-    __syncthreads();
-    return loss;
+    s.mb0 = om_b1 * sg0 + b1 * s.mb0;
+    s.mb1 = om_b1 * sg1 + b1 * s.mb1;
+    s.vb0 = om_b2 * (sg0 * sg0) + b2 * s.vb0;
+    s.vb1 = om_b2 * (sg1 * sg1) + b2 * s.vb1;
+    float u0 = -((s.mb0 / c1) / (sqrtf(s.vb0 / c2) + eps));
+    float u1 = -((s.mb1 / c1) / (sqrtf(s.vb1 / c2) + eps));
+    if (s.bc + u0 < 0.f) u0 = -s.bc;  // optax.keep_params_nonnegative
+    if (s.bh + u1 < 0.f) u1 = -s.bh;
+    s.bc += u0;
+    s.bh += u1;
+    s.have_prev = 1;
+    s.cf = cf1;
+    s.mask_idx = (s.step >= cfg.initial_steps) ? 1 : s.mask_idx;
+    s.step += 1;
   }
-  // ---- uptake kinds ----
-  const bool centre = kind == JAXENT_LOSS_UPTAKE_MC_EYE_MSE;
-  const bool sigma = kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE && mp.W != nullptr;
-  const int n = P * T;
-  for (int i = tid; i < n; i += nt) {
-    const int p = i / T, t = i - p * T;
-    double pred = 0.0;
-    for (int j = mp.row_ptr[p]; j < mp.row_ptr[p + 1]; ++j) pred += (double)mp.val[j] * (1.0 - sE[t * R + mp.col[j]]);
-    sres[i] = pred;  // pred[p,t]
-  }
-  __syncthreads();
-  if (centre) {
-    // per-timepoint means of prediction and target (opt/losses.py:1814-1819)
-    for (int t = tid; t < T; t += nt) {
-      double mp_ = 0.0, my = 0.0;
-      for (int p = 0; p < P; ++p) {
-        mp_ += sres[p * T + t];
-        my += (double)mp.y[p * T + t];
-      }
-      smean[t] = mp_ / P;
-      smean[T + t] = my / P;
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < n; i += nt) {
-    const int t = i % T;
-    double r = sres[i] - (double)mp.y[i];
-    if (centre) r -= smean[t] - smean[T + t];
-    sres[i] = r;  // residual[p,t]
-  }
-  __syncthreads();
-  double part = 0.0;
-  for (int i = tid; i < n; i += nt) {
-    const int p = i / T, t = i - p * T;
-    double wr, sym;
-    if (sigma) {
-      double a1 = 0.0, a2 = 0.0;
-      for (int p2 = 0; p2 < P; ++p2) {
-        const double rr = sres[p2 * T + t];
-        a1 += (double)mp.W[(size_t)p * P + p2] * rr;
-        a2 += (double)mp.W[(size_t)p2 * P + p] * rr;
-      }
-      wr = a1;
-      sym = 0.5 * (a1 + a2);
-    } else {
-      wr = sres[i];
-      sym = sres[i];
-    }
-    part += 0.5 * sres[i] * wr;
-    sgp[i] = sym;
-  }
-  const double loss = block_sum(part, scratch) / ((double)T * (double)P);
-  if (grad) {
-    const double g = scale / ((double)T * (double)P);
-    if (centre) {
-      for (int t = tid; t < T; t += nt) {
-        double mg = 0.0;
-        for (int p = 0; p < P; ++p) mg += sgp[p * T + t];
-        smean[t] = mg / P;
-      }
-      __syncthreads();
-      for (int i = tid; i < n; i += nt) sgp[i] -= smean[i % T];
-      __syncthreads();
-    }
-    for (int r = tid; r < R; r += nt) {
-      const double kr = (double)k_ints[r], xe = sxe[r];
-      double acc = 0.0;
-      for (int t = 0; t < T; ++t) {
-        double back = 0.0;
-        for (int j = mp.t_ptr[r]; j < mp.t_ptr[r + 1]; ++j) back += (double)mp.t_val[j] * sgp[mp.t_row[j] * T + t];
-        const double x = kr * (double)tps[t] * xe;
-        acc += back * (-x * sE[t * R + r]);  // du/dlnPF = -x exp(-x)
-      }
-      sc[r] += g * acc;
-    }
-  }
-  __syncthreads();
-  return loss;
+  s.S = s.d ? SB : SA;
+  // speculative rates of the NEXT update (state.step == step): opt/optimiser.py:365-381,403-413
+  const bool switched = s.step >= cfg.initial_steps;
+  const int mi = switched ? 1 : s.mask_idx;
+  const float base_lr = switched ? cfg.learning_rate : s.lr;
+  const float base_mlr = switched ? cfg.learning_rate * cfg.model_parameters_lr_scale : s.mlr;
+  s.lrA = base_lr;
+  s.lrB = base_lr / cfg.plateau_denominator;
+  s.mlrA = base_mlr;
+  s.mlrB = base_mlr / cfg.plateau_denominator;
+  s.mask_frame = (mi == 0) ? 1.f : (cfg.optimise_frame_weights ? 1.f : 0.f);
+  s.mask_model = (mi == 0) ? 0.f : (cfg.optimise_model_parameters ? 1.f : 0.f);
+  s.bc1 = 1.0f - pw2;
+  s.bc2 = 1.0f - pw3;
+  s.lse_new = (float)((double)s.lse_old + (s.d ? lgB : lgA));
+  *out = s;
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS) bv_tail_kernel(const TailArgs a) {
+// ------------------------------------------------------------------------------------------ blobs
+// word layout of one data slot's blob == its shared-memory image
+__host__ __device__ inline BlobLayout blob_layout(int R, int Tm, int p_tr, int nnz_tr, int p_va, int nnz_va) {
+  BlobLayout b;
+  int o = 0;
+  b.tr_ptr = o;  o += p_tr + 1;
+  b.tr_col = o;  o += nnz_tr;
+  b.tr_tptr = o; o += R + 1;
+  b.tr_trow = o; o += nnz_tr;
+  b.va_ptr = o;  o += p_va + 1;
+  b.va_col = o;  o += nnz_va;
+  b.tr_val = o;  o += nnz_tr;
+  b.tr_tval = o; o += nnz_tr;
+  b.tr_y = o;    o += p_tr * Tm;
+  b.va_val = o;  o += nnz_va;
+  b.va_y = o;    o += p_va * Tm;
+  b.words = (o + 3) & ~3;
+  return b;
+}
+
+__global__ void build_blobs_kernel(JaxentBvProblem pb, BlobSet bs) {
+  const int R = pb.R, Tm = (pb.uptake && pb.T > 0) ? pb.T : 1;
+  const int tid = threadIdx.x, nt = blockDim.x;  // single block
+  auto cp = [&](int* dst, const void* src, int n) {
+    const int* s = static_cast<const int*>(src);
+    for (int i = tid; i < n; i += nt) dst[i] = s[i];
+  };
+  for (int i = 0; i < pb.n_slots; ++i) {
+    const JaxentLossSlot& sl = pb.slots[i];
+    if (sl.kind > JAXENT_LOSS_PF_L2 || bs.blob[i] == nullptr) continue;
+    const BlobLayout b = blob_layout(R, Tm, sl.train.n_pep, sl.train.nnz, sl.val.n_pep, sl.val.nnz);
+    int* w = bs.blob[i];
+    for (int k = tid; k < b.words; k += nt) w[k] = 0;
+  }
+  __syncthreads();  // zero fill before the copies
+  for (int i = 0; i < pb.n_slots; ++i) {
+    const JaxentLossSlot& sl = pb.slots[i];
+    if (sl.kind > JAXENT_LOSS_PF_L2 || bs.blob[i] == nullptr) continue;
+    const BlobLayout b = blob_layout(R, Tm, sl.train.n_pep, sl.train.nnz, sl.val.n_pep, sl.val.nnz);
+    int* w = bs.blob[i];
+    cp(w + b.tr_ptr, sl.train.row_ptr, sl.train.n_pep + 1);
+    cp(w + b.tr_col, sl.train.col, sl.train.nnz);
+    cp(w + b.tr_tptr, sl.train.t_ptr, R + 1);
+    cp(w + b.tr_trow, sl.train.t_row, sl.train.nnz);
+    cp(w + b.tr_val, sl.train.val, sl.train.nnz);
+    cp(w + b.tr_tval, sl.train.t_val, sl.train.nnz);
+    cp(w + b.tr_y, sl.train.y, sl.train.n_pep * Tm);
+    if (sl.val.n_pep > 0) {
+      cp(w + b.va_ptr, sl.val.row_ptr, sl.val.n_pep + 1);
+      cp(w + b.va_col, sl.val.col, sl.val.nnz);
+      cp(w + b.va_val, sl.val.val, sl.val.nnz);
+      cp(w + b.va_y, sl.val.y, sl.val.n_pep * Tm);
+    }
+  }
+}
+
+int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_t s) {
+  build_blobs_kernel<<<1, 1024, 0, s>>>(pb, bs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("build_blobs launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ the tail
+// GENERAL = the mean-centred / sigma MSE kinds are compiled in (host picks the instantiation), so the
+// common eye-MSE / PF-L2 configuration executes the shortest possible instruction stream.
+template <bool GENERAL>
+__global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ TailShared sh;
-  __shared__ double scratch[40];
+  __shared__ double s_red[32][16];  // per-warp partials of the multi-value reductions
+  __shared__ double s_fin[16];
+  __shared__ __align__(16) Ctl s_old;
+  __shared__ StepScalars s_sc;
   __shared__ int s_last;
 
   const JaxentBvProblem& pb = a.prob;
-  const int R = pb.R, T = pb.uptake ? pb.T : 0;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int R = pb.R, T = pb.uptake ? pb.T : 0, Tm = T > 0 ? T : 1;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const unsigned ep = *a.epoch;
-  const Ctl* __restrict__ old = a.ctl + ((ep - 1u) & 1u);
+  const Ctl* __restrict__ old_g = a.ctl + ((ep - 1u) & 1u);
   Ctl* __restrict__ neu = a.ctl + (ep & 1u);
   const int cur_set = ep & 1u;
+  const bool tail_cta = blockIdx.x == 0;
+  const bool frame_cta = (gridDim.x == 1) || blockIdx.x > 0;
+  const float invR = 1.0f / (float)R, invTm = 1.0f / (float)Tm;
 
-  // ------------------------------------------------------------------ A. branch decision (all CTAs)
-  if (tid == 0) {
-    int d = 0;
-    if (old->pending) {
-      const double dot = a.red[4 * R + 2] + (double)(old->have_prev ? old->gb_prev[0] : old->gb[0]) * (double)old->gb[0] +
-                         (double)(old->have_prev ? old->gb_prev[1] : old->gb[1]) * (double)old->gb[1];
-      d = ((float)dot < 0.f && old->step > 1) ? 1 : 0;  // opt/optimiser.py:403
-      scratch[34] = dot;
-    }
-    sh.d = d;
-    sh.pending = old->pending;
-    sh.S = a.red[4 * R + d];
-    sh.lse_old = old->lse;
-    sh.off = d * 2 * R;
+  // shared-memory carve-up (CTA 0)
+  double* slp = reinterpret_cast<double*>(smem_raw);    // [R] lnPF
+  double* sxe = slp + R;                                 // [R] exp(-lnPF)
+  double* sc_rt = sxe + R;                               // [Tm][R] back-projection items
+  double* sU = sc_rt + (size_t)Tm * R;                   // [T][R] uptake
+  double* res_tr = sU + (size_t)T * R;                   // [P_tr * Tm] (GENERAL only)
+  double* gp_tr = res_tr + (size_t)a.p_max_tr * Tm;      // [P_tr * Tm] pred -> residual -> dL/dpred
+  double* res_va = gp_tr + (size_t)a.p_max_tr * Tm;      // [P_va * Tm]
+  double* smean = res_va + (size_t)a.p_max_va * Tm;      // [4 * Tm]
+  float* s_k = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smean + 4 * Tm) + 15) & ~uintptr_t(15));
+  float* s_tp = s_k + ((R + 3) & ~3);
+  int* s_blob = reinterpret_cast<int*>(s_tp + ((Tm + 3) & ~3));  // 16-byte aligned blob image
+
+  // ---- stage (one global round trip): warp 0 derives the step scalars, the rest copies
+  int first_data = -1;
+  if (tail_cta) {
+#pragma unroll 1
+    for (int i = pb.n_slots - 1; i >= 0; --i)
+      if (pb.slots[i].kind <= JAXENT_LOSS_PF_L2) first_data = i;
   }
-  __syncthreads();
-  const int d = sh.d;
-  const double S = sh.S;
-
-  // ------------------------------------------------------------------ B. the R x T tail (CTA 0)
-  if (blockIdx.x == 0) {
-    double* sa = reinterpret_cast<double*>(smem_raw);
-    double* sb = sa + R;
-    double* slp = sb + R;
-    double* sc = slp + R;
-    double* sxe = sc + R;
-    double* sE = sxe + R;                 // [T][R] exp(-x)
-    double* sres = sE + (size_t)T * R;    // [p_max * max(T,1)]
-    double* sgp = sres + (size_t)a.p_max * (T > 0 ? T : 1);
-    double* smean = sgp + (size_t)a.p_max * (T > 0 ? T : 1);  // [2*max(T,1)]
-
-    // B1. BV-parameter Adam for the update that led to the current parameters
-    if (tid == 0) {
-      float bc = old->bc, bh = old->bh;
-      float mb0 = old->mb[0], mb1 = old->mb[1], vb0 = old->vb[0], vb1 = old->vb[1];
-      int cm = old->count_model, cf = old->count_frame, step = old->step, mask_idx = old->mask_idx;
-      float lr = old->lr, mlr = old->model_lr;
-      if (old->pending) {
-        lr = d ? old->lrB : old->lrA;
-        mlr = d ? old->mlrB : old->mlrA;
-        const float b1 = (float)a.cfg.b1, b2 = (float)a.cfg.b2, eps = (float)a.cfg.eps, clip = a.cfg.clip_value;
-        const float om_b1 = (float)(1.0 - a.cfg.b1), om_b2 = (float)(1.0 - a.cfg.b2);
-        cm += 1;
-        cf += 1;
-        const float c1 = 1.0f - powf(b1, (float)cm), c2 = 1.0f - powf(b2, (float)cm);
-        float par[2] = {bc, bh};
-        float mm[2] = {mb0, mb1}, vv[2] = {vb0, vb1};
-        for (int i = 0; i < 2; ++i) {
-          float sg = old->gb[i] * mlr;
-          if (clip > 0.f) sg = fminf(fmaxf(sg, -clip), clip);
-          mm[i] = om_b1 * sg + b1 * mm[i];
-          vv[i] = om_b2 * (sg * sg) + b2 * vv[i];
-          float u = -((mm[i] / c1) / (sqrtf(vv[i] / c2) + eps));
-          if (par[i] + u < 0.f) u = -par[i];  // optax.keep_params_nonnegative
-          par[i] = par[i] + u;
-        }
-        bc = par[0]; bh = par[1];
-        mb0 = mm[0]; mb1 = mm[1]; vb0 = vv[0]; vb1 = vv[1];
-        mask_idx = (step >= a.cfg.initial_steps) ? 1 : mask_idx;
-        step += 1;
-      }
-      sh.bc = bc;
-      sh.bh = bh;
-      neu->step = step;
-      neu->mask_idx = mask_idx;
-      neu->branch = d;
-      neu->pending = 1;
-      neu->have_prev = old->pending ? 1 : old->have_prev;
-      neu->count_frame = cf;
-      neu->count_model = cm;
-      neu->kl_slot = old->kl_slot;
-      neu->lr = lr;
-      neu->model_lr = mlr;
-      neu->bc = bc;
-      neu->bh = bh;
-      neu->mb[0] = mb0; neu->mb[1] = mb1; neu->vb[0] = vb0; neu->vb[1] = vb1;
-      neu->gb_prev[0] = old->gb[0];
-      neu->gb_prev[1] = old->gb[1];
-      neu->last_dot = old->pending ? (float)scratch[34] : 0.f;
-      neu->last_lr = lr;
-      neu->last_branch = d;
-      neu->kl_scale = old->kl_scale;
-      for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) { neu->fw[i] = old->fw[i]; neu->fs[i] = old->fs[i]; }
-      // speculative rates of the NEXT update (state.step == step): opt/optimiser.py:365-381,403-413
-      const bool switched = step >= a.cfg.initial_steps;
-      const int mi = switched ? 1 : mask_idx;
-      const float base_lr = switched ? a.cfg.learning_rate : lr;
-      const float base_mlr = switched ? a.cfg.learning_rate * a.cfg.model_parameters_lr_scale : mlr;
-      neu->lrA = base_lr;
-      neu->lrB = base_lr / a.cfg.plateau_denominator;
-      neu->mlrA = base_mlr;
-      neu->mlrB = base_mlr / a.cfg.plateau_denominator;
-      neu->mask_frame = (mi == 0) ? 1.f : (a.cfg.optimise_frame_weights ? 1.f : 0.f);
-      neu->mask_model = (mi == 0) ? 0.f : (a.cfg.optimise_model_parameters ? 1.f : 0.f);
-      neu->bc1 = 1.0f - powf((float)a.cfg.b1, (float)(cf + 1));
-      neu->bc2 = 1.0f - powf((float)a.cfg.b2, (float)(cf + 1));
-      neu->lse = (float)((double)old->lse + log(S));
-      neu->rec_idx = step % JAXENT_RECORD_RING;
+  double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
+  if (warp == 0) {
+    derive_scalars(&s_sc, old_g, a.red, R, a.cfg);
+  } else {
+    const int t2 = tid - 32, n2 = nt - 32;
+    {
+      const int4* src = reinterpret_cast<const int4*>(old_g);
+      int4* dst = reinterpret_cast<int4*>(&s_old);
+      if (t2 < (int)(sizeof(Ctl) / 16)) dst[t2] = src[t2];
     }
-    __syncthreads();
-    const double bc = (double)sh.bc, bh = (double)sh.bh;
-
-    // B2. frame averages, ln PF, uptake
-    for (int r = tid; r < R; r += nt) {
-      const double av = a.red[sh.off + r] / S, bv = a.red[sh.off + R + r] / S;
-      const double lp = bc * av + bh * bv;
-      sa[r] = av;
-      sb[r] = bv;
-      slp[r] = lp;
-      sc[r] = 0.0;
-      a.avg[r] = (float)av;
-      a.avg[R + r] = (float)bv;
-      a.logpf[r] = (float)lp;
+    if (tail_cta) {
+      if (first_data >= 0) {
+        const int4* src = reinterpret_cast<const int4*>(a.blobs.blob[first_data]);
+        int4* dst = reinterpret_cast<int4*>(s_blob);
+        const int n4 = a.blobs.words[first_data] >> 2;
+#pragma unroll 4
+        for (int i = t2; i < n4; i += n2) dst[i] = src[i];
+      }
       if (T > 0) {
-        const double xe = exp(-lp), kr = (double)pb.k_ints[r];
-        sxe[r] = xe;
-        for (int t = 0; t < T; ++t) {
-          const double E = exp(-(kr * (double)pb.timepoints[t] * xe));
-          sE[t * R + r] = E;
-          a.uptake[t * R + r] = (float)(1.0 - E);
+#pragma unroll 1
+        for (int i = t2; i < R; i += n2) s_k[i] = pb.k_ints[i];
+        if (t2 < T) s_tp[t2] = pb.timepoints[t2];
+      }
+    }
+  }
+  if (tail_cta) {
+    if (tid < R) {
+      accA0 = a.red[0 * R + tid];
+      accA1 = a.red[1 * R + tid];
+      accB0 = a.red[2 * R + tid];
+      accB1 = a.red[3 * R + tid];
+    }
+    if (lane < 16) s_red[warp][lane] = 0.0;
+  }
+  __syncthreads();  // (1) everything staged, scalars broadcast
+  const int d = s_sc.d;
+  const double S = s_sc.S;
+
+  // ================================================================== the R x T tail (CTA 0)
+  if (tail_cta) {
+    const double bc = (double)s_sc.bc, bh = (double)s_sc.bh;
+    double my_a = 0, my_b = 0, my_lp = 0, my_c = 0;
+    if (tid < R) {
+      const double invS = __drcp_rn(S);
+      my_a = (d ? accB0 : accA0) * invS;
+      my_b = (d ? accB1 : accA1) * invS;
+      my_lp = bc * my_a + bh * my_b;
+      slp[tid] = my_lp;
+      a.avg[tid] = (float)my_a;
+      a.avg[R + tid] = (float)my_b;
+      a.logpf[tid] = (float)my_lp;
+      // exp(-lnPF) and the T uptakes of this residue: one call site, 1 + T evaluations
+      double xe = 0.0;
+      const double kr = (T > 0) ? (double)s_k[tid] : 0.0;
+#pragma unroll 1
+      for (int k = 0; k <= T && T > 0; ++k) {
+        const double arg = (k == 0) ? -my_lp : -(kr * (double)s_tp[k - 1] * xe);
+        const double e = dexp(arg);
+        if (k == 0) {
+          xe = e;
+          sxe[tid] = e;
+        } else {
+          sU[(size_t)(k - 1) * R + tid] = 1.0 - e;
+          a.uptake[(size_t)(k - 1) * R + tid] = (float)(1.0 - e);
         }
       }
     }
-    __syncthreads();
+    __syncthreads();  // (2) lnPF / uptake visible
 
-    // B3. loss slots
-    JaxentLossRecord* rec = a.records + (neu->step % JAXENT_RECORD_RING);
+    // ---- loss slots
     double gbc_reg = 0.0, gbh_reg = 0.0;
+#pragma unroll 1
     for (int i = 0; i < pb.n_slots; ++i) {
-      const JaxentLossSlot& sl = pb.slots[i];
-      const double scale = (double)old->fw[i] * (double)old->fs[i];
-      double ltr = 0.0, lva = 0.0;
-      if (sl.kind <= JAXENT_LOSS_PF_L2) {
-        ltr = map_loss(sl.train, sl.kind, R, T, pb.uptake, sE, slp, sxe, pb.k_ints, pb.timepoints, sres, sgp, smean,
-                       scratch, true, scale, sc);
-        lva = map_loss(sl.val, sl.kind, R, T, pb.uptake, sE, slp, sxe, pb.k_ints, pb.timepoints, sres, sgp, smean,
-                       scratch, false, scale, sc);
-      } else if (sl.kind == JAXENT_LOSS_PARAMS_L1) {
-        const double dc = bc - (double)sl.prior_bc, dh = bh - (double)sl.prior_bh;
-        ltr = lva = fabs(dc) + fabs(dh);
-        gbc_reg += scale * ((dc > 0) - (dc < 0));
-        gbh_reg += scale * ((dh > 0) - (dh < 0));
-      } else if (sl.kind == JAXENT_LOSS_PARAMS_L2) {
-        const double dc = bc - (double)sl.prior_bc, dh = bh - (double)sl.prior_bh;
-        ltr = lva = dc * dc + dh * dh;
-        gbc_reg += scale * 2.0 * dc;
-        gbh_reg += scale * 2.0 * dh;
+      const int kind = pb.slots[i].kind;
+      const double scale = (double)s_old.fw[i] * (double)s_old.fs[i];
+      if (kind == JAXENT_LOSS_PARAMS_L1 || kind == JAXENT_LOSS_PARAMS_L2) {
+        const bool l1 = kind == JAXENT_LOSS_PARAMS_L1;
+        const double dc = bc - (double)pb.slots[i].prior_bc, dh = bh - (double)pb.slots[i].prior_bh;
+        if (tid == 0) s_red[0][i] = s_red[0][JAXENT_MAX_SLOTS + i] = l1 ? fabs(dc) + fabs(dh) : dc * dc + dh * dh;
+        gbc_reg += scale * (l1 ? (double)((dc > 0) - (dc < 0)) : 2.0 * dc);
+        gbh_reg += scale * (l1 ? (double)((dh > 0) - (dh < 0)) : 2.0 * dh);
+        continue;
       }
-      if (tid == 0) {
-        rec->train[i] = (float)ltr;
-        rec->val[i] = (float)lva;
+      if (kind > JAXENT_LOSS_PF_L2) continue;  // MaxEnt: handled per frame
+      if (i != first_data) {
+        __syncthreads();
+        const int4* src = reinterpret_cast<const int4*>(a.blobs.blob[i]);
+        int4* dst = reinterpret_cast<int4*>(s_blob);
+        const int n4 = a.blobs.words[i] >> 2;
+#pragma unroll 1
+        for (int k = tid; k < n4; k += nt) dst[k] = src[k];
+        __syncthreads();
       }
-    }
-    __syncthreads();
+      const int Ptr = pb.slots[i].train.n_pep, Pva = pb.slots[i].val.n_pep;
+      const BlobLayout bl = blob_layout(R, Tm, Ptr, pb.slots[i].train.nnz, Pva, pb.slots[i].val.nnz);
+      const bool pf = kind == JAXENT_LOSS_PF_L2;
+      const bool centre = GENERAL && kind == JAXENT_LOSS_UPTAKE_MC_EYE_MSE;
+      const bool sigma = GENERAL && kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE;
+      const double half = pf ? 1.0 : 0.5;
 
-    // B4. row coefficients for the next pass, hbar (data part), BV-parameter gradients
-    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
-    for (int r = tid; r < R; r += nt) {
-      const double c = sc[r];
-      a.cc[r] = (float)(c * bc);
-      a.ch[r] = (float)(c * bh);
-      p0 += c * slp[r];
-      p1 += c * sa[r];
-      p2 += c * sb[r];
+      // (a) predictions of train and val peptides; the eye / PF kinds finish residual + loss here
+#pragma unroll 1
+      for (int set = 0; set < 2; ++set) {
+        const int P = set ? Pva : Ptr;
+        const int* ptr = s_blob + (set ? bl.va_ptr : bl.tr_ptr);
+        const int* col = s_blob + (set ? bl.va_col : bl.tr_col);
+        const float* val = reinterpret_cast<const float*>(s_blob + (set ? bl.va_val : bl.tr_val));
+        const float* y = reinterpret_cast<const float*>(s_blob + (set ? bl.va_y : bl.tr_y));
+        double* out = set ? res_va : ((centre || sigma) ? res_tr : gp_tr);
+        double pl = 0.0;
+#pragma unroll 1
+        for (int j = tid; j < P * Tm; j += nt) {
+          const int p = fdiv(j, invTm), t = j - p * Tm;
+          const double* x = pf ? slp : sU + (size_t)t * R;
+          double pred = 0.0;
+#pragma unroll 1
+          for (int q = ptr[p]; q < ptr[p + 1]; ++q) pred += (double)val[q] * x[col[q]];
+          if (!(centre || sigma)) {
+            pred -= (double)y[j];
+            pl += half * pred * pred;
+          }
+          out[j] = pred;
+        }
+        if (!(centre || sigma)) {
+          const double nrm = (P > 0) ? __drcp_rn(pf ? (double)P : (double)T * (double)P) : 0.0;
+          pl = wsum(pl * nrm);
+          if (lane == 0) s_red[warp][set * JAXENT_MAX_SLOTS + i] = pl;
+        }
+      }
+      if (GENERAL && (centre || sigma)) {
+        const float* tr_y = reinterpret_cast<const float*>(s_blob + bl.tr_y);
+        const float* va_y = reinterpret_cast<const float*>(s_blob + bl.va_y);
+        __syncthreads();
+        if (centre) {
+          // per-timepoint means of prediction and target (opt/losses.py:1814-1819): one warp per (set, t)
+#pragma unroll 1
+          for (int job = warp; job < 2 * T; job += nw) {
+            const bool tr = job < T;
+            const int t = tr ? job : job - T;
+            const int P = tr ? Ptr : Pva;
+            const double* rs = tr ? res_tr : res_va;
+            const float* yy = tr ? tr_y : va_y;
+            double s0 = 0.0;
+#pragma unroll 1
+            for (int p = lane; p < P; p += 32) s0 += rs[p * T + t] - (double)yy[p * T + t];
+            s0 = wsum(s0);
+            if (lane == 0) smean[job] = (P > 0) ? s0 / P : 0.0;  // mean(pred) - mean(y)
+          }
+          __syncthreads();
+        }
+        double pl2[2] = {0.0, 0.0};
+#pragma unroll 1
+        for (int set = 0; set < 2; ++set) {
+          const int n = (set ? Pva : Ptr) * T;
+          double* buf = set ? res_va : res_tr;
+          const float* y = set ? va_y : tr_y;
+#pragma unroll 1
+          for (int j = tid; j < n; j += nt) {
+            double r = buf[j] - (double)y[j];
+            if (centre) r -= smean[set * T + (j - fdiv(j, invTm) * T)];
+            buf[j] = r;
+            if (!sigma) {
+              pl2[set] += 0.5 * r * r;
+              if (set == 0) gp_tr[j] = r;
+            }
+          }
+        }
+        if (sigma) {
+          __syncthreads();
+#pragma unroll 1
+          for (int set = 0; set < 2; ++set) {
+            const int P = set ? Pva : Ptr;
+            const float* W = set ? pb.slots[i].val.W : pb.slots[i].train.W;
+            const double* rs = set ? res_va : res_tr;
+#pragma unroll 1
+            for (int j = tid; j < P * T; j += nt) {
+              const int p = fdiv(j, invTm), t = j - p * T;
+              double a1 = 0.0, a2 = 0.0;
+#pragma unroll 1
+              for (int p2 = 0; p2 < P; ++p2) {
+                const double rr = rs[p2 * T + t];
+                a1 += (double)W[(size_t)p * P + p2] * rr;
+                a2 += (double)W[(size_t)p2 * P + p] * rr;
+              }
+              pl2[set] += 0.5 * rs[j] * a1;
+              if (set == 0) gp_tr[j] = 0.5 * (a1 + a2);
+            }
+          }
+        }
+#pragma unroll 1
+        for (int set = 0; set < 2; ++set) {
+          const int P = set ? Pva : Ptr;
+          const double nrm = (P > 0) ? __drcp_rn((double)T * (double)P) : 0.0;
+          const double t = wsum((set ? pl2[1] : pl2[0]) * nrm);
+          if (lane == 0) s_red[warp][set * JAXENT_MAX_SLOTS + i] = t;
+        }
+        if (centre) {
+          __syncthreads();
+#pragma unroll 1
+          for (int t = warp; t < T; t += nw) {
+            double s0 = 0.0;
+#pragma unroll 1
+            for (int p = lane; p < Ptr; p += 32) s0 += gp_tr[p * T + t];
+            s0 = wsum(s0);
+            if (lane == 0) smean[2 * T + t] = s0 / Ptr;
+          }
+        }
+      }
+      __syncthreads();  // (3) dL/dpred visible
+
+      // (b) back-projection to dL/d lnPF, parallel over (t, r)
+      {
+        const int* tptr = s_blob + bl.tr_tptr;
+        const int* trow = s_blob + bl.tr_trow;
+        const float* tval = reinterpret_cast<const float*>(s_blob + bl.tr_tval);
+        const double g = scale * (pf ? 2.0 : 1.0) * __drcp_rn(pf ? (double)Ptr : (double)T * (double)Ptr);
+#pragma unroll 1
+        for (int it = tid; it < R * Tm; it += nt) {
+          const int t = fdiv(it, invR), r = it - t * R;
+          double back = 0.0, colsum = 0.0;
+#pragma unroll 1
+          for (int q = tptr[r]; q < tptr[r + 1]; ++q) {
+            back += (double)tval[q] * gp_tr[trow[q] * Tm + t];
+            if (GENERAL) colsum += (double)tval[q];
+          }
+          if (centre) back -= colsum * smean[2 * T + t];  // centred gradient: minus mean_p(gp) through the column
+          if (!pf) {
+            const double x = (double)s_k[r] * (double)s_tp[t] * sxe[r];
+            back *= -x * (1.0 - sU[it]);  // du/dlnPF = -x exp(-x)
+          }
+          sc_rt[it] = g * back;
+        }
+      }
+      __syncthreads();  // (4) items visible
+      if (tid < R) {
+#pragma unroll 1
+        for (int t = 0; t < Tm; ++t) my_c += sc_rt[(size_t)t * R + tid];
+      }
     }
-    const double hbar = block_sum(p0, scratch);
-    const double gbc = block_sum(p1, scratch) + gbc_reg;
-    const double gbh = block_sum(p2, scratch) + gbh_reg;
-    if (tid == 0) {
-      neu->hbar_data = hbar;
-      neu->gb[0] = (float)gbc * neu->mask_model;
-      neu->gb[1] = (float)gbh * neu->mask_model;
-      rec->step = neu->step;
-      rec->branch = d;
-      rec->lr = neu->last_lr;
-      rec->grad_dot = neu->last_dot;
-      rec->bc = (float)bc;
-      rec->bh = (float)bh;
-      rec->grad_bc = neu->gb[0];
-      rec->grad_bh = neu->gb[1];
-      rec->complete = 0;
-      for (int i = pb.n_slots; i < JAXENT_MAX_SLOTS; ++i) { rec->train[i] = 0.f; rec->val[i] = 0.f; }
-      if (old->kl_slot < 0) finish_record(neu, a.klsum, a.records, pb.n_slots);
+
+    // ---- row coefficients for the next pass + one multi-value block reduction
+    {
+      double v12 = 0.0, v13 = 0.0, v14 = 0.0;
+      if (tid < R) {
+        a.cc[tid] = (float)(my_c * bc);
+        a.ch[tid] = (float)(my_c * bh);
+        v12 = my_c * my_lp;  // hbar (data part) = sum_r c_r lnPF_r = sum_j w_j h_j
+        v13 = my_c * my_a;   // dL/dbc
+        v14 = my_c * my_b;   // dL/dbh
+      }
+      if (warp * 32 < R) {
+        v12 = wsum(v12);
+        v13 = wsum(v13);
+        v14 = wsum(v14);
+        if (lane == 0) {
+          s_red[warp][12] = v12;
+          s_red[warp][13] = v13;
+          s_red[warp][14] = v14;
+        }
+      }
+    }
+    __syncthreads();  // (5)
+    if (tid < 15) {
+      double t = 0.0;
+#pragma unroll 1
+      for (int w = 0; w < nw; ++w) t += s_red[w][tid];  // fixed order
+      s_fin[tid] = t;
+    }
+    __syncthreads();  // (6)
+
+    if (tid < 32) {
+      // the new control block and the loss record, written by one warp
+      const StepScalars& sc = s_sc;
+      const float gb0 = (float)(s_fin[13] + gbc_reg) * sc.mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * sc.mask_model;
+      if (lane == 0) {
+        neu->step = sc.step;
+        neu->mask_idx = sc.mask_idx;
+        neu->branch = sc.d;
+        neu->pending = 1;
+        neu->have_prev = sc.have_prev;
+        neu->count_frame = sc.cf;
+        neu->count_model = sc.cm;
+        neu->kl_slot = s_old.kl_slot;
+        neu->lr = sc.lr;
+        neu->model_lr = sc.mlr;
+        neu->bc = sc.bc;
+        neu->bh = sc.bh;
+        neu->mb[0] = sc.mb0; neu->mb[1] = sc.mb1; neu->vb[0] = sc.vb0; neu->vb[1] = sc.vb1;
+        neu->gb_prev[0] = s_old.gb[0];
+        neu->gb_prev[1] = s_old.gb[1];
+        neu->gb[0] = gb0;
+        neu->gb[1] = gb1;
+        neu->lrA = sc.lrA;
+        neu->lrB = sc.lrB;
+        neu->mlrA = sc.mlrA;
+        neu->mlrB = sc.mlrB;
+        neu->mask_frame = sc.mask_frame;
+        neu->mask_model = sc.mask_model;
+        neu->bc1 = sc.bc1;
+        neu->bc2 = sc.bc2;
+        neu->lse = sc.lse_new;
+        neu->kl_scale = s_old.kl_scale;
+        neu->last_dot = (float)sc.dot;
+        neu->last_lr = sc.lr;
+        neu->last_branch = sc.d;
+        neu->rec_idx = sc.step % JAXENT_RECORD_RING;
+        neu->hbar_data = s_fin[12];
+      }
+      if (lane < JAXENT_MAX_SLOTS) {
+        neu->fw[lane] = s_old.fw[lane];
+        neu->fs[lane] = s_old.fs[lane];
+      }
+      JaxentLossRecord* rec = a.records + (sc.step % JAXENT_RECORD_RING);
+      if (lane == 1) {
+        rec->step = sc.step;
+        rec->branch = sc.d;
+        rec->lr = sc.lr;
+        rec->grad_dot = (float)sc.dot;
+        rec->bc = sc.bc;
+        rec->bh = sc.bh;
+        rec->grad_bc = gb0;
+        rec->grad_bh = gb1;
+        rec->complete = 0;
+      }
+      if (lane < JAXENT_MAX_SLOTS) {
+        rec->train[lane] = (lane < pb.n_slots) ? (float)s_fin[lane] : 0.f;
+        rec->val[lane] = (lane < pb.n_slots) ? (float)s_fin[JAXENT_MAX_SLOTS + lane] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0 && s_old.kl_slot < 0) finish_record(neu, a.klsum, a.records, pb.n_slots);
     }
   }
 
-  // ------------------------------------------------------------------ C. per-frame MaxEnt terms (all CTAs)
-  {
-    const float* __restrict__ z = a.st.z[cur_set][d];
-    const long long G = gridDim.x, cta = blockIdx.x;
-    const long long f0 = pb.F * cta / G, f1 = pb.F * (cta + 1) / G;
-    const float lse_old = sh.lse_old;
-    const float Sf = (float)S;
-    const bool has_kl = old->kl_slot >= 0 && pb.prior != nullptr;
-    const float eps = a.eps_kl;
-    const float lam = old->kl_scale;
-    const double pnorm = pb.prior_norm;
+  // ================================================================== per-frame MaxEnt terms
+  if (!frame_cta) {
+    // CTA 0 of a multi-CTA grid holds no frames: contribute zeros and take a ticket
+    if (tid < KL_N) a.klpart[tid] = 0.0;
+  } else {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const float* __restrict__ z = a.st.z[cur_set][d];
+    const long long cta = (gridDim.x == 1) ? 0 : blockIdx.x - 1;
+    const long long f0 = cta * a.frames_per_cta;
+    const long long f1 = (f0 + a.frames_per_cta < pb.F) ? f0 + a.frames_per_cta : pb.F;
+    const float Sf = (float)S;
+    const float lse_old = s_sc.lse_old;
+    const bool has_kl = s_old.kl_slot >= 0 && pb.prior != nullptr;
+    const float eps = a.eps_kl;
+    const float lam = s_old.kl_scale;
+    const double inv_pnorm = __drcp_rn(pb.prior_norm);
+#pragma unroll 1
     for (long long f = f0 + tid; f < f1; f += nt) {
       const float w = expf(z[f] - lse_old) / Sf;  // jax.nn.softmax: exp(x - shift) / sum
       a.w[f] = w;
@@ -375,54 +596,79 @@ __global__ void __launch_bounds__(TAIL_THREADS) bv_tail_kernel(const TailArgs a)
       if (has_kl) {
         // q = (|w|+eps)/sum(|w|+eps); the denominator is 1 + F*eps = 1 + 1e-10 == 1 in fp32
         const float q = fabsf(w) + eps;
-        const float p = (float)(((double)fabsf(pb.prior[f]) + (double)eps) / pnorm);
+        const float p = (float)(((double)fabsf(pb.prior[f]) + (double)eps) * inv_pnorm);
         // p/q and log(p/q) in fp64: differencing two fp32 logs leaves a rounding error that is
         // identical on every frame of a uniform prior and so does not average out over F
-        const double ratio = (double)p / (double)q;
+        const double ratio = (double)p * __drcp_rn((double)q);
         const float G_ = (float)(1.0 - ratio);
         kap = (w > 0.f) ? lam * G_ : 0.f;  // d|w|/dw = sign(w); softmax weights are >= 0
         s0 += (double)w * (double)kap;
-        if (p > 0.f) s1 += (double)p * log(ratio);
+        if (p > 0.f) s1 += (double)p * dlog(ratio);
         s2 += (double)q - (double)p;
       }
       a.kappa[f] = kap;
       s3 += (double)w;
     }
-    s0 = block_sum(s0, scratch);
-    s1 = block_sum(s1, scratch);
-    s2 = block_sum(s2, scratch);
-    s3 = block_sum(s3, scratch);
-    if (tid == 0) {
-      double* kp = a.klpart + (size_t)blockIdx.x * KL_N;
-      kp[0] = s0; kp[1] = s1; kp[2] = s2; kp[3] = s3;
-      __threadfence();
-      const unsigned ticket = atomicAdd(a.counter, 1u);
-      s_last = (ticket == gridDim.x - 1);
-    }
+    s0 = wsum(s0);
+    s1 = wsum(s1);
+    s2 = wsum(s2);
+    s3 = wsum(s3);
     __syncthreads();
-    if (s_last && tid < KL_N) {
-      __threadfence();
+    if (lane == 0) { s_red[warp][0] = s0; s_red[warp][1] = s1; s_red[warp][2] = s2; s_red[warp][3] = s3; }
+    __syncthreads();
+    if (tid < KL_N) {
       double t = 0.0;
-      for (unsigned c = 0; c < gridDim.x; ++c) t += a.klpart[(size_t)c * KL_N + tid];  // fixed order
-      a.klsum[tid] = t;
-      if (tid == 0) *a.counter = 0u;
+#pragma unroll 1
+      for (int w = 0; w < nw; ++w) t += s_red[w][tid];
+      if (gridDim.x == 1) a.klsum[tid] = t;  // single CTA: done
+      else a.klpart[(size_t)blockIdx.x * KL_N + tid] = t;
     }
+  }
+  if (gridDim.x == 1) return;
+  // last-arriving CTA folds the per-CTA sums in a fixed order (deterministic)
+  if (tid < KL_N) __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(a.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && warp < KL_N) {
+    __threadfence();
+    double t = 0.0;
+#pragma unroll 1
+    for (unsigned cc = lane; cc < gridDim.x; cc += 32) t += a.klpart[(size_t)cc * KL_N + warp];
+    t = wsum(t);
+    if (lane == 0) a.klsum[warp] = t;
+    if (tid == 0) *a.counter = 0u;
   }
 }
 
-size_t tail_smem_bytes(int R, int T, int p_max) {
-  const size_t t = T > 0 ? T : 1;
-  return sizeof(double) * ((size_t)5 * R + (size_t)T * R + 2 * (size_t)p_max * t + 2 * t + 8);
+size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va) {
+  const size_t Tm = T > 0 ? T : 1;
+  const size_t dbl = (size_t)4 * R + (size_t)Tm * R + (size_t)T * R + 2 * (size_t)p_tr * Tm + (size_t)p_va * Tm + 4 * Tm;
+  const size_t f32 = (((size_t)R + 3) & ~(size_t)3) + ((Tm + 3) & ~(size_t)3);
+  const BlobLayout b = blob_layout(R, (int)Tm, p_tr, nnz_tr, p_va, nnz_va);
+  return dbl * 8 + f32 * 4 + (size_t)b.words * 4 + 64;
+}
+
+int blob_words(int R, int T, int p_tr, int nnz_tr, int p_va, int nnz_va) {
+  return blob_layout(R, T > 0 ? T : 1, p_tr, nnz_tr, p_va, nnz_va).words;
 }
 
 int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(bv_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  bool general = false;
+  for (int i = 0; i < a.prob.n_slots; ++i)
+    general = general || a.prob.slots[i].kind == JAXENT_LOSS_UPTAKE_MC_EYE_MSE || a.prob.slots[i].kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[general]) {
+    cudaError_t e = general ? cudaFuncSetAttribute(bv_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(bv_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tail kernel needs %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return JAXENT_E_UNSUPPORTED; }
-    configured = smem;
+    configured[general] = smem;
   }
-  bv_tail_kernel<<<ctas, TAIL_THREADS, smem, s>>>(a);
+  if (general) bv_tail_kernel<true><<<ctas, TAIL_THREADS, smem, s>>>(a);
+  else bv_tail_kernel<false><<<ctas, TAIL_THREADS, smem, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bv_tail_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;

@@ -11,12 +11,12 @@ constexpr int FT = 8;           // frames per tile (2 quads of 4 frames)
 constexpr int QT = FT / 4;      // quads per tile
 constexpr int MAX_STAGES = 8;   // bulk-copy ring depth upper bound
 constexpr int PASS_THREADS_MAX = 512;
-constexpr int TAIL_THREADS = 512;
+constexpr int TAIL_THREADS = 1024;
 constexpr int KL_N = 4;         // MaxEnt partial sums: sum w*kappa, sum p(log p - log q), sum(q - p), sum w
 
 // Device-resident control block; two copies, indexed by (epoch & 1).  Written only by the tail
 // kernel (and state_init), read by the pass kernel that follows it.
-struct Ctl {
+struct alignas(16) Ctl {
   int step;         // number of updates applied to the current parameters (reference state.step)
   int mask_idx;     // optimizer._current_gradient_mask_idx
   int branch;       // which plateau branch of state set (epoch & 1) holds the current z/m/v
@@ -40,6 +40,16 @@ struct Ctl {
   int rec_idx;                 // ring index of this step's loss record
   double hbar_data;            // sum_r c_r * log_Pf_r  (= sum_j w_j h_j, data part)
   float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
+};
+static_assert(sizeof(Ctl) % 16 == 0, "Ctl is staged to shared memory with 16-byte vector copies");
+
+// one data slot's peptide maps / targets gathered into one contiguous word array (see bv_tail.cu)
+struct BlobLayout {
+  int tr_ptr, tr_col, tr_tptr, tr_trow, va_ptr, va_col, tr_val, tr_tval, tr_y, va_val, va_y, words;
+};
+struct BlobSet {
+  int* blob[JAXENT_MAX_SLOTS];
+  int words[JAXENT_MAX_SLOTS];
 };
 
 struct StateSets {
@@ -98,7 +108,9 @@ struct TailArgs {
   double* klpart;
   double* klsum;
   JaxentLossRecord* records;
-  int p_max;
+  BlobSet blobs;
+  int p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
+  long long frames_per_cta;  // frames handled by each per-frame CTA of the tail kernel
   float eps_kl;   // 1e-10 / F_total
 };
 
@@ -109,7 +121,9 @@ int launch_reduce(const ReduceArgs& a, cudaStream_t s);
 int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
 int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const double* klsum, JaxentLossRecord* rec, int n_slots,
                          cudaStream_t s);
-size_t tail_smem_bytes(int R, int T, int p_max);
+size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va);
+int blob_words(int R, int T, int p_tr, int nnz_tr, int p_va, int nnz_va);
+int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_t s);
 int configure_kernels();
 
 __device__ __forceinline__ void finish_record(const Ctl* c, const double* klsum, JaxentLossRecord* records, int n_slots) {

@@ -246,6 +246,7 @@ class BvEngine:
         ptr, col, val = _csr(S)
         tptr, trow, tval = _csr(S.T)
         m.n_pep = P
+        m.nnz = int(ptr[-1])
         m.row_ptr, m.col, m.val = self._dev(ptr).data_ptr(), self._dev(col).data_ptr(), self._dev(val).data_ptr()
         m.t_ptr, m.t_row, m.t_val = self._dev(tptr).data_ptr(), self._dev(trow).data_ptr(), self._dev(tval).data_ptr()
         m.y = self._dev(y).data_ptr()
