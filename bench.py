@@ -255,12 +255,12 @@ def run_ours(args, wl):
     prior = torch.full((Fl,), 1.0 / F, device=dev)
     fw, fs = [0.5, 0.5], [1000.0, 1000.0]
 
-    # ---- end-to-end job through the host-facing API: features start in pinned host memory (N=1 only keeps a host copy)
+    # ---- end-to-end job through the host-facing API: every rank's shard of the features starts in pinned host memory
     e2e = None
     host_h = host_a = None
-    if world == 1 and not args.no_e2e:
-        host_h = torch.empty((R, F), dtype=torch.float32, pin_memory=True)
-        host_a = torch.empty((R, F), dtype=torch.float32, pin_memory=True)
+    if not args.no_e2e:
+        host_h = torch.empty((R, Fl), dtype=torch.float32, pin_memory=True)
+        host_a = torch.empty((R, Fl), dtype=torch.float32, pin_memory=True)
         host_h.copy_(heavy)
         host_a.copy_(acc)
         torch.cuda.synchronize()
@@ -319,6 +319,8 @@ def run_ours(args, wl):
     # ---- CUDA-graph replay of the same step (informational)
     graph_ms = None
     try:
+        if world > 1:
+            raise RuntimeError("graph replay is only measured on a single GPU (NCCL collectives stay eager)")
         eng.capture(2)
         eng.step_graph(2)
         barrier()
@@ -340,16 +342,16 @@ def run_ours(args, wl):
         dist.all_reduce(wsum)
     wsum = float(wsum)
 
-    # ---- e2e (N=1): whole job from pinned host buffers through the public engine API, loss read back every step
+    # ---- e2e: whole job from pinned host buffers through the public engine API, loss read back every step
     if host_h is not None:
         del eng
         torch.cuda.empty_cache()
-        torch.cuda.synchronize()
         import ctypes
 
         rec_bytes = ctypes.sizeof(L.LossRecord)
+        barrier()
         t0 = time.perf_counter()
-        eng2 = BvEngine(host_h, host_a, small.k_ints, small.timepoints, slots, True, settings, prior=prior, device=dev, F_total=F)
+        eng2 = BvEngine(host_h, host_a, small.k_ints, small.timepoints, slots, True, settings, prior=prior, device=dev, F_total=F, group=group)
         eng2.init_state(torch.ones(Fl, device=dev), 0.35, 2.0, fw, fs)
         torch.cuda.synchronize()
         t_setup = time.perf_counter() - t0
@@ -365,16 +367,20 @@ def run_ours(args, wl):
             last = float(np.frombuffer(pinned_rec.numpy().tobytes(), dtype=np.float32)[6])
         w_host = eng2.weights.cpu()
         t_steps = time.perf_counter() - t1
+        tt = torch.tensor([t_setup, t_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_setup, t_steps = float(tt[0]), float(tt[1])
         job = t_setup + t_steps
-        h2d = (2 * R * F * 4 + Fl * 4 * 2)
+        h2d = (2 * R * F * 4 + F * 4 * 2)
         e2e = {
             "value": K / job,
             "unit": "steps/s",
             "h2d_bytes_per_step": h2d / K,
-            "d2h_bytes_per_step": rec_bytes + Fl * 4 / K,
+            "d2h_bytes_per_step": rec_bytes * world + F * 4 / K,
             "steady_value": K / t_steps,
             "setup_s": t_setup,
-            "note": "value = whole K-step job from pinned host features (upload+pack+init inside the timed region, loss record "
+            "note": "whole job, max over ranks, byte counts summed over ranks; value = whole K-step job from pinned host features (upload+pack+init inside the timed region, loss record "
                     "read back and host-synchronised every step, final weights read back); steady_value excludes the one-off upload",
             "last_loss": last,
         }
@@ -387,7 +393,7 @@ def run_ours(args, wl):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            if host_h is not None:
+            if host_h is not None and world == 1:
                 hh, aa = host_h.numpy(), host_a.numpy()
             else:
                 hh, aa = host_features(F, R)

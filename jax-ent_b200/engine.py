@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .sharding import ShardComm
 
 
 @dataclass
@@ -80,6 +81,18 @@ def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
     return int(s.cuda_stream)
 
 
+class PackedFeatures:
+    """The packed (tile layout) copy of one rank's BV features; can be shared by several engines
+    (e.g. the optimiser's engine and the forward-only engine behind ``Simulation.forward``)."""
+
+    def __init__(self, packed: torch.Tensor, n_residues: int, n_frames: int):
+        self.packed, self.R, self.F = packed, int(n_residues), int(n_frames)
+
+    @property
+    def shape(self):
+        return (self.R, self.F)
+
+
 class BvEngine:
     def __init__(
         self,
@@ -100,20 +113,25 @@ class BvEngine:
         self.lib = L.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.group = group
-        self.sharded = group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+        self.comm = ShardComm(group)
+        self.sharded = self.comm.active
         self.settings = settings
         self.uptake = bool(uptake)
         self._keep = []  # device tensors referenced by raw pointer from the plan
 
         R, F = int(heavy.shape[0]), int(heavy.shape[1])
-        if tuple(acceptor.shape) != (R, F):
+        if not isinstance(heavy, PackedFeatures) and tuple(acceptor.shape) != (R, F):
             raise ValueError("Input features have different shapes")  # reference models/core.py:61-62
         self.R, self.F = R, F
         self.F_total = int(F_total) if F_total is not None else F
         self.T = int(np.asarray(timepoints).reshape(-1).shape[0]) if self.uptake else 0
 
         with torch.cuda.device(self.device):
-            self.packed = self._pack(heavy, acceptor)
+            if isinstance(heavy, PackedFeatures):
+                self.features = heavy
+            else:
+                self.features = PackedFeatures(self._pack(heavy, acceptor), R, F)
+            self.packed = self.features.packed
             prob = L.BvProblem()
             prob.R, prob.T, prob.uptake, prob.n_slots = R, self.T, int(self.uptake), len(slots)
             prob.F, prob.F_total = F, self.F_total
@@ -139,8 +157,7 @@ class BvEngine:
                 eps = 1e-10 / self.F_total
                 tmp = torch.zeros(1, dtype=torch.float64, device=self.device)
                 L.check(self.lib.jaxent_bv_prior_partial(self.prior.data_ptr(), F, eps, tmp.data_ptr(), _stream_ptr()))
-                if self.sharded:
-                    torch.distributed.all_reduce(tmp, group=self.group)
+                self.comm.sum_(tmp)
                 prob.prior = self.prior.data_ptr()
                 prob.prior_norm = float(tmp.item())
             for i, s in enumerate(slots):
@@ -267,8 +284,7 @@ class BvEngine:
                 raise ValueError("frame_weights must have one entry per frame")
             zmax = torch.empty(1, dtype=torch.float32, device=self.device)
             L.check(self.lib.jaxent_bv_max(z0.data_ptr(), self.F, zmax.data_ptr(), _stream_ptr()))
-            if self.sharded:
-                torch.distributed.all_reduce(zmax, op=torch.distributed.ReduceOp.MAX, group=self.group)
+            self.comm.max_(zmax)
             n = len(self.kinds)
             fw = np.asarray(fw, np.float32).reshape(-1)
             fs = np.asarray(fs, np.float32).reshape(-1)
@@ -289,11 +305,9 @@ class BvEngine:
         s = _stream_ptr()
         L.check(self.lib.jaxent_bv_pass(self.plan, mode, s))
         L.check(self.lib.jaxent_bv_reduce(self.plan, s))
-        if self.sharded:
-            torch.distributed.all_reduce(self.red, group=self.group)
+        self.comm.sum_(self.red)
         L.check(self.lib.jaxent_bv_tail(self.plan, s))
-        if self.sharded:
-            torch.distributed.all_reduce(self.klsum, group=self.group)
+        self.comm.sum_(self.klsum)
         self.launches += 3
 
     def step(self, n: int = 1) -> None:

@@ -1,0 +1,136 @@
+"""Simulation (reference jaxent/src/models/core.py:21-315) over the fused CUDA engine.
+
+Same constructor, `initialise()`, static `forward(sim, params, mutate)`, `.params`, `.outputs`,
+`.outputs_by_key`.  The path covers ONE Best-Vendruscolo forward model per Simulation
+(`BV_ForwardPass` or `BV_uptake_ForwardPass`, `average_first=True`); other forward models stay on the
+reference's JAX path.  `initialise()` packs the (R,F) contact arrays into the tile layout once
+(this replaces `cast_to_jax`, custom_types/features.py:82-89)."""
+from __future__ import annotations
+
+import logging
+from typing import Any, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .._arrays import scalar, to_device, to_numpy
+from ..engine import BvEngine, OptSettings, PackedFeatures, SlotSpec
+from ..interfaces.simulation import Simulation_Parameters, _replace
+from .HDX.BV.features import BV_input_features, BV_output_features, uptake_BV_output_features
+
+LOGGER = logging.getLogger("jaxent.models")
+
+
+def _forwardpass_of(model):
+    return getattr(model, "forwardpass", model)
+
+
+class Simulation:
+    """The core object used during optimisation."""
+
+    def __init__(self, input_features: Sequence[Any], forward_models: Sequence[Any], params: Optional[Simulation_Parameters],
+                 raise_jit_failure: bool = False, device: Optional[str] = None) -> None:
+        self.input_features = input_features
+        self.forward_models = forward_models
+        self.params = params
+        self.forwardpass = tuple(_forwardpass_of(m) for m in forward_models)
+        self.outputs: tuple = tuple()
+        self.raise_jit_failure = raise_jit_failure
+        self.device = torch.device(device) if device is not None else None
+        self._features: Optional[PackedFeatures] = None
+        self._fwd_engine: Optional[BvEngine] = None
+
+    def __repr__(self) -> str:
+        return f"Simulation(raise_jit_failure={self.raise_jit_failure})"
+
+    # ------------------------------------------------------------------ initialise
+    def initialise(self) -> bool:
+        lengths = [f.features_shape[-1] for f in self.input_features]
+        if len(set(lengths)) != 1:
+            raise AssertionError("Input features have different frame counts")
+        self.length = lengths[0]
+        if self.params is None:
+            raise ValueError("No simulation parameters were provided. Exiting.")
+        if len(self.forward_models) != len(self.params.model_parameters):
+            raise AssertionError("Number of forward models must equal number of model parameters")
+        if len(self.forward_models) != 1 or not isinstance(self.input_features[0], BV_input_features):
+            raise NotImplementedError("the fused B200 path covers exactly one BV forward model per Simulation")
+        fp = self.forwardpass[0]
+        if not getattr(fp, "average_first", True):
+            raise NotImplementedError("average_first=False (per-frame uptake) is not on the fused path yet (SURVEY.md 8f.2)")
+        if not hasattr(fp, "uptake"):
+            raise NotImplementedError(f"forward pass {type(fp).__name__} is not a BV forward pass of the fused path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("jaxent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if self.device is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        logits = self.params.frame_weights
+        self.params = Simulation_Parameters.normalize_weights(self.params)
+        self.params = Simulation_Parameters.normalize_masked_loss_scalingweights(self.params)
+
+        feat = self.input_features[0]
+        if tuple(np.shape(feat.heavy_contacts)) != tuple(np.shape(feat.acceptor_contacts)) or len(np.shape(feat.heavy_contacts)) != 2:
+            raise ValueError("BV features must be two (n_residues, n_frames) arrays of equal shape")
+        self._uptake = bool(fp.uptake)
+        mp = self.params.model_parameters[0]
+        self._timepoints = to_numpy(mp.timepoints).reshape(-1) if self._uptake else None
+        self._k_ints = to_numpy(feat.k_ints).reshape(-1) if (self._uptake and feat.k_ints is not None) else None
+        if self._uptake and self._k_ints is None:
+            raise ValueError("Failed to apply forward models without JIT: BV_uptake_ForwardPass needs k_ints")
+        try:
+            self._fwd_engine = BvEngine(feat.heavy_contacts, feat.acceptor_contacts, self._k_ints, self._timepoints,
+                                        [SlotSpec(L.LOSS_PARAMS_L2)], self._uptake, OptSettings(), device=self.device)
+        except Exception as e:
+            raise ValueError(f"Failed to apply forward models without JIT: {e}")
+        self._features = self._fwd_engine.features
+        # the reference re-applies the softmax here (models/core.py:72,97-98): params end up softmax(softmax(w0))
+        _sim, _outputs = Simulation.forward(self, self.params, mutate=False)
+        self.params = _sim.params
+        self.outputs = _outputs
+        LOGGER.info("Simulation initialised successfully.")
+        return True
+
+    # ------------------------------------------------------------------ forward
+    def _forward_logits(self, logits, norm_params: Simulation_Parameters):
+        eng = self._fwd_engine
+        mp = norm_params.model_parameters[0]
+        eng.init_state(to_device(logits, self.device).reshape(-1), scalar(mp.bv_bc), scalar(mp.bv_bh), [0.0], [0.0])
+        if self._uptake:
+            out = uptake_BV_output_features(uptake=eng.uptake_out.clone())
+        else:
+            out = BV_output_features(log_Pf=eng.log_pf.clone(), k_ints=None)
+        new_sim = self._shallow_copy()
+        new_sim.params = _replace(norm_params, frame_weights=eng.weights.clone())
+        new_sim.outputs = (out,)
+        return new_sim, (out,)
+
+    @staticmethod
+    def forward(sim: "Simulation", params: Simulation_Parameters, mutate: bool = True):
+        """normalize_weights(params) (softmax of params.frame_weights) -> frame average -> BV forward pass.
+        Returns (new_sim, outputs) when mutate=False, else updates and returns `sim` (:131-163)."""
+        if sim._fwd_engine is None:
+            raise RuntimeError("Simulation must be initialised before calling forward")
+        norm = Simulation_Parameters.normalize_weights(params)
+        new_sim, outputs = sim._forward_logits(params.frame_weights, norm)
+        if mutate:
+            sim.params, sim.outputs = new_sim.params, new_sim.outputs
+            return sim
+        return new_sim, outputs
+
+    def predict(self, params):
+        raise NotImplementedError("per-frame prediction (Simulation.predict) is not on the fused path (SURVEY.md 8f.2)")
+
+    @property
+    def outputs_by_key(self) -> dict:
+        result = {}
+        for o in self.outputs:
+            if o.key in result:
+                raise KeyError(f"Duplicate output key '{o.key}' — each forward model must produce outputs with unique m_keys.")
+            result[o.key] = o
+        return result
+
+    def _shallow_copy(self) -> "Simulation":
+        new = Simulation.__new__(Simulation)
+        new.__dict__.update(self.__dict__)
+        return new

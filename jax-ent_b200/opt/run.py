@@ -1,0 +1,107 @@
+"""run_optimise / _optimise (reference jaxent/src/opt/run.py:235-461): the Python optimisation loop with
+relative-convergence thresholds, history snapshots and best-state selection, over the fused CUDA step.
+
+Same semantics as the reference loop; the differences are mechanical: the per-step scalars (loss, grad-dot)
+come from the device-side loss record in ONE small device->host read per step (the reference does 5-8
+separate host syncs), and frame-sized arrays are only copied when a threshold snapshot is taken."""
+from __future__ import annotations
+
+import logging
+import math
+import time
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from ..custom_types.config import OptimiserSettings
+from ..interfaces.simulation import Simulation_Parameters, _replace
+from ..models.core import Simulation
+from .base import OptimizationHistory, OptimizationState
+from .optimiser import OptaxOptimizer
+from .track import ConvergenceTracker
+
+LOGGER = logging.getLogger("jaxent.opt")
+
+
+def _optimise(_simulation: Simulation, data_to_fit: Sequence, n_steps: int, tolerance: float, convergence, indexes: Sequence[int],
+              loss_functions: Sequence, opt_state: OptimizationState, optimizer: OptaxOptimizer, ema_alpha: float = 0.5,
+              min_steps_per_threshold: int = 2, logger: Optional[logging.Logger] = None, silent: bool = False):
+    _logger = logger if logger is not None else LOGGER
+    if isinstance(convergence, float):
+        convergence = [convergence]
+    tracker = ConvergenceTracker(convergence, optimizer.learning_rate, ema_alpha, min_steps_per_threshold)
+    previous_loss = None
+    save_state = None
+    optimizer.history = OptimizationHistory()
+    t_start = time.time()
+    step = 0
+    data_targets, losses_t, idx_t = tuple(data_to_fit), tuple(loss_functions), tuple(indexes)
+    try:
+        for step in range(n_steps):
+            opt_state, current_loss, save_state, _simulation = optimizer.step(
+                optimizer=optimizer, state=opt_state, simulation=_simulation, data_targets=data_targets,
+                loss_functions=losses_t, indexes=idx_t)
+            eng = optimizer._engine
+            # one device->host read: the record of the step just taken (loss) and of the next (grad-dot, lr)
+            rec, nxt = eng.records(step, 2)
+            loss_val = float(rec.total_train)
+            optimizer._current_lr = float(nxt.lr)
+            optimizer._current_model_lr = float(nxt.lr) * optimizer.model_parameters_lr_scale
+            optimizer._current_gradient_mask_idx = 1 if step >= optimizer.initial_steps else 0
+            tracker.update(previous_loss, loss_val, save_state.params)
+            previous_loss = loss_val
+            grad_dot = float(nxt.grad_dot) if step > 0 else 0.0  # check_gradient_oscillation: zeros before the first step
+            if not silent:
+                _logger.debug("step %d/%d loss %.6g rel-conv %.3e thr %.3e grad-dot %.3e lr %.4g", step, n_steps, loss_val,
+                              tracker.get_relative_convergence(loss_val), tracker.current_threshold, grad_dot, nxt.lr)
+            if grad_dot < 0:
+                tracker.reset_threshold_steps()
+            if loss_val < tolerance or math.isnan(loss_val) or math.isinf(loss_val):
+                _logger.info("Stopping optimisation at step %s due to tolerance/non-finite loss.", step)
+                break
+            if step == 0 or tracker.is_threshold_met(loss_val, step, optimizer.initial_steps):
+                optimizer = optimizer.update_history_compute_ema_loss(
+                    optimizer=optimizer, simulation=_simulation, data_targets=data_targets, indexes=idx_t,
+                    loss_functions=losses_t, state=save_state, ema_params=tracker.ema_params)
+                if step > 0:
+                    if tracker.advance_threshold():
+                        _logger.info("Moving to threshold %s/%s: %.2e", tracker.current_threshold_idx + 1,
+                                     len(tracker.convergence_thresholds), tracker.current_threshold)
+                    else:
+                        _logger.info("All relative thresholds completed at step %s", step)
+                        break
+    except Exception as e:  # reference opt/run.py:350-353
+        raise RuntimeError(f"Optimisation failed at step {step}: {e}") from e
+    if optimizer.history.states:
+        best = optimizer.history.get_best_state()
+        if best is not None:
+            _simulation.params = optimizer.history.best_state.params
+    if not silent:
+        dt = time.time() - t_start
+        _logger.info("Optimisation finished: %d steps in %.3f s (%.1f it/s)", step + 1, dt, (step + 1) / max(dt, 1e-9))
+    return _simulation, optimizer
+
+
+def run_optimise(simulation: Simulation, data_to_fit: Sequence, config: OptimiserSettings, forward_models: Sequence,
+                 indexes: Sequence[int], loss_functions: list, optimizer: Optional[OptaxOptimizer] = None,
+                 optimisable_funcs=None, initialise: Optional[bool] = False, _opt_fn: Callable = _optimise,
+                 jit_update_step: bool = False, logger: Optional[logging.Logger] = None, silent: bool = False):
+    """Run the optimisation (reference opt/run.py:376-461) -> (simulation, OptimizationHistory)."""
+    _logger = logger if logger is not None else LOGGER
+    if initialise:
+        if not simulation.initialise():
+            raise ValueError("Failed to initialise simulation")
+    if len(data_to_fit) != len(loss_functions):
+        raise ValueError("Number of data targets and loss functions must match")
+    if optimizer is None:
+        optimizer = OptaxOptimizer(learning_rate=config.learning_rate, optimizer=config.optimiser_type)
+    jit_test_args = (data_to_fit, loss_functions, indexes) if jit_update_step else None
+    opt_state = optimizer.initialise(simulation, optimisable_funcs, _jit_test_args=jit_test_args)
+    kw = dict(ema_alpha=config.ema_alpha, min_steps_per_threshold=config.min_steps_per_threshold)
+    if _opt_fn is _optimise:
+        kw.update(logger=_logger, silent=silent)
+    simulation, optimizer = _opt_fn(simulation, data_to_fit, config.n_steps, config.tolerance, config.convergence, indexes,
+                                    loss_functions, opt_state, optimizer, **kw)
+    if optimizer:
+        return simulation, optimizer.history
+    raise ValueError("Optimisation failed")

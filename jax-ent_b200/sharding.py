@@ -1,0 +1,79 @@
+"""Frame sharding of the ensemble across ranks.
+
+Every per-frame quantity (feature columns, logits, Adam moments, prior, weights) is local to the rank
+that owns the frame; ranks couple only through three tiny collectives:
+
+  * once, at initialisation:  max(z0) (MAX) and sum(|prior|+eps) (SUM)
+  * every step, after `reduce`:  the (4R+4)-double partial-sum vector  JAXENT_BUF_RED   (SUM)
+  * every step, after `tail`  :  the 4-double MaxEnt vector             JAXENT_BUF_KLSUM (SUM)
+
+BV parameters, the R x T tail and the plateau decision are replicated: every rank computes them from
+the same all-reduced numbers, so they stay bit-identical without a broadcast.
+
+The same code drives NCCL on GPUs (engine.py) and gloo on CPU (tests/test_sharding_gloo.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+FRAME_ALIGN = 8  # shards start on a tile boundary (8 frames) so every rank packs whole tiles
+
+
+@dataclass(frozen=True)
+class FrameShard:
+    rank: int
+    world: int
+    start: int
+    stop: int
+    total: int
+
+    @property
+    def size(self) -> int:
+        return self.stop - self.start
+
+    def slice(self) -> slice:
+        return slice(self.start, self.stop)
+
+
+def frame_shard(total_frames: int, rank: int, world: int, align: int = FRAME_ALIGN) -> FrameShard:
+    """Contiguous, tile-aligned block of frames owned by `rank`; remainders go to the last ranks."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"invalid rank {rank} / world {world}")
+    if total_frames < world:
+        raise ValueError(f"cannot shard {total_frames} frames over {world} ranks")
+    tiles = (total_frames + align - 1) // align
+    lo = (tiles * rank // world) * align
+    hi = (tiles * (rank + 1) // world) * align
+    lo, hi = min(lo, total_frames), min(hi, total_frames)
+    if rank == world - 1:
+        hi = total_frames
+    if hi <= lo:
+        raise ValueError(f"rank {rank} would own no frames ({total_frames} frames over {world} ranks)")
+    return FrameShard(rank, world, lo, hi, total_frames)
+
+
+class ShardComm:
+    """The collectives of the sharded step; a no-op for a single rank."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.active = bool(group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1)
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.calls = 0
+
+    def sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.active:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.calls += 1
+        return t
+
+    def max_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.active:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self.calls += 1
+        return t

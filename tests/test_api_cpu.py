@@ -1,0 +1,148 @@
+"""CPU tests of the host-side mirror of the reference interface (no compute calls)."""
+import numpy as np
+import pytest
+import torch
+
+import jaxent_b200 as J
+from jaxent_b200.opt.losses import loss_kind
+from jaxent_b200.opt.track import ConvergenceTracker, create_convergence_thresholds
+from oracle import bv_oracle as O
+
+
+def _params(F=16, L=3):
+    return J.Simulation_Parameters(
+        frame_weights=np.linspace(0.1, 2.0, F).astype(np.float32),
+        frame_mask=np.ones(F, np.float32),
+        model_parameters=[J.BV_Model_Parameters()],
+        forward_model_weights=np.array([2.0, 1.0, 5.0], np.float32)[:L],
+        normalise_loss_functions=np.array([1.0, 1.0, 0.0], np.float32)[:L],
+        forward_model_scaling=np.full(L, 100.0, np.float32),
+    )
+
+
+def test_simulation_parameters_normalisers_match_reference_semantics():
+    p = _params()
+    q = J.Simulation_Parameters.normalize_masked_loss_scalingweights(p)
+    np.testing.assert_allclose(q.forward_model_weights, [2 / 3, 1 / 3, 5.0], rtol=1e-6)  # simulation.py:45-76
+    np.testing.assert_allclose(q.forward_model_weights, O.normalize_masked_loss_scalingweights(p.forward_model_weights, p.normalise_loss_functions))
+    n = J.Simulation_Parameters.normalize_weights(p)
+    np.testing.assert_allclose(n.frame_weights, O.softmax(p.frame_weights), rtol=1e-6)
+    np.testing.assert_allclose(n.frame_mask, 1 / (1 + np.exp(-5.0)), rtol=1e-6)
+    assert n.model_parameters[0] is p.model_parameters[0]  # passed through unclamped
+    nt = J.Simulation_Parameters.normalize_weights(J.Simulation_Parameters(
+        torch.tensor(p.frame_weights), torch.ones(16), p.model_parameters, p.forward_model_weights, p.normalise_loss_functions, p.forward_model_scaling))
+    np.testing.assert_allclose(nt.frame_weights.numpy(), n.frame_weights, rtol=1e-6)
+    with pytest.raises(ValueError):
+        J.Simulation_Parameters.normalize_weights(J.Simulation_Parameters(np.ones((2, 2)), np.ones((2, 2)), [], None, None, None))
+
+
+def test_simulation_parameters_arithmetic():
+    p = _params()
+    s = 0.5 * p + 0.5 * p
+    np.testing.assert_allclose(s.frame_weights, p.frame_weights, rtol=1e-6)
+    np.testing.assert_allclose(s.model_parameters[0].bv_bc, p.model_parameters[0].bv_bc)
+    d = p - p
+    assert float(np.abs(d.frame_weights).max()) == 0.0 and float(d.model_parameters[0].bv_bh[0]) == 0.0
+    with pytest.raises(TypeError):
+        p + "x"
+
+
+def test_bv_model_parameters_pytree_and_update():
+    mp = J.BV_Model_Parameters(bv_bc=np.array([0.4]), bv_bh=np.array([1.9]), timepoints=np.array([1.0, 2.0]))
+    arrays, static = mp.tree_flatten()
+    assert len(arrays) == 2 and set(J.BV_Model_Parameters.static_params) == {"temperature", "key", "timepoints"}
+    mp2 = J.BV_Model_Parameters.tree_unflatten(static, arrays)
+    assert float(mp2.bv_bc[0]) == 0.4 and np.array_equal(mp2.timepoints, mp.timepoints)
+    mp3 = mp.update_parameters(J.BV_Model_Parameters(bv_bc=np.array([1.0]), bv_bh=np.array([3.0]), timepoints=np.array([9.0])))
+    assert float(mp3.bv_bc[0]) == 1.0 and np.array_equal(mp3.timepoints, mp.timepoints)  # static fields preserved
+
+
+def test_feature_containers():
+    f = J.BV_input_features(np.zeros((5, 7)), np.zeros((5, 7)), np.ones(5))
+    assert f.features_shape == (5, 7) and f.__features__ == {"heavy_contacts", "acceptor_contacts", "k_ints"}
+    assert J.BV_input_features(np.zeros(5), np.zeros(5)).features_shape == (5, 1)
+    with pytest.raises(TypeError):
+        J.BV_input_features(np.zeros((5, 7)), torch.zeros(5, 7)).features_shape
+    assert J.uptake_BV_output_features(np.zeros((3, 5))).output_shape == (3, 5)
+    assert J.BV_output_features(np.zeros(5)).output_shape == (1, 5)
+    assert J.BV_ForwardPass.average_first and J.BV_uptake_ForwardPass.average_first
+
+
+def test_loss_tokens():
+    assert J.hdx_uptake_eye_MSE_loss.__name__ == "hdx_uptake_eye_MSE_loss"
+    assert loss_kind(J.maxent_convexKL_loss) == 4
+
+    def hdx_pf_l2_loss(model, dataset, idx):  # a reference function of the same name maps to the same kernel
+        return 0, 0
+
+    assert loss_kind(hdx_pf_l2_loss) == 3
+
+    def maxent_JSD_loss(model, dataset, idx):
+        return 0, 0
+
+    with pytest.raises(ValueError, match="not on the fused B200 path"):
+        loss_kind(maxent_JSD_loss)
+    with pytest.raises(NotImplementedError, match="no host implementation"):
+        J.hdx_pf_l2_loss(None, None, 0)
+    with pytest.raises(NotImplementedError, match="no host implementation"):
+        J.BV_ForwardPass()(None, None)
+
+
+def test_optimizer_argument_validation():
+    with pytest.raises(ValueError, match="Unsupported optimizer"):
+        J.OptaxOptimizer(optimizer="nadam")
+    with pytest.raises(NotImplementedError, match="only 'adam'"):
+        J.OptaxOptimizer(optimizer="sgd")
+    with pytest.raises(NotImplementedError, match="Frame mask optimization"):
+        J.OptaxOptimizer(parameter_partition_masks={J.Optimisable_Parameters.frame_mask})
+    o = J.OptaxOptimizer(learning_rate=0.3, initial_learning_rate=2.0, model_parameters_lr_scale=0.5)
+    assert o.current_learning_rate == 2.0 and o.current_model_learning_rate == 1.0
+    s = o._settings()
+    assert s.optimise_frame_weights and not s.optimise_model_parameters and s.clip_value == 1.0
+
+
+def test_convergence_tracker_matches_oracle_tracker():
+    assert create_convergence_thresholds([1e-3, 1e-1, 1e-2], 0.5) == pytest.approx([0.05, 0.005, 0.0005])
+    a = ConvergenceTracker([1e-2, 1e-1], 1.0, 0.5, 2)
+    b = O.ConvergenceTracker([1e-2, 1e-1], 1.0, 0.5, 2)
+    rng = np.random.default_rng(0)
+    prev = None
+    loss = 10.0
+    for step in range(40):
+        loss = loss * (0.5 + 0.5 * rng.random())
+        w = rng.random(4)
+        a.update(prev, loss, w)
+        b.update(prev, loss, w)
+        prev = loss
+        assert a.is_threshold_met(loss, step, 0) == b.met(loss, step, 0)
+        assert a.get_relative_convergence(loss) == pytest.approx(b.rel(loss))
+        if a.is_threshold_met(loss, step, 0):
+            assert a.advance_threshold() == b.advance()
+    np.testing.assert_allclose(a.ema_params, b.ema_params)
+
+
+def test_simulation_requires_cuda_and_valid_inputs():
+    f = J.BV_input_features(np.zeros((5, 8), np.float32), np.zeros((5, 8), np.float32), np.ones(5, np.float32))
+    p = J.Simulation_Parameters(np.full(8, 1 / 8, np.float32), np.ones(8, np.float32), [J.BV_Model_Parameters()],
+                                np.ones(1, np.float32), np.ones(1, np.float32), np.ones(1, np.float32))
+    sim = J.Simulation([f], [J.BV_uptake_ForwardPass()], None)
+    with pytest.raises(ValueError, match="No simulation parameters"):
+        sim.initialise()
+    with pytest.raises(AssertionError, match="must equal number of model parameters"):
+        J.Simulation([f], [J.BV_ForwardPass(), J.BV_ForwardPass()], p).initialise()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            J.Simulation([f], [J.BV_uptake_ForwardPass()], p).initialise()
+    with pytest.raises(RuntimeError, match="initialised"):
+        J.Simulation.forward(J.Simulation([f], [J.BV_ForwardPass()], p), p)
+
+
+def test_dataloader_containers():
+    S = np.eye(3, 5, dtype=np.float32)
+    ds = J.Dataset([], np.zeros((3, 2, 1)), J.SparseFragmentMapping(S))
+    assert ds.residue_feature_ouput_mapping is S and ds.covariance_matrix is None
+    np.testing.assert_array_equal(J.SparseFragmentMapping(torch.tensor(S)).dense(), S)
+    dl = J.ExpD_Dataloader(train=ds, val=ds)
+    assert dl.train is ds and dl.key == "unknown"
+    with pytest.raises(NotImplementedError):
+        J.ExpD_Dataloader(data=[1])

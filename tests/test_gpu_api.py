@@ -1,0 +1,135 @@
+"""GPU tests of the reference-API mirror: Simulation / OptaxOptimizer.step / compute_loss / run_optimise, used
+the way examples/common/optimization.py:85-261 uses the reference, checked against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import jaxent_b200 as J
+from oracle import bv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _Model:  # a ForwardModel stand-in: only `.forwardpass` is read on this path (models/core.py:42-44)
+    def __init__(self, fp):
+        self.forwardpass = fp
+
+
+def _setup(F=600, R=41, T=4, kind=O.UPTAKE_EYE_MSE, opt_model=False, gamma=2.0, scaling=100.0, lr=0.5):
+    case = H.make_case(F, R, T, kind, extra=(O.PARAMS_L2,), seed=13, gamma=gamma, scaling=scaling)
+    ens, pb = case["ens"], case["problem"]
+    uptake = kind != O.PF_L2
+    feats = J.BV_input_features(ens.heavy, ens.acceptor, ens.k_ints)
+    mp = J.BV_Model_Parameters(bv_bc=np.array([0.35], np.float32), bv_bh=np.array([2.0], np.float32), timepoints=ens.timepoints)
+    yt = lambda y: y[:, :, None] if uptake else y  # the loader's (P,T,1) layout (data/loader.py:219-221)
+    loader = J.ExpD_Dataloader(
+        train=J.Dataset([], yt(ens.y_train), J.SparseFragmentMapping(ens.S_train)),
+        val=J.Dataset([], yt(ens.y_val), J.SparseFragmentMapping(ens.S_val)))
+    n = 3
+    params = J.Simulation_Parameters(
+        frame_weights=np.full(F, 1.0 / F, np.float32), frame_mask=np.ones(F, np.float32), model_parameters=[mp],
+        forward_model_weights=np.array([gamma, 1.0, 1.0], np.float32), normalise_loss_functions=np.ones(n, np.float32),
+        forward_model_scaling=np.full(n, scaling, np.float32))
+    prior_mp = J.BV_Model_Parameters(bv_bc=np.array([0.3], np.float32), bv_bh=np.array([2.2], np.float32), timepoints=ens.timepoints)
+    prior = J.Simulation_Parameters(params.frame_weights, params.frame_mask, [prior_mp], params.forward_model_weights,
+                                    params.normalise_loss_functions, params.forward_model_scaling)
+    fp = J.BV_uptake_ForwardPass() if uptake else J.BV_ForwardPass()
+    sim = J.Simulation(input_features=(feats,), forward_models=(_Model(fp),), params=params)
+    data = (loader, prior, prior)
+    primary = J.hdx_uptake_eye_MSE_loss if uptake else J.hdx_pf_l2_loss
+    losses = (primary, J.maxent_convexKL_loss, J.model_params_L2_loss)
+    masks = {J.Optimisable_Parameters.frame_weights}
+    if opt_model:
+        masks.add(J.Optimisable_Parameters.model_parameters)
+    opt = J.OptaxOptimizer(learning_rate=lr, parameter_partition_masks=masks, clip_value=None, optimizer="adam",
+                           initial_learning_rate=1.0, initial_steps=2)
+    cfg = O.OptConfig(learning_rate=lr, initial_learning_rate=1.0, initial_steps=2, clip_value=None,
+                      optimise_model_parameters=opt_model)
+    return case, sim, data, losses, opt, cfg
+
+
+def test_simulation_initialise_and_forward():
+    case, sim, *_ = _setup()
+    assert sim.initialise() is True
+    F = 600
+    w = sim.params.frame_weights
+    assert isinstance(w, torch.Tensor) and w.is_cuda and abs(float(w.sum()) - 1) < 1e-5
+    np.testing.assert_allclose(sim.params.forward_model_weights, [0.5, 0.25, 0.25], rtol=1e-6)
+    assert isinstance(sim.outputs[0], J.uptake_BV_output_features) and tuple(sim.outputs[0].uptake.shape) == (4, 41)
+    assert sim.outputs_by_key["HDX_peptide"] is sim.outputs[0]
+    # forward at non-uniform logits vs the oracle
+    z = np.random.default_rng(0).normal(size=F).astype(np.float32)
+    p2 = J.Simulation_Parameters(z, sim.params.frame_mask, sim.params.model_parameters, sim.params.forward_model_weights,
+                                 sim.params.normalise_loss_functions, sim.params.forward_model_scaling)
+    new_sim, outs = J.Simulation.forward(sim, p2, mutate=False)
+    par = case["params"]
+    _, npar, out = O.compute_loss(case["problem"], O.Params(z, par.frame_mask, 0.35, 2.0, par.fw, par.fs, par.nlf), np.float64)
+    np.testing.assert_allclose(outs[0].uptake.cpu().numpy(), out["uptake"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(new_sim.params.frame_weights.cpu().numpy(), npar.z, rtol=3e-6)
+    assert new_sim is not sim and sim.outputs[0] is not outs[0]
+
+
+@pytest.mark.parametrize("kind,opt_model", [(O.UPTAKE_EYE_MSE, True), (O.PF_L2, False)])
+def test_step_api_tracks_oracle(kind, opt_model):
+    case, sim, data, losses, opt, cfg = _setup(kind=kind, T=4 if kind != O.PF_L2 else 1, opt_model=opt_model)
+    sim.initialise()
+    state = opt.initialise(sim, _jit_test_args=(data, losses, (0, 0, 0)))
+    assert float(state.params.frame_weights[0]) == pytest.approx(1.0)  # z0 = w * n_frames (optimiser.py:243)
+    par = case["params"]
+    par = O.Params(par.z, par.frame_mask, par.bc, par.bh, O.normalize_masked_loss_scalingweights([2.0, 1.0, 1.0], np.ones(3)), par.fs, par.nlf)
+    ost = O.optimizer_initialise(par, cfg, np.float64)
+    for k in range(6):
+        state, loss, save, usim = opt.step(optimizer=opt, state=state, simulation=sim, data_targets=data,
+                                           loss_functions=losses, indexes=(0, 0, 0))
+        ost, ol, ow = O.step_with_rates(case["problem"], ost, cfg, np.float64)
+        assert int(state.step) == k + 1 and isinstance(state, J.OptimizationState)
+        # step 0 starts from identical states (tight); later steps are free-running, not teacher-forced (loose)
+        rt = 2e-5 if k == 0 else 3e-3
+        np.testing.assert_allclose(float(loss), ol, rtol=rt)
+        np.testing.assert_allclose(state.losses.train_losses.cpu().numpy(), ost.losses.train_losses, rtol=rt, atol=1e-6)
+        np.testing.assert_allclose(state.losses.val_losses.cpu().numpy(), ost.losses.val_losses, rtol=rt, atol=1e-6)
+        np.testing.assert_allclose(save.params.frame_weights.cpu().numpy(), ow, rtol=1e-3, atol=1e-7)
+        g = state.gradients.frame_weights.cpu().numpy()
+        # free-running comparison (not teacher-forced): trajectories separate slowly, so 1e-3 of the gradient scale
+        gerr = float(np.abs(g - ost.gradients.z).max() / np.abs(ost.gradients.z).max())
+        assert gerr <= 1e-3, f"step {k}: free-running gradient error {gerr:.2e}"
+        np.testing.assert_allclose(float(state.params.model_parameters[0].bv_bc[0]), ost.params.bc, rtol=1e-4)
+        assert abs(float(save.params.frame_weights.sum()) - 1.0) < 1e-5
+    with pytest.raises(RuntimeError, match="device-resident optimiser state"):
+        opt.step(optimizer=opt, state=state._replace(step=2), simulation=sim, data_targets=data, loss_functions=losses, indexes=(0, 0, 0))
+
+
+def test_compute_loss_matches_oracle():
+    case, sim, data, losses, opt, cfg = _setup()
+    sim.initialise()
+    z = np.random.default_rng(1).normal(size=600).astype(np.float32)
+    p = sim.params
+    q = J.Simulation_Parameters(z, p.frame_mask, p.model_parameters, p.forward_model_weights, p.normalise_loss_functions, p.forward_model_scaling)
+    lc, new_sim = J.compute_loss(sim, q, data, (0, 0, 0), losses)
+    par = case["params"]
+    fw = O.normalize_masked_loss_scalingweights([2.0, 1.0, 1.0], np.ones(3))
+    ol, _, _ = O.compute_loss(case["problem"], O.Params(z, par.frame_mask, 0.35, 2.0, fw, par.fs, par.nlf), np.float64)
+    assert isinstance(lc, J.LossComponents)
+    np.testing.assert_allclose(lc.train_losses.cpu().numpy(), ol.train_losses, rtol=1e-5)
+    np.testing.assert_allclose(lc.val_losses.cpu().numpy(), ol.val_losses, rtol=1e-5)
+    np.testing.assert_allclose(float(lc.total_train_loss), ol.total_train_loss, rtol=1e-5)
+    np.testing.assert_allclose(float(lc.total_val_loss), ol.total_val_loss, rtol=1e-5)
+
+
+def test_run_optimise_loop_semantics():
+    case, sim, data, losses, opt, cfg = _setup(lr=0.1, scaling=100.0)
+    settings = J.OptimiserSettings(name="t", n_steps=80, tolerance=1e-10, convergence=[1e-2, 1e-3], learning_rate=0.1)
+    sim2, history = J.run_optimise(sim, data, settings, forward_models=[], indexes=[0, 0, 0], loss_functions=list(losses),
+                                   optimizer=opt, initialise=True, silent=True)
+    par = case["params"]
+    par = O.Params(par.z, par.frame_mask, par.bc, par.bh, O.normalize_masked_loss_scalingweights([2.0, 1.0, 1.0], np.ones(3)), par.fs, par.nlf)
+    res = O.optimise(case["problem"], par, cfg.__class__(**{**cfg.__dict__, "learning_rate": 0.1}), 80, tolerance=1e-10,
+                     convergence=[1e-2, 1e-3], dtype=np.float32)
+    assert len(history.states) == len(res["history"]) >= 1
+    assert [int(s.step) for s in history.states] == [h["step"] for h in res["history"]]
+    for s, h in zip(history.states, res["history"]):
+        np.testing.assert_allclose(s.params.frame_weights.cpu().numpy(), h["weights"], atol=1e-4)
+    assert history.best_state is not None
+    assert opt.ema_history is not None and len(opt.ema_history.states) == len(history.states) - 1  # no EMA yet at step 0
+    np.testing.assert_allclose(sim2.params.frame_weights.cpu().numpy(), res["best"]["weights"], atol=1e-4)
