@@ -387,6 +387,13 @@ def run_ours(args, wl):
         del eng2, w_host
 
     peak, peak_src = peaks()
+    traffic = None
+    try:  # dram__bytes_read+write per bv_pass_kernel launch from the committed ncu --set full capture of this workload
+        prof = json.load(open(os.path.join(ROOT, "profiles", f"ncu_pass_r1_{args.workload}.json")))
+        if world == 1:
+            traffic = prof["dram_bytes_per_launch"]
+    except Exception:
+        pass
     alg_bytes = 8 * R * Fl + 28 * Fl
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
 
@@ -419,7 +426,7 @@ def run_ours(args, wl):
                        "l2": f"inputs {8 * R * Fl / 1e9:.2f} GB per GPU per step >> 126 MB L2, no flush needed" if 8 * R * Fl > 4e8 else "inputs fit in L2 (latency-bound config; steps/s only)",
                        "losses": ["hdx_uptake_eye_MSE_loss", "maxent_convexKL_loss"], "optimizer": "adam lr=1.0, plateau 1.005"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "bv_pass_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": traffic, "kernel": "bv_pass_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": pass_ms, "peak_source": peak_src, "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
             "e2e": e2e,

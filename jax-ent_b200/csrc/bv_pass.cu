@@ -126,7 +126,7 @@ __global__ void max_kernel(const float* __restrict__ z, long long F, float* out)
 //
 // so the serial per-frame optimiser chain of tile i runs while the consumers stream tile i+1.
 constexpr int BAR_PART0 = 1, BAR_E0 = 3;  // named barrier ids (0 is __syncthreads)
-constexpr int FLUSH_TILES = 16;           // fp32 tile sums are folded into the fp64 partials every 16 tiles
+constexpr int FLUSH_TILES = 128;          // fp32 tile sums are folded into the fp64 partials every 128 tiles (1024 frames)
 
 __device__ __forceinline__ void bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
