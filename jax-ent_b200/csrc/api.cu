@@ -25,13 +25,14 @@ struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
   size_t off_w, off_kappa, off_cc, off_ch, off_logpf, off_uptake, off_avg;
   size_t off_partials, off_red, off_klpart, off_klsum, off_ctl, off_epoch, off_counter, off_records;
+  size_t off_cl_scratch;
   size_t off_blob[JAXENT_MAX_SLOTS];
   int blob_words[JAXENT_MAX_SLOTS];
   size_t total;
 };
 
 constexpr int MAX_PASS_CTAS = 2 * 160;
-constexpr int MAX_TAIL_CTAS = 160;
+constexpr int MAX_TAIL_CTAS = 176;
 
 static Layout make_layout(const JaxentBvProblem* pb) {
   const int R = pb->R, T = pb->uptake ? pb->T : 0;
@@ -67,6 +68,12 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_epoch = take(sizeof(unsigned));
   L.off_counter = take(sizeof(unsigned));
   L.off_records = take((size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord));
+  {
+    int p_tr = 1;
+    for (int i = 0; i < pb->n_slots && i < JAXENT_MAX_SLOTS; ++i)
+      if (pb->slots[i].kind <= JAXENT_LOSS_PF_L2 && pb->slots[i].train.n_pep > p_tr) p_tr = pb->slots[i].train.n_pep;
+    L.off_cl_scratch = take(tail_cluster_scratch_doubles(R, T, p_tr) * sizeof(double));
+  }
   for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
     L.off_blob[i] = 0;
     L.blob_words[i] = 0;
@@ -135,7 +142,7 @@ struct JaxentPlan {
   jx::Layout lay;
   unsigned char* ws;
   jx::StateSets st;
-  int pass_threads, rpt, pass_ctas, stages, tail_ctas, p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
+  int pass_threads, rpt, pass_ctas, stages, tail_ctas, tail_clustered, p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
   uint32_t tile_bytes, stage_stride;
   size_t pass_smem, tail_smem;
   long long n_tiles;
@@ -299,7 +306,13 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   p->p_max_va = p_va;
   p->nnz_max_tr = nnz_tr;
   p->nnz_max_va = nnz_va;
-  p->tail_smem = tail_smem_bytes(R, T, p_tr, p_va, nnz_tr, nnz_va);
+  // the clustered tail covers the eye-MSE / PF-L2 data kinds with R >= 64; everything else runs on one CTA
+  p->tail_clustered = (R >= 64) && (getenv("JAXENT_TAIL_CLUSTER") != nullptr);  // opt-in: measured no faster than one CTA
+  for (int i = 0; i < problem->n_slots; ++i)
+    if (problem->slots[i].kind == JAXENT_LOSS_UPTAKE_MC_EYE_MSE || problem->slots[i].kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE)
+      p->tail_clustered = 0;
+  p->tail_smem = p->tail_clustered ? tail_cluster_smem_bytes(R, T, p_tr, p_va, nnz_tr, nnz_va)
+                                   : tail_smem_bytes(R, T, p_tr, p_va, nnz_tr, nnz_va);
   if (p->tail_smem > 220 * 1024) {
     const size_t need = p->tail_smem;
     delete p;
@@ -310,6 +323,16 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   long long fctas = (problem->F + 4095) / 4096;
   if (fctas > device_sm_count - 1) fctas = device_sm_count - 1;
   p->tail_ctas = (fctas <= 1) ? 1 : (int)fctas + 1;
+  if (p->tail_clustered) {
+    // cluster 0 (8 CTAs) runs the tail; the frames go to further clusters of 8 (or to cluster 0 itself when F is small)
+    long long fc = (problem->F + 4095) / 4096;
+    // clusters of 8 are placed inside one GPC (16-20 SMs): at most 2 per GPC are co-resident, 16 on the chip; keep one wave
+    long long max_fc = ((device_sm_count - TAIL_CLUSTER) / TAIL_CLUSTER) * TAIL_CLUSTER;
+    if (max_fc > 15 * TAIL_CLUSTER) max_fc = 15 * TAIL_CLUSTER;
+    if (fc > max_fc) fc = max_fc;
+    fc = (fc + TAIL_CLUSTER - 1) / TAIL_CLUSTER * TAIL_CLUSTER;
+    p->tail_ctas = (fc <= TAIL_CLUSTER) ? TAIL_CLUSTER : TAIL_CLUSTER + (int)fc;
+  }
   p->initialised = 0;
   *out = p;
   return JAXENT_OK;
@@ -455,14 +478,17 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
     a.blobs.blob[i] = a.blobs.words[i] ? reinterpret_cast<int*>(p->ws + p->lay.off_blob[i]) : nullptr;
   }
   {
-    const long long fc = (p->tail_ctas == 1) ? 1 : p->tail_ctas - 1;
+    long long fc = (p->tail_ctas == 1) ? 1 : p->tail_ctas - 1;
+    if (p->tail_clustered) fc = (p->tail_ctas == TAIL_CLUSTER) ? TAIL_CLUSTER : p->tail_ctas - TAIL_CLUSTER;
     a.frames_per_cta = (p->prob.F + fc - 1) / fc;
   }
+  a.cl_scratch = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
   a.p_max_tr = p->p_max_tr;
   a.p_max_va = p->p_max_va;
   a.nnz_max_tr = p->nnz_max_tr;
   a.nnz_max_va = p->nnz_max_va;
   a.eps_kl = (float)(1e-10 / (double)p->prob.F_total);
+  if (p->tail_clustered) return launch_tail_cluster(a, p->tail_ctas, p->tail_smem, (cudaStream_t)stream);
   return launch_tail(a, p->tail_ctas, p->tail_smem, (cudaStream_t)stream);
 }
 

@@ -245,8 +245,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
   float* s_part = reinterpret_cast<float*>(bars + MAX_STAGES);  // [2][16 warps][8 frames]
   float* s_e = s_part + 2 * 16 * FT;                            // [2][2 branches][8 frames], 16-byte aligned
 
-  const unsigned ep = *a.epoch;
-  const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
   const int mode = a.mode;
 
   // static, deterministic tile partition
@@ -262,17 +260,23 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
   }
   __syncthreads();
 
+  // The first tiles only need the (constant) features: start them before waiting on the previous kernel (PDL).
+  if (is_adam && lane == 0) {
+    const int pre = n < a.stages ? n : a.stages;
+    for (int s = 0; s < pre; ++s) {
+      const uint32_t bar = smem_u32(&bars[s]);
+      mbar_expect_tx(bar, a.tile_bytes);
+      bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(t0 + s) * a.tile_bytes, a.tile_bytes, bar);
+    }
+  }
+  pdl_wait();               // everything the tail kernel wrote (ctl, cc/ch, w, kappa, klsum) is visible from here on
+  pdl_launch_dependents();  // lets the reduce kernel's launch overlap this kernel
+
   if (is_adam) {
     // ================================================================== Adam warp
-    if (lane == 0) {
-      const int pre = n < a.stages ? n : a.stages;
-      for (int s = 0; s < pre; ++s) {
-        const uint32_t bar = smem_u32(&bars[s]);
-        mbar_expect_tx(bar, a.tile_bytes);
-        bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(t0 + s) * a.tile_bytes, a.tile_bytes, bar);
-      }
-      if (blockIdx.x == 0 && mode == 1) finish_record(ctl, a.klsum, a.records, JAXENT_MAX_SLOTS);
-    }
+    const unsigned ep = *a.epoch;
+    const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
+    if (lane == 0 && blockIdx.x == 0 && mode == 1) finish_record(ctl, a.klsum, a.records, JAXENT_MAX_SLOTS);
     const int in_set = ep & 1u, out_set = in_set ^ 1;
     const int in_br = ctl->branch;
     const float* __restrict__ zin = a.st.z[in_set][in_br];
@@ -477,6 +481,8 @@ __global__ void __launch_bounds__(1024) reduce_kernel(const ReduceArgs a) {
   // 32 columns x 32 partial-groups per block: every load is independent (latency overlapped) and
   // the summation order is fixed (group-strided, then groups 0..31) -> bitwise reproducible.
   __shared__ double sh[32][33];
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
   double s = 0.0;
@@ -512,20 +518,21 @@ int configure_kernels() {
 }
 
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s) {
+  cudaError_t le = cudaSuccess;
   switch (rpt) {
-    case 1: bv_pass_kernel<1><<<ctas, threads, smem, s>>>(a); break;
-    case 2: bv_pass_kernel<2><<<ctas, threads, smem, s>>>(a); break;
+    case 1: le = launch_pdl(bv_pass_kernel<1>, ctas, threads, smem, s, a); break;
+    case 2: le = launch_pdl(bv_pass_kernel<2>, ctas, threads, smem, s, a); break;
     default: set_error("unsupported rows-per-thread %d", rpt); return JAXENT_E_UNSUPPORTED;
   }
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = (le != cudaSuccess) ? le : cudaGetLastError();
   if (e != cudaSuccess) { set_error("bv_pass_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;
 }
 
 int launch_reduce(const ReduceArgs& a, cudaStream_t s) {
   const int blocks = (a.part_n + 31) / 32;
-  reduce_kernel<<<blocks, 1024, 0, s>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(reduce_kernel, blocks, 1024, 0, s, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("reduce_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;
 }

@@ -196,6 +196,144 @@ int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_
   return JAXENT_OK;
 }
 
+// ------------------------------------------------------------------------------------------ shared pieces
+// the new control block and the loss record, written by one warp (lane 0 the scalars, lanes 0..5 the slots)
+__device__ __forceinline__ void write_ctl_and_record(Ctl* __restrict__ neu, JaxentLossRecord* records, const StepScalars& sc,
+                                                     const Ctl& s_old, const double* s_fin, double gbc_reg, double gbh_reg,
+                                                     int n_slots, const double* klsum, int lane) {
+  const float gb0 = (float)(s_fin[13] + gbc_reg) * sc.mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * sc.mask_model;
+  if (lane == 0) {
+    neu->step = sc.step;
+    neu->mask_idx = sc.mask_idx;
+    neu->branch = sc.d;
+    neu->pending = 1;
+    neu->have_prev = sc.have_prev;
+    neu->count_frame = sc.cf;
+    neu->count_model = sc.cm;
+    neu->kl_slot = s_old.kl_slot;
+    neu->lr = sc.lr;
+    neu->model_lr = sc.mlr;
+    neu->bc = sc.bc;
+    neu->bh = sc.bh;
+    neu->mb[0] = sc.mb0; neu->mb[1] = sc.mb1; neu->vb[0] = sc.vb0; neu->vb[1] = sc.vb1;
+    neu->gb_prev[0] = s_old.gb[0];
+    neu->gb_prev[1] = s_old.gb[1];
+    neu->gb[0] = gb0;
+    neu->gb[1] = gb1;
+    neu->lrA = sc.lrA;
+    neu->lrB = sc.lrB;
+    neu->mlrA = sc.mlrA;
+    neu->mlrB = sc.mlrB;
+    neu->mask_frame = sc.mask_frame;
+    neu->mask_model = sc.mask_model;
+    neu->bc1 = sc.bc1;
+    neu->bc2 = sc.bc2;
+    neu->lse = sc.lse_new;
+    neu->kl_scale = s_old.kl_scale;
+    neu->last_dot = (float)sc.dot;
+    neu->last_lr = sc.lr;
+    neu->last_branch = sc.d;
+    neu->rec_idx = sc.step % JAXENT_RECORD_RING;
+    neu->hbar_data = s_fin[12];
+  }
+  if (lane < JAXENT_MAX_SLOTS) {
+    neu->fw[lane] = s_old.fw[lane];
+    neu->fs[lane] = s_old.fs[lane];
+  }
+  JaxentLossRecord* rec = records + (sc.step % JAXENT_RECORD_RING);
+  if (lane == 1) {
+    rec->step = sc.step;
+    rec->branch = sc.d;
+    rec->lr = sc.lr;
+    rec->grad_dot = (float)sc.dot;
+    rec->bc = sc.bc;
+    rec->bh = sc.bh;
+    rec->grad_bc = gb0;
+    rec->grad_bh = gb1;
+    rec->complete = 0;
+  }
+  if (lane < JAXENT_MAX_SLOTS) {
+    rec->train[lane] = (lane < n_slots) ? (float)s_fin[lane] : 0.f;
+    rec->val[lane] = (lane < n_slots) ? (float)s_fin[JAXENT_MAX_SLOTS + lane] : 0.f;
+  }
+  __syncwarp();
+  if (lane == 0 && s_old.kl_slot < 0) finish_record(neu, klsum, records, n_slots);
+}
+
+// per-frame MaxEnt terms of frames [cta*frames_per_cta, ...): softmax weights, dKL/dw and the KL sums of this CTA
+__device__ __forceinline__ void frame_terms(const TailArgs& a, const StepScalars& sc, const Ctl& s_old, int cur_set, long long cta,
+                                            long long /*n_frame_ctas*/, double (*s_red)[16]) {
+  const JaxentBvProblem& pb = a.prob;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const float* __restrict__ z = a.st.z[cur_set][sc.d];
+  const long long f0 = cta * a.frames_per_cta;
+  const long long f1 = (f0 + a.frames_per_cta < pb.F) ? f0 + a.frames_per_cta : pb.F;
+  const float Sf = (float)sc.S;
+  const float lse_old = sc.lse_old;
+  const bool has_kl = s_old.kl_slot >= 0 && pb.prior != nullptr;
+  const float eps = a.eps_kl;
+  const float lam = s_old.kl_scale;
+  const double inv_pnorm = __drcp_rn(pb.prior_norm);
+#pragma unroll 1
+  for (long long f = f0 + tid; f < f1; f += nt) {
+    const float w = expf(z[f] - lse_old) / Sf;  // jax.nn.softmax: exp(x - shift) / sum
+    a.w[f] = w;
+    float kap = 0.f;
+    if (has_kl) {
+      // q = (|w|+eps)/sum(|w|+eps); the denominator is 1 + F*eps = 1 + 1e-10 == 1 in fp32
+      const float q = fabsf(w) + eps;
+      const float p = (float)(((double)fabsf(pb.prior[f]) + (double)eps) * inv_pnorm);
+      // p/q and log(p/q) in fp64: differencing two fp32 logs leaves a rounding error that is
+      // identical on every frame of a uniform prior and so does not average out over F
+      const double ratio = (double)p * __drcp_rn((double)q);
+      const float G_ = (float)(1.0 - ratio);
+      kap = (w > 0.f) ? lam * G_ : 0.f;  // d|w|/dw = sign(w); softmax weights are >= 0
+      s0 += (double)w * (double)kap;
+      if (p > 0.f) s1 += (double)p * dlog(ratio);
+      s2 += (double)q - (double)p;
+    }
+    a.kappa[f] = kap;
+    s3 += (double)w;
+  }
+  s0 = wsum(s0);
+  s1 = wsum(s1);
+  s2 = wsum(s2);
+  s3 = wsum(s3);
+  __syncthreads();
+  if (lane == 0) { s_red[warp][0] = s0; s_red[warp][1] = s1; s_red[warp][2] = s2; s_red[warp][3] = s3; }
+  __syncthreads();
+  if (tid < KL_N) {
+    double t = 0.0;
+#pragma unroll 1
+    for (int w = 0; w < nw; ++w) t += s_red[w][tid];
+    if (gridDim.x == 1) a.klsum[tid] = t;  // single CTA: done
+    else a.klpart[(size_t)blockIdx.x * KL_N + tid] = t;
+  }
+}
+
+// last-arriving CTA folds the per-CTA KL sums in CTA order (deterministic)
+__device__ __forceinline__ void fold_kl_partials(const TailArgs& a, int* s_last) {
+  if (gridDim.x == 1) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < KL_N) __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(a.counter, 1u);
+    *s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (*s_last && warp < KL_N) {
+    __threadfence();
+    double t = 0.0;
+#pragma unroll 1
+    for (unsigned cc = lane; cc < gridDim.x; cc += 32) t += a.klpart[(size_t)cc * KL_N + warp];
+    t = wsum(t);
+    if (lane == 0) a.klsum[warp] = t;
+    if (tid == 0) *a.counter = 0u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ the tail
 // GENERAL = the mean-centred / sigma MSE kinds are compiled in (host picks the instantiation), so the
 // common eye-MSE / PF-L2 configuration executes the shortest possible instruction stream.
@@ -211,10 +349,6 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   const JaxentBvProblem& pb = a.prob;
   const int R = pb.R, T = pb.uptake ? pb.T : 0, Tm = T > 0 ? T : 1;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  const unsigned ep = *a.epoch;
-  const Ctl* __restrict__ old_g = a.ctl + ((ep - 1u) & 1u);
-  Ctl* __restrict__ neu = a.ctl + (ep & 1u);
-  const int cur_set = ep & 1u;
   const bool tail_cta = blockIdx.x == 0;
   const bool frame_cta = (gridDim.x == 1) || blockIdx.x > 0;
   const float invR = 1.0f / (float)R, invTm = 1.0f / (float)Tm;
@@ -232,37 +366,40 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   float* s_tp = s_k + ((R + 3) & ~3);
   int* s_blob = reinterpret_cast<int*>(s_tp + ((Tm + 3) & ~3));  // 16-byte aligned blob image
 
-  // ---- stage (one global round trip): warp 0 derives the step scalars, the rest copies
+  // ---- constant data first (peptide-map blob, rates, time points): independent of the previous kernel (PDL)
   int first_data = -1;
   if (tail_cta) {
 #pragma unroll 1
     for (int i = pb.n_slots - 1; i >= 0; --i)
       if (pb.slots[i].kind <= JAXENT_LOSS_PF_L2) first_data = i;
+    if (first_data >= 0) {
+      const int4* src = reinterpret_cast<const int4*>(a.blobs.blob[first_data]);
+      int4* dst = reinterpret_cast<int4*>(s_blob);
+      const int n4 = a.blobs.words[first_data] >> 2;
+#pragma unroll 4
+      for (int i = tid; i < n4; i += nt) dst[i] = src[i];
+    }
+    if (T > 0) {
+#pragma unroll 1
+      for (int i = tid; i < R; i += nt) s_k[i] = pb.k_ints[i];
+      if (tid < T) s_tp[tid] = pb.timepoints[tid];
+    }
   }
+  pdl_wait();               // the reduced partial sums and the previous control block are visible from here on
+  pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
+  const unsigned ep = *a.epoch;
+  const Ctl* __restrict__ old_g = a.ctl + ((ep - 1u) & 1u);
+  Ctl* __restrict__ neu = a.ctl + (ep & 1u);
+  const int cur_set = ep & 1u;
+
+  // ---- one global round trip: warp 0 derives the step scalars, another warp copies the control block
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (warp == 0) {
     derive_scalars(&s_sc, old_g, a.red, R, a.cfg);
-  } else {
-    const int t2 = tid - 32, n2 = nt - 32;
-    {
-      const int4* src = reinterpret_cast<const int4*>(old_g);
-      int4* dst = reinterpret_cast<int4*>(&s_old);
-      if (t2 < (int)(sizeof(Ctl) / 16)) dst[t2] = src[t2];
-    }
-    if (tail_cta) {
-      if (first_data >= 0) {
-        const int4* src = reinterpret_cast<const int4*>(a.blobs.blob[first_data]);
-        int4* dst = reinterpret_cast<int4*>(s_blob);
-        const int n4 = a.blobs.words[first_data] >> 2;
-#pragma unroll 4
-        for (int i = t2; i < n4; i += n2) dst[i] = src[i];
-      }
-      if (T > 0) {
-#pragma unroll 1
-        for (int i = t2; i < R; i += n2) s_k[i] = pb.k_ints[i];
-        if (t2 < T) s_tp[t2] = pb.timepoints[t2];
-      }
-    }
+  } else if (warp == 1) {
+    const int4* src = reinterpret_cast<const int4*>(old_g);
+    int4* dst = reinterpret_cast<int4*>(&s_old);
+    if (lane < (int)(sizeof(Ctl) / 16)) dst[lane] = src[lane];
   }
   if (tail_cta) {
     if (tid < R) {
@@ -509,67 +646,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     }
     __syncthreads();  // (6)
 
-    if (tid < 32) {
-      // the new control block and the loss record, written by one warp
-      const StepScalars& sc = s_sc;
-      const float gb0 = (float)(s_fin[13] + gbc_reg) * sc.mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * sc.mask_model;
-      if (lane == 0) {
-        neu->step = sc.step;
-        neu->mask_idx = sc.mask_idx;
-        neu->branch = sc.d;
-        neu->pending = 1;
-        neu->have_prev = sc.have_prev;
-        neu->count_frame = sc.cf;
-        neu->count_model = sc.cm;
-        neu->kl_slot = s_old.kl_slot;
-        neu->lr = sc.lr;
-        neu->model_lr = sc.mlr;
-        neu->bc = sc.bc;
-        neu->bh = sc.bh;
-        neu->mb[0] = sc.mb0; neu->mb[1] = sc.mb1; neu->vb[0] = sc.vb0; neu->vb[1] = sc.vb1;
-        neu->gb_prev[0] = s_old.gb[0];
-        neu->gb_prev[1] = s_old.gb[1];
-        neu->gb[0] = gb0;
-        neu->gb[1] = gb1;
-        neu->lrA = sc.lrA;
-        neu->lrB = sc.lrB;
-        neu->mlrA = sc.mlrA;
-        neu->mlrB = sc.mlrB;
-        neu->mask_frame = sc.mask_frame;
-        neu->mask_model = sc.mask_model;
-        neu->bc1 = sc.bc1;
-        neu->bc2 = sc.bc2;
-        neu->lse = sc.lse_new;
-        neu->kl_scale = s_old.kl_scale;
-        neu->last_dot = (float)sc.dot;
-        neu->last_lr = sc.lr;
-        neu->last_branch = sc.d;
-        neu->rec_idx = sc.step % JAXENT_RECORD_RING;
-        neu->hbar_data = s_fin[12];
-      }
-      if (lane < JAXENT_MAX_SLOTS) {
-        neu->fw[lane] = s_old.fw[lane];
-        neu->fs[lane] = s_old.fs[lane];
-      }
-      JaxentLossRecord* rec = a.records + (sc.step % JAXENT_RECORD_RING);
-      if (lane == 1) {
-        rec->step = sc.step;
-        rec->branch = sc.d;
-        rec->lr = sc.lr;
-        rec->grad_dot = (float)sc.dot;
-        rec->bc = sc.bc;
-        rec->bh = sc.bh;
-        rec->grad_bc = gb0;
-        rec->grad_bh = gb1;
-        rec->complete = 0;
-      }
-      if (lane < JAXENT_MAX_SLOTS) {
-        rec->train[lane] = (lane < pb.n_slots) ? (float)s_fin[lane] : 0.f;
-        rec->val[lane] = (lane < pb.n_slots) ? (float)s_fin[JAXENT_MAX_SLOTS + lane] : 0.f;
-      }
-      __syncwarp();
-      if (lane == 0 && s_old.kl_slot < 0) finish_record(neu, a.klsum, a.records, pb.n_slots);
-    }
+    if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, a.klsum, lane);
   }
 
   // ================================================================== per-frame MaxEnt terms
@@ -577,71 +654,52 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     // CTA 0 of a multi-CTA grid holds no frames: contribute zeros and take a ticket
     if (tid < KL_N) a.klpart[tid] = 0.0;
   } else {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const float* __restrict__ z = a.st.z[cur_set][d];
-    const long long cta = (gridDim.x == 1) ? 0 : blockIdx.x - 1;
-    const long long f0 = cta * a.frames_per_cta;
-    const long long f1 = (f0 + a.frames_per_cta < pb.F) ? f0 + a.frames_per_cta : pb.F;
-    const float Sf = (float)S;
-    const float lse_old = s_sc.lse_old;
-    const bool has_kl = s_old.kl_slot >= 0 && pb.prior != nullptr;
-    const float eps = a.eps_kl;
-    const float lam = s_old.kl_scale;
-    const double inv_pnorm = __drcp_rn(pb.prior_norm);
-#pragma unroll 1
-    for (long long f = f0 + tid; f < f1; f += nt) {
-      const float w = expf(z[f] - lse_old) / Sf;  // jax.nn.softmax: exp(x - shift) / sum
-      a.w[f] = w;
-      float kap = 0.f;
-      if (has_kl) {
-        // q = (|w|+eps)/sum(|w|+eps); the denominator is 1 + F*eps = 1 + 1e-10 == 1 in fp32
-        const float q = fabsf(w) + eps;
-        const float p = (float)(((double)fabsf(pb.prior[f]) + (double)eps) * inv_pnorm);
-        // p/q and log(p/q) in fp64: differencing two fp32 logs leaves a rounding error that is
-        // identical on every frame of a uniform prior and so does not average out over F
-        const double ratio = (double)p * __drcp_rn((double)q);
-        const float G_ = (float)(1.0 - ratio);
-        kap = (w > 0.f) ? lam * G_ : 0.f;  // d|w|/dw = sign(w); softmax weights are >= 0
-        s0 += (double)w * (double)kap;
-        if (p > 0.f) s1 += (double)p * dlog(ratio);
-        s2 += (double)q - (double)p;
-      }
-      a.kappa[f] = kap;
-      s3 += (double)w;
-    }
-    s0 = wsum(s0);
-    s1 = wsum(s1);
-    s2 = wsum(s2);
-    s3 = wsum(s3);
-    __syncthreads();
-    if (lane == 0) { s_red[warp][0] = s0; s_red[warp][1] = s1; s_red[warp][2] = s2; s_red[warp][3] = s3; }
-    __syncthreads();
-    if (tid < KL_N) {
-      double t = 0.0;
-#pragma unroll 1
-      for (int w = 0; w < nw; ++w) t += s_red[w][tid];
-      if (gridDim.x == 1) a.klsum[tid] = t;  // single CTA: done
-      else a.klpart[(size_t)blockIdx.x * KL_N + tid] = t;
-    }
+    frame_terms(a, s_sc, s_old, cur_set, (gridDim.x == 1) ? 0 : (long long)blockIdx.x - 1, 0, s_red);
   }
-  if (gridDim.x == 1) return;
-  // last-arriving CTA folds the per-CTA sums in a fixed order (deterministic)
-  if (tid < KL_N) __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned ticket = atomicAdd(a.counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
+  fold_kl_partials(a, &s_last);
+}
+
+#include "bv_tail_cluster.cuh"
+
+size_t tail_cluster_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va) {
+  const size_t Tm = T > 0 ? T : 1;
+  const size_t nrs = (size_t)R / TAILC + 1;
+  const size_t dbl = 2 * nrs + Tm * nrs + Tm * (size_t)R + (size_t)p_tr * Tm;
+  const size_t f32 = (((size_t)R + 3) & ~(size_t)3) + ((Tm + 3) & ~(size_t)3);
+  const BlobLayout b = blob_layout(R, (int)Tm, p_tr, nnz_tr, p_va, nnz_va);
+  return dbl * 8 + f32 * 4 + (size_t)b.words * 4 + 64;
+}
+
+size_t tail_cluster_scratch_doubles(int R, int T, int p_tr) {
+  const size_t Tm = T > 0 ? T : 1;
+  return Tm * (size_t)R + (size_t)R + (size_t)p_tr * Tm + (size_t)TAILC * 16;
+}
+
+int launch_tail_cluster(const TailArgs& a, int ctas, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(bv_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("clustered tail kernel needs %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return JAXENT_E_UNSUPPORTED; }
+    configured = smem;
   }
-  __syncthreads();
-  if (s_last && warp < KL_N) {
-    __threadfence();
-    double t = 0.0;
-#pragma unroll 1
-    for (unsigned cc = lane; cc < gridDim.x; cc += 32) t += a.klpart[(size_t)cc * KL_N + warp];
-    t = wsum(t);
-    if (lane == 0) a.klsum[warp] = t;
-    if (tid == 0) *a.counter = 0u;
-  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(TAIL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = TAILC;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, bv_tail_cluster_kernel, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("bv_tail_cluster_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
 }
 
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va) {
@@ -667,9 +725,9 @@ int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s) {
     if (e != cudaSuccess) { set_error("tail kernel needs %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return JAXENT_E_UNSUPPORTED; }
     configured[general] = smem;
   }
-  if (general) bv_tail_kernel<true><<<ctas, TAIL_THREADS, smem, s>>>(a);
-  else bv_tail_kernel<false><<<ctas, TAIL_THREADS, smem, s>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = general ? launch_pdl(bv_tail_kernel<true>, ctas, TAIL_THREADS, smem, s, a)
+                          : launch_pdl(bv_tail_kernel<false>, ctas, TAIL_THREADS, smem, s, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bv_tail_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;
 }

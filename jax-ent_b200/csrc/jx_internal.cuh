@@ -109,12 +109,34 @@ struct TailArgs {
   double* klsum;
   JaxentLossRecord* records;
   BlobSet blobs;
+  double* cl_scratch;  // L2 exchange buffer of the clustered tail (tail_cluster_scratch_doubles())
   int p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
   long long frames_per_cta;  // frames handled by each per-frame CTA of the tail kernel
   float eps_kl;   // 1e-10 / F_total
 };
 
 void set_error(const char* fmt, ...);
+
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its
+// predecessor in the stream is still draining; everything before pdl_wait() must only touch data the
+// predecessor does not write (features, constants, shared memory).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename Kernel, typename Args>
+inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t s, const Args& args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args);
+}
 
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s);
 int launch_reduce(const ReduceArgs& a, cudaStream_t s);
@@ -123,6 +145,10 @@ int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const double* kl
                          cudaStream_t s);
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va);
 int blob_words(int R, int T, int p_tr, int nnz_tr, int p_va, int nnz_va);
+size_t tail_cluster_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va);
+size_t tail_cluster_scratch_doubles(int R, int T, int p_tr);
+int launch_tail_cluster(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
+constexpr int TAIL_CLUSTER = 8;
 int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_t s);
 int configure_kernels();
 
