@@ -121,6 +121,32 @@ typedef struct {
   int32_t pad;
 } JaxentLossRecord;
 
+/* One history snapshot of the on-device loop: what OptimizationHistory.add_state(save_state) keeps
+ * (opt/run.py:318-348), minus the frame-sized arrays, which live in the caller's snapshot buffers. */
+typedef struct {
+  int32_t loop_step;   /* loop index k of the step that met the threshold (0 for the initial snapshot) */
+  int32_t state_step;  /* save_state.step = k + 1 */
+  int32_t have_ema;    /* EMA parameters exist (tracker.ema_params is not None) */
+  int32_t threshold_idx;
+  float bc, bh;        /* BV parameters of the saved state */
+  float ema_bc, ema_bh;
+  JaxentLossRecord losses; /* LossComponents of the saved state (evaluated at step k) */
+} JaxentTrackSnapshot;
+
+/* status of the on-device loop */
+typedef struct {
+  int32_t stop;        /* 1 once the loop has ended; further step launches are no-ops */
+  int32_t reason;      /* 1 all relative thresholds completed, 2 tolerance reached or non-finite loss */
+  int32_t stop_step;   /* loop index of the step that ended the loop */
+  int32_t n_snapshots;
+  int32_t steps_done;  /* state.step: optimiser updates applied */
+  int32_t threshold_idx;
+  float last_loss;
+  float ema_loss_delta;
+} JaxentTrackStatus;
+
+#define JAXENT_TRACK_MAX_THRESHOLDS 8
+
 typedef struct JaxentPlan JaxentPlan; /* opaque, host memory */
 
 /* identifiers for jaxent_bv_plan_buffer() */
@@ -186,6 +212,17 @@ int jaxent_bv_finish_record(JaxentPlan* plan, jaxent_stream_t stream);
 /* single-rank conveniences: init = pass(0)+reduce+tail ; step = pass(1)+reduce+tail */
 int jaxent_bv_forward_init(JaxentPlan* plan, jaxent_stream_t stream);
 int jaxent_bv_step(JaxentPlan* plan, jaxent_stream_t stream);
+
+/* ---- on-device optimise loop (replaces the host-synchronising loop of _optimise, opt/run.py:235-373) ----
+ * Call before jaxent_bv_state_init.  thresholds: n (<= 8) relative-convergence thresholds, descending and already
+ * multiplied by the learning rate (create_convergence_thresholds, opt/track.py:12-21).  ema_w: float[F];
+ * snap_w, snap_ema: float[(n+1)*F]; snaps: JaxentTrackSnapshot[n+1] -- all caller-owned device memory.
+ * Every tail launch then updates the ConvergenceTracker state, the EMA parameters, takes the history snapshots
+ * and raises the stop flag exactly where the reference loop would `break`. */
+int jaxent_bv_track_init(JaxentPlan* plan, const float* thresholds, int32_t n, float ema_alpha, int32_t min_steps_per_threshold,
+                         float tolerance, float* ema_w, float* snap_w, float* snap_ema, JaxentTrackSnapshot* snaps);
+/* writes a JaxentTrackStatus to `status` (device memory) */
+int jaxent_bv_track_status(JaxentPlan* plan, JaxentTrackStatus* status, jaxent_stream_t stream);
 
 /* copy the current optimiser state (chosen plateau branch) to caller buffers; any pointer may be NULL.
  * z/m/v: float[F] logits and Adam moments; g: float[F] masked d loss / d z of the last completed update;

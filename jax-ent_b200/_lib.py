@@ -105,6 +105,35 @@ class LossRecord(C.Structure):
     ]
 
 
+class TrackSnapshot(C.Structure):
+    _fields_ = [
+        ("loop_step", C.c_int32),
+        ("state_step", C.c_int32),
+        ("have_ema", C.c_int32),
+        ("threshold_idx", C.c_int32),
+        ("bc", C.c_float),
+        ("bh", C.c_float),
+        ("ema_bc", C.c_float),
+        ("ema_bh", C.c_float),
+        ("losses", LossRecord),
+    ]
+
+
+class TrackStatus(C.Structure):
+    _fields_ = [
+        ("stop", C.c_int32),
+        ("reason", C.c_int32),
+        ("stop_step", C.c_int32),
+        ("n_snapshots", C.c_int32),
+        ("steps_done", C.c_int32),
+        ("threshold_idx", C.c_int32),
+        ("last_loss", C.c_float),
+        ("ema_loss_delta", C.c_float),
+    ]
+
+
+TRACK_MAX_THRESHOLDS = 8
+
 # every symbol include/jaxent_b200.h declares: name -> (restype, argtypes)
 _VP, _I32, _I64, _SZ, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
 SYMBOLS = {
@@ -126,6 +155,8 @@ SYMBOLS = {
     "jaxent_bv_finish_record": (C.c_int, [_VP, _VP]),
     "jaxent_bv_forward_init": (C.c_int, [_VP, _VP]),
     "jaxent_bv_step": (C.c_int, [_VP, _VP]),
+    "jaxent_bv_track_init": (C.c_int, [_VP, C.POINTER(_F), _I32, _F, _I32, _F, _VP, _VP, _VP, _VP]),
+    "jaxent_bv_track_status": (C.c_int, [_VP, _VP, _VP]),
     "jaxent_bv_export_state": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
 }
 

@@ -134,6 +134,18 @@ __global__ void export_kernel(StateSets st, const Ctl* ctl, const unsigned* epoc
   }
 }
 
+__global__ void track_status_kernel(const Ctl* ctl, const unsigned* epoch, const JaxentLossRecord* records, JaxentTrackStatus* out) {
+  const Ctl* c = ctl + (*epoch & 1u);
+  out->stop = c->trk_stop;
+  out->reason = c->trk_reason;
+  out->stop_step = c->trk_stop_step;
+  out->n_snapshots = c->trk_nsnap;
+  out->steps_done = c->step;
+  out->threshold_idx = c->trk_idx;
+  out->last_loss = (float)c->trk_prev_loss;
+  out->ema_loss_delta = (float)c->trk_ema;
+}
+
 }  // namespace jx
 
 struct JaxentPlan {
@@ -147,6 +159,7 @@ struct JaxentPlan {
   size_t pass_smem, tail_smem;
   long long n_tiles;
   int initialised;
+  jx::TrackConfig trk;
 };
 
 using namespace jx;
@@ -223,6 +236,8 @@ extern "C" int jaxent_abi_sizeof(int which) {
     case 2: return (int)sizeof(JaxentLossRecord);
     case 3: return (int)sizeof(JaxentLossSlot);
     case 4: return (int)sizeof(JaxentPeptideMap);
+    case 5: return (int)sizeof(JaxentTrackSnapshot);
+    case 6: return (int)sizeof(JaxentTrackStatus);
     default: return -1;
   }
 }
@@ -334,6 +349,7 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
     p->tail_ctas = (fc <= TAIL_CLUSTER) ? TAIL_CLUSTER : TAIL_CLUSTER + (int)fc;
   }
   p->initialised = 0;
+  memset(&p->trk, 0, sizeof(p->trk));
   *out = p;
   return JAXENT_OK;
 }
@@ -443,6 +459,7 @@ extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t stream) {
   int rc = check_ready(p, "reduce");
   if (rc) return rc;
   ReduceArgs a;
+  a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
   a.partials = reinterpret_cast<const double*>(p->ws + p->lay.off_partials);
   a.red = reinterpret_cast<double*>(p->ws + p->lay.off_red);
   a.epoch = reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch);
@@ -457,6 +474,7 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   TailArgs a;
   memset(&a, 0, sizeof(a));
   a.prob = p->prob;
+  a.trk = p->trk;
   a.cfg = p->cfg;
   a.st = p->st;
   a.red = reinterpret_cast<const double*>(p->ws + p->lay.off_red);
@@ -516,6 +534,46 @@ extern "C" int jaxent_bv_step(JaxentPlan* p, jaxent_stream_t stream) {
   rc = jaxent_bv_reduce(p, stream);
   if (rc) return rc;
   return jaxent_bv_tail(p, stream);
+}
+
+extern "C" int jaxent_bv_track_init(JaxentPlan* p, const float* thresholds, int32_t n, float ema_alpha, int32_t min_steps,
+                                    float tolerance, float* ema_w, float* snap_w, float* snap_ema, JaxentTrackSnapshot* snaps) {
+  if (!p) { set_error("track_init: plan is NULL"); return JAXENT_E_INVALID; }
+  if (!thresholds || n < 1 || n > TRK_MAX_THR || !ema_w || !snap_w || !snap_ema || !snaps) {
+    set_error("track_init: need 1..%d thresholds and the EMA / snapshot buffers", TRK_MAX_THR);
+    return JAXENT_E_INVALID;
+  }
+  if (!(ema_alpha >= 0.f && ema_alpha <= 1.f) || min_steps < 0) { set_error("track_init: invalid ema_alpha / min_steps"); return JAXENT_E_INVALID; }
+  for (int i = 1; i < n; ++i)
+    if (thresholds[i] > thresholds[i - 1]) { set_error("track_init: thresholds must be in descending order"); return JAXENT_E_INVALID; }
+  TrackConfig t;
+  memset(&t, 0, sizeof(t));
+  t.on = 1;
+  t.n_thr = n;
+  t.min_steps = min_steps;
+  t.initial_steps = p->cfg.initial_steps;
+  for (int i = 0; i < n; ++i) t.thr[i] = thresholds[i];
+  t.ema_alpha = ema_alpha;
+  t.tolerance = tolerance;
+  t.ema_w = ema_w;
+  t.snap_w = snap_w;
+  t.snap_ema = snap_ema;
+  t.snaps = snaps;
+  p->trk = t;
+  p->initialised = 0;  // the tracker state lives in the control block: state_init must follow
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bv_track_status(JaxentPlan* p, JaxentTrackStatus* status, jaxent_stream_t stream) {
+  int rc = check_ready(p, "track_status");
+  if (rc) return rc;
+  if (!status) { set_error("track_status: NULL output"); return JAXENT_E_INVALID; }
+  track_status_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl),
+                                                         reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch),
+                                                         reinterpret_cast<const JaxentLossRecord*>(p->ws + p->lay.off_records), status);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("track_status launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
 }
 
 extern "C" int jaxent_bv_export_state(JaxentPlan* p, float* z, float* m, float* v, float* g, float* scalars,

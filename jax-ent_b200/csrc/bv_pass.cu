@@ -272,9 +272,18 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
   pdl_wait();               // everything the tail kernel wrote (ctl, cc/ch, w, kappa, klsum) is visible from here on
   pdl_launch_dependents();  // lets the reduce kernel's launch overlap this kernel
 
+  const unsigned ep = *a.epoch;
+  if (a.ctl[ep & 1u].trk_stop) {
+    // the on-device loop has ended: drain the prefetched tiles and leave everything untouched
+    if (is_adam && lane == 0) {
+      const int pre = n < a.stages ? n : a.stages;
+      for (int s = 0; s < pre; ++s) mbar_wait(smem_u32(&bars[s]), 0);
+    }
+    return;
+  }
+
   if (is_adam) {
     // ================================================================== Adam warp
-    const unsigned ep = *a.epoch;
     const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
     if (lane == 0 && blockIdx.x == 0 && mode == 1) finish_record(ctl, a.klsum, a.records, JAXENT_MAX_SLOTS);
     const int in_set = ep & 1u, out_set = in_set ^ 1;
@@ -483,6 +492,7 @@ __global__ void __launch_bounds__(1024) reduce_kernel(const ReduceArgs a) {
   __shared__ double sh[32][33];
   pdl_wait();
   pdl_launch_dependents();
+  if (a.ctl[*a.epoch & 1u].trk_stop) return;  // on-device loop ended: keep red and the epoch as they are
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
   double s = 0.0;

@@ -44,13 +44,21 @@ struct StepScalars {
   float lr, mlr, bc, bh, mb0, mb1, vb0, vb1;
   float lrA, lrB, mlrA, mlrB, mask_frame, mask_model, bc1, bc2, lse_new, lse_old;
   double S, dot;
+  // on-device loop (ConvergenceTracker state after this step + what this launch has to do)
+  int trk_stop, trk_reason, trk_stop_step, trk_have_prev, trk_have_ema, trk_steps_since, trk_idx, trk_nsnap;
+  int snap_now;             // snapshot slot to fill in this launch, or -1
+  int ema_update, ema_first; // update the EMA parameters in this launch / first EMA value
+  int loop_step;            // loop index k of the step being resolved
+  float trk_ema_bc, trk_ema_bh;
+  double trk_prev_loss, trk_ema;
 };
 
 // warp 0 only.  Reads the previous control block straight from global memory (one round trip that
 // overlaps the staging done by the other warps); the four powf and two log evaluations run on
 // separate lanes behind single call sites.
 __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restrict__ old, const double* __restrict__ red,
-                                            int R, const JaxentOptConfig cfg) {
+                                            int R, const JaxentOptConfig cfg, const TrackConfig trk,
+                                            const JaxentLossRecord* __restrict__ records) {
   const int lane = threadIdx.x & 31;
   StepScalars s;
   const double SA = red[4 * R + 0], SB = red[4 * R + 1], gdot = red[4 * R + 2];
@@ -130,6 +138,69 @@ __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restr
   s.bc1 = 1.0f - pw2;
   s.bc2 = 1.0f - pw3;
   s.lse_new = (float)((double)s.lse_old + (s.d ? lgB : lgA));
+
+  // ---- ConvergenceTracker for loop step k = old->step (reference opt/run.py:285-348, opt/track.py:150-197)
+  s.trk_stop = old->trk_stop;
+  s.trk_reason = old->trk_reason;
+  s.trk_stop_step = old->trk_stop_step;
+  s.trk_have_prev = old->trk_have_prev;
+  s.trk_have_ema = old->trk_have_ema;
+  s.trk_steps_since = old->trk_steps_since;
+  s.trk_idx = old->trk_idx;
+  s.trk_nsnap = old->trk_nsnap;
+  s.trk_prev_loss = old->trk_prev_loss;
+  s.trk_ema = old->trk_ema;
+  s.trk_ema_bc = old->trk_ema_bc;
+  s.trk_ema_bh = old->trk_ema_bh;
+  s.snap_now = -1;
+  s.ema_update = 0;
+  s.ema_first = 0;
+  s.loop_step = old->step;
+  if (trk.on && s.pending && !s.trk_stop) {
+    const int k = old->step;
+    const double loss = (double)records[k % JAXENT_RECORD_RING].total_train;
+    const double alpha = (double)trk.ema_alpha;
+    if (s.trk_have_prev) {  // tracker.update
+      const double raw = fabs(s.trk_prev_loss - loss);
+      if (!s.trk_have_ema) {
+        s.trk_ema = raw;
+        s.trk_have_ema = 1;
+        s.ema_first = 1;
+      } else {
+        s.trk_ema = alpha * raw + (1.0 - alpha) * s.trk_ema;
+      }
+      s.ema_update = 1;
+      s.trk_ema_bc = s.ema_first ? s.bc : (float)(alpha * (double)s.bc + (1.0 - alpha) * (double)s.trk_ema_bc);
+      s.trk_ema_bh = s.ema_first ? s.bh : (float)(alpha * (double)s.bh + (1.0 - alpha) * (double)s.trk_ema_bh);
+    }
+    s.trk_steps_since += 1;
+    s.trk_prev_loss = loss;
+    s.trk_have_prev = 1;
+    const double gd = (k > 0) ? s.dot : 0.0;  // check_gradient_oscillation: zeros before the first step
+    if (gd < 0.0) s.trk_steps_since = 0;
+    if (loss < (double)trk.tolerance || isnan(loss) || isinf(loss)) {
+      s.trk_stop = 1;
+      s.trk_reason = 2;
+      s.trk_stop_step = k;
+    } else {
+      const double rel = (s.trk_have_ema && loss > 0.0) ? s.trk_ema / loss : 0.0;
+      const int ti = s.trk_idx < trk.n_thr ? s.trk_idx : trk.n_thr - 1;
+      const bool met = s.trk_steps_since >= trk.min_steps && s.trk_have_ema && rel < (double)trk.thr[ti] && k > trk.initial_steps;
+      if (k == 0 || met) {
+        s.snap_now = s.trk_nsnap;
+        s.trk_nsnap += 1;
+        if (k > 0) {
+          s.trk_idx += 1;
+          s.trk_steps_since = 0;
+          if (s.trk_idx >= trk.n_thr) {
+            s.trk_stop = 1;
+            s.trk_reason = 1;
+            s.trk_stop_step = k;
+          }
+        }
+      }
+    }
+  }
   *out = s;
 }
 
@@ -200,7 +271,33 @@ int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_
 // the new control block and the loss record, written by one warp (lane 0 the scalars, lanes 0..5 the slots)
 __device__ __forceinline__ void write_ctl_and_record(Ctl* __restrict__ neu, JaxentLossRecord* records, const StepScalars& sc,
                                                      const Ctl& s_old, const double* s_fin, double gbc_reg, double gbh_reg,
-                                                     int n_slots, const double* klsum, int lane) {
+                                                     int n_slots, const double* klsum, int lane, const TrackConfig& trk) {
+  if (lane == 2) {
+    neu->trk_stop = sc.trk_stop;
+    neu->trk_reason = sc.trk_reason;
+    neu->trk_stop_step = sc.trk_stop_step;
+    neu->trk_have_prev = sc.trk_have_prev;
+    neu->trk_have_ema = sc.trk_have_ema;
+    neu->trk_steps_since = sc.trk_steps_since;
+    neu->trk_idx = sc.trk_idx;
+    neu->trk_nsnap = sc.trk_nsnap;
+    neu->trk_ema_bc = sc.trk_ema_bc;
+    neu->trk_ema_bh = sc.trk_ema_bh;
+    neu->trk_prev_loss = sc.trk_prev_loss;
+    neu->trk_ema = sc.trk_ema;
+    if (sc.snap_now >= 0 && trk.snaps != nullptr) {
+      JaxentTrackSnapshot* sn = trk.snaps + sc.snap_now;
+      sn->loop_step = sc.loop_step;
+      sn->state_step = sc.step;
+      sn->have_ema = sc.trk_have_ema;
+      sn->threshold_idx = sc.trk_idx;
+      sn->bc = sc.bc;
+      sn->bh = sc.bh;
+      sn->ema_bc = sc.trk_ema_bc;
+      sn->ema_bh = sc.trk_ema_bh;
+      sn->losses = records[sc.loop_step % JAXENT_RECORD_RING];
+    }
+  }
   const float gb0 = (float)(s_fin[13] + gbc_reg) * sc.mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * sc.mask_model;
   if (lane == 0) {
     neu->step = sc.step;
@@ -275,6 +372,7 @@ __device__ __forceinline__ void frame_terms(const TailArgs& a, const StepScalars
   const float eps = a.eps_kl;
   const float lam = s_old.kl_scale;
   const double inv_pnorm = __drcp_rn(pb.prior_norm);
+  const float trk_alpha = a.trk.ema_alpha;
 #pragma unroll 1
   for (long long f = f0 + tid; f < f1; f += nt) {
     const float w = expf(z[f] - lse_old) / Sf;  // jax.nn.softmax: exp(x - shift) / sum
@@ -295,6 +393,12 @@ __device__ __forceinline__ void frame_terms(const TailArgs& a, const StepScalars
     }
     a.kappa[f] = kap;
     s3 += (double)w;
+    if (sc.ema_update) {  // tracker.ema_params (opt/track.py:160-165): EMA of the normalised weights
+      const float e = sc.ema_first ? w : trk_alpha * w + (1.0f - trk_alpha) * a.trk.ema_w[f];
+      a.trk.ema_w[f] = e;
+      if (sc.snap_now >= 0) a.trk.snap_ema[(size_t)sc.snap_now * pb.F + f] = e;
+    }
+    if (sc.snap_now >= 0) a.trk.snap_w[(size_t)sc.snap_now * pb.F + f] = w;
   }
   s0 = wsum(s0);
   s1 = wsum(s1);
@@ -388,6 +492,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   pdl_wait();               // the reduced partial sums and the previous control block are visible from here on
   pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
   const unsigned ep = *a.epoch;
+  if (a.ctl[ep & 1u].trk_stop) return;  // the on-device loop has ended (reduce did not advance the epoch): no-op
   const Ctl* __restrict__ old_g = a.ctl + ((ep - 1u) & 1u);
   Ctl* __restrict__ neu = a.ctl + (ep & 1u);
   const int cur_set = ep & 1u;
@@ -395,7 +500,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   // ---- one global round trip: warp 0 derives the step scalars, another warp copies the control block
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (warp == 0) {
-    derive_scalars(&s_sc, old_g, a.red, R, a.cfg);
+    derive_scalars(&s_sc, old_g, a.red, R, a.cfg, a.trk, a.records);
   } else if (warp == 1) {
     const int4* src = reinterpret_cast<const int4*>(old_g);
     int4* dst = reinterpret_cast<int4*>(&s_old);
@@ -646,7 +751,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     }
     __syncthreads();  // (6)
 
-    if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, a.klsum, lane);
+    if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, a.klsum, lane, a.trk);
   }
 
   // ================================================================== per-frame MaxEnt terms

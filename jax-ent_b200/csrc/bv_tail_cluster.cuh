@@ -77,13 +77,14 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_cluster_kernel(const 
   pdl_wait();
   pdl_launch_dependents();
   const unsigned ep = *a.epoch;
+  if (a.ctl[ep & 1u].trk_stop) return;  // the on-device loop has ended: no-op (cluster-uniform)
   const Ctl* __restrict__ old_g = a.ctl + ((ep - 1u) & 1u);
   Ctl* __restrict__ neu = a.ctl + (ep & 1u);
   const int cur_set = ep & 1u;
 
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (warp == 0) {
-    derive_scalars(&s_sc, old_g, a.red, R, a.cfg);
+    derive_scalars(&s_sc, old_g, a.red, R, a.cfg, a.trk, a.records);
   } else if (warp == 1) {
     const int4* src = reinterpret_cast<const int4*>(old_g);
     int4* dst = reinterpret_cast<int4*>(&s_old);
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_cluster_kernel(const 
         s_fin[tid] = t;
       }
       __syncthreads();
-      if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, a.klsum, lane);
+      if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, a.klsum, lane, a.trk);
     }
   }
 

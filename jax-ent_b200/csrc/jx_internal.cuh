@@ -40,6 +40,15 @@ struct alignas(16) Ctl {
   int rec_idx;                 // ring index of this step's loss record
   double hbar_data;            // sum_r c_r * log_Pf_r  (= sum_j w_j h_j, data part)
   float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
+  // ---- on-device convergence tracking (reference opt/run.py:272-348, opt/track.py:128-197)
+  int trk_stop;                // 1: the loop has ended; pass / reduce / tail launches become no-ops
+  int trk_reason;              // 1 all thresholds completed, 2 tolerance reached / non-finite loss
+  int trk_stop_step;           // loop index of the step that ended the loop
+  int trk_have_prev, trk_have_ema;
+  int trk_steps_since, trk_idx, trk_nsnap;
+  float trk_ema_bc, trk_ema_bh;
+  int trk_pad[2];
+  double trk_prev_loss, trk_ema;
 };
 static_assert(sizeof(Ctl) % 16 == 0, "Ctl is staged to shared memory with 16-byte vector copies");
 
@@ -83,6 +92,7 @@ struct PassArgs {
 };
 
 struct ReduceArgs {
+  const Ctl* ctl;
   const double* partials;
   double* red;
   unsigned* epoch;
@@ -90,8 +100,25 @@ struct ReduceArgs {
   int part_n;
 };
 
+constexpr int TRK_MAX_THR = 8;
+// static configuration of the on-device loop (jaxent_bv_track_init)
+struct TrackConfig {
+  int on;
+  int n_thr;
+  int min_steps;
+  int initial_steps;
+  float thr[TRK_MAX_THR];     // descending, already multiplied by the learning rate (opt/track.py:12-21)
+  float ema_alpha;
+  float tolerance;
+  float* ema_w;               // [F] EMA of the softmax weights
+  float* snap_w;              // [n_thr + 1][F] snapshots of the softmax weights
+  float* snap_ema;            // [n_thr + 1][F] snapshots of the EMA weights
+  JaxentTrackSnapshot* snaps; // [n_thr + 1]
+};
+
 struct TailArgs {
   JaxentBvProblem prob;   // by value: device pointers + dims
+  TrackConfig trk;
   JaxentOptConfig cfg;
   StateSets st;
   const double* red;

@@ -372,3 +372,59 @@ class BvEngine:
     def algorithmic_bytes_per_step(self) -> int:
         """8*R*F (features once) + 28*F (z,m,v,prior read; z,m,v written)."""
         return 8 * self.R * self.F + 28 * self.F
+
+    # ------------------------------------------------------------------ on-device loop (SURVEY.md 8f.1)
+    def enable_tracking(self, convergence, learning_rate: float, ema_alpha: float = 0.5, min_steps_per_threshold: int = 2,
+                        tolerance: float = 1e-10) -> None:
+        """Arm the on-device ConvergenceTracker (reference opt/track.py:128-197, opt/run.py:272-348).  Must be
+        called before init_state().  Thresholds are sorted descending and scaled by the learning rate exactly
+        like create_convergence_thresholds (opt/track.py:12-21)."""
+        thr = np.sort(np.atleast_1d(np.asarray(convergence, np.float32)))[::-1] * np.float32(learning_rate)
+        n = int(thr.shape[0])
+        if n < 1 or n > L.TRACK_MAX_THRESHOLDS:
+            raise ValueError(f"between 1 and {L.TRACK_MAX_THRESHOLDS} convergence thresholds are supported on the device")
+        with torch.cuda.device(self.device):
+            self._trk_ema = torch.zeros(self.F, dtype=torch.float32, device=self.device)
+            self._trk_snap_w = torch.zeros((n + 1, self.F), dtype=torch.float32, device=self.device)
+            self._trk_snap_ema = torch.zeros((n + 1, self.F), dtype=torch.float32, device=self.device)
+            self._trk_snaps = torch.zeros((n + 1) * C.sizeof(L.TrackSnapshot), dtype=torch.uint8, device=self.device)
+            self._trk_status = torch.zeros(C.sizeof(L.TrackStatus), dtype=torch.uint8, device=self.device)
+        arr = (C.c_float * n)(*[float(t) for t in thr])
+        L.check(self.lib.jaxent_bv_track_init(self.plan, arr, n, float(ema_alpha), int(min_steps_per_threshold), float(tolerance),
+                                              self._trk_ema.data_ptr(), self._trk_snap_w.data_ptr(), self._trk_snap_ema.data_ptr(),
+                                              self._trk_snaps.data_ptr()))
+        self._trk_n = n
+        self.tracking = True
+
+    def track_status(self) -> "L.TrackStatus":
+        """Device -> host read of the loop status (the only host synchronisation of the on-device loop)."""
+        with torch.cuda.device(self.device):
+            L.check(self.lib.jaxent_bv_track_status(self.plan, self._trk_status.data_ptr(), _stream_ptr()))
+            return L.TrackStatus.from_buffer_copy(self._trk_status.cpu().numpy().tobytes())
+
+    def track_snapshots(self, n: int):
+        """[(TrackSnapshot, weights[F] view, ema_weights[F] view or None)] for the first n snapshots."""
+        sz = C.sizeof(L.TrackSnapshot)
+        host = self._trk_snaps.cpu().numpy()
+        out = []
+        for i in range(n):
+            sn = L.TrackSnapshot.from_buffer_copy(host[i * sz : (i + 1) * sz].tobytes())
+            out.append((sn, self._trk_snap_w[i], self._trk_snap_ema[i] if sn.have_ema else None))
+        return out
+
+    def run(self, n_steps: int, chunk: int = 32):
+        """Up to n_steps optimise steps with the stop decision taken on the device; the host only looks at
+        the status every `chunk` steps (kernels launched after the stop are no-ops).  Returns TrackStatus."""
+        if not getattr(self, "tracking", False):
+            raise RuntimeError("enable_tracking() has not been called")
+        done = 0
+        st = None
+        while done < n_steps:
+            m = min(chunk, n_steps - done)
+            self.step(m)
+            done += m
+            st = self.track_status()
+            if st.stop:
+                break
+        self.finish_record()
+        return st if st is not None else self.track_status()

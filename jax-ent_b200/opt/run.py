@@ -105,3 +105,55 @@ def run_optimise(simulation: Simulation, data_to_fit: Sequence, config: Optimise
     if optimizer:
         return simulation, optimizer.history
     raise ValueError("Optimisation failed")
+
+
+def _optimise_device(_simulation: Simulation, data_to_fit: Sequence, n_steps: int, tolerance: float, convergence, indexes: Sequence[int],
+                     loss_functions: Sequence, opt_state: OptimizationState, optimizer: OptaxOptimizer, ema_alpha: float = 0.5,
+                     min_steps_per_threshold: int = 2, chunk: int = 32, **_unused):
+    """Drop-in replacement for `_optimise` (pass it as `run_optimise(..., _opt_fn=_optimise_device)`) that keeps the
+    whole loop on the device: ConvergenceTracker, EMA parameters, history snapshots and the stop decision are evaluated
+    by the tail kernel every step; the host reads one 32-byte status per `chunk` steps instead of synchronising 5-8
+    times per step.  Produces the same OptimizationHistory / ema_history / best state."""
+    from .optimiser import B200OptState, _build_engine, _losses_from_record, compute_loss
+    from .._arrays import scalar, to_device, to_numpy
+    from .. import _lib as L
+    import ctypes as C
+    import numpy as np
+
+    if isinstance(convergence, float):
+        convergence = [convergence]
+    data_targets, losses_t, idx_t = tuple(data_to_fit), tuple(loss_functions), tuple(indexes)
+    params = opt_state.params
+    eng = _build_engine(_simulation, data_targets, losses_t, idx_t, optimizer._settings())
+    eng.enable_tracking(convergence, optimizer.learning_rate, ema_alpha, min_steps_per_threshold, tolerance)
+    mp = params.model_parameters[0]
+    eng.init_state(to_device(params.frame_weights, _simulation.device).reshape(-1), scalar(mp.bv_bc), scalar(mp.bv_bh),
+                   to_numpy(params.forward_model_weights), to_numpy(params.forward_model_scaling))
+    optimizer._engine, optimizer._engine_key, optimizer._n_losses = eng, None, len(losses_t)
+    optimizer.history = OptimizationHistory()
+    if optimizer.save_ema_history:
+        optimizer.ema_history = OptimizationHistory()
+    t0 = time.time()
+    st = eng.run(n_steps, chunk=chunk)
+    n = len(losses_t)
+    for sn, w, ema_w in eng.track_snapshots(st.n_snapshots):
+        mp_s = type(mp)(bv_bc=torch.tensor([sn.bc], device=eng.device), bv_bh=torch.tensor([sn.bh], device=eng.device),
+                        temperature=mp.temperature, timepoints=mp.timepoints)
+        sp = _replace(Simulation_Parameters.normalize_weights(params), frame_weights=w.clone(), model_parameters=[mp_s])
+        rec = torch.frombuffer(bytearray(bytes(sn.losses)), dtype=torch.float32).to(eng.device)
+        state = OptimizationState(sp, B200OptState(eng, sn.state_step), sn.state_step, _losses_from_record(rec, n), None)
+        optimizer.history.add_state(state)
+        if optimizer.save_ema_history and optimizer.ema_history is not None and ema_w is not None:
+            mp_e = type(mp)(bv_bc=torch.tensor([sn.ema_bc], device=eng.device), bv_bh=torch.tensor([sn.ema_bh], device=eng.device),
+                            temperature=mp.temperature, timepoints=mp.timepoints)
+            ep = _replace(sp, frame_weights=ema_w.clone(), model_parameters=[mp_e])
+            el, _ = compute_loss(_simulation, ep, data_targets, idx_t, losses_t)
+            optimizer.ema_history.add_state(OptimizationState(ep, state.opt_state, sn.state_step, el, None))
+    if optimizer.history.states:
+        best = optimizer.history.get_best_state()
+        if best is not None:
+            _simulation.params = best.params
+    optimizer._device_status = st
+    LOGGER.info("On-device optimisation: %d updates, %d snapshots, stop=%d (reason %d) in %.3f s", st.steps_done, st.n_snapshots,
+                st.stop, st.reason, time.time() - t0)
+    return _simulation, optimizer

@@ -133,3 +133,36 @@ def test_run_optimise_loop_semantics():
     assert history.best_state is not None
     assert opt.ema_history is not None and len(opt.ema_history.states) == len(history.states) - 1  # no EMA yet at step 0
     np.testing.assert_allclose(sim2.params.frame_weights.cpu().numpy(), res["best"]["weights"], atol=1e-4)
+
+
+def test_on_device_loop_matches_host_loop():
+    """_optimise_device (tracker / EMA / snapshots / stop flag in the tail kernel) == _optimise (host loop)."""
+    hist = {}
+    for name, fn in (("host", J._optimise), ("device", J._optimise_device)):
+        case, sim, data, losses, opt, cfg = _setup(lr=0.1, scaling=100.0)
+        settings = J.OptimiserSettings(name="t", n_steps=120, tolerance=1e-10, convergence=[1e-2, 1e-3, 1e-4], learning_rate=0.1)
+        sim2, history = J.run_optimise(sim, data, settings, forward_models=[], indexes=[0, 0, 0], loss_functions=list(losses),
+                                       optimizer=opt, initialise=True, silent=True, _opt_fn=fn)
+        hist[name] = (history, opt, sim2)
+    h, d = hist["host"][0], hist["device"][0]
+    assert len(d.states) == len(h.states) >= 2
+    assert [int(s.step) for s in d.states] == [int(s.step) for s in h.states]
+    for a, b in zip(d.states, h.states):
+        assert torch.equal(a.params.frame_weights, b.params.frame_weights)  # same kernels, same order: bitwise
+        np.testing.assert_allclose(a.losses.train_losses.cpu().numpy(), b.losses.train_losses.cpu().numpy(), rtol=0, atol=0)
+        np.testing.assert_allclose(float(a.losses.total_val_loss), float(b.losses.total_val_loss), rtol=0, atol=0)
+    eh, ed = hist["host"][1].ema_history, hist["device"][1].ema_history
+    assert len(ed.states) == len(eh.states)
+    for a, b in zip(ed.states, eh.states):
+        np.testing.assert_allclose(a.params.frame_weights.cpu().numpy(), b.params.frame_weights.cpu().numpy(), rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(float(a.losses.total_train_loss), float(b.losses.total_train_loss), rtol=1e-5)
+    assert torch.equal(hist["device"][2].params.frame_weights, hist["host"][2].params.frame_weights)
+    st = hist["device"][1]._device_status
+    assert st.n_snapshots == len(d.states)
+    # after the stop, further launches are no-ops
+    eng = hist["device"][1]._engine
+    if st.stop:
+        z0 = eng.export_state(("z",))[0]["z"].clone()
+        eng.step(3)
+        torch.cuda.synchronize()
+        assert torch.equal(eng.export_state(("z",))[0]["z"], z0) and eng.track_status().steps_done == st.steps_done
