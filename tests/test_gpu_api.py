@@ -166,3 +166,32 @@ def test_on_device_loop_matches_host_loop():
         eng.step(3)
         torch.cuda.synchronize()
         assert torch.equal(eng.export_state(("z",))[0]["z"], z0) and eng.track_status().steps_done == st.steps_done
+
+
+def test_batch_optimise_equals_sequential_runs():
+    """reference modules/optimise/test_module_batch_optimise.py:163-229: batch == sequential (loss rtol 1e-4, weights atol 1e-4)."""
+    case, sim, data, losses, opt, cfg = _setup(lr=0.1, scaling=100.0)
+    sim.initialise()
+    settings = J.OptimiserSettings(name="b", n_steps=60, tolerance=1e-10, convergence=[1e-2, 1e-3], learning_rate=0.1)
+    fw = np.array([[0.5, 0.25, 0.25], [0.8, 0.1, 0.1], [0.2, 0.6, 0.2]], np.float32)
+    fs = np.full((3, 3), 100.0, np.float32)
+    lr = np.array([0.1, 0.05, 0.2], np.float32)
+    res = J.batch_optimise(sim, J.HParamBatch(fw, fs, lr), batch_size=2, data_to_fit=data, config=settings, indexes=[0, 0, 0],
+                           loss_functions=list(losses), optimizer=opt)
+    assert len(res.histories) == 3 and res.convergence_steps.shape == (3,)
+    for i in range(3):
+        o = J.OptaxOptimizer(learning_rate=float(lr[i]), parameter_partition_masks=set(opt.parameter_partition_masks), clip_value=None,
+                             initial_learning_rate=1.0, initial_steps=2, save_ema_history=False)
+        s2 = sim._shallow_copy()
+        p = sim.params
+        s2.params = J.Simulation_Parameters(p.frame_weights, p.frame_mask, p.model_parameters, fw[i], p.normalise_loss_functions, fs[i])
+        st = o.initialise(s2)
+        _, o = J._optimise(s2, data, 60, 1e-10, [1e-2, 1e-3], [0, 0, 0], list(losses), st, o, silent=True)
+        assert [int(s.step) for s in o.history.states] == [int(s.step) for s in res.histories[i].states]
+        a, b = o.history.get_best_state(), res.best_states[i]
+        np.testing.assert_allclose(b.params.frame_weights.cpu().numpy(), a.params.frame_weights.cpu().numpy(), atol=1e-4)
+        np.testing.assert_allclose(float(b.losses.total_train_loss), float(a.losses.total_train_loss), rtol=1e-4)
+    with pytest.raises(ValueError, match="batch_size"):
+        J.batch_optimise(sim, J.HParamBatch(fw, fs), 0, data, settings, [0, 0, 0], list(losses))
+    with pytest.raises(ValueError, match="same n_hparams"):
+        J.batch_optimise(sim, J.HParamBatch(fw, fs[:2]), 2, data, settings, [0, 0, 0], list(losses))
