@@ -91,6 +91,8 @@ typedef struct {
   const float* prior;   /* (F) this rank's slice of the MaxEnt prior frame weights, or NULL */
   double prior_norm;    /* sum over ALL ranks of (|prior_f| + eps); see jaxent_bv_prior_partial() */
   JaxentLossSlot slots[JAXENT_MAX_SLOTS];
+  int32_t feature_format; /* layout of `packed`: 0 = fp32 (jaxent_bv_pack_features_f32), 1 = u8 (jaxent_bv_pack_features_u8) */
+  int32_t pad_;
 } JaxentBvProblem;
 
 /* OptaxOptimizer.__init__ arguments (opt/optimiser.py:68-82) */
@@ -173,6 +175,16 @@ size_t jaxent_bv_packed_bytes(int32_t R, int64_t F);
 /* heavy / acceptor: (R, F) row-major fp32 on the device with leading dimension ld (>= F). */
 int jaxent_bv_pack_features_f32(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld,
                                 int64_t frame_offset, int64_t F_dst, float* packed, jaxent_stream_t stream);
+
+/* Lossless u8 storage of the features (hard-cutoff BV contacts are integer counts, reference
+ * jaxent/src/models/func/contacts.py:236-240): a quarter of the HBM traffic per step, bit-identical results.
+ * layout [ceil(F/32)*4 tiles of 8 frames][2 arrays][R rows][8 bytes].  features_fit_u8 clears *flag (device int,
+ * preset to 1 by the caller) if any value is not an integer in [0,255]. */
+size_t jaxent_bv_packed_bytes_fmt(int32_t R, int64_t F, int32_t format);
+int jaxent_bv_features_fit_u8(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld, int32_t* flag,
+                              jaxent_stream_t stream);
+int jaxent_bv_pack_features_u8(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld,
+                               unsigned char* packed, jaxent_stream_t stream);
 
 /* per-rank partial of sum_f (|prior_f| + eps) written to out[0] (device double) */
 int jaxent_bv_prior_partial(const float* prior, int64_t F, double eps, double* out, jaxent_stream_t stream);

@@ -65,6 +65,8 @@ class BvProblem(C.Structure):
         ("prior", C.c_void_p),
         ("prior_norm", C.c_double),
         ("slots", LossSlot * MAX_SLOTS),
+        ("feature_format", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -142,6 +144,9 @@ SYMBOLS = {
     "jaxent_abi_sizeof": (C.c_int, [C.c_int]),
     "jaxent_bv_packed_bytes": (_SZ, [_I32, _I64]),
     "jaxent_bv_pack_features_f32": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _I64, _I64, _VP, _VP]),
+    "jaxent_bv_packed_bytes_fmt": (_SZ, [_I32, _I64, _I32]),
+    "jaxent_bv_features_fit_u8": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _VP, _VP]),
+    "jaxent_bv_pack_features_u8": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _VP, _VP]),
     "jaxent_bv_prior_partial": (C.c_int, [_VP, _I64, C.c_double, _VP, _VP]),
     "jaxent_bv_max": (C.c_int, [_VP, _I64, _VP, _VP]),
     "jaxent_bv_workspace_bytes": (_SZ, [C.POINTER(BvProblem)]),

@@ -155,7 +155,9 @@ struct JaxentPlan {
   unsigned char* ws;
   jx::StateSets st;
   int pass_threads, rpt, pass_ctas, stages, tail_ctas, tail_clustered, p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
-  uint32_t tile_bytes, stage_stride;
+  uint32_t tile_bytes, stage_stride, subtile_bytes;
+  int sub_tiles;
+  long long n_stage_units;
   size_t pass_smem, tail_smem;
   long long n_tiles;
   int initialised;
@@ -292,7 +294,10 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   const int rows_per_thread_threads = (R + p->rpt - 1) / p->rpt;
   p->pass_threads = ((rows_per_thread_threads + 31) / 32) * 32;
   if (p->pass_threads < 32) p->pass_threads = 32;
-  p->tile_bytes = (uint32_t)(FT * R * 2 * sizeof(float));
+  if (problem->feature_format != 0 && problem->feature_format != 1) { delete p; set_error("unknown feature_format %d", problem->feature_format); return JAXENT_E_INVALID; }
+  p->sub_tiles = problem->feature_format == 1 ? U8_SUB_TILES : 1;
+  p->subtile_bytes = (uint32_t)(FT * R * 2 * (problem->feature_format == 1 ? 1 : sizeof(float)));
+  p->tile_bytes = p->subtile_bytes * p->sub_tiles;
   p->stage_stride = (uint32_t)align_up(p->tile_bytes, 128);
   const size_t smem_budget = (p->rpt == 1 ? 108 : 216) * 1024;
   const size_t fixed = MAX_STAGES * 8 + 2 * 16 * FT * 4 + 2 * 2 * FT * 4 + 128;
@@ -302,9 +307,10 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   p->stages = stages;
   p->pass_smem = (size_t)stages * p->stage_stride + fixed;
   p->n_tiles = (problem->F + FT - 1) / FT;
+  p->n_stage_units = (p->n_tiles + p->sub_tiles - 1) / p->sub_tiles;
   const int per_sm = (p->rpt == 1) ? 2 : 1;
   long long ctas = (long long)device_sm_count * per_sm;
-  if (ctas > p->n_tiles) ctas = p->n_tiles;
+  if (ctas > p->n_stage_units) ctas = p->n_stage_units;
   if (ctas > MAX_PASS_CTAS) ctas = MAX_PASS_CTAS;
   p->pass_ctas = (int)ctas;
 
@@ -432,6 +438,10 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.mode = mode;
   a.stages = p->stages;
   a.part_n = 4 * p->prob.R + 4;
+  a.format = p->prob.feature_format;
+  a.sub_tiles = p->sub_tiles;
+  a.subtile_bytes = p->subtile_bytes;
+  a.n_stage_units = p->n_stage_units;
   a.tile_bytes = p->tile_bytes;
   a.stage_stride = p->stage_stride;
   a.n_tiles = p->n_tiles;

@@ -87,6 +87,53 @@ __global__ void pack_kernel(const float* __restrict__ heavy, const float* __rest
   }
 }
 
+// (R,F) fp32 row-major -> u8 [tile of 8 frames][array][row][8 bytes]; values must be integers in [0,255]
+__global__ void pack_u8_kernel(const float* __restrict__ heavy, const float* __restrict__ acceptor, int R, long long F,
+                               long long ld, long long Fpad, unsigned char* __restrict__ packed) {
+  __shared__ float tile[2][32][33];
+  const long long fb = (long long)blockIdx.x * 32;
+  const int rb = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = rb + i;
+    const long long f = fb + tx;
+    float a = 0.f, b = 0.f;
+    if (r < R && f < F) {
+      a = heavy[(long long)r * ld + f];
+      b = acceptor[(long long)r * ld + f];
+    }
+    tile[0][i][tx] = a;
+    tile[1][i][tx] = b;
+  }
+  __syncthreads();
+  // thread (tx = row, ty = tile-of-8 within the block (4 of them) x array (2))
+  const int r = rb + tx;
+  const int t8 = ty >> 1, arr = ty & 1;
+  const long long f0 = fb + (long long)t8 * 8;
+  if (r < R && f0 < Fpad) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      lo |= ((uint32_t)__float2int_rn(tile[arr][tx][t8 * 8 + j]) & 0xffu) << (8 * j);
+      hi |= ((uint32_t)__float2int_rn(tile[arr][tx][t8 * 8 + 4 + j]) & 0xffu) << (8 * j);
+    }
+    const long long tix = f0 / 8;
+    reinterpret_cast<uint2*>(packed)[(tix * 2 + arr) * R + r] = make_uint2(lo, hi);
+  }
+}
+
+// flag[0] <- 0 if any value is not an integer in [0,255] (flag must be initialised to 1 by the caller)
+__global__ void fit_u8_kernel(const float* __restrict__ x, long long n_rows, long long F, long long ld, int* flag) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (long long i = i0; i < n_rows * F; i += stride) {
+    const long long r = i / F, f = i - r * F;
+    const float v = x[r * ld + f];
+    bad = bad || !(v >= 0.f && v <= 255.f && v == rintf(v));
+  }
+  if (bad) *flag = 0;
+}
+
 // ------------------------------------------------------------------------------------------ small reductions
 __global__ void prior_partial_kernel(const float* __restrict__ prior, long long F, double eps, double* out) {
   __shared__ double sh[32];
@@ -140,15 +187,30 @@ struct TileRegs {
   float4 nc[RPT][QT], nh[RPT][QT];
 };
 
-template <int RPT>
-__device__ __forceinline__ void load_tile(TileRegs<RPT>& d, const unsigned char* stage, uint32_t r16, const uint32_t (&rowoff)[RPT]) {
+// FMT 0: fp32 features, sub-tile = [quad][array][row][4 floats];  FMT 1: u8 features (lossless for integer contact
+// counts <= 255), sub-tile = [array][row][8 bytes].  `rstride` = bytes between consecutive (quad,array) / array blocks.
+__device__ __forceinline__ float4 u8x4_to_float4(uint32_t v) {
+  return make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu), (float)((v >> 16) & 0xffu), (float)(v >> 24));
+}
+
+template <int RPT, int FMT>
+__device__ __forceinline__ void load_tile(TileRegs<RPT>& d, const unsigned char* sub, uint32_t rstride, const uint32_t (&rowoff)[RPT]) {
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    const unsigned char* p = stage + rowoff[i];
-    d.nc[i][0] = *reinterpret_cast<const float4*>(p);
-    d.nh[i][0] = *reinterpret_cast<const float4*>(p + r16);
-    d.nc[i][1] = *reinterpret_cast<const float4*>(p + 2 * r16);
-    d.nh[i][1] = *reinterpret_cast<const float4*>(p + 3 * r16);
+    const unsigned char* p = sub + rowoff[i];
+    if (FMT == 0) {
+      d.nc[i][0] = *reinterpret_cast<const float4*>(p);
+      d.nh[i][0] = *reinterpret_cast<const float4*>(p + rstride);
+      d.nc[i][1] = *reinterpret_cast<const float4*>(p + 2 * rstride);
+      d.nh[i][1] = *reinterpret_cast<const float4*>(p + 3 * rstride);
+    } else {
+      const uint2 c = *reinterpret_cast<const uint2*>(p);
+      const uint2 h = *reinterpret_cast<const uint2*>(p + rstride);
+      d.nc[i][0] = u8x4_to_float4(c.x);
+      d.nc[i][1] = u8x4_to_float4(c.y);
+      d.nh[i][0] = u8x4_to_float4(h.x);
+      d.nh[i][1] = u8x4_to_float4(h.y);
+    }
   }
 }
 
@@ -231,7 +293,7 @@ __device__ __forceinline__ void phase_b(const TileRegs<RPT>& d, const float* s_e
   }
 }
 
-template <int RPT>
+template <int RPT, int FMT>
 __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.R;
@@ -249,8 +311,11 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
 
   // static, deterministic tile partition
   const long long G = gridDim.x, cta = blockIdx.x;
-  const long long t0 = a.n_tiles * cta / G, t1 = a.n_tiles * (cta + 1) / G;
-  const int n = (int)(t1 - t0);
+  const int S = a.sub_tiles;  // 8-frame tiles per bulk-copy stage
+  const long long s0 = a.n_stage_units * cta / G, s1 = a.n_stage_units * (cta + 1) / G;
+  const int ns = (int)(s1 - s0);        // stages of this CTA
+  const long long t0 = s0 * S;          // first tile
+  const int n = ns * S;                 // tiles of this CTA (frames past F are zero padding)
   const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
   double* part = a.partials + (size_t)blockIdx.x * a.part_n;
 
@@ -262,11 +327,11 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
 
   // The first tiles only need the (constant) features: start them before waiting on the previous kernel (PDL).
   if (is_adam && lane == 0) {
-    const int pre = n < a.stages ? n : a.stages;
+    const int pre = ns < a.stages ? ns : a.stages;
     for (int s = 0; s < pre; ++s) {
       const uint32_t bar = smem_u32(&bars[s]);
       mbar_expect_tx(bar, a.tile_bytes);
-      bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(t0 + s) * a.tile_bytes, a.tile_bytes, bar);
+      bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(s0 + s) * a.tile_bytes, a.tile_bytes, bar);
     }
   }
   pdl_wait();               // everything the tail kernel wrote (ctl, cc/ch, w, kappa, klsum) is visible from here on
@@ -276,7 +341,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
   if (a.ctl[ep & 1u].trk_stop) {
     // the on-device loop has ended: drain the prefetched tiles and leave everything untouched
     if (is_adam && lane == 0) {
-      const int pre = n < a.stages ? n : a.stages;
+      const int pre = ns < a.stages ? ns : a.stages;
       for (int s = 0; s < pre; ++s) mbar_wait(smem_u32(&bars[s]), 0);
     }
     return;
@@ -309,7 +374,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
     const int fj = lane & 7, fk = lane >> 3;  // frame within tile, partial-sum group
     double sumA = 0.0, sumB = 0.0, gdot = 0.0;
 
-    int slot = 0;
+    int slot = 0, sub = 0, stage_it = 0;
     for (int it = 0; it < n; ++it) {
       const int b = it & 1;
       const long long f = (t0 + it) * FT + fj;
@@ -326,13 +391,17 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
         }
       }
       bar_sync(BAR_PART0 + b, nbar);  // partials(it) visible, every consumer has ring[slot] in registers
-      if (lane == 0 && it + a.stages < n) {
-        const uint32_t bar = smem_u32(&bars[slot]);
-        mbar_expect_tx(bar, a.tile_bytes);
-        bulk_g2s(smem_u32(ring + (size_t)slot * a.stage_stride), gsrc + (size_t)(t0 + it + a.stages) * a.tile_bytes,
-                 a.tile_bytes, bar);
+      if (++sub == S) {  // last sub-tile of the stage is in the consumers' registers: refill the slot
+        sub = 0;
+        if (lane == 0 && stage_it + a.stages < ns) {
+          const uint32_t bar = smem_u32(&bars[slot]);
+          mbar_expect_tx(bar, a.tile_bytes);
+          bulk_g2s(smem_u32(ring + (size_t)slot * a.stage_stride), gsrc + (size_t)(s0 + stage_it + a.stages) * a.tile_bytes,
+                   a.tile_bytes, bar);
+        }
+        ++stage_it;
+        if (++slot == a.stages) slot = 0;
       }
-      if (++slot == a.stages) slot = 0;
       // H_f: 4 lanes per frame sum a quarter of the warps each, fixed order
       float H = 0.f;
       const float* sp = s_part + b * 16 * FT;
@@ -403,7 +472,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
     row[i] = tid + i * NTc;
     const bool ok = row[i] < R;
     const int rc = ok ? row[i] : R - 1;  // clamp: finite data, zero coefficients, result never stored
-    rowoff[i] = (uint32_t)rc * 16u;
+    rowoff[i] = (uint32_t)rc * (FMT == 0 ? 16u : 8u);
     ccr[i] = (ok && mode) ? a.cc[rc] : 0.f;
     chr[i] = (ok && mode) ? a.ch[rc] : 0.f;
     if (ok) {
@@ -413,7 +482,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
       part[3 * R + rc] = 0.0;
     }
   }
-  const uint32_t r16 = (uint32_t)R * 16u;
+  const uint32_t rstride = (uint32_t)R * (FMT == 0 ? 16u : 8u);
   const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   float acc[RPT][4];
 #pragma unroll
@@ -432,14 +501,17 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
     }
   };
 
-  int slot = 0;
+  int slot = 0, sub = 0;
   uint32_t parity = 0;
   auto fetch = [&](TileRegs<RPT>& D) {
-    mbar_wait(smem_u32(&bars[slot]), parity);
-    load_tile<RPT>(D, ring + (size_t)slot * a.stage_stride, r16, rowoff);
-    if (++slot == a.stages) {
-      slot = 0;
-      parity ^= 1u;
+    if (sub == 0) mbar_wait(smem_u32(&bars[slot]), parity);
+    load_tile<RPT, FMT>(D, ring + (size_t)slot * a.stage_stride + (size_t)sub * a.subtile_bytes, rstride, rowoff);
+    if (++sub == S) {
+      sub = 0;
+      if (++slot == a.stages) {
+        slot = 0;
+        parity ^= 1u;
+      }
     }
   };
   float* spw0 = s_part + warp * FT;
@@ -520,18 +592,24 @@ __global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, cons
 // ------------------------------------------------------------------------------------------ launchers
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(bv_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<1>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  e = cudaFuncSetAttribute(bv_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<2>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  e = cudaFuncSetAttribute(bv_pass_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<1,0>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  e = cudaFuncSetAttribute(bv_pass_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<2,0>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  e = cudaFuncSetAttribute(bv_pass_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<1,1>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  e = cudaFuncSetAttribute(bv_pass_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<2,1>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;
 }
 
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s) {
   cudaError_t le = cudaSuccess;
-  switch (rpt) {
-    case 1: le = launch_pdl(bv_pass_kernel<1>, ctas, threads, smem, s, a); break;
-    case 2: le = launch_pdl(bv_pass_kernel<2>, ctas, threads, smem, s, a); break;
+  switch (rpt * 2 + (a.format ? 1 : 0)) {
+    case 2: le = launch_pdl(bv_pass_kernel<1, 0>, ctas, threads, smem, s, a); break;
+    case 3: le = launch_pdl(bv_pass_kernel<1, 1>, ctas, threads, smem, s, a); break;
+    case 4: le = launch_pdl(bv_pass_kernel<2, 0>, ctas, threads, smem, s, a); break;
+    case 5: le = launch_pdl(bv_pass_kernel<2, 1>, ctas, threads, smem, s, a); break;
     default: set_error("unsupported rows-per-thread %d", rpt); return JAXENT_E_UNSUPPORTED;
   }
   cudaError_t e = (le != cudaSuccess) ? le : cudaGetLastError();
@@ -584,6 +662,39 @@ extern "C" int jaxent_bv_pack_features_f32(const float* heavy, const float* acce
   jx::pack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(heavy, acceptor, R, F, ld, frame_offset, F_dst, packed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { jx::set_error("pack_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}
+
+extern "C" size_t jaxent_bv_packed_bytes_fmt(int32_t R, int64_t F, int32_t format) {
+  if (R <= 0 || F <= 0) return 0;
+  if (format == 0) return jaxent_bv_packed_bytes(R, F);
+  if (format != 1) return 0;
+  const int64_t frames_per_stage = (int64_t)jx::FT * jx::U8_SUB_TILES;
+  const int64_t stages = (F + frames_per_stage - 1) / frames_per_stage;
+  return (size_t)stages * frames_per_stage * (size_t)R * 2;
+}
+
+extern "C" int jaxent_bv_features_fit_u8(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld, int32_t* flag,
+                                         jaxent_stream_t stream) {
+  if (!heavy || !acceptor || !flag || R <= 0 || F <= 0 || ld < F) { jx::set_error("features_fit_u8: invalid argument"); return JAXENT_E_INVALID; }
+  jx::fit_u8_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(heavy, R, F, ld, flag);
+  jx::fit_u8_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(acceptor, R, F, ld, flag);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { jx::set_error("fit_u8 launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bv_pack_features_u8(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld,
+                                          unsigned char* packed, jaxent_stream_t stream) {
+  if (!heavy || !acceptor || !packed || R <= 0 || F <= 0 || ld < F) { jx::set_error("pack_features_u8: invalid argument"); return JAXENT_E_INVALID; }
+  if ((reinterpret_cast<uintptr_t>(packed) & 15u) != 0) { jx::set_error("pack_features_u8: packed buffer must be 16-byte aligned"); return JAXENT_E_INVALID; }
+  const int64_t fps = (int64_t)jx::FT * jx::U8_SUB_TILES;
+  const int64_t Fpad = (F + fps - 1) / fps * fps;
+  dim3 grid((unsigned)((Fpad + 31) / 32), (unsigned)((R + 31) / 32));
+  dim3 block(32, 8);
+  jx::pack_u8_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(heavy, acceptor, R, F, ld, Fpad, packed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { jx::set_error("pack_u8_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;
 }
 

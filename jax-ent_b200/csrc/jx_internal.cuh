@@ -10,6 +10,7 @@ namespace jx {
 constexpr int FT = 8;           // frames per tile (2 quads of 4 frames)
 constexpr int QT = FT / 4;      // quads per tile
 constexpr int MAX_STAGES = 8;   // bulk-copy ring depth upper bound
+constexpr int U8_SUB_TILES = 4; // u8 features: one bulk-copy stage carries 4 tiles of 8 frames (32 frames)
 constexpr int PASS_THREADS_MAX = 512;
 constexpr int TAIL_THREADS = 1024;
 constexpr int KL_N = 4;         // MaxEnt partial sums: sum w*kappa, sum p(log p - log q), sum(q - p), sum w
@@ -74,8 +75,12 @@ struct PassArgs {
   int mode;
   int stages;
   int part_n;         // 4R + 4
-  uint32_t tile_bytes;
+  int format;          // 0 fp32 features, 1 u8 features
+  int sub_tiles;       // 8-frame tiles per bulk-copy stage
+  uint32_t subtile_bytes;
+  uint32_t tile_bytes; // bytes of one stage (= sub_tiles * subtile_bytes)
   uint32_t stage_stride;
+  long long n_stage_units;
   long long n_tiles;
   long long F;
   StateSets st;

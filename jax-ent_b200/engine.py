@@ -85,8 +85,12 @@ class PackedFeatures:
     """The packed (tile layout) copy of one rank's BV features; can be shared by several engines
     (e.g. the optimiser's engine and the forward-only engine behind ``Simulation.forward``)."""
 
-    def __init__(self, packed: torch.Tensor, n_residues: int, n_frames: int):
-        self.packed, self.R, self.F = packed, int(n_residues), int(n_frames)
+    def __init__(self, packed: torch.Tensor, n_residues: int, n_frames: int, fmt: int = 0):
+        self.packed, self.R, self.F, self.format = packed, int(n_residues), int(n_frames), int(fmt)
+
+    @property
+    def nbytes(self) -> int:
+        return self.packed.numel() * self.packed.element_size()
 
     @property
     def shape(self):
@@ -107,6 +111,7 @@ class BvEngine:
         device: Optional[torch.device] = None,
         F_total: Optional[int] = None,
         group=None,
+        feature_dtype: str = "f32",
     ):
         if not torch.cuda.is_available():
             raise RuntimeError("jaxent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -130,12 +135,13 @@ class BvEngine:
             if isinstance(heavy, PackedFeatures):
                 self.features = heavy
             else:
-                self.features = PackedFeatures(self._pack(heavy, acceptor), R, F)
+                self.features = self._pack(heavy, acceptor, feature_dtype)
             self.packed = self.features.packed
             prob = L.BvProblem()
             prob.R, prob.T, prob.uptake, prob.n_slots = R, self.T, int(self.uptake), len(slots)
             prob.F, prob.F_total = F, self.F_total
             prob.packed = self.packed.data_ptr()
+            prob.feature_format = self.features.format
             if self.uptake:
                 if k_ints is None:
                     raise ValueError("BV_uptake_ForwardPass needs k_ints")
@@ -221,20 +227,35 @@ class BvEngine:
         off = ptr.value - self.ws.data_ptr()
         return self.ws[off : off + nb.value].view(dtype)
 
-    def _pack(self, heavy, acceptor) -> torch.Tensor:
-        """(R,F) fp32 -> packed tile layout (csrc/bv_pass.cu pack_kernel); replaces cast_to_jax
-        (reference custom_types/features.py:82-89)."""
+    def _pack(self, heavy, acceptor, feature_dtype: str = "f32") -> PackedFeatures:
+        """(R,F) fp32 -> packed tile layout (csrc/bv_pass.cu pack kernels); replaces cast_to_jax
+        (reference custom_types/features.py:82-89).  feature_dtype: "f32" keeps fp32 values; "u8" stores the
+        features as bytes (lossless for integer contact counts <= 255, raises otherwise); "auto" picks u8 when
+        it is lossless."""
+        if feature_dtype not in ("f32", "u8", "auto"):
+            raise ValueError("feature_dtype must be 'f32', 'u8' or 'auto'")
         R, F = int(heavy.shape[0]), int(heavy.shape[1])
-        nbytes = self.lib.jaxent_bv_packed_bytes(R, F)
-        packed = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
         h = self._to_dev_matrix(heavy)
         a = self._to_dev_matrix(acceptor)
-        L.check(
-            self.lib.jaxent_bv_pack_features_f32(h.data_ptr(), a.data_ptr(), R, F, F, 0, F, packed.data_ptr(), _stream_ptr())
-        )
+        fmt = 0
+        if feature_dtype in ("u8", "auto"):
+            flag = torch.ones(1, dtype=torch.int32, device=self.device)
+            L.check(self.lib.jaxent_bv_features_fit_u8(h.data_ptr(), a.data_ptr(), R, F, F, flag.data_ptr(), _stream_ptr()))
+            fits = bool(flag.item())
+            if feature_dtype == "u8" and not fits:
+                raise ValueError("feature_dtype='u8' needs integer-valued features in [0, 255] (hard-cutoff BV contacts)")
+            fmt = 1 if fits else 0
+        if fmt == 1:
+            nbytes = self.lib.jaxent_bv_packed_bytes_fmt(R, F, 1)
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            L.check(self.lib.jaxent_bv_pack_features_u8(h.data_ptr(), a.data_ptr(), R, F, F, packed.data_ptr(), _stream_ptr()))
+        else:
+            nbytes = self.lib.jaxent_bv_packed_bytes(R, F)
+            packed = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            L.check(self.lib.jaxent_bv_pack_features_f32(h.data_ptr(), a.data_ptr(), R, F, F, 0, F, packed.data_ptr(), _stream_ptr()))
         torch.cuda.current_stream().synchronize()
         del h, a
-        return packed
+        return PackedFeatures(packed, R, F, fmt)
 
     def _to_dev_matrix(self, x) -> torch.Tensor:
         if isinstance(x, torch.Tensor):
@@ -372,6 +393,10 @@ class BvEngine:
     def algorithmic_bytes_per_step(self) -> int:
         """8*R*F (features once) + 28*F (z,m,v,prior read; z,m,v written)."""
         return 8 * self.R * self.F + 28 * self.F
+
+    def actual_bytes_per_step(self) -> int:
+        """bytes the pass really streams: the packed features (fp32 or u8) once + the 28 B/frame of optimiser state."""
+        return self.features.nbytes + 28 * self.F
 
     # ------------------------------------------------------------------ on-device loop (SURVEY.md 8f.1)
     def enable_tracking(self, convergence, learning_rate: float, ema_alpha: float = 0.5, min_steps_per_threshold: int = 2,

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match():
     lib = L.load()
-    for i, st in enumerate((L.BvProblem, L.OptConfig, L.LossRecord, L.LossSlot, L.PeptideMap)):
+    for i, st in enumerate((L.BvProblem, L.OptConfig, L.LossRecord, L.LossSlot, L.PeptideMap, L.TrackSnapshot, L.TrackStatus)):
         assert lib.jaxent_abi_sizeof(i) == C.sizeof(st)
     assert lib.jaxent_abi_sizeof(99) == -1
 
@@ -42,6 +42,9 @@ def test_packed_and_workspace_sizes():
     assert lib.jaxent_bv_packed_bytes(500, 1_000_000) == 8 * 500 * 1_000_000
     assert lib.jaxent_bv_packed_bytes(53, 500) == 8 * 53 * 504  # frames padded to a multiple of 8
     assert lib.jaxent_bv_packed_bytes(0, 10) == 0
+    assert lib.jaxent_bv_packed_bytes_fmt(500, 1_000_000, 1) == 2 * 500 * 1_000_000  # u8: a quarter of the fp32 bytes
+    assert lib.jaxent_bv_packed_bytes_fmt(53, 500, 1) == 2 * 53 * 512  # frames padded to a multiple of 32
+    assert lib.jaxent_bv_packed_bytes_fmt(53, 500, 0) == lib.jaxent_bv_packed_bytes(53, 500)
     pb = L.BvProblem()
     pb.R, pb.T, pb.uptake, pb.n_slots, pb.F, pb.F_total = 500, 8, 1, 2, 100_000, 100_000
     n = lib.jaxent_bv_workspace_bytes(C.byref(pb))

@@ -252,3 +252,42 @@ def test_errors_surface_as_exceptions():
         BvEngine(z, z, None, None, [SlotSpec(L.LOSS_UPTAKE_EYE_MSE, S, np.zeros((4, 0)), S, np.zeros((4, 0)))], False, OptSettings())
     with pytest.raises(ValueError, match="different shapes"):
         BvEngine(z, np.zeros((4, 8), np.float32), None, None, [SlotSpec(L.LOSS_PARAMS_L2)], False, OptSettings())
+
+
+@pytest.mark.parametrize("F,R", [(3001, 500), (77, 53), (1001, 513)])
+def test_u8_features_match_fp32_storage(F, R):
+    """lossless u8 storage of the integer contact counts: same per-element arithmetic, a quarter of the feature bytes.
+    Only the grouping of the fp64 partial sums differs (32-frame instead of 8-frame work units), so results agree to
+    fp32 rounding rather than bit for bit."""
+    case = H.make_case(F, R, 5, O.UPTAKE_EYE_MSE, extra=(O.PARAMS_L2,), seed=F, n_pep=max(4, R // 3))
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=True)
+    outs = []
+    for fd in ("f32", "u8", "auto"):
+        eng = H.make_engine(case, cfg, feature_dtype=fd)
+        assert eng.features.format == (0 if fd == "f32" else 1)
+        H.init_engine(eng, case)
+        eng.step(3)  # few steps: lr=1 Adam dynamics amplify last-bit differences quickly
+        eng.finish_record()
+        _sync()
+        bufs, sc = eng.export_state()
+        outs.append((bufs["z"].clone(), bufs["m"].clone(), bufs["v"].clone(), bufs["g"].clone(), eng.weights.clone(), sc["bc"],
+                     eng.records(3, 1)[0].total_train, eng.actual_bytes_per_step()))
+    for o in outs[1:]:
+        for a, b in zip(o[:5], outs[0][:5]):
+            scale = float(b.abs().max())
+            assert float((a - b).abs().max()) <= 2e-5 * scale
+        np.testing.assert_allclose(o[5], outs[0][5], rtol=1e-5)
+        np.testing.assert_allclose(o[6], outs[0][6], rtol=1e-5)
+    assert torch.equal(outs[1][0], outs[2][0])  # "u8" and "auto" take the same path: bitwise
+    if F >= 1000:  # tiny ensembles are dominated by padding and the 28 B/frame of optimiser state
+        assert outs[1][7] < 0.3 * outs[0][7]
+
+
+def test_u8_rejected_for_fractional_features():
+    case = H.make_case(64, 16, 3, O.UPTAKE_EYE_MSE, seed=2, n_pep=6)
+    case["problem"].heavy = case["problem"].heavy + 0.5
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None)
+    with pytest.raises(ValueError, match="integer-valued"):
+        H.make_engine(case, cfg, feature_dtype="u8")
+    eng = H.make_engine(case, cfg, feature_dtype="auto")  # falls back to fp32 storage
+    assert eng.features.format == 0
