@@ -159,7 +159,8 @@ enum {
   JAXENT_BUF_RECORDS = 4,  /* JaxentLossRecord[JAXENT_RECORD_RING]                                      */
   JAXENT_BUF_LOGPF = 5,    /* float[R]      log_Pf of the current step                                  */
   JAXENT_BUF_UPTAKE = 6,   /* float[T*R]    uptake (T,R) of the current step (uptake mode)              */
-  JAXENT_BUF_AVG = 7       /* float[2R]     frame-averaged heavy / acceptor contacts                    */
+  JAXENT_BUF_AVG = 7,      /* float[2R]     frame-averaged heavy / acceptor contacts                    */
+  JAXENT_BUF_XCHG_ERR = 9  /* uint64[1]     non-zero once a wait of the NVLink exchange timed out               */
 };
 #define JAXENT_RECORD_RING 4096
 
@@ -197,6 +198,28 @@ int jaxent_bv_plan_create(const JaxentBvProblem* problem, const JaxentOptConfig*
                           size_t workspace_bytes, int32_t device_sm_count, JaxentPlan** plan);
 void jaxent_bv_plan_destroy(JaxentPlan* plan);
 int jaxent_bv_plan_buffer(const JaxentPlan* plan, int32_t which, void** ptr, size_t* bytes);
+
+/* ---- frame-sharded exchange over NVLink peer memory ----
+ * Without it a sharded run all-reduces JAXENT_BUF_RED / JAXENT_BUF_KLSUM between the phases (NCCL).  With it the
+ * two exchanges are fused into the kernels: `reduce` / `tail` store this rank's partial sums straight into every
+ * peer's inbox as self-validating 16-byte words (value + epoch stamp, the NCCL "LL" idea: no flags, no fences), the
+ * consumers (`tail`, the next `pass`) spin on the words of their local inbox and add the slots in rank order, so
+ * every rank computes bit-identical sums and a step is three kernel launches on any number of GPUs.
+ * The exchange buffer of each rank (jaxent_bv_exchange_bytes) must be mapped into every process: jaxent_peer_alloc
+ * (cudaMalloc + zero fill + cudaIpcGetMemHandle) on the owner, jaxent_peer_open (cudaIpcOpenMemHandle) on the
+ * peers -- set-up time only; the step itself never allocates.  peers[world] lists the mapped base pointers in rank
+ * order (peers[rank] is the local buffer).  Call before jaxent_bv_state_init; every rank must then complete
+ * jaxent_bv_state_init (which clears the local inbox) before any rank launches the first pass. */
+#define JAXENT_MAX_RANKS 8
+#define JAXENT_IPC_HANDLE_BYTES 64
+size_t jaxent_bv_exchange_bytes(int32_t R, int32_t world);
+int jaxent_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle);
+int jaxent_peer_open(const unsigned char* handle, void** dev_ptr);
+int jaxent_peer_close(void* dev_ptr);
+int jaxent_peer_free(void* dev_ptr);
+int jaxent_bv_plan_set_exchange(JaxentPlan* plan, int32_t rank, int32_t world, void* const* peers);
+/* copies the exchange error word (JAXENT_BUF_XCHG_ERR) to out[0] (device uint64) on the stream */
+int jaxent_bv_exchange_error(JaxentPlan* plan, uint64_t* out, jaxent_stream_t stream);
 
 /* ---- state ----
  * OptaxOptimizer.initialise (opt/optimiser.py:221-304): z0 are the logits (w_init * F_total), zmax

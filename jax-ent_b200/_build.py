@@ -47,6 +47,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-o",
         LIB,
     ] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("JAXENT_NVCC_FLAGS")
+    if extra:
+        cmd[1:1] = extra.split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -22,6 +22,9 @@ LOSS_PARAMS_L1 = 5
 LOSS_PARAMS_L2 = 6
 
 BUF_RED, BUF_KLSUM, BUF_WEIGHTS, BUF_RECORDS, BUF_LOGPF, BUF_UPTAKE, BUF_AVG = 0, 1, 2, 4, 5, 6, 7
+BUF_XCHG_ERR = 9
+MAX_RANKS = 8
+IPC_HANDLE_BYTES = 64
 
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_WORKSPACE = -1, -2, -3, -4
 
@@ -153,6 +156,13 @@ SYMBOLS = {
     "jaxent_bv_plan_create": (C.c_int, [C.POINTER(BvProblem), C.POINTER(OptConfig), _VP, _SZ, _I32, C.POINTER(_VP)]),
     "jaxent_bv_plan_destroy": (None, [_VP]),
     "jaxent_bv_plan_buffer": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_SZ)]),
+    "jaxent_bv_exchange_bytes": (_SZ, [_I32, _I32]),
+    "jaxent_peer_alloc": (C.c_int, [_SZ, C.POINTER(_VP), C.c_char_p]),
+    "jaxent_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    "jaxent_peer_close": (C.c_int, [_VP]),
+    "jaxent_peer_free": (C.c_int, [_VP]),
+    "jaxent_bv_plan_set_exchange": (C.c_int, [_VP, _I32, _I32, C.POINTER(_VP)]),
+    "jaxent_bv_exchange_error": (C.c_int, [_VP, _VP, _VP]),
     "jaxent_bv_state_init": (C.c_int, [_VP, _VP, _F, _F, _F, C.POINTER(_F), C.POINTER(_F), _VP]),
     "jaxent_bv_pass": (C.c_int, [_VP, _I32, _VP]),
     "jaxent_bv_reduce": (C.c_int, [_VP, _VP]),
@@ -189,6 +199,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
+    override = os.environ.get("JAXENT_B200_LIB")  # A/B experiments against another build of the same ABI
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing and _build.needs_build():
         try:
             _build.build()
@@ -199,6 +212,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         raise RuntimeError(f"{path} is missing and could not be built; jaxent_b200 has no CPU fallback")
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
+        if override and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

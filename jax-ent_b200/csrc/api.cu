@@ -24,7 +24,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
   size_t off_w, off_kappa, off_cc, off_ch, off_logpf, off_uptake, off_avg;
-  size_t off_partials, off_red, off_klpart, off_klsum, off_ctl, off_epoch, off_counter, off_records;
+  size_t off_partials, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_ticket, off_records;
   size_t off_cl_scratch;
   size_t off_blob[JAXENT_MAX_SLOTS];
   int blob_words[JAXENT_MAX_SLOTS];
@@ -61,19 +61,14 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_uptake = take((size_t)(T > 0 ? T : 1) * R * 4);
   L.off_avg = take((size_t)2 * R * 4);
   L.off_partials = take((size_t)MAX_PASS_CTAS * (4 * R + 4) * sizeof(double));
-  L.off_red = take((size_t)(4 * R + 4) * sizeof(double));
+  L.off_xchg = take(xchg_bytes(4 * R + 4, 1));  // single-rank exchange buffer (red / kl inbox of world = 1)
   L.off_klpart = take((size_t)MAX_TAIL_CTAS * KL_N * sizeof(double));
-  L.off_klsum = take(KL_N * sizeof(double));
   L.off_ctl = take(2 * sizeof(Ctl));
   L.off_epoch = take(sizeof(unsigned));
   L.off_counter = take(sizeof(unsigned));
+  L.off_ticket = take(sizeof(unsigned));
   L.off_records = take((size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord));
-  {
-    int p_tr = 1;
-    for (int i = 0; i < pb->n_slots && i < JAXENT_MAX_SLOTS; ++i)
-      if (pb->slots[i].kind <= JAXENT_LOSS_PF_L2 && pb->slots[i].train.n_pep > p_tr) p_tr = pb->slots[i].train.n_pep;
-    L.off_cl_scratch = take(tail_cluster_scratch_doubles(R, T, p_tr) * sizeof(double));
-  }
+  L.off_cl_scratch = take(64 * sizeof(double));
   for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
     L.off_blob[i] = 0;
     L.blob_words[i] = 0;
@@ -88,7 +83,8 @@ static Layout make_layout(const JaxentBvProblem* pb) {
 }
 
 __global__ void state_init_kernel(const float* __restrict__ z0, long long F, StateSets st, Ctl* ctl, Ctl init,
-                                  unsigned* epoch, unsigned* counter, double* klsum, JaxentLossRecord* records) {
+                                  unsigned* epoch, unsigned* counter, unsigned* ticket, unsigned long long* xchg_local,
+                                  long long xchg_words, JaxentLossRecord* records) {
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long f = i0; f < F; f += stride) {
@@ -103,8 +99,10 @@ __global__ void state_init_kernel(const float* __restrict__ z0, long long F, Sta
     ctl[1] = init;
     *epoch = 0u;
     *counter = 0u;
-    for (int i = 0; i < KL_N; ++i) klsum[i] = 0.0;
+    *ticket = 0u;
   }
+  // the local exchange buffer: inboxes, flags and the error word (peers only write here after every rank's state_init)
+  for (long long i = i0; i < xchg_words; i += stride) xchg_local[i] = 0ull;
   for (long long i = i0; i < (long long)(JAXENT_RECORD_RING * sizeof(JaxentLossRecord) / 4); i += stride)
     reinterpret_cast<int*>(records)[i] = 0;
 }
@@ -154,7 +152,8 @@ struct JaxentPlan {
   jx::Layout lay;
   unsigned char* ws;
   jx::StateSets st;
-  int pass_threads, rpt, pass_ctas, stages, tail_ctas, tail_clustered, p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
+  int pass_threads, rpt, pass_ctas, stages, tail_ctas, p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
+  jx::Xchg x;
   uint32_t tile_bytes, stage_stride, subtile_bytes;
   int sub_tiles;
   long long n_stage_units;
@@ -327,13 +326,7 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   p->p_max_va = p_va;
   p->nnz_max_tr = nnz_tr;
   p->nnz_max_va = nnz_va;
-  // the clustered tail covers the eye-MSE / PF-L2 data kinds with R >= 64; everything else runs on one CTA
-  p->tail_clustered = (R >= 64) && (getenv("JAXENT_TAIL_CLUSTER") != nullptr);  // opt-in: measured no faster than one CTA
-  for (int i = 0; i < problem->n_slots; ++i)
-    if (problem->slots[i].kind == JAXENT_LOSS_UPTAKE_MC_EYE_MSE || problem->slots[i].kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE)
-      p->tail_clustered = 0;
-  p->tail_smem = p->tail_clustered ? tail_cluster_smem_bytes(R, T, p_tr, p_va, nnz_tr, nnz_va)
-                                   : tail_smem_bytes(R, T, p_tr, p_va, nnz_tr, nnz_va);
+  p->tail_smem = tail_smem_bytes(R, T, p_tr, p_va, nnz_tr, nnz_va);
   if (p->tail_smem > 220 * 1024) {
     const size_t need = p->tail_smem;
     delete p;
@@ -344,16 +337,12 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   long long fctas = (problem->F + 4095) / 4096;
   if (fctas > device_sm_count - 1) fctas = device_sm_count - 1;
   p->tail_ctas = (fctas <= 1) ? 1 : (int)fctas + 1;
-  if (p->tail_clustered) {
-    // cluster 0 (8 CTAs) runs the tail; the frames go to further clusters of 8 (or to cluster 0 itself when F is small)
-    long long fc = (problem->F + 4095) / 4096;
-    // clusters of 8 are placed inside one GPC (16-20 SMs): at most 2 per GPC are co-resident, 16 on the chip; keep one wave
-    long long max_fc = ((device_sm_count - TAIL_CLUSTER) / TAIL_CLUSTER) * TAIL_CLUSTER;
-    if (max_fc > 15 * TAIL_CLUSTER) max_fc = 15 * TAIL_CLUSTER;
-    if (fc > max_fc) fc = max_fc;
-    fc = (fc + TAIL_CLUSTER - 1) / TAIL_CLUSTER * TAIL_CLUSTER;
-    p->tail_ctas = (fc <= TAIL_CLUSTER) ? TAIL_CLUSTER : TAIL_CLUSTER + (int)fc;
-  }
+  memset(&p->x, 0, sizeof(p->x));
+  p->x.world = 1;
+  p->x.rank = 0;
+  p->x.part_n = 4 * R + 4;
+  p->x.base[0] = p->ws + L.off_xchg;
+  p->x.local = p->x.base[0];
   p->initialised = 0;
   memset(&p->trk, 0, sizeof(p->trk));
   *out = p;
@@ -366,13 +355,16 @@ extern "C" int jaxent_bv_plan_buffer(const JaxentPlan* p, int32_t which, void** 
   if (!p || !ptr || !bytes) { set_error("plan_buffer: NULL argument"); return JAXENT_E_INVALID; }
   const int R = p->prob.R, T = p->prob.uptake ? p->prob.T : 0;
   switch (which) {
-    case JAXENT_BUF_RED: *ptr = p->ws + p->lay.off_red; *bytes = (size_t)(4 * R + 4) * 8; break;
-    case JAXENT_BUF_KLSUM: *ptr = p->ws + p->lay.off_klsum; *bytes = KL_N * 8; break;
+    case JAXENT_BUF_RED:  // plain doubles; meaningful when the exchange is not fused (one rank, or NCCL between the phases)
+      *ptr = p->x.local + xchg_plain_red_off(p->x); *bytes = (size_t)(4 * R + 4) * 8; break;
+    case JAXENT_BUF_KLSUM: *ptr = p->x.local + xchg_plain_kl_off(p->x); *bytes = KL_N * 8; break;
+    case JAXENT_BUF_XCHG_ERR: *ptr = p->x.local + xchg_err_off(p->x); *bytes = 8; break;
     case JAXENT_BUF_WEIGHTS: *ptr = p->ws + p->lay.off_w; *bytes = (size_t)p->prob.F * 4; break;
     case JAXENT_BUF_RECORDS: *ptr = p->ws + p->lay.off_records; *bytes = (size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord); break;
     case JAXENT_BUF_LOGPF: *ptr = p->ws + p->lay.off_logpf; *bytes = (size_t)R * 4; break;
     case JAXENT_BUF_UPTAKE: *ptr = p->ws + p->lay.off_uptake; *bytes = (size_t)T * R * 4; break;
     case JAXENT_BUF_AVG: *ptr = p->ws + p->lay.off_avg; *bytes = (size_t)2 * R * 4; break;
+    case 8: *ptr = p->ws + p->lay.off_cl_scratch; *bytes = 64 * 8; break;  // debug timestamps (JX_TAIL_PROFILE builds)
     default: set_error("plan_buffer: unknown buffer id %d", which); return JAXENT_E_INVALID;
   }
   return JAXENT_OK;
@@ -406,7 +398,8 @@ extern "C" int jaxent_bv_state_init(JaxentPlan* p, const float* z0, float zmax, 
   Ctl* ctl = reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl);
   state_init_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(
       z0, p->prob.F, p->st, ctl, c, reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch),
-      reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter), reinterpret_cast<double*>(p->ws + p->lay.off_klsum),
+      reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter), reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket),
+      reinterpret_cast<unsigned long long*>(p->x.local), (long long)(xchg_bytes(p->x.part_n, p->x.world) / 8),
       reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("state_init launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
@@ -452,7 +445,7 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.cc = reinterpret_cast<const float*>(p->ws + p->lay.off_cc);
   a.ch = reinterpret_cast<const float*>(p->ws + p->lay.off_ch);
   a.partials = reinterpret_cast<double*>(p->ws + p->lay.off_partials);
-  a.klsum = reinterpret_cast<const double*>(p->ws + p->lay.off_klsum);
+  a.x = p->x;
   a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
   a.epoch = reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch);
   a.records = reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records);
@@ -462,6 +455,7 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.om_b2 = (float)(1.0 - p->cfg.b2);
   a.eps = (float)p->cfg.eps;
   a.clip = p->cfg.clip_value;
+  a.dbg = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
   return launch_pass(a, p->pass_threads + 32, p->rpt, p->pass_ctas, p->pass_smem, (cudaStream_t)stream);
 }
 
@@ -471,8 +465,10 @@ extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t stream) {
   ReduceArgs a;
   a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
   a.partials = reinterpret_cast<const double*>(p->ws + p->lay.off_partials);
-  a.red = reinterpret_cast<double*>(p->ws + p->lay.off_red);
+  a.x = p->x;
   a.epoch = reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch);
+  a.ticket = reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket);
+  a.dbg = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
   a.n_part = p->pass_ctas;
   a.part_n = 4 * p->prob.R + 4;
   return launch_reduce(a, (cudaStream_t)stream);
@@ -487,7 +483,7 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.trk = p->trk;
   a.cfg = p->cfg;
   a.st = p->st;
-  a.red = reinterpret_cast<const double*>(p->ws + p->lay.off_red);
+  a.x = p->x;
   a.ctl = reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl);
   a.epoch = reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch);
   a.counter = reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter);
@@ -499,15 +495,13 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.uptake = reinterpret_cast<float*>(p->ws + p->lay.off_uptake);
   a.avg = reinterpret_cast<float*>(p->ws + p->lay.off_avg);
   a.klpart = reinterpret_cast<double*>(p->ws + p->lay.off_klpart);
-  a.klsum = reinterpret_cast<double*>(p->ws + p->lay.off_klsum);
   a.records = reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records);
   for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
     a.blobs.words[i] = p->lay.blob_words[i];
     a.blobs.blob[i] = a.blobs.words[i] ? reinterpret_cast<int*>(p->ws + p->lay.off_blob[i]) : nullptr;
   }
   {
-    long long fc = (p->tail_ctas == 1) ? 1 : p->tail_ctas - 1;
-    if (p->tail_clustered) fc = (p->tail_ctas == TAIL_CLUSTER) ? TAIL_CLUSTER : p->tail_ctas - TAIL_CLUSTER;
+    const long long fc = (p->tail_ctas == 1) ? 1 : p->tail_ctas - 1;
     a.frames_per_cta = (p->prob.F + fc - 1) / fc;
   }
   a.cl_scratch = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
@@ -516,7 +510,6 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.nnz_max_tr = p->nnz_max_tr;
   a.nnz_max_va = p->nnz_max_va;
   a.eps_kl = (float)(1e-10 / (double)p->prob.F_total);
-  if (p->tail_clustered) return launch_tail_cluster(a, p->tail_ctas, p->tail_smem, (cudaStream_t)stream);
   return launch_tail(a, p->tail_ctas, p->tail_smem, (cudaStream_t)stream);
 }
 
@@ -525,8 +518,7 @@ extern "C" int jaxent_bv_finish_record(JaxentPlan* p, jaxent_stream_t stream) {
   if (rc) return rc;
   return launch_finish_record(reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl),
                               reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch),
-                              reinterpret_cast<const double*>(p->ws + p->lay.off_klsum),
-                              reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records), p->prob.n_slots,
+                              p->x, reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records), p->prob.n_slots,
                               (cudaStream_t)stream);
 }
 
@@ -544,6 +536,77 @@ extern "C" int jaxent_bv_step(JaxentPlan* p, jaxent_stream_t stream) {
   rc = jaxent_bv_reduce(p, stream);
   if (rc) return rc;
   return jaxent_bv_tail(p, stream);
+}
+
+// ---- NVLink peer exchange (set-up time only)
+extern "C" size_t jaxent_bv_exchange_bytes(int32_t R, int32_t world) {
+  if (R <= 0 || world < 1 || world > JAXENT_MAX_RANKS) return 0;
+  return xchg_bytes(4 * R + 4, world);
+}
+
+extern "C" int jaxent_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle) {
+  if (!dev_ptr || !handle || bytes == 0) { set_error("peer_alloc: invalid argument"); return JAXENT_E_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == JAXENT_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    set_error("peer_alloc: %s", cudaGetErrorString(e));
+    return JAXENT_E_CUDA;
+  }
+  memcpy(handle, &h, sizeof(h));
+  *dev_ptr = p;
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_peer_open(const unsigned char* handle, void** dev_ptr) {
+  if (!dev_ptr || !handle) { set_error("peer_open: invalid argument"); return JAXENT_E_INVALID; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_error("peer_open: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  *dev_ptr = p;
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_peer_close(void* dev_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  if (e != cudaSuccess) { set_error("peer_close: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_peer_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  if (e != cudaSuccess) { set_error("peer_free: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bv_plan_set_exchange(JaxentPlan* p, int32_t rank, int32_t world, void* const* peers) {
+  if (!p || !peers || world < 1 || world > JAXENT_MAX_RANKS || rank < 0 || rank >= world) {
+    set_error("set_exchange: need 1..%d ranks and one mapped exchange buffer per rank", JAXENT_MAX_RANKS);
+    return JAXENT_E_INVALID;
+  }
+  for (int r = 0; r < world; ++r)
+    if (!peers[r] || (reinterpret_cast<uintptr_t>(peers[r]) & 15u)) { set_error("set_exchange: peer %d buffer is NULL or misaligned", r); return JAXENT_E_INVALID; }
+  memset(&p->x, 0, sizeof(p->x));
+  p->x.world = world;
+  p->x.rank = rank;
+  p->x.part_n = 4 * p->prob.R + 4;
+  for (int r = 0; r < world; ++r) p->x.base[r] = static_cast<unsigned char*>(peers[r]);
+  p->x.local = p->x.base[rank];
+  p->initialised = 0;  // state_init clears the local flags; it must follow
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bv_exchange_error(JaxentPlan* p, uint64_t* out, jaxent_stream_t stream) {
+  if (!p || !out) { set_error("exchange_error: NULL argument"); return JAXENT_E_INVALID; }
+  cudaError_t e = cudaMemcpyAsync(out, p->x.local + xchg_err_off(p->x), 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("exchange_error: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
 }
 
 extern "C" int jaxent_bv_track_init(JaxentPlan* p, const float* thresholds, int32_t n, float ema_alpha, int32_t min_steps,

@@ -293,6 +293,16 @@ __device__ __forceinline__ void phase_b(const TileRegs<RPT>& d, const float* s_e
   }
 }
 
+// Adam warp, once per launch: the MaxEnt sums of the tail that preceded this pass (all ranks; spins on the peers'
+// words when frame-sharded) -> hbar = sum_j w_j h_j; CTA 0 also completes that step's loss record.  Kept out of line
+// so that its registers do not weigh on the per-tile loop.
+__device__ __noinline__ float adam_prologue(const Xchg x, unsigned ep, const Ctl* __restrict__ ctl, JaxentLossRecord* records, int lane) {
+  double kl[KL_N];
+  kl_gather_warp(x, ep, lane, kl);
+  if (lane == 0 && blockIdx.x == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
+  return (float)(ctl->hbar_data + kl[0]);
+}
+
 template <int RPT, int FMT>
 __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -334,8 +344,10 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
       bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(s0 + s) * a.tile_bytes, a.tile_bytes, bar);
     }
   }
+  if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 40);
   pdl_wait();               // everything the tail kernel wrote (ctl, cc/ch, w, kappa, klsum) is visible from here on
   pdl_launch_dependents();  // lets the reduce kernel's launch overlap this kernel
+  if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 41);
 
   const unsigned ep = *a.epoch;
   if (a.ctl[ep & 1u].trk_stop) {
@@ -350,7 +362,9 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
   if (is_adam) {
     // ================================================================== Adam warp
     const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
-    if (lane == 0 && blockIdx.x == 0 && mode == 1) finish_record(ctl, a.klsum, a.records, JAXENT_MAX_SLOTS);
+    // MaxEnt sums of the tail that preceded this pass (all ranks; waits on the peers' flags when frame-sharded)
+    const float hbar = mode ? adam_prologue(a.x, ep, ctl, a.records, lane) : 0.f;
+    if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 42);
     const int in_set = ep & 1u, out_set = in_set ^ 1;
     const int in_br = ctl->branch;
     const float* __restrict__ zin = a.st.z[in_set][in_br];
@@ -369,7 +383,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
     const float maskf = ctl->mask_frame;
     const float bc1 = ctl->bc1, bc2 = ctl->bc2;
     const int have_prev = ctl->have_prev;
-    const float hbar = (float)(ctl->hbar_data + a.klsum[0]);
     const float b1 = a.b1, b2 = a.b2, om_b1 = a.om_b1, om_b2 = a.om_b2, eps = a.eps, clip = a.clip;
     const int fj = lane & 7, fk = lane >> 3;  // frame within tile, partial-sum group
     double sumA = 0.0, sumB = 0.0, gdot = 0.0;
@@ -454,6 +467,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
       sumB += __shfl_xor_sync(0xffffffffu, sumB, o);
       gdot += __shfl_xor_sync(0xffffffffu, gdot, o);
     }
+    if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 43);
     if (lane == 0) {
       part[4 * R + 0] = sumA;
       part[4 * R + 1] = sumB;
@@ -557,14 +571,19 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
 }
 
 // ------------------------------------------------------------------------------------------ reduce
-// red[j] = sum_cta partials[cta][j] in CTA order (deterministic); also advances the epoch.
+// sum_cta partials[cta][j] in CTA order (deterministic), stored into the red inbox of EVERY rank (slot = this rank);
+// the last block to finish advances the epoch.
 __global__ void __launch_bounds__(1024) reduce_kernel(const ReduceArgs a) {
   // 32 columns x 32 partial-groups per block: every load is independent (latency overlapped) and
   // the summation order is fixed (group-strided, then groups 0..31) -> bitwise reproducible.
   __shared__ double sh[32][33];
+  if (blockIdx.x == 0 && threadIdx.x == 0) JPROF(a.dbg, 44);
   pdl_wait();
   pdl_launch_dependents();
-  if (a.ctl[*a.epoch & 1u].trk_stop) return;  // on-device loop ended: keep red and the epoch as they are
+  if (blockIdx.x == 0 && threadIdx.x == 0) JPROF(a.dbg, 45);
+  const unsigned ep = *a.epoch;         // every block reads the epoch before the last one advances it (ticket below)
+  if (a.ctl[ep & 1u].trk_stop) return;  // on-device loop ended: keep the sums and the epoch as they are
+  const unsigned nep = ep + 1u;
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
   double s = 0.0;
@@ -578,15 +597,24 @@ __global__ void __launch_bounds__(1024) reduce_kernel(const ReduceArgs a) {
     double t = 0.0;
 #pragma unroll
     for (int g2 = 0; g2 < 32; ++g2) t += sh[g2][lane];
-    a.red[col] = t;
+    red_publish(a.x, nep, col, t);  // plain store (one rank) or stamped 16-byte stores into every rank's inbox
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.epoch = *a.epoch + 1u;
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(a.ticket, 1u);
+    if (ticket == gridDim.x - 1) {  // every block has read the old epoch by now
+      *a.ticket = 0u;
+      *a.epoch = nep;
+      JPROF(a.dbg, 46);
+    }
+  }
 }
 
-__global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, const double* klsum, JaxentLossRecord* rec,
-                                     int n_slots) {
-  const Ctl* c = ctl + (*epoch & 1u);
-  finish_record(c, klsum, rec, n_slots);
+__global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, const Xchg x, JaxentLossRecord* rec, int n_slots) {
+  const unsigned ep = *epoch;
+  const Ctl* c = ctl + (ep & 1u);
+  double kl[KL_N];
+  kl_gather_warp(x, ep, threadIdx.x & 31, kl);
+  if (threadIdx.x == 0) finish_record(c, kl[1] + kl[2], rec, n_slots);
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -625,9 +653,8 @@ int launch_reduce(const ReduceArgs& a, cudaStream_t s) {
   return JAXENT_OK;
 }
 
-int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const double* klsum, JaxentLossRecord* rec, int n_slots,
-                         cudaStream_t s) {
-  finish_record_kernel<<<1, 1, 0, s>>>(ctl, epoch, klsum, rec, n_slots);
+int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const Xchg& x, JaxentLossRecord* rec, int n_slots, cudaStream_t s) {
+  finish_record_kernel<<<1, 32, 0, s>>>(ctl, epoch, x, rec, n_slots);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("finish_record launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;

@@ -25,6 +25,14 @@
 
 namespace jx {
 
+#ifdef JX_PROFILE
+#define TPROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<long long*>(a.cl_scratch)[i] = gtime(); } while (0)
+#define TPROF_F(i) do { if (blockIdx.x == 1 && threadIdx.x == 0) reinterpret_cast<long long*>(a.cl_scratch)[32 + i] = gtime(); } while (0)
+#else
+#define TPROF(i) do {} while (0)
+#define TPROF_F(i) do {} while (0)
+#endif
+
 // ---- code-size discipline: this kernel runs a long straight-line path once per launch, so its cost is
 // dominated by instruction fetch.  Heavy math lives behind single __noinline__ call sites.
 __device__ __noinline__ double wsum(double v) {
@@ -56,12 +64,11 @@ struct StepScalars {
 // warp 0 only.  Reads the previous control block straight from global memory (one round trip that
 // overlaps the staging done by the other warps); the four powf and two log evaluations run on
 // separate lanes behind single call sites.
-__device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restrict__ old, const double* __restrict__ red,
-                                            int R, const JaxentOptConfig cfg, const TrackConfig trk,
+__device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restrict__ old, double SA, double SB, double gdot,
+                                            const JaxentOptConfig cfg, const TrackConfig trk,
                                             const JaxentLossRecord* __restrict__ records) {
   const int lane = threadIdx.x & 31;
   StepScalars s;
-  const double SA = red[4 * R + 0], SB = red[4 * R + 1], gdot = red[4 * R + 2];
   s.pending = old->pending;
   s.step = old->step;
   s.mask_idx = old->mask_idx;
@@ -271,7 +278,7 @@ int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_
 // the new control block and the loss record, written by one warp (lane 0 the scalars, lanes 0..5 the slots)
 __device__ __forceinline__ void write_ctl_and_record(Ctl* __restrict__ neu, JaxentLossRecord* records, const StepScalars& sc,
                                                      const Ctl& s_old, const double* s_fin, double gbc_reg, double gbh_reg,
-                                                     int n_slots, const double* klsum, int lane, const TrackConfig& trk) {
+                                                     int n_slots, int lane, const TrackConfig& trk) {
   if (lane == 2) {
     neu->trk_stop = sc.trk_stop;
     neu->trk_reason = sc.trk_reason;
@@ -354,7 +361,7 @@ __device__ __forceinline__ void write_ctl_and_record(Ctl* __restrict__ neu, Jaxe
     rec->val[lane] = (lane < n_slots) ? (float)s_fin[JAXENT_MAX_SLOTS + lane] : 0.f;
   }
   __syncwarp();
-  if (lane == 0 && s_old.kl_slot < 0) finish_record(neu, klsum, records, n_slots);
+  if (lane == 0 && s_old.kl_slot < 0) finish_record(neu, 0.0, records, n_slots);
 }
 
 // per-frame MaxEnt terms of frames [cta*frames_per_cta, ...): softmax weights, dKL/dw and the KL sums of this CTA
@@ -411,29 +418,32 @@ __device__ __forceinline__ void frame_terms(const TailArgs& a, const StepScalars
     double t = 0.0;
 #pragma unroll 1
     for (int w = 0; w < nw; ++w) t += s_red[w][tid];
-    if (gridDim.x == 1) a.klsum[tid] = t;  // single CTA: done
-    else a.klpart[(size_t)blockIdx.x * KL_N + tid] = t;
+    a.klpart[(size_t)blockIdx.x * KL_N + tid] = t;
   }
 }
 
-// last-arriving CTA folds the per-CTA KL sums in CTA order (deterministic)
-__device__ __forceinline__ void fold_kl_partials(const TailArgs& a, int* s_last) {
-  if (gridDim.x == 1) return;
+// last-arriving CTA folds the per-CTA KL sums in CTA order (deterministic) and publishes them: a plain store on one
+// rank, stamped 16-byte stores into the kl inbox of every rank (slot = this rank) when frame-sharded
+__device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep, int* s_last) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < KL_N) __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned ticket = atomicAdd(a.counter, 1u);
-    *s_last = (ticket == gridDim.x - 1);
+  if (gridDim.x > 1) {
+    if (tid < KL_N) __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned ticket = atomicAdd(a.counter, 1u);
+      *s_last = (ticket == gridDim.x - 1);
+    }
+  } else if (tid == 0) {
+    *s_last = 1;
   }
   __syncthreads();
   if (*s_last && warp < KL_N) {
     __threadfence();
     double t = 0.0;
 #pragma unroll 1
-    for (unsigned cc = lane; cc < gridDim.x; cc += 32) t += a.klpart[(size_t)cc * KL_N + warp];
+    for (unsigned cc = lane; cc < gridDim.x; cc += 32) t += __ldcg(&a.klpart[(size_t)cc * KL_N + warp]);
     t = wsum(t);
-    if (lane == 0) a.klsum[warp] = t;
+    if (lane == 0) kl_publish(a.x, ep, warp, t);
     if (tid == 0) *a.counter = 0u;
   }
 }
@@ -470,6 +480,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   float* s_tp = s_k + ((R + 3) & ~3);
   int* s_blob = reinterpret_cast<int*>(s_tp + ((Tm + 3) & ~3));  // 16-byte aligned blob image
 
+  TPROF(0); TPROF_F(0);
   // ---- constant data first (peptide-map blob, rates, time points): independent of the previous kernel (PDL)
   int first_data = -1;
   if (tail_cta) {
@@ -489,8 +500,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       if (tid < T) s_tp[tid] = pb.timepoints[tid];
     }
   }
+  TPROF(1);
   pdl_wait();               // the reduced partial sums and the previous control block are visible from here on
   pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
+  TPROF(2); TPROF_F(1);
   const unsigned ep = *a.epoch;
   if (a.ctl[ep & 1u].trk_stop) return;  // the on-device loop has ended (reduce did not advance the epoch): no-op
   const Ctl* __restrict__ old_g = a.ctl + ((ep - 1u) & 1u);
@@ -500,7 +513,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   // ---- one global round trip: warp 0 derives the step scalars, another warp copies the control block
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (warp == 0) {
-    derive_scalars(&s_sc, old_g, a.red, R, a.cfg, a.trk, a.records);
+    const double SA = red_total(a.x, ep, 4 * R + 0), SB = red_total(a.x, ep, 4 * R + 1), gdot = red_total(a.x, ep, 4 * R + 2);
+    derive_scalars(&s_sc, old_g, SA, SB, gdot, a.cfg, a.trk, a.records);
   } else if (warp == 1) {
     const int4* src = reinterpret_cast<const int4*>(old_g);
     int4* dst = reinterpret_cast<int4*>(&s_old);
@@ -508,14 +522,15 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   }
   if (tail_cta) {
     if (tid < R) {
-      accA0 = a.red[0 * R + tid];
-      accA1 = a.red[1 * R + tid];
-      accB0 = a.red[2 * R + tid];
-      accB1 = a.red[3 * R + tid];
+      accA0 = red_total(a.x, ep, 0 * R + tid);
+      accA1 = red_total(a.x, ep, 1 * R + tid);
+      accB0 = red_total(a.x, ep, 2 * R + tid);
+      accB1 = red_total(a.x, ep, 3 * R + tid);
     }
     if (lane < 16) s_red[warp][lane] = 0.0;
   }
   __syncthreads();  // (1) everything staged, scalars broadcast
+  TPROF(3); TPROF_F(2);
   const int d = s_sc.d;
   const double S = s_sc.S;
 
@@ -549,6 +564,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       }
     }
     __syncthreads();  // (2) lnPF / uptake visible
+    TPROF(4);
 
     // ---- loss slots
     double gbc_reg = 0.0, gbh_reg = 0.0;
@@ -610,6 +626,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
           if (lane == 0) s_red[warp][set * JAXENT_MAX_SLOTS + i] = pl;
         }
       }
+      TPROF(5);
       if (GENERAL && (centre || sigma)) {
         const float* tr_y = reinterpret_cast<const float*>(s_blob + bl.tr_y);
         const float* va_y = reinterpret_cast<const float*>(s_blob + bl.va_y);
@@ -690,6 +707,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
         }
       }
       __syncthreads();  // (3) dL/dpred visible
+      TPROF(6);
 
       // (b) back-projection to dL/d lnPF, parallel over (t, r)
       {
@@ -715,6 +733,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
         }
       }
       __syncthreads();  // (4) items visible
+      TPROF(7);
       if (tid < R) {
 #pragma unroll 1
         for (int t = 0; t < Tm; ++t) my_c += sc_rt[(size_t)t * R + tid];
@@ -743,6 +762,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       }
     }
     __syncthreads();  // (5)
+    TPROF(8);
     if (tid < 15) {
       double t = 0.0;
 #pragma unroll 1
@@ -750,8 +770,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       s_fin[tid] = t;
     }
     __syncthreads();  // (6)
+    TPROF(9);
 
-    if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, a.klsum, lane, a.trk);
+    if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, lane, a.trk);
+    TPROF(10);
   }
 
   // ================================================================== per-frame MaxEnt terms
@@ -761,50 +783,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   } else {
     frame_terms(a, s_sc, s_old, cur_set, (gridDim.x == 1) ? 0 : (long long)blockIdx.x - 1, 0, s_red);
   }
-  fold_kl_partials(a, &s_last);
-}
-
-#include "bv_tail_cluster.cuh"
-
-size_t tail_cluster_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va) {
-  const size_t Tm = T > 0 ? T : 1;
-  const size_t nrs = (size_t)R / TAILC + 1;
-  const size_t dbl = 2 * nrs + Tm * nrs + Tm * (size_t)R + (size_t)p_tr * Tm;
-  const size_t f32 = (((size_t)R + 3) & ~(size_t)3) + ((Tm + 3) & ~(size_t)3);
-  const BlobLayout b = blob_layout(R, (int)Tm, p_tr, nnz_tr, p_va, nnz_va);
-  return dbl * 8 + f32 * 4 + (size_t)b.words * 4 + 64;
-}
-
-size_t tail_cluster_scratch_doubles(int R, int T, int p_tr) {
-  const size_t Tm = T > 0 ? T : 1;
-  return Tm * (size_t)R + (size_t)R + (size_t)p_tr * Tm + (size_t)TAILC * 16;
-}
-
-int launch_tail_cluster(const TailArgs& a, int ctas, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(bv_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("clustered tail kernel needs %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return JAXENT_E_UNSUPPORTED; }
-    configured = smem;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)ctas);
-  cfg.blockDim = dim3(TAIL_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  at[1].id = cudaLaunchAttributeClusterDimension;
-  at[1].val.clusterDim.x = TAILC;
-  at[1].val.clusterDim.y = 1;
-  at[1].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, bv_tail_cluster_kernel, a);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("bv_tail_cluster_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  return JAXENT_OK;
+  TPROF(11); TPROF_F(3);
+  fold_kl_partials(a, ep, &s_last);
+  TPROF(12); TPROF_F(4);
 }
 
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va) {

@@ -62,6 +62,118 @@ struct BlobSet {
   int words[JAXENT_MAX_SLOTS];
 };
 
+// ---- exchange buffer of the frame-sharded step (one per rank, mapped into every peer; see jaxent_b200.h)
+//   plain  red [part_n] double, kl [KL_N] double              world == 1 (also what an NCCL-driven run all-reduces)
+//   LL     red [2 parities][world][part_n] x 16 B             written by every rank's reduce kernel (slot = source rank)
+//          kl  [2 parities][world][KL_N]  x 16 B              written by every rank's tail kernel
+//   err    u64                                                 set when a wait timed out
+// LL ("low latency") words carry their own validity stamp, as in NCCL's LL protocol: a double travels as one
+// 16-byte store {lo, stamp, hi, stamp} whose two 8-byte halves are each written atomically, the stamp being the
+// epoch of the step.  The consumer spins on the word itself until both stamps match -- no flags, no memory fences
+// and no ordering requirement between words, so an exchange costs one NVLink store latency.  Parity double
+// buffering keeps a fast rank's stores of epoch e+2 out of the slots a slow rank may still be reading for epoch e
+// (a rank cannot publish e+2 before every rank has published e+1, i.e. finished reading e).
+struct Xchg {
+  int world, rank, part_n, pad;
+  unsigned char* local;                    // == base[rank]; kernels never index base[] dynamically (the struct is a
+  unsigned char* base[JAXENT_MAX_RANKS];   // by-value kernel parameter: a dynamic index would force a local-memory copy)
+};
+__host__ __device__ inline size_t xchg_plain_red_off(const Xchg&) { return 0; }
+__host__ __device__ inline size_t xchg_plain_kl_off(const Xchg& x) { return (size_t)x.part_n * 8; }
+__host__ __device__ inline size_t xchg_ll_base(const Xchg& x) { return ((size_t)(x.part_n + KL_N) * 8 + 255) / 256 * 256; }
+__host__ __device__ inline size_t xchg_red_off(const Xchg& x, int par, int src) {
+  return xchg_ll_base(x) + ((size_t)(par * x.world + src) * x.part_n) * 16;
+}
+__host__ __device__ inline size_t xchg_kl_off(const Xchg& x, int par, int src) {
+  return xchg_ll_base(x) + (size_t)2 * x.world * x.part_n * 16 + (size_t)(par * x.world + src) * KL_N * 16;
+}
+__host__ __device__ inline size_t xchg_err_off(const Xchg& x) {
+  return xchg_ll_base(x) + (x.world > 1 ? (size_t)2 * x.world * (x.part_n + KL_N) * 16 : 0);
+}
+__host__ __device__ inline size_t xchg_bytes(int part_n, int world) {
+  Xchg x;
+  x.world = world;
+  x.part_n = part_n;
+  return (xchg_err_off(x) + 8 + 255) / 256 * 256;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void ll_store(unsigned char* slot, double v, unsigned stamp) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(stamp), "r"(hi), "r"(stamp) : "memory");
+}
+// bounded spin (a few seconds): a peer that never arrives must not hang the GPU; the error word is raised instead
+__device__ __forceinline__ double ll_load(unsigned char* err_word, const unsigned char* slot, unsigned stamp) {
+  unsigned a = 0, b = 0, c = 0, d = 0;
+  for (long long i = 0; i < (1ll << 24); ++i) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(slot) : "memory");
+    if (b == stamp && d == stamp) return __hiloint2double((int)c, (int)a);
+    if (i > 1024) __nanosleep(100);
+  }
+  *reinterpret_cast<volatile unsigned long long*>(err_word) = 1ull;
+  return __hiloint2double((int)c, (int)a);
+}
+// element j of the partial sums of epoch `ep`, summed over the ranks in rank order (identical on every rank).
+// All ranks' words are requested at once (independent loads, one L2 round trip); only words that have not landed
+// yet are polled again.
+static __device__ __noinline__ double red_total_ll(const unsigned char* slot0, size_t rstride, int world, unsigned ep, unsigned char* err_word) {
+  uint4 w[JAXENT_MAX_RANKS];
+#pragma unroll
+  for (int r = 0; r < JAXENT_MAX_RANKS; ++r)
+    if (r < world) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[r].x), "=r"(w[r].y), "=r"(w[r].z), "=r"(w[r].w) : "l"(slot0 + r * rstride) : "memory");
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < JAXENT_MAX_RANKS; ++r)
+    if (r < world) {
+      double v = __hiloint2double((int)w[r].z, (int)w[r].x);
+      if (w[r].y != ep || w[r].w != ep) v = ll_load(err_word, slot0 + r * rstride, ep);
+      t += v;
+    }
+  return t;
+}
+__device__ __forceinline__ double red_total(const Xchg& x, unsigned ep, int j) {
+  if (x.world == 1) return __ldcg(reinterpret_cast<const double*>(x.local + xchg_plain_red_off(x)) + j);
+  return red_total_ll(x.local + xchg_red_off(x, (int)(ep & 1u), 0) + (size_t)j * 16, (size_t)x.part_n * 16, x.world, ep, x.local + xchg_err_off(x));
+}
+__device__ __forceinline__ void red_publish(const Xchg& x, unsigned ep, int j, double v) {
+  if (x.world == 1) {
+    reinterpret_cast<double*>(x.local + xchg_plain_red_off(x))[j] = v;
+    return;
+  }
+  const size_t off = xchg_red_off(x, (int)(ep & 1u), x.rank) + (size_t)j * 16;
+#pragma unroll
+  for (int r = 0; r < JAXENT_MAX_RANKS; ++r)
+    if (r < x.world) ll_store(x.base[r] + off, v, ep);
+}
+__device__ __forceinline__ void kl_publish(const Xchg& x, unsigned ep, int k, double v) {
+  if (x.world == 1) {
+    reinterpret_cast<double*>(x.local + xchg_plain_kl_off(x))[k] = v;
+    return;
+  }
+  const size_t off = xchg_kl_off(x, (int)(ep & 1u), x.rank) + (size_t)k * 16;
+#pragma unroll
+  for (int r = 0; r < JAXENT_MAX_RANKS; ++r)
+    if (r < x.world) ll_store(x.base[r] + off, v, ep);
+}
+// MaxEnt sums of epoch `ep`, gathered by one whole warp (spins on the peers' words when sharded)
+__device__ __forceinline__ void kl_gather_warp(const Xchg& x, unsigned ep, int lane, double (&kl)[KL_N]) {
+  const int W = x.world;
+  double v = 0.0;
+  if (lane < W * KL_N) {
+    const int r = lane / KL_N, k = lane % KL_N;
+    if (W == 1) v = __ldcg(reinterpret_cast<const double*>(x.local + xchg_plain_kl_off(x)) + k);
+    else v = ll_load(x.local + xchg_err_off(x), x.local + xchg_kl_off(x, (int)(ep & 1u), r) + (size_t)k * 16, ep);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < KL_N; ++k) kl[k] = 0.0;
+  for (int r = 0; r < W; ++r) {
+#pragma unroll
+    for (int k = 0; k < KL_N; ++k) kl[k] += __shfl_sync(0xffffffffu, v, r * KL_N + k);
+  }
+}
+#endif
+
 struct StateSets {
   float* z[2][2];
   float* m[2][2];
@@ -89,20 +201,23 @@ struct PassArgs {
   const float* cc;
   const float* ch;
   double* partials;
-  const double* klsum;
+  Xchg x;
   const Ctl* ctl;
   const unsigned* epoch;
   JaxentLossRecord* records;
   float b1, b2, om_b1, om_b2, eps, clip;
+  double* dbg;
 };
 
 struct ReduceArgs {
   const Ctl* ctl;
   const double* partials;
-  double* red;
+  Xchg x;
   unsigned* epoch;
+  unsigned* ticket;
   int n_part;
   int part_n;
+  double* dbg;
 };
 
 constexpr int TRK_MAX_THR = 8;
@@ -126,7 +241,7 @@ struct TailArgs {
   TrackConfig trk;
   JaxentOptConfig cfg;
   StateSets st;
-  const double* red;
+  Xchg x;
   Ctl* ctl;
   const unsigned* epoch;
   unsigned* counter;
@@ -138,14 +253,20 @@ struct TailArgs {
   float* uptake;
   float* avg;
   double* klpart;
-  double* klsum;
   JaxentLossRecord* records;
   BlobSet blobs;
-  double* cl_scratch;  // L2 exchange buffer of the clustered tail (tail_cluster_scratch_doubles())
+  double* cl_scratch;  // 64 words of debug timestamps (JX_TAIL_PROFILE builds)
   int p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
   long long frames_per_cta;  // frames handled by each per-frame CTA of the tail kernel
   float eps_kl;   // 1e-10 / F_total
 };
+
+#ifdef JX_PROFILE
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define JPROF(buf, i) do { reinterpret_cast<long long*>(buf)[i] = jx::gtime(); } while (0)
+#else
+#define JPROF(buf, i) do {} while (0)
+#endif
 
 void set_error(const char* fmt, ...);
 
@@ -173,21 +294,16 @@ inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, c
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s);
 int launch_reduce(const ReduceArgs& a, cudaStream_t s);
 int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
-int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const double* klsum, JaxentLossRecord* rec, int n_slots,
-                         cudaStream_t s);
+int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const Xchg& x, JaxentLossRecord* rec, int n_slots, cudaStream_t s);
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va);
 int blob_words(int R, int T, int p_tr, int nnz_tr, int p_va, int nnz_va);
-size_t tail_cluster_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va);
-size_t tail_cluster_scratch_doubles(int R, int T, int p_tr);
-int launch_tail_cluster(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
-constexpr int TAIL_CLUSTER = 8;
 int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_t s);
 int configure_kernels();
 
-__device__ __forceinline__ void finish_record(const Ctl* c, const double* klsum, JaxentLossRecord* records, int n_slots) {
+__device__ __forceinline__ void finish_record(const Ctl* c, double kl_value, JaxentLossRecord* records, int n_slots) {
   JaxentLossRecord* r = records + c->rec_idx;
   if (c->kl_slot >= 0) {
-    const float kl = (float)(klsum[1] + klsum[2]);
+    const float kl = (float)kl_value;
     r->train[c->kl_slot] = kl;
     r->val[c->kl_slot] = kl;
   }

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .sharding import ShardComm
+from .sharding import PeerExchange, ShardComm
 
 
 @dataclass
@@ -112,6 +112,7 @@ class BvEngine:
         F_total: Optional[int] = None,
         group=None,
         feature_dtype: str = "f32",
+        exchange: str = "auto",
     ):
         if not torch.cuda.is_available():
             raise RuntimeError("jaxent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -187,6 +188,23 @@ class BvEngine:
                 )
             )
             self.plan = plan
+            # frame-sharded: fuse the two per-step exchanges into the kernels over NVLink peer memory when the
+            # exchange buffers can be mapped ("nvlink"); otherwise NCCL all-reduces between the phases ("nccl")
+            if exchange not in ("auto", "nvlink", "nccl"):
+                raise ValueError("exchange must be 'auto', 'nvlink' or 'nccl'")
+            self.peer = None
+            self.exchange = "none"
+            if self.sharded:
+                self.exchange = "nccl"
+                if exchange in ("auto", "nvlink"):
+                    try:
+                        self.peer = PeerExchange(self.lib, group, R, self.device)
+                        self.peer.attach(self.plan)
+                        self.exchange = "nvlink"
+                    except RuntimeError:
+                        if exchange == "nvlink":
+                            raise
+            self.fused = self.exchange == "nvlink"
             self.red = self._view(L.BUF_RED, torch.float64)
             self.klsum = self._view(L.BUF_KLSUM, torch.float64)
             self.weights = self._view(L.BUF_WEIGHTS, torch.float32)
@@ -205,6 +223,10 @@ class BvEngine:
             if getattr(self, "plan", None):
                 self.lib.jaxent_bv_plan_destroy(self.plan)
                 self.plan = None
+            if getattr(self, "peer", None) is not None:
+                torch.cuda.synchronize(self.device)
+                self.peer.close()
+                self.peer = None
         except Exception:
             pass
 
@@ -225,6 +247,8 @@ class BvEngine:
         ptr, nb = C.c_void_p(), C.c_size_t()
         L.check(self.lib.jaxent_bv_plan_buffer(self.plan, which, C.byref(ptr), C.byref(nb)))
         off = ptr.value - self.ws.data_ptr()
+        if off < 0 or off + nb.value > self.ws.numel():
+            return None  # lives in the peer-mapped exchange buffer, not in the workspace (fused exchange)
         return self.ws[off : off + nb.value].view(dtype)
 
     def _pack(self, heavy, acceptor, feature_dtype: str = "f32") -> PackedFeatures:
@@ -318,6 +342,9 @@ class BvEngine:
                     self.plan, z0.data_ptr(), float(zmax.item()), float(bc), float(bh), fwc, fsc, _stream_ptr()
                 )
             )
+            if self.fused:
+                # every rank's state_init (which clears its local flags) must complete before any peer stores to it
+                self.comm.sum_(torch.zeros(1, device=self.device))
             self._phase(0)
             self.steps_done = 0
             self._graph = None
@@ -326,9 +353,11 @@ class BvEngine:
         s = _stream_ptr()
         L.check(self.lib.jaxent_bv_pass(self.plan, mode, s))
         L.check(self.lib.jaxent_bv_reduce(self.plan, s))
-        self.comm.sum_(self.red)
+        if not self.fused:
+            self.comm.sum_(self.red)
         L.check(self.lib.jaxent_bv_tail(self.plan, s))
-        self.comm.sum_(self.klsum)
+        if not self.fused:
+            self.comm.sum_(self.klsum)
         self.launches += 3
 
     def step(self, n: int = 1) -> None:
@@ -360,6 +389,15 @@ class BvEngine:
             self._graph.replay()
         self.steps_done += n_graphs * self._graph_steps
         self.launches += 3 * n_graphs * self._graph_steps
+
+    def exchange_error(self) -> int:
+        """non-zero once a peer-flag wait of the fused exchange timed out (a peer never arrived)"""
+        if not self.fused:
+            return 0
+        out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.jaxent_bv_exchange_error(self.plan, out.data_ptr(), _stream_ptr()))
+        return int(out.item())
 
     def finish_record(self) -> None:
         L.check(self.lib.jaxent_bv_finish_record(self.plan, _stream_ptr()))

@@ -7,6 +7,11 @@ that owns the frame; ranks couple only through three tiny collectives:
   * every step, after `reduce`:  the (4R+4)-double partial-sum vector  JAXENT_BUF_RED   (SUM)
   * every step, after `tail`  :  the 4-double MaxEnt vector             JAXENT_BUF_KLSUM (SUM)
 
+On GPUs with peer access (NVLink / NVSwitch) the two per-step exchanges are fused into the kernels
+(`PeerExchange`: every rank's reduce / tail kernel stores its partial sums straight into the peers'
+inboxes and the consumers wait on flags; include/jaxent_b200.h "frame-sharded exchange"), so a step
+launches no collective at all; NCCL all-reduces remain the fallback when peer mapping is unavailable.
+
 BV parameters, the R x T tail and the plateau decision are replicated: every rank computes them from
 the same all-reduced numbers, so they stay bit-identical without a broadcast.
 
@@ -77,3 +82,67 @@ class ShardComm:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             self.calls += 1
         return t
+
+
+class PeerExchange:
+    """Maps one exchange buffer per rank into every process (CUDA IPC over NVLink peer access) for the
+    fused in-kernel all-reduce.  Set-up only; raises if any rank cannot map its peers (the caller then
+    falls back to NCCL collectives on all ranks together)."""
+
+    def __init__(self, lib, group, n_residues: int, device: torch.device):
+        import ctypes as C
+
+        from . import _lib as L
+
+        self.lib, self.group = lib, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.own = None
+        self.opened = []
+        self.ptrs = [None] * self.world
+        if self.world > L.MAX_RANKS:
+            raise RuntimeError(f"the fused exchange supports at most {L.MAX_RANKS} ranks")
+        nbytes = lib.jaxent_bv_exchange_bytes(int(n_residues), self.world)
+        ok, err = 1, ""
+        handle = C.create_string_buffer(L.IPC_HANDLE_BYTES)
+        ptr = C.c_void_p()
+        with torch.cuda.device(device):
+            if lib.jaxent_peer_alloc(nbytes, C.byref(ptr), handle) != 0:
+                ok, err = 0, lib.jaxent_last_error().decode()
+            else:
+                self.own = ptr.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (ok, handle.raw), group=group)
+            if all(h[0] for h in handles):
+                for r, (_, raw) in enumerate(handles):
+                    if r == self.rank:
+                        self.ptrs[r] = self.own
+                        continue
+                    q = C.c_void_p()
+                    if lib.jaxent_peer_open(raw, C.byref(q)) != 0:
+                        ok, err = 0, lib.jaxent_last_error().decode()
+                        break
+                    self.opened.append(q.value)
+                    self.ptrs[r] = q.value
+            else:
+                ok = 0
+            flag = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                self.close()
+                raise RuntimeError(f"peer mapping of the exchange buffers failed on some rank ({err or 'see other ranks'})")
+
+    def attach(self, plan) -> None:
+        import ctypes as C
+
+        from . import _lib as L
+
+        arr = (C.c_void_p * self.world)(*self.ptrs)
+        L.check(self.lib.jaxent_bv_plan_set_exchange(plan, self.rank, self.world, arr))
+
+    def close(self) -> None:
+        for q in self.opened:
+            self.lib.jaxent_peer_close(q)
+        self.opened = []
+        if self.own is not None:
+            self.lib.jaxent_peer_free(self.own)
+            self.own = None

@@ -51,7 +51,7 @@ def make_case(F, R, T, data_kind=O.UPTAKE_EYE_MSE, extra=(), seed=0, n_pep=None,
     return {"problem": problem, "params": params, "ens": ens, "prior": pr}
 
 
-def make_engine(case, cfg: O.OptConfig, device=None, frames=None, F_total=None, group=None, feature_dtype="f32"):
+def make_engine(case, cfg: O.OptConfig, device=None, frames=None, F_total=None, group=None, feature_dtype="f32", exchange="auto"):
     """BvEngine over the same arrays (optionally a frame shard `frames` = slice)."""
     from jaxent_b200.engine import BvEngine, OptSettings, SlotSpec
 
@@ -64,7 +64,8 @@ def make_engine(case, cfg: O.OptConfig, device=None, frames=None, F_total=None, 
                      cfg.model_parameters_lr_scale, cfg.clip_value, cfg.optimise_frame_weights, cfg.optimise_model_parameters,
                      cfg.b1, cfg.b2, cfg.eps)
     eng = BvEngine(np.ascontiguousarray(pb.heavy[:, sl]), np.ascontiguousarray(pb.acceptor[:, sl]), pb.k_ints, pb.timepoints, specs,
-                   pb.uptake, st, prior=case["prior"][sl], device=device, F_total=F_total, group=group, feature_dtype=feature_dtype)
+                   pb.uptake, st, prior=case["prior"][sl], device=device, F_total=F_total, group=group, feature_dtype=feature_dtype,
+                   exchange=exchange)
     return eng
 
 

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, F, R, T, n_steps, out):
+def _worker(rank, world, port, F, R, T, n_steps, exchange, out):
     import torch.distributed as dist
 
     from jaxent_b200.sharding import frame_shard
@@ -32,13 +32,27 @@ def _worker(rank, world, port, F, R, T, n_steps, out):
         case = H.make_case(F, R, T, O.UPTAKE_EYE_MSE, extra=(O.PARAMS_L2,), seed=6, prior="random")
         cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=True)
         sh = frame_shard(F, rank, world)
-        eng = H.make_engine(case, cfg, device=f"cuda:{rank}", frames=sh.slice(), F_total=F, group=dist.group.WORLD)
+        eng = H.make_engine(case, cfg, device=f"cuda:{rank}", frames=sh.slice(), F_total=F, group=dist.group.WORLD, exchange=exchange)
+        assert eng.exchange == exchange
         H.init_engine(eng, case, frames=sh.slice())
         eng.step(n_steps)
         eng.finish_record()
         torch.cuda.synchronize()
+        assert eng.exchange_error() == 0
         recs = eng.records(0, n_steps + 1)
         w = eng.weights.cpu().numpy()
+        if exchange == "nvlink":
+            # a second run on the same plan (flags are re-armed by state_init) and CUDA-graph replay of the fused step
+            H.init_engine(eng, case, frames=sh.slice())
+            eng.capture(2)
+            eng.step_graph(n_steps // 2)
+            eng.finish_record()
+            torch.cuda.synchronize()
+            assert eng.exchange_error() == 0
+            recs2 = eng.records(0, n_steps + 1)
+            for a, b in zip(recs, recs2):
+                assert a.step == b.step and a.total_train == b.total_train and a.bc == b.bc  # bitwise
+            np.testing.assert_array_equal(w, eng.weights.cpu().numpy())
         gathered = [None] * world
         dist.all_gather_object(gathered, (sh.start, sh.stop, w))
         if rank == 0:
@@ -66,12 +80,13 @@ def _worker(rank, world, port, F, R, T, n_steps, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("exchange", ["nvlink", "nccl"])
 @pytest.mark.parametrize("world", [2])
-def test_sharded_matches_single_gpu(world):
+def test_sharded_matches_single_gpu(world, exchange):
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < world:
         pytest.skip("not enough GPUs")
     out = mp.get_context("spawn").Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), 5003, 97, 5, 6, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 5003, 97, 5, 6, exchange, out), nprocs=world, join=True)
     assert out.get("ok") == 1
