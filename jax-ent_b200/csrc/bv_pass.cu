@@ -588,8 +588,15 @@ __global__ void __launch_bounds__(1024) reduce_kernel(const ReduceArgs a) {
   const int col = blockIdx.x * 32 + lane;
   double s = 0.0;
   if (col < a.part_n) {
-#pragma unroll 4
-    for (int c = grp; c < a.n_part; c += 32) s += a.partials[(size_t)c * a.part_n + col];
+    // at most 320 partial vectors: all (<= 10) loads of this thread are in flight together, summed in fixed order
+    double v[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const int c = grp + 32 * k;
+      v[k] = (c < a.n_part) ? __ldcg(&a.partials[(size_t)c * a.part_n + col]) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) s += v[k];
   }
   sh[grp][lane] = s;
   __syncthreads();

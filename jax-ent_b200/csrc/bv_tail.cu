@@ -418,7 +418,7 @@ __device__ __forceinline__ void frame_terms(const TailArgs& a, const StepScalars
     double t = 0.0;
 #pragma unroll 1
     for (int w = 0; w < nw; ++w) t += s_red[w][tid];
-    a.klpart[(size_t)blockIdx.x * KL_N + tid] = t;
+    a.klpart[(size_t)cta * KL_N + tid] = t;
   }
 }
 
@@ -426,12 +426,13 @@ __device__ __forceinline__ void frame_terms(const TailArgs& a, const StepScalars
 // rank, stamped 16-byte stores into the kl inbox of every rank (slot = this rank) when frame-sharded
 __device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep, int* s_last) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (gridDim.x > 1) {
+  const unsigned n_frame_ctas = gridDim.x > 1 ? gridDim.x - 1 : 1;
+  if (n_frame_ctas > 1) {
     if (tid < KL_N) __threadfence();
     __syncthreads();
     if (tid == 0) {
       const unsigned ticket = atomicAdd(a.counter, 1u);
-      *s_last = (ticket == gridDim.x - 1);
+      *s_last = (ticket == n_frame_ctas - 1);
     }
   } else if (tid == 0) {
     *s_last = 1;
@@ -441,7 +442,7 @@ __device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep,
     __threadfence();
     double t = 0.0;
 #pragma unroll 1
-    for (unsigned cc = lane; cc < gridDim.x; cc += 32) t += __ldcg(&a.klpart[(size_t)cc * KL_N + warp]);
+    for (unsigned cc = lane; cc < n_frame_ctas; cc += 32) t += __ldcg(&a.klpart[(size_t)cc * KL_N + warp]);
     t = wsum(t);
     if (lane == 0) kl_publish(a.x, ep, warp, t);
     if (tid == 0) *a.counter = 0u;
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[32][16];  // per-warp partials of the multi-value reductions
   __shared__ double s_fin[16];
-  __shared__ __align__(16) Ctl s_old;
+  __shared__ __align__(16) Ctl s_ctl2[2];  // both control blocks, fetched before the epoch is known
   __shared__ StepScalars s_sc;
   __shared__ int s_last;
 
@@ -504,21 +505,23 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   pdl_wait();               // the reduced partial sums and the previous control block are visible from here on
   pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
   TPROF(2); TPROF_F(1);
-  const unsigned ep = *a.epoch;
-  if (a.ctl[ep & 1u].trk_stop) return;  // the on-device loop has ended (reduce did not advance the epoch): no-op
-  const Ctl* __restrict__ old_g = a.ctl + ((ep - 1u) & 1u);
+  // ---- one global round trip: the epoch, BOTH control blocks (which of them is current depends on the epoch, so
+  // fetching both removes a dependent load) and the reduced sums are requested together
+  {
+    constexpr int CW = (int)(sizeof(Ctl) / 16);
+    if (tid >= 64 && tid < 64 + 2 * CW) reinterpret_cast<int4*>(s_ctl2)[tid - 64] = __ldcg(reinterpret_cast<const int4*>(a.ctl) + (tid - 64));
+  }
+  const unsigned ep = __ldcg(a.epoch);
+  __syncthreads();  // (0) control blocks staged
+  if (s_ctl2[ep & 1u].trk_stop) return;  // the on-device loop has ended (reduce did not advance the epoch): no-op
+  const Ctl& s_old = s_ctl2[(ep - 1u) & 1u];
   Ctl* __restrict__ neu = a.ctl + (ep & 1u);
   const int cur_set = ep & 1u;
 
-  // ---- one global round trip: warp 0 derives the step scalars, another warp copies the control block
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (warp == 0) {
     const double SA = red_total(a.x, ep, 4 * R + 0), SB = red_total(a.x, ep, 4 * R + 1), gdot = red_total(a.x, ep, 4 * R + 2);
-    derive_scalars(&s_sc, old_g, SA, SB, gdot, a.cfg, a.trk, a.records);
-  } else if (warp == 1) {
-    const int4* src = reinterpret_cast<const int4*>(old_g);
-    int4* dst = reinterpret_cast<int4*>(&s_old);
-    if (lane < (int)(sizeof(Ctl) / 16)) dst[lane] = src[lane];
+    derive_scalars(&s_sc, &s_old, SA, SB, gdot, a.cfg, a.trk, a.records);
   }
   if (tail_cta) {
     if (tid < R) {
@@ -547,20 +550,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       a.avg[tid] = (float)my_a;
       a.avg[R + tid] = (float)my_b;
       a.logpf[tid] = (float)my_lp;
-      // exp(-lnPF) and the T uptakes of this residue: one call site, 1 + T evaluations
-      double xe = 0.0;
-      const double kr = (T > 0) ? (double)s_k[tid] : 0.0;
+      if (T > 0) sxe[tid] = dexp(-my_lp);
+    }
+    if (T > 0) {
+      __syncthreads();  // exp(-lnPF) visible
 #pragma unroll 1
-      for (int k = 0; k <= T && T > 0; ++k) {
-        const double arg = (k == 0) ? -my_lp : -(kr * (double)s_tp[k - 1] * xe);
-        const double e = dexp(arg);
-        if (k == 0) {
-          xe = e;
-          sxe[tid] = e;
-        } else {
-          sU[(size_t)(k - 1) * R + tid] = 1.0 - e;
-          a.uptake[(size_t)(k - 1) * R + tid] = (float)(1.0 - e);
-        }
+      for (int it = tid; it < R * T; it += nt) {
+        const int t = fdiv(it, invR), r = it - t * R;
+        const double e = dexp(-((double)s_k[r] * (double)s_tp[t] * sxe[r]));
+        sU[it] = 1.0 - e;
+        a.uptake[it] = (float)(1.0 - e);
       }
     }
     __syncthreads();  // (2) lnPF / uptake visible
@@ -597,33 +596,65 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       const bool sigma = GENERAL && kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE;
       const double half = pf ? 1.0 : 0.5;
 
-      // (a) predictions of train and val peptides; the eye / PF kinds finish residual + loss here
+      // (a) predictions of train and val peptides, one (peptide, chunk of 4 time points) item per thread: the row's
+      // indices / values are read once per 4 products and the 4 accumulation chains are independent.  The eye / PF
+      // kinds finish residual + loss here.
+      {
+        const int nch = (Tm + 3) >> 2;
+        const float inv_nch = 1.0f / (float)nch;
+        const int items = (Ptr + Pva) * nch;
+        double pl_tr = 0.0, pl_va = 0.0;
 #pragma unroll 1
-      for (int set = 0; set < 2; ++set) {
-        const int P = set ? Pva : Ptr;
-        const int* ptr = s_blob + (set ? bl.va_ptr : bl.tr_ptr);
-        const int* col = s_blob + (set ? bl.va_col : bl.tr_col);
-        const float* val = reinterpret_cast<const float*>(s_blob + (set ? bl.va_val : bl.tr_val));
-        const float* y = reinterpret_cast<const float*>(s_blob + (set ? bl.va_y : bl.tr_y));
-        double* out = set ? res_va : ((centre || sigma) ? res_tr : gp_tr);
-        double pl = 0.0;
-#pragma unroll 1
-        for (int j = tid; j < P * Tm; j += nt) {
-          const int p = fdiv(j, invTm), t = j - p * Tm;
-          const double* x = pf ? slp : sU + (size_t)t * R;
-          double pred = 0.0;
-#pragma unroll 1
-          for (int q = ptr[p]; q < ptr[p + 1]; ++q) pred += (double)val[q] * x[col[q]];
-          if (!(centre || sigma)) {
-            pred -= (double)y[j];
-            pl += half * pred * pred;
+        for (int j = tid; j < items; j += nt) {
+          const int row = fdiv(j, inv_nch), t0 = (j - row * nch) << 2;
+          const bool va = row >= Ptr;
+          const int p = va ? row - Ptr : row;
+          const int* ptr = s_blob + (va ? bl.va_ptr : bl.tr_ptr);
+          const int* col = s_blob + (va ? bl.va_col : bl.tr_col);
+          const float* val = reinterpret_cast<const float*>(s_blob + (va ? bl.va_val : bl.tr_val));
+          const float* y = reinterpret_cast<const float*>(s_blob + (va ? bl.va_y : bl.tr_y));
+          double* out = va ? res_va : ((centre || sigma) ? res_tr : gp_tr);
+          // clamped time indices keep the loads in bounds; surplus lanes of the last chunk are discarded
+          const int t1 = min(t0 + 1, Tm - 1), t2 = min(t0 + 2, Tm - 1), t3 = min(t0 + 3, Tm - 1);
+          const double* x0 = pf ? slp : sU + (size_t)t0 * R;
+          const double* x1 = pf ? slp : sU + (size_t)t1 * R;
+          const double* x2 = pf ? slp : sU + (size_t)t2 * R;
+          const double* x3 = pf ? slp : sU + (size_t)t3 * R;
+          double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+          const int qe = ptr[p + 1];
+#pragma unroll 2
+          for (int q = ptr[p]; q < qe; ++q) {
+            const int c = col[q];
+            const double v = (double)val[q];
+            p0 += v * x0[c];
+            p1 += v * x1[c];
+            p2 += v * x2[c];
+            p3 += v * x3[c];
           }
-          out[j] = pred;
+          const double pr[4] = {p0, p1, p2, p3};
+          double pl = 0.0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (t0 + k < Tm) {
+              double pred = pr[k];
+              if (!(centre || sigma)) {
+                pred -= (double)y[p * Tm + t0 + k];
+                pl += half * pred * pred;
+              }
+              out[p * Tm + t0 + k] = pred;
+            }
+          }
+          if (va) pl_va += pl; else pl_tr += pl;
         }
         if (!(centre || sigma)) {
-          const double nrm = (P > 0) ? __drcp_rn(pf ? (double)P : (double)T * (double)P) : 0.0;
-          pl = wsum(pl * nrm);
-          if (lane == 0) s_red[warp][set * JAXENT_MAX_SLOTS + i] = pl;
+          const double nrm_tr = (Ptr > 0) ? __drcp_rn(pf ? (double)Ptr : (double)T * (double)Ptr) : 0.0;
+          const double nrm_va = (Pva > 0) ? __drcp_rn(pf ? (double)Pva : (double)T * (double)Pva) : 0.0;
+          pl_tr = wsum(pl_tr * nrm_tr);
+          pl_va = wsum(pl_va * nrm_va);
+          if (lane == 0) {
+            s_red[warp][i] = pl_tr;
+            s_red[warp][JAXENT_MAX_SLOTS + i] = pl_va;
+          }
         }
       }
       TPROF(5);
@@ -709,27 +740,44 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       __syncthreads();  // (3) dL/dpred visible
       TPROF(6);
 
-      // (b) back-projection to dL/d lnPF, parallel over (t, r)
+      // (b) back-projection to dL/d lnPF, one (residue, chunk of 4 time points) item per thread
       {
         const int* tptr = s_blob + bl.tr_tptr;
         const int* trow = s_blob + bl.tr_trow;
         const float* tval = reinterpret_cast<const float*>(s_blob + bl.tr_tval);
         const double g = scale * (pf ? 2.0 : 1.0) * __drcp_rn(pf ? (double)Ptr : (double)T * (double)Ptr);
+        const int nch = (Tm + 3) >> 2;
+        const int items = R * nch;
 #pragma unroll 1
-        for (int it = tid; it < R * Tm; it += nt) {
-          const int t = fdiv(it, invR), r = it - t * R;
-          double back = 0.0, colsum = 0.0;
-#pragma unroll 1
-          for (int q = tptr[r]; q < tptr[r + 1]; ++q) {
-            back += (double)tval[q] * gp_tr[trow[q] * Tm + t];
-            if (GENERAL) colsum += (double)tval[q];
+        for (int it = tid; it < items; it += nt) {
+          const int ch = fdiv(it, invR), r = it - ch * R, t0 = ch << 2;
+          const int o1 = min(t0 + 1, Tm - 1) - t0, o2 = min(t0 + 2, Tm - 1) - t0, o3 = min(t0 + 3, Tm - 1) - t0;
+          double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, colsum = 0.0;
+          const int qe = tptr[r + 1];
+#pragma unroll 2
+          for (int q = tptr[r]; q < qe; ++q) {
+            const double v = (double)tval[q];
+            const double* gp = gp_tr + trow[q] * Tm + t0;
+            b0 += v * gp[0];
+            b1 += v * gp[o1];
+            b2 += v * gp[o2];
+            b3 += v * gp[o3];
+            if (GENERAL) colsum += v;
           }
-          if (centre) back -= colsum * smean[2 * T + t];  // centred gradient: minus mean_p(gp) through the column
-          if (!pf) {
-            const double x = (double)s_k[r] * (double)s_tp[t] * sxe[r];
-            back *= -x * (1.0 - sU[it]);  // du/dlnPF = -x exp(-x)
+          const double bk[4] = {b0, b1, b2, b3};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int t = t0 + k;
+            if (t < Tm) {
+              double back = bk[k];
+              if (centre) back -= colsum * smean[2 * T + t];  // centred gradient: minus mean_p(gp) through the column
+              if (!pf) {
+                const double x = (double)s_k[r] * (double)s_tp[t] * sxe[r];
+                back *= -x * (1.0 - sU[(size_t)t * R + r]);  // du/dlnPF = -x exp(-x)
+              }
+              sc_rt[(size_t)t * R + r] = g * back;
+            }
           }
-          sc_rt[it] = g * back;
         }
       }
       __syncthreads();  // (4) items visible
@@ -777,15 +825,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   }
 
   // ================================================================== per-frame MaxEnt terms
-  if (!frame_cta) {
-    // CTA 0 of a multi-CTA grid holds no frames: contribute zeros and take a ticket
-    if (tid < KL_N) a.klpart[tid] = 0.0;
-  } else {
+  // CTA 0 of a multi-CTA grid holds no frames and stays out of the fold: the last *frame* CTA publishes the sums,
+  // typically well before the R x T tail above has finished.
+  TPROF(11);
+  if (frame_cta) {
     frame_terms(a, s_sc, s_old, cur_set, (gridDim.x == 1) ? 0 : (long long)blockIdx.x - 1, 0, s_red);
+    TPROF_F(3);
+    fold_kl_partials(a, ep, &s_last);
+    TPROF_F(4);
   }
-  TPROF(11); TPROF_F(3);
-  fold_kl_partials(a, ep, &s_last);
-  TPROF(12); TPROF_F(4);
+  TPROF(12);
 }
 
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va) {
