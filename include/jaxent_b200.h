@@ -265,6 +265,25 @@ int jaxent_bv_track_status(JaxentPlan* plan, JaxentTrackStatus* status, jaxent_s
 int jaxent_bv_export_state(JaxentPlan* plan, float* z, float* m, float* v, float* g, float* scalars,
                            jaxent_stream_t stream);
 
+/* ---- batched (replicate / hyper-parameter sweep) mode: tensor-core building blocks (csrc/bg_gemm.cu) ----
+ * With B replicas sharing the features (reference opt/batch.py:51-192 vmaps _optimise_pure over the hyper-parameter
+ * batch) the two sweeps of a step are dense GEMMs on the tcgen05 tensor cores:
+ *   gemm1:  H[f, b]            = sum_{a, r} N_a[r, f] * c_a[r, b]     (backward: transpose product)
+ *   gemm2:  P[ks][a*Rp + r, b] = sum_{f in split ks} N_a[r, f] * e[f, b]   (forward: frame_average_features)
+ * Layouts (all bf16, byte images of the UMMA no-swizzle canonical layout; Rp = R padded to 128, Fp = F padded to 128,
+ * Bn = replicas padded to 16, NS = number of bf16 pieces the fp32 operand is split into):
+ *   features  [Fp/128][2][Rp/8][16][8 rows][8 frames]              jaxent_bg_pack_features
+ *   cc3       [NS][2][Rp/8][Bn][8 residues]
+ *   e3        [Fp/128][NS][16][Bn][8 frames]
+ * exact_flag (device int preset to 1, may be NULL) is cleared when a feature value is not exactly representable in bf16. */
+size_t jaxent_bg_features_bytes(int32_t R, int64_t F);
+int jaxent_bg_pack_features(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld, void* out,
+                            int32_t* exact_flag, jaxent_stream_t stream);
+int jaxent_bg_gemm1(const void* features, const void* cc3, float* H, int32_t n_fb, int32_t n_rg, int32_t Bn, int32_t NS,
+                    int32_t sm_count, jaxent_stream_t stream);
+int jaxent_bg_gemm2(const void* features, const void* e3, float* partials, int32_t n_fb, int32_t n_rg, int32_t Bn, int32_t NS,
+                    int32_t ksplit, jaxent_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

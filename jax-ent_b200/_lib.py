@@ -163,6 +163,10 @@ SYMBOLS = {
     "jaxent_peer_free": (C.c_int, [_VP]),
     "jaxent_bv_plan_set_exchange": (C.c_int, [_VP, _I32, _I32, C.POINTER(_VP)]),
     "jaxent_bv_exchange_error": (C.c_int, [_VP, _VP, _VP]),
+    "jaxent_bg_features_bytes": (_SZ, [_I32, _I64]),
+    "jaxent_bg_pack_features": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _VP, _VP, _VP]),
+    "jaxent_bg_gemm1": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "jaxent_bg_gemm2": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "jaxent_bv_state_init": (C.c_int, [_VP, _VP, _F, _F, _F, C.POINTER(_F), C.POINTER(_F), _VP]),
     "jaxent_bv_pass": (C.c_int, [_VP, _I32, _VP]),
     "jaxent_bv_reduce": (C.c_int, [_VP, _VP]),
