@@ -21,6 +21,7 @@
 //  * the back-projection is parallel over (residue, time point) and the loss sums are reduced once.
 #include <cmath>
 
+#include "bv_tail_body.cuh"
 #include "jx_internal.cuh"
 
 namespace jx {
@@ -32,18 +33,6 @@ namespace jx {
 #define TPROF(i) do {} while (0)
 #define TPROF_F(i) do {} while (0)
 #endif
-
-// ---- code-size discipline: this kernel runs a long straight-line path once per launch, so its cost is
-// dominated by instruction fetch.  Heavy math lives behind single __noinline__ call sites.
-__device__ __noinline__ double wsum(double v) {
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __noinline__ double dexp(double x) { return exp(x); }
-__device__ __noinline__ double dlog(double x) { return log(x); }
-__device__ __noinline__ float fpow(float a, float b) { return powf(a, b); }
-// floor(x / d) for 0 <= x < 2^21 with inv = 1/d (exact: the fraction is >= 0.5/d away from an integer)
-__device__ __forceinline__ int fdiv(int x, float inv) { return (int)(((float)x + 0.5f) * inv); }
 
 // step scalars, derived once by warp 0 and broadcast through shared memory
 struct StepScalars {
@@ -212,25 +201,6 @@ __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restr
 }
 
 // ------------------------------------------------------------------------------------------ blobs
-// word layout of one data slot's blob == its shared-memory image
-__host__ __device__ inline BlobLayout blob_layout(int R, int Tm, int p_tr, int nnz_tr, int p_va, int nnz_va) {
-  BlobLayout b;
-  int o = 0;
-  b.tr_ptr = o;  o += p_tr + 1;
-  b.tr_col = o;  o += nnz_tr;
-  b.tr_tptr = o; o += R + 1;
-  b.tr_trow = o; o += nnz_tr;
-  b.va_ptr = o;  o += p_va + 1;
-  b.va_col = o;  o += nnz_va;
-  b.tr_val = o;  o += nnz_tr;
-  b.tr_tval = o; o += nnz_tr;
-  b.tr_y = o;    o += p_tr * Tm;
-  b.va_val = o;  o += nnz_va;
-  b.va_y = o;    o += p_va * Tm;
-  b.words = (o + 3) & ~3;
-  return b;
-}
-
 __global__ void build_blobs_kernel(JaxentBvProblem pb, BlobSet bs) {
   const int R = pb.R, Tm = (pb.uptake && pb.T > 0) ? pb.T : 1;
   const int tid = threadIdx.x, nt = blockDim.x;  // single block
@@ -468,39 +438,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   const bool frame_cta = (gridDim.x == 1) || blockIdx.x > 0;
   const float invR = 1.0f / (float)R, invTm = 1.0f / (float)Tm;
 
-  // shared-memory carve-up (CTA 0)
-  double* slp = reinterpret_cast<double*>(smem_raw);    // [R] lnPF
-  double* sxe = slp + R;                                 // [R] exp(-lnPF)
-  double* sc_rt = sxe + R;                               // [Tm][R] back-projection items
-  double* sU = sc_rt + (size_t)Tm * R;                   // [T][R] uptake
-  double* res_tr = sU + (size_t)T * R;                   // [P_tr * Tm] (GENERAL only)
-  double* gp_tr = res_tr + (size_t)a.p_max_tr * Tm;      // [P_tr * Tm] pred -> residual -> dL/dpred
-  double* res_va = gp_tr + (size_t)a.p_max_tr * Tm;      // [P_va * Tm]
-  double* smean = res_va + (size_t)a.p_max_va * Tm;      // [4 * Tm]
-  float* s_k = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smean + 4 * Tm) + 15) & ~uintptr_t(15));
-  float* s_tp = s_k + ((R + 3) & ~3);
-  int* s_blob = reinterpret_cast<int*>(s_tp + ((Tm + 3) & ~3));  // 16-byte aligned blob image
+  const TailSmem tsm = carve_tail_smem(smem_raw, R, T, a.p_max_tr, a.p_max_va);
 
   TPROF(0); TPROF_F(0);
   // ---- constant data first (peptide-map blob, rates, time points): independent of the previous kernel (PDL)
   int first_data = -1;
-  if (tail_cta) {
-#pragma unroll 1
-    for (int i = pb.n_slots - 1; i >= 0; --i)
-      if (pb.slots[i].kind <= JAXENT_LOSS_PF_L2) first_data = i;
-    if (first_data >= 0) {
-      const int4* src = reinterpret_cast<const int4*>(a.blobs.blob[first_data]);
-      int4* dst = reinterpret_cast<int4*>(s_blob);
-      const int n4 = a.blobs.words[first_data] >> 2;
-#pragma unroll 4
-      for (int i = tid; i < n4; i += nt) dst[i] = src[i];
-    }
-    if (T > 0) {
-#pragma unroll 1
-      for (int i = tid; i < R; i += nt) s_k[i] = pb.k_ints[i];
-      if (tid < T) s_tp[tid] = pb.timepoints[tid];
-    }
-  }
+  if (tail_cta) first_data = stage_tail_constants(pb, a.blobs, tsm);
   TPROF(1);
   pdl_wait();               // the reduced partial sums and the previous control block are visible from here on
   pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
@@ -540,284 +483,17 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   // ================================================================== the R x T tail (CTA 0)
   if (tail_cta) {
     const double bc = (double)s_sc.bc, bh = (double)s_sc.bh;
-    double my_a = 0, my_b = 0, my_lp = 0, my_c = 0;
-    if (tid < R) {
-      const double invS = __drcp_rn(S);
-      my_a = (d ? accB0 : accA0) * invS;
-      my_b = (d ? accB1 : accA1) * invS;
-      my_lp = bc * my_a + bh * my_b;
-      slp[tid] = my_lp;
-      a.avg[tid] = (float)my_a;
-      a.avg[R + tid] = (float)my_b;
-      a.logpf[tid] = (float)my_lp;
-      if (T > 0) sxe[tid] = dexp(-my_lp);
+    double my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg;
+    TailIO io;
+    io.avg = a.avg;
+    io.logpf = a.logpf;
+    io.uptake = a.uptake;
+    tail_body<GENERAL>(pb, a.blobs, first_data, tsm, d ? accB0 : accA0, d ? accB1 : accA1, S, bc, bh, s_old.fw, s_old.fs, io, s_red, s_fin,
+                       my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg);
+    if (tid < R) {  // row coefficients of the next pass
+      a.cc[tid] = (float)(my_c * bc);
+      a.ch[tid] = (float)(my_c * bh);
     }
-    if (T > 0) {
-      __syncthreads();  // exp(-lnPF) visible
-#pragma unroll 1
-      for (int it = tid; it < R * T; it += nt) {
-        const int t = fdiv(it, invR), r = it - t * R;
-        const double e = dexp(-((double)s_k[r] * (double)s_tp[t] * sxe[r]));
-        sU[it] = 1.0 - e;
-        a.uptake[it] = (float)(1.0 - e);
-      }
-    }
-    __syncthreads();  // (2) lnPF / uptake visible
-    TPROF(4);
-
-    // ---- loss slots
-    double gbc_reg = 0.0, gbh_reg = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < pb.n_slots; ++i) {
-      const int kind = pb.slots[i].kind;
-      const double scale = (double)s_old.fw[i] * (double)s_old.fs[i];
-      if (kind == JAXENT_LOSS_PARAMS_L1 || kind == JAXENT_LOSS_PARAMS_L2) {
-        const bool l1 = kind == JAXENT_LOSS_PARAMS_L1;
-        const double dc = bc - (double)pb.slots[i].prior_bc, dh = bh - (double)pb.slots[i].prior_bh;
-        if (tid == 0) s_red[0][i] = s_red[0][JAXENT_MAX_SLOTS + i] = l1 ? fabs(dc) + fabs(dh) : dc * dc + dh * dh;
-        gbc_reg += scale * (l1 ? (double)((dc > 0) - (dc < 0)) : 2.0 * dc);
-        gbh_reg += scale * (l1 ? (double)((dh > 0) - (dh < 0)) : 2.0 * dh);
-        continue;
-      }
-      if (kind > JAXENT_LOSS_PF_L2) continue;  // MaxEnt: handled per frame
-      if (i != first_data) {
-        __syncthreads();
-        const int4* src = reinterpret_cast<const int4*>(a.blobs.blob[i]);
-        int4* dst = reinterpret_cast<int4*>(s_blob);
-        const int n4 = a.blobs.words[i] >> 2;
-#pragma unroll 1
-        for (int k = tid; k < n4; k += nt) dst[k] = src[k];
-        __syncthreads();
-      }
-      const int Ptr = pb.slots[i].train.n_pep, Pva = pb.slots[i].val.n_pep;
-      const BlobLayout bl = blob_layout(R, Tm, Ptr, pb.slots[i].train.nnz, Pva, pb.slots[i].val.nnz);
-      const bool pf = kind == JAXENT_LOSS_PF_L2;
-      const bool centre = GENERAL && kind == JAXENT_LOSS_UPTAKE_MC_EYE_MSE;
-      const bool sigma = GENERAL && kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE;
-      const double half = pf ? 1.0 : 0.5;
-
-      // (a) predictions of train and val peptides, one (peptide, chunk of 4 time points) item per thread: the row's
-      // indices / values are read once per 4 products and the 4 accumulation chains are independent.  The eye / PF
-      // kinds finish residual + loss here.
-      {
-        const int nch = (Tm + 3) >> 2;
-        const float inv_nch = 1.0f / (float)nch;
-        const int items = (Ptr + Pva) * nch;
-        double pl_tr = 0.0, pl_va = 0.0;
-#pragma unroll 1
-        for (int j = tid; j < items; j += nt) {
-          const int row = fdiv(j, inv_nch), t0 = (j - row * nch) << 2;
-          const bool va = row >= Ptr;
-          const int p = va ? row - Ptr : row;
-          const int* ptr = s_blob + (va ? bl.va_ptr : bl.tr_ptr);
-          const int* col = s_blob + (va ? bl.va_col : bl.tr_col);
-          const float* val = reinterpret_cast<const float*>(s_blob + (va ? bl.va_val : bl.tr_val));
-          const float* y = reinterpret_cast<const float*>(s_blob + (va ? bl.va_y : bl.tr_y));
-          double* out = va ? res_va : ((centre || sigma) ? res_tr : gp_tr);
-          // clamped time indices keep the loads in bounds; surplus lanes of the last chunk are discarded
-          const int t1 = min(t0 + 1, Tm - 1), t2 = min(t0 + 2, Tm - 1), t3 = min(t0 + 3, Tm - 1);
-          const double* x0 = pf ? slp : sU + (size_t)t0 * R;
-          const double* x1 = pf ? slp : sU + (size_t)t1 * R;
-          const double* x2 = pf ? slp : sU + (size_t)t2 * R;
-          const double* x3 = pf ? slp : sU + (size_t)t3 * R;
-          double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-          const int qe = ptr[p + 1];
-#pragma unroll 2
-          for (int q = ptr[p]; q < qe; ++q) {
-            const int c = col[q];
-            const double v = (double)val[q];
-            p0 += v * x0[c];
-            p1 += v * x1[c];
-            p2 += v * x2[c];
-            p3 += v * x3[c];
-          }
-          const double pr[4] = {p0, p1, p2, p3};
-          double pl = 0.0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (t0 + k < Tm) {
-              double pred = pr[k];
-              if (!(centre || sigma)) {
-                pred -= (double)y[p * Tm + t0 + k];
-                pl += half * pred * pred;
-              }
-              out[p * Tm + t0 + k] = pred;
-            }
-          }
-          if (va) pl_va += pl; else pl_tr += pl;
-        }
-        if (!(centre || sigma)) {
-          const double nrm_tr = (Ptr > 0) ? __drcp_rn(pf ? (double)Ptr : (double)T * (double)Ptr) : 0.0;
-          const double nrm_va = (Pva > 0) ? __drcp_rn(pf ? (double)Pva : (double)T * (double)Pva) : 0.0;
-          pl_tr = wsum(pl_tr * nrm_tr);
-          pl_va = wsum(pl_va * nrm_va);
-          if (lane == 0) {
-            s_red[warp][i] = pl_tr;
-            s_red[warp][JAXENT_MAX_SLOTS + i] = pl_va;
-          }
-        }
-      }
-      TPROF(5);
-      if (GENERAL && (centre || sigma)) {
-        const float* tr_y = reinterpret_cast<const float*>(s_blob + bl.tr_y);
-        const float* va_y = reinterpret_cast<const float*>(s_blob + bl.va_y);
-        __syncthreads();
-        if (centre) {
-          // per-timepoint means of prediction and target (opt/losses.py:1814-1819): one warp per (set, t)
-#pragma unroll 1
-          for (int job = warp; job < 2 * T; job += nw) {
-            const bool tr = job < T;
-            const int t = tr ? job : job - T;
-            const int P = tr ? Ptr : Pva;
-            const double* rs = tr ? res_tr : res_va;
-            const float* yy = tr ? tr_y : va_y;
-            double s0 = 0.0;
-#pragma unroll 1
-            for (int p = lane; p < P; p += 32) s0 += rs[p * T + t] - (double)yy[p * T + t];
-            s0 = wsum(s0);
-            if (lane == 0) smean[job] = (P > 0) ? s0 / P : 0.0;  // mean(pred) - mean(y)
-          }
-          __syncthreads();
-        }
-        double pl2[2] = {0.0, 0.0};
-#pragma unroll 1
-        for (int set = 0; set < 2; ++set) {
-          const int n = (set ? Pva : Ptr) * T;
-          double* buf = set ? res_va : res_tr;
-          const float* y = set ? va_y : tr_y;
-#pragma unroll 1
-          for (int j = tid; j < n; j += nt) {
-            double r = buf[j] - (double)y[j];
-            if (centre) r -= smean[set * T + (j - fdiv(j, invTm) * T)];
-            buf[j] = r;
-            if (!sigma) {
-              pl2[set] += 0.5 * r * r;
-              if (set == 0) gp_tr[j] = r;
-            }
-          }
-        }
-        if (sigma) {
-          __syncthreads();
-#pragma unroll 1
-          for (int set = 0; set < 2; ++set) {
-            const int P = set ? Pva : Ptr;
-            const float* W = set ? pb.slots[i].val.W : pb.slots[i].train.W;
-            const double* rs = set ? res_va : res_tr;
-#pragma unroll 1
-            for (int j = tid; j < P * T; j += nt) {
-              const int p = fdiv(j, invTm), t = j - p * T;
-              double a1 = 0.0, a2 = 0.0;
-#pragma unroll 1
-              for (int p2 = 0; p2 < P; ++p2) {
-                const double rr = rs[p2 * T + t];
-                a1 += (double)W[(size_t)p * P + p2] * rr;
-                a2 += (double)W[(size_t)p2 * P + p] * rr;
-              }
-              pl2[set] += 0.5 * rs[j] * a1;
-              if (set == 0) gp_tr[j] = 0.5 * (a1 + a2);
-            }
-          }
-        }
-#pragma unroll 1
-        for (int set = 0; set < 2; ++set) {
-          const int P = set ? Pva : Ptr;
-          const double nrm = (P > 0) ? __drcp_rn((double)T * (double)P) : 0.0;
-          const double t = wsum((set ? pl2[1] : pl2[0]) * nrm);
-          if (lane == 0) s_red[warp][set * JAXENT_MAX_SLOTS + i] = t;
-        }
-        if (centre) {
-          __syncthreads();
-#pragma unroll 1
-          for (int t = warp; t < T; t += nw) {
-            double s0 = 0.0;
-#pragma unroll 1
-            for (int p = lane; p < Ptr; p += 32) s0 += gp_tr[p * T + t];
-            s0 = wsum(s0);
-            if (lane == 0) smean[2 * T + t] = s0 / Ptr;
-          }
-        }
-      }
-      __syncthreads();  // (3) dL/dpred visible
-      TPROF(6);
-
-      // (b) back-projection to dL/d lnPF, one (residue, chunk of 4 time points) item per thread
-      {
-        const int* tptr = s_blob + bl.tr_tptr;
-        const int* trow = s_blob + bl.tr_trow;
-        const float* tval = reinterpret_cast<const float*>(s_blob + bl.tr_tval);
-        const double g = scale * (pf ? 2.0 : 1.0) * __drcp_rn(pf ? (double)Ptr : (double)T * (double)Ptr);
-        const int nch = (Tm + 3) >> 2;
-        const int items = R * nch;
-#pragma unroll 1
-        for (int it = tid; it < items; it += nt) {
-          const int ch = fdiv(it, invR), r = it - ch * R, t0 = ch << 2;
-          const int o1 = min(t0 + 1, Tm - 1) - t0, o2 = min(t0 + 2, Tm - 1) - t0, o3 = min(t0 + 3, Tm - 1) - t0;
-          double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, colsum = 0.0;
-          const int qe = tptr[r + 1];
-#pragma unroll 2
-          for (int q = tptr[r]; q < qe; ++q) {
-            const double v = (double)tval[q];
-            const double* gp = gp_tr + trow[q] * Tm + t0;
-            b0 += v * gp[0];
-            b1 += v * gp[o1];
-            b2 += v * gp[o2];
-            b3 += v * gp[o3];
-            if (GENERAL) colsum += v;
-          }
-          const double bk[4] = {b0, b1, b2, b3};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int t = t0 + k;
-            if (t < Tm) {
-              double back = bk[k];
-              if (centre) back -= colsum * smean[2 * T + t];  // centred gradient: minus mean_p(gp) through the column
-              if (!pf) {
-                const double x = (double)s_k[r] * (double)s_tp[t] * sxe[r];
-                back *= -x * (1.0 - sU[(size_t)t * R + r]);  // du/dlnPF = -x exp(-x)
-              }
-              sc_rt[(size_t)t * R + r] = g * back;
-            }
-          }
-        }
-      }
-      __syncthreads();  // (4) items visible
-      TPROF(7);
-      if (tid < R) {
-#pragma unroll 1
-        for (int t = 0; t < Tm; ++t) my_c += sc_rt[(size_t)t * R + tid];
-      }
-    }
-
-    // ---- row coefficients for the next pass + one multi-value block reduction
-    {
-      double v12 = 0.0, v13 = 0.0, v14 = 0.0;
-      if (tid < R) {
-        a.cc[tid] = (float)(my_c * bc);
-        a.ch[tid] = (float)(my_c * bh);
-        v12 = my_c * my_lp;  // hbar (data part) = sum_r c_r lnPF_r = sum_j w_j h_j
-        v13 = my_c * my_a;   // dL/dbc
-        v14 = my_c * my_b;   // dL/dbh
-      }
-      if (warp * 32 < R) {
-        v12 = wsum(v12);
-        v13 = wsum(v13);
-        v14 = wsum(v14);
-        if (lane == 0) {
-          s_red[warp][12] = v12;
-          s_red[warp][13] = v13;
-          s_red[warp][14] = v14;
-        }
-      }
-    }
-    __syncthreads();  // (5)
-    TPROF(8);
-    if (tid < 15) {
-      double t = 0.0;
-#pragma unroll 1
-      for (int w = 0; w < nw; ++w) t += s_red[w][tid];  // fixed order
-      s_fin[tid] = t;
-    }
-    __syncthreads();  // (6)
     TPROF(9);
 
     if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, lane, a.trk);
