@@ -284,6 +284,28 @@ int jaxent_bg_gemm1(const void* features, const void* cc3, float* H, int32_t n_f
 int jaxent_bg_gemm2(const void* features, const void* e3, float* partials, int32_t n_fb, int32_t n_rg, int32_t Bn, int32_t NS,
                     int32_t ksplit, jaxent_stream_t stream);
 
+/* ---- batched optimise step (csrc/bg_step.cu): n_replicas runs of OptaxOptimizer._step_with_rates that share the
+ * features, the data and the starting point and differ in (forward_model_weights, forward_model_scaling, learning_rate)
+ * -- what batch_optimise (opt/batch.py:51-192) vmaps.  problem->packed must hold the bf16 GEMM layout
+ * (jaxent_bg_pack_features) and problem->feature_format must be 2; n_replicas is a multiple of 16 (<= 256; pad by
+ * repeating the last replica as the reference does, batch.py:25-29); n_pieces in 1..3.
+ * fw / fs: host float[n_replicas][JAXENT_MAX_SLOTS]; lr: host float[n_replicas] or NULL (cfg->learning_rate).
+ * jaxent_bg_state_init = OptaxOptimizer.initialise + the step-0 forward; jaxent_bg_step = one optimise step of every replica.
+ * Buffers (jaxent_bg_plan_buffer): 0 logits float[F][Bn], 1 exp(z - lse) float[F][Bn] (softmax weights = column / S),
+ * 2 JaxentLossRecord[256][Bn] ring (index step % 256), 3 control blocks (jaxent_bg_ctl_sizeof() bytes each; double S at
+ * jaxent_bg_ctl_offset(0)), 4 log_Pf float[Bn][R], 5 uptake float[Bn][T*R]. */
+typedef struct JaxentBatchPlan JaxentBatchPlan;
+size_t jaxent_bg_workspace_bytes(const JaxentBvProblem* problem, int32_t n_replicas, int32_t n_pieces, int32_t sm_count);
+int jaxent_bg_plan_create(const JaxentBvProblem* problem, const JaxentOptConfig* cfg, int32_t n_replicas, int32_t n_pieces,
+                          void* workspace, size_t workspace_bytes, int32_t sm_count, JaxentBatchPlan** plan);
+void jaxent_bg_plan_destroy(JaxentBatchPlan* plan);
+int jaxent_bg_state_init(JaxentBatchPlan* plan, const float* z0, float zmax, float bc, float bh, const float* fw_host,
+                         const float* fs_host, const float* lr_host, jaxent_stream_t stream);
+int jaxent_bg_step(JaxentBatchPlan* plan, jaxent_stream_t stream);
+int jaxent_bg_plan_buffer(const JaxentBatchPlan* plan, int32_t which, void** ptr, size_t* bytes);
+int jaxent_bg_ctl_sizeof(void);
+int jaxent_bg_ctl_offset(int32_t field); /* 0: double S, 1: float bc, 2: float bh, 3: int step, 4: float lse */
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,6 +167,14 @@ SYMBOLS = {
     "jaxent_bg_pack_features": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _VP, _VP, _VP]),
     "jaxent_bg_gemm1": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "jaxent_bg_gemm2": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "jaxent_bg_workspace_bytes": (_SZ, [C.POINTER(BvProblem), _I32, _I32, _I32]),
+    "jaxent_bg_plan_create": (C.c_int, [C.POINTER(BvProblem), C.POINTER(OptConfig), _I32, _I32, _VP, _SZ, _I32, C.POINTER(_VP)]),
+    "jaxent_bg_plan_destroy": (None, [_VP]),
+    "jaxent_bg_state_init": (C.c_int, [_VP, _VP, _F, _F, _F, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), _VP]),
+    "jaxent_bg_step": (C.c_int, [_VP, _VP]),
+    "jaxent_bg_plan_buffer": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_SZ)]),
+    "jaxent_bg_ctl_sizeof": (C.c_int, []),
+    "jaxent_bg_ctl_offset": (C.c_int, [_I32]),
     "jaxent_bv_state_init": (C.c_int, [_VP, _VP, _F, _F, _F, C.POINTER(_F), C.POINTER(_F), _VP]),
     "jaxent_bv_pass": (C.c_int, [_VP, _I32, _VP]),
     "jaxent_bv_reduce": (C.c_int, [_VP, _VP]),

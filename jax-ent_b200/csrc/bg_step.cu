@@ -1,0 +1,777 @@
+// Batched optimise step: B replicas (hyper-parameter sweep / replicates) that share one feature matrix.
+//
+// Reference: batch_optimise (opt/batch.py:51-192) vmaps _optimise_pure (opt/run.py:141-232) over
+// (forward_model_weights, forward_model_scaling, learning_rate); every replica runs the optimise step of
+// OptaxOptimizer._step_with_rates (opt/optimiser.py:337-445).  Here the two feature sweeps of all replicas are
+// dense tensor-core GEMMs (bg_gemm.cu) and the per-(frame, replica) work is elementwise:
+//
+//   gemm1      H[f,b] = sum_{a,r} N_a[r,f] c_a[r,b]                         backward of step k
+//   bt_grad    g = mask * w * (H + kappa - hbar), per-replica grad-dot      opt/optimiser.py:394-401
+//   bt_decide  plateau rule -> learning rate, BV-parameter Adam, counters   opt/optimiser.py:403-424
+//   bt_adam    optax adam on the frame logits, e' = exp(z' - lse), bf16 pieces of e' for gemm2
+//   gemm2      Acc[a*Rp+r, b] = sum_f N_a[r,f] e'[f,b]                      forward of step k+1
+//   bt_reduce2 k-split partials -> per-replica row sums (fp64) and S_b = sum_f e'
+//   bt_tail    one CTA per replica: the R x T tail (bv_tail_body.cuh), c -> bf16 pieces for gemm1, loss record,
+//              learning rates / masks of the coming update
+//   bt_kl      maxent_convexKL_loss terms per (frame, replica), sums folded by the last block, loss record completed
+//
+// State arrays are [frame][replica] fp32 (replica contiguous): z, m, v, e, g (two buffers).  All reductions are
+// carried in fp64 and folded in a fixed order (bitwise reproducible).
+#include <cuda_bf16.h>
+
+#include <cstddef>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "bv_tail_body.cuh"
+#include "jx_internal.cuh"
+
+namespace jx {
+namespace bg {
+
+constexpr int RB = 256;          // loss-record ring depth per replica
+constexpr int MAX_EW_BLOCKS = 592;
+
+struct alignas(16) BCtl {
+  int step, mask_idx, have_prev, count_frame, count_model, kl_slot, stop, last_branch;
+  float lr, model_lr, cfg_lr, lse;
+  float bc, bh, mb[2], vb[2], gb_prev[2], gb[2];
+  float lrA, lrB, mlrA, mlrB, mask_frame, mask_model;
+  float lr_eff, bc1, bc2, kl_scale, last_dot, pad0;
+  double S, hbar_data;
+  double klsum[KL_N];
+  float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
+};
+static_assert(sizeof(BCtl) % 16 == 0, "BCtl is copied with 16-byte loads");
+
+struct BatchArgs {
+  JaxentBvProblem prob;  // .packed = GF bf16 features
+  JaxentOptConfig cfg;
+  BlobSet blobs;
+  int Bn, NS, n_fb, n_rg, Rp, ksplit;
+  long long F;
+  float *z, *m, *v, *e, *g[2];
+  float* H;               // [Fp][Bn]
+  float* P;               // [ksplit][2Rp][Bn]
+  unsigned char* cc3;     // [NS][2][Rp/8][Bn][8] bf16
+  unsigned char* e3;      // [n_fb][NS][16][Bn][8] bf16
+  double* red;            // [Bn][2Rp]
+  double* part_dot;       // [MAX_EW_BLOCKS][Bn]
+  double* part_s;         // [MAX_EW_BLOCKS][Bn]
+  double* part_kl;        // [MAX_EW_BLOCKS][KL_N][Bn]
+  BCtl* ctl;              // [Bn]
+  JaxentLossRecord* records;  // [RB][Bn]
+  float* avg;             // [Bn][2R]
+  float* logpf;           // [Bn][R]
+  float* uptake;          // [Bn][T*R]
+  unsigned* gsel;         // which g buffer holds the current masked gradients
+  unsigned* counter;      // ticket of bt_kl
+  int p_max_tr, p_max_va;
+  int blob_words_max;     // words reserved for the blob image in the tail's shared memory
+  int ew_blocks, fy;      // elementwise grid / frames per block iteration
+  float eps_kl;
+};
+
+// fp32 -> NS bf16 pieces (round to nearest at every level): x ~= p0 + p1 + p2
+__device__ __forceinline__ void split3(float x, int NS, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+  p0 = __float2bfloat16_rn(x);
+  float r = x - __bfloat162float(p0);
+  p1 = (NS > 1) ? __float2bfloat16_rn(r) : __float2bfloat16_rn(0.f);
+  r -= __bfloat162float(p1);
+  p2 = (NS > 2) ? __float2bfloat16_rn(r) : __float2bfloat16_rn(0.f);
+}
+
+// kappa (= d KL / d w, scaled) and the normalised weight of one (frame, replica); same arithmetic as frame_terms (bv_tail.cu)
+__device__ __forceinline__ void weight_terms(float e, float Sf, float prior_f, bool has_kl, float eps, double inv_pnorm, float lam, float& w,
+                                             float& kap, float& q, float& p, double& ratio) {
+  w = e / Sf;
+  kap = 0.f;
+  q = p = 0.f;
+  ratio = 1.0;
+  if (has_kl) {
+    q = fabsf(w) + eps;
+    p = (float)(((double)fabsf(prior_f) + (double)eps) * inv_pnorm);
+    ratio = (double)p * __drcp_rn((double)q);
+    const float G_ = (float)(1.0 - ratio);
+    kap = (w > 0.f) ? lam * G_ : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bt_grad
+// thread = (replica b = tid % Bn, frame lane fy = tid / Bn); frames strided over the grid
+__global__ void __launch_bounds__(1024) bt_grad_kernel(const BatchArgs a) {
+  extern __shared__ double sh_d[];  // [fy][Bn]
+  const int Bn = a.Bn, b = threadIdx.x % Bn, fy = threadIdx.x / Bn;
+  const BCtl* c = a.ctl + b;
+  const unsigned sel = *a.gsel;
+  const float* __restrict__ gprev = a.g[sel];
+  float* __restrict__ gout = a.g[sel ^ 1u];
+  const float Sf = (float)c->S, lam = c->kl_scale, maskf = c->mask_frame;
+  const float hbar = (float)(c->hbar_data + c->klsum[0]);
+  const int have_prev = c->have_prev;
+  const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
+  const bool active = !c->stop;
+  const double inv_pnorm = has_kl ? __drcp_rn(a.prob.prior_norm) : 0.0;
+  double dot = 0.0;
+  for (long long f = (long long)blockIdx.x * a.fy + fy; f < a.F; f += (long long)gridDim.x * a.fy) {
+    const size_t i = (size_t)f * Bn + b;
+    float w, kap, q, p;
+    double ratio;
+    weight_terms(a.e[i], Sf, has_kl ? a.prob.prior[f] : 0.f, has_kl, a.eps_kl, inv_pnorm, lam, w, kap, q, p, ratio);
+    const float gf = active ? maskf * (w * ((a.H[i] + kap) - hbar)) : 0.f;
+    const float gpv = have_prev ? gprev[i] : gf;
+    dot += (double)(gpv * gf);
+    gout[i] = gf;
+  }
+  sh_d[fy * Bn + b] = dot;
+  __syncthreads();
+  if (fy == 0) {
+    double t = 0.0;
+    for (int k = 0; k < a.fy; ++k) t += sh_d[k * Bn + b];
+    a.part_dot[(size_t)blockIdx.x * Bn + b] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bt_decide
+// one thread per replica: plateau rule, BV-parameter Adam (optax adam + keep_params_nonnegative), counters
+__global__ void bt_decide_kernel(const BatchArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *a.gsel = *a.gsel ^ 1u;  // bt_grad wrote the other buffer: it now holds the current gradients
+  if (b >= a.Bn) return;
+  BCtl* c = a.ctl + b;
+  if (c->stop) return;
+  const JaxentOptConfig& cfg = a.cfg;
+  double gdot = 0.0;
+  for (int k = 0; k < a.ew_blocks; ++k) gdot += a.part_dot[(size_t)k * a.Bn + b];
+  const float g0 = c->gb[0], g1 = c->gb[1];
+  const float p0 = c->have_prev ? c->gb_prev[0] : g0, p1 = c->have_prev ? c->gb_prev[1] : g1;
+  const double dot = gdot + (double)p0 * (double)g0 + (double)p1 * (double)g1;
+  const int d = ((float)dot < 0.f && c->step > 1) ? 1 : 0;  // opt/optimiser.py:403
+  const float lr = d ? c->lrB : c->lrA, mlr = d ? c->mlrB : c->mlrA;
+  const float b1 = (float)cfg.b1, b2 = (float)cfg.b2, eps = (float)cfg.eps, clip = cfg.clip_value;
+  const float om_b1 = (float)(1.0 - cfg.b1), om_b2 = (float)(1.0 - cfg.b2);
+  const int cm = c->count_model + 1, cf = c->count_frame + 1;
+  const float c1 = 1.0f - fpow(b1, (float)cm), c2 = 1.0f - fpow(b2, (float)cm);
+  float sg0 = g0 * mlr, sg1 = g1 * mlr;
+  if (clip > 0.f) {
+    sg0 = fminf(fmaxf(sg0, -clip), clip);
+    sg1 = fminf(fmaxf(sg1, -clip), clip);
+  }
+  const float mb0 = om_b1 * sg0 + b1 * c->mb[0], mb1 = om_b1 * sg1 + b1 * c->mb[1];
+  const float vb0 = om_b2 * (sg0 * sg0) + b2 * c->vb[0], vb1 = om_b2 * (sg1 * sg1) + b2 * c->vb[1];
+  float u0 = -((mb0 / c1) / (sqrtf(vb0 / c2) + eps));
+  float u1 = -((mb1 / c1) / (sqrtf(vb1 / c2) + eps));
+  if (c->bc + u0 < 0.f) u0 = -c->bc;  // optax.keep_params_nonnegative
+  if (c->bh + u1 < 0.f) u1 = -c->bh;
+  c->bc += u0;
+  c->bh += u1;
+  c->mb[0] = mb0; c->mb[1] = mb1; c->vb[0] = vb0; c->vb[1] = vb1;
+  c->gb_prev[0] = g0; c->gb_prev[1] = g1;
+  c->count_model = cm;
+  c->count_frame = cf;
+  c->have_prev = 1;
+  c->mask_idx = (c->step >= cfg.initial_steps) ? 1 : c->mask_idx;
+  c->step += 1;
+  c->lr = lr;
+  c->model_lr = mlr;
+  c->lr_eff = lr;
+  c->bc1 = 1.0f - fpow(b1, (float)cf);
+  c->bc2 = 1.0f - fpow(b2, (float)cf);
+  c->last_dot = (float)dot;
+  c->last_branch = d;
+}
+
+// ------------------------------------------------------------------------------------------ bt_adam
+// thread = (replica b, chunk lane cy); a chunk is 8 consecutive frames: z, m, v updated in place, e' written, and the
+// bf16 pieces of e' stored as 16-byte K-chunks of the gemm2 B operand.  update = 0: initial forward (no Adam).
+__global__ void __launch_bounds__(1024) bt_adam_kernel(const BatchArgs a, int update) {
+  extern __shared__ double sh_d[];  // [cy][Bn]
+  const int Bn = a.Bn, b = threadIdx.x % Bn, cy = threadIdx.x / Bn, ncy = blockDim.x / Bn;
+  const BCtl* c = a.ctl + b;
+  const float* __restrict__ g = a.g[*a.gsel];
+  const float lr = c->lr_eff, bc1 = c->bc1, bc2 = c->bc2, lse = c->lse;
+  const bool active = update && !c->stop;
+  const float b1 = (float)a.cfg.b1, b2 = (float)a.cfg.b2, eps = (float)a.cfg.eps, clip = a.cfg.clip_value;
+  const float om_b1 = (float)(1.0 - a.cfg.b1), om_b2 = (float)(1.0 - a.cfg.b2);
+  const int NS = a.NS;
+  const long long n_chunks = (long long)a.n_fb * 16;
+  double sum = 0.0;
+  for (long long ch = (long long)blockIdx.x * ncy + cy; ch < n_chunks; ch += (long long)gridDim.x * ncy) {
+    __nv_bfloat16 p0[8], p1[8], p2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long f = ch * 8 + k;
+      float en = 0.f;
+      if (f < a.F) {
+        const size_t i = (size_t)f * Bn + b;
+        float z_ = a.z[i];
+        if (active) {
+          const float m_ = a.m[i], v_ = a.v[i];
+          float s = g[i] * lr;
+          if (clip > 0.f) s = fminf(fmaxf(s, -clip), clip);
+          const float m1 = om_b1 * s + b1 * m_;
+          const float v1 = om_b2 * (s * s) + b2 * v_;
+          z_ = z_ - (m1 / bc1) / (sqrtf(v1 / bc2) + eps);
+          a.z[i] = z_;
+          a.m[i] = m1;
+          a.v[i] = v1;
+        }
+        en = expf(z_ - lse);
+        a.e[i] = en;
+        sum += (double)en;
+      }
+      split3(en, NS, p0[k], p1[k], p2[k]);
+    }
+    const long long fb = ch >> 4;
+    const int kc = (int)(ch & 15);
+    uint4* dst = reinterpret_cast<uint4*>(a.e3);
+    dst[(((size_t)fb * NS + 0) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p0);
+    if (NS > 1) dst[(((size_t)fb * NS + 1) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p1);
+    if (NS > 2) dst[(((size_t)fb * NS + 2) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p2);
+  }
+  sh_d[cy * Bn + b] = sum;
+  __syncthreads();
+  if (cy == 0) {
+    double t = 0.0;
+    for (int k = 0; k < ncy; ++k) t += sh_d[k * Bn + b];
+    a.part_s[(size_t)blockIdx.x * Bn + b] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bt_reduce2
+// red[b][row] = sum_ks P[ks][row][b]  (32 x 32 transposing tiles);  block row 0 also folds S_b
+__global__ void __launch_bounds__(1024) bt_reduce2_kernel(const BatchArgs a) {
+  __shared__ double tile[32][33];
+  const int Bn = a.Bn, R2 = 2 * a.Rp;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  {
+    const int row = row0 + ty, b = b0 + tx;
+    double s = 0.0;
+    if (row < R2 && b < Bn)
+      for (int ks = 0; ks < a.ksplit; ++ks) s += (double)a.P[((size_t)ks * R2 + row) * Bn + b];
+    tile[ty][tx] = s;
+  }
+  __syncthreads();
+  {
+    const int b = b0 + ty, row = row0 + tx;
+    if (row < R2 && b < Bn) a.red[(size_t)b * R2 + row] = tile[tx][ty];
+  }
+  if (blockIdx.x == 0 && ty == 0) {
+    const int b = b0 + tx;
+    if (b < Bn) {
+      double s = 0.0;
+      for (int k = 0; k < a.ew_blocks; ++k) s += a.part_s[(size_t)k * Bn + b];
+      a.ctl[b].S = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bt_tail
+template <bool GENERAL>
+__global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red[32][16];
+  __shared__ double s_fin[16];
+  __shared__ __align__(16) BCtl s_c;
+  const JaxentBvProblem& pb = a.prob;
+  const int R = pb.R, T = pb.uptake ? pb.T : 0, Rp = a.Rp, Bn = a.Bn;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const TailSmem tsm = carve_tail_smem(smem_raw, R, T, a.p_max_tr, a.p_max_va);
+  // the body's smem is followed by the (cc, ch) staging rows of this replica
+  float* s_cc = reinterpret_cast<float*>(tsm.s_blob + ((a.blob_words_max + 3) & ~3));
+  float* s_ch = s_cc + Rp;
+
+  const int first_data = stage_tail_constants(pb, a.blobs, tsm);
+  if (tid < (int)(sizeof(BCtl) / 16)) reinterpret_cast<int4*>(&s_c)[tid] = reinterpret_cast<const int4*>(a.ctl + b)[tid];
+  double acc0 = 0.0, acc1 = 0.0;
+  if (tid < R) {
+    acc0 = a.red[(size_t)b * 2 * Rp + tid];
+    acc1 = a.red[(size_t)b * 2 * Rp + Rp + tid];
+  }
+  if (lane < 16) s_red[warp][lane] = 0.0;
+  for (int i = tid; i < 2 * Rp; i += blockDim.x) s_cc[i] = 0.f;
+  __syncthreads();
+  if (s_c.stop) return;
+  const double S = s_c.S;
+  const double bc = (double)s_c.bc, bh = (double)s_c.bh;
+  double my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg;
+  TailIO io;
+  io.avg = a.avg + (size_t)b * 2 * R;
+  io.logpf = a.logpf + (size_t)b * R;
+  io.uptake = a.uptake + (size_t)b * (T > 0 ? T : 1) * R;
+  tail_body<GENERAL>(pb, a.blobs, first_data, tsm, acc0, acc1, S, bc, bh, s_c.fw, s_c.fs, io, s_red, s_fin, my_c, my_a, my_b, my_lp, gbc_reg,
+                     gbh_reg);
+  if (tid < R) {
+    s_cc[tid] = (float)(my_c * bc);
+    s_ch[tid] = (float)(my_c * bh);
+  }
+  __syncthreads();
+  // c -> bf16 pieces, one 16-byte K-chunk (8 residues) per thread and piece
+  {
+    const int n_kc = Rp / 8;
+    for (int it = tid; it < 2 * n_kc; it += blockDim.x) {
+      const int arr = it / n_kc, kc = it - arr * n_kc;
+      const float* src = (arr ? s_ch : s_cc) + kc * 8;
+      __nv_bfloat16 p0[8], p1[8], p2[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) split3(src[k], a.NS, p0[k], p1[k], p2[k]);
+      uint4* dst = reinterpret_cast<uint4*>(a.cc3);
+      dst[(((size_t)0 * 2 + arr) * n_kc + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p0);
+      if (a.NS > 1) dst[(((size_t)1 * 2 + arr) * n_kc + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p1);
+      if (a.NS > 2) dst[(((size_t)2 * 2 + arr) * n_kc + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p2);
+    }
+  }
+  // control block of the coming update + loss record
+  if (tid == 0) {
+    BCtl* c = a.ctl + b;
+    const JaxentOptConfig& cfg = a.cfg;
+    const int step = s_c.step;
+    const bool switched = step >= cfg.initial_steps;
+    const int mi = switched ? 1 : s_c.mask_idx;
+    const float base_lr = switched ? s_c.cfg_lr : s_c.lr;
+    const float base_mlr = switched ? s_c.cfg_lr * cfg.model_parameters_lr_scale : s_c.model_lr;
+    const float mask_model = (mi == 0) ? 0.f : (cfg.optimise_model_parameters ? 1.f : 0.f);
+    c->lrA = base_lr;
+    c->lrB = base_lr / cfg.plateau_denominator;
+    c->mlrA = base_mlr;
+    c->mlrB = base_mlr / cfg.plateau_denominator;
+    c->mask_frame = (mi == 0) ? 1.f : (cfg.optimise_frame_weights ? 1.f : 0.f);
+    c->mask_model = mask_model;
+    c->lse = (float)((double)s_c.lse + dlog(S));
+    c->hbar_data = s_fin[12];
+    const float gb0 = (float)(s_fin[13] + gbc_reg) * mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * mask_model;
+    c->gb[0] = gb0;
+    c->gb[1] = gb1;
+    JaxentLossRecord* rec = a.records + (size_t)(step % RB) * Bn + b;
+    rec->step = step;
+    rec->branch = s_c.last_branch;
+    rec->lr = s_c.lr;
+    rec->grad_dot = s_c.last_dot;
+    rec->bc = s_c.bc;
+    rec->bh = s_c.bh;
+    rec->grad_bc = gb0;
+    rec->grad_bh = gb1;
+    rec->complete = 0;
+    float tt = 0.f, tv = 0.f;
+    for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
+      const bool on = i < pb.n_slots;
+      rec->train[i] = on ? (float)s_fin[i] : 0.f;
+      rec->val[i] = on ? (float)s_fin[JAXENT_MAX_SLOTS + i] : 0.f;
+      rec->scaled_train[i] = rec->train[i] * s_c.fw[i] * s_c.fs[i];
+      rec->scaled_val[i] = rec->val[i] * s_c.fw[i] * s_c.fs[i];
+      tt += rec->scaled_train[i];
+      tv += rec->scaled_val[i];
+    }
+    rec->total_train = tt;
+    rec->total_val = tv;
+    if (s_c.kl_slot < 0) rec->complete = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bt_kl
+// MaxEnt terms per (frame, replica); the last block folds the per-block sums (fixed order) into the control blocks
+// and completes the loss records of this step
+__global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
+  extern __shared__ double sh_d[];  // [fy][KL_N][Bn]
+  __shared__ int s_last;
+  const int Bn = a.Bn, b = threadIdx.x % Bn, fy = threadIdx.x / Bn;
+  const BCtl* c = a.ctl + b;
+  const float Sf = (float)c->S, lam = c->kl_scale;
+  const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
+  const double inv_pnorm = has_kl ? __drcp_rn(a.prob.prior_norm) : 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (!c->stop) {
+    for (long long f = (long long)blockIdx.x * a.fy + fy; f < a.F; f += (long long)gridDim.x * a.fy) {
+      float w, kap, q, p;
+      double ratio;
+      weight_terms(a.e[(size_t)f * Bn + b], Sf, has_kl ? a.prob.prior[f] : 0.f, has_kl, a.eps_kl, inv_pnorm, lam, w, kap, q, p, ratio);
+      if (has_kl) {
+        s0 += (double)w * (double)kap;
+        if (p > 0.f) s1 += (double)p * dlog(ratio);
+        s2 += (double)q - (double)p;
+      }
+      s3 += (double)w;
+    }
+  }
+  double* mine = sh_d + ((size_t)fy * KL_N) * Bn + b;
+  mine[0 * Bn] = s0;
+  mine[1 * Bn] = s1;
+  mine[2 * Bn] = s2;
+  mine[3 * Bn] = s3;
+  __syncthreads();
+  if (fy == 0) {
+    for (int k = 0; k < KL_N; ++k) {
+      double t = 0.0;
+      for (int y = 0; y < a.fy; ++y) t += sh_d[((size_t)y * KL_N + k) * Bn + b];
+      a.part_kl[((size_t)blockIdx.x * KL_N + k) * Bn + b] = t;
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *a.counter = 0u;
+  if (fy == 0) {
+    BCtl* cw = a.ctl + b;
+    if (cw->stop) return;
+    double kl[KL_N];
+    for (int k = 0; k < KL_N; ++k) {
+      double t = 0.0;
+      for (unsigned blk = 0; blk < gridDim.x; ++blk) t += __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]);
+      kl[k] = t;
+      cw->klsum[k] = t;
+    }
+    if (cw->kl_slot >= 0) {
+      JaxentLossRecord* rec = a.records + (size_t)(cw->step % RB) * Bn + b;
+      const float klv = (float)(kl[1] + kl[2]);
+      const int i = cw->kl_slot;
+      rec->train[i] = klv;
+      rec->val[i] = klv;
+      float tt = 0.f, tv = 0.f;
+      for (int k = 0; k < a.prob.n_slots; ++k) {
+        rec->scaled_train[k] = rec->train[k] * cw->fw[k] * cw->fs[k];
+        rec->scaled_val[k] = rec->val[k] * cw->fw[k] * cw->fs[k];
+        tt += rec->scaled_train[k];
+        tv += rec->scaled_val[k];
+      }
+      rec->total_train = tt;
+      rec->total_val = tv;
+      rec->complete = 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ init
+__global__ void bt_init_kernel(const BatchArgs a, const float* __restrict__ z0, const BCtl* __restrict__ init) {
+  const long long n = (long long)a.F * a.Bn;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < n; i += stride) {
+    const long long f = i / a.Bn;
+    a.z[i] = z0[f];
+    a.m[i] = 0.f;
+    a.v[i] = 0.f;
+    a.g[0][i] = 0.f;
+    a.g[1][i] = 0.f;
+  }
+  if (i0 < a.Bn) a.ctl[i0] = init[i0];
+  if (i0 == 0) {
+    *a.gsel = 0u;
+    *a.counter = 0u;
+  }
+  const long long nrec = (long long)RB * a.Bn * (long long)(sizeof(JaxentLossRecord) / 4);
+  for (long long i = i0; i < nrec; i += stride) reinterpret_cast<int*>(a.records)[i] = 0;
+}
+
+}  // namespace bg
+}  // namespace jx
+
+// ============================================================================================== host side
+using namespace jx;
+
+struct JaxentBatchPlan {
+  bg::BatchArgs a;
+  unsigned char* ws;
+  size_t off_ctl_init;
+  size_t tail_smem;
+  int general;
+  int sm_count;
+  int initialised;
+  long long steps;
+};
+
+namespace {
+struct BLayout {
+  size_t z, m, v, e, g0, g1, H, P, cc3, e3, red, part_dot, part_s, part_kl, ctl, ctl_init, records, avg, logpf, uptake, gsel, counter;
+  size_t blob[JAXENT_MAX_SLOTS];
+  int blob_words[JAXENT_MAX_SLOTS];
+  size_t total;
+};
+size_t up(size_t x) { return (x + 255) / 256 * 256; }
+
+BLayout b_layout(const JaxentBvProblem* pb, int Bn, int NS, int ksplit) {
+  const size_t F = (size_t)pb->F, R = pb->R, T = pb->uptake ? pb->T : 1;
+  const size_t Rp = (R + 127) / 128 * 128, Fp = (F + 127) / 128 * 128;
+  BLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = up(o + bytes); return r; };
+  const size_t fb = F * Bn * 4;
+  L.z = take(fb); L.m = take(fb); L.v = take(fb); L.e = take(fb); L.g0 = take(fb); L.g1 = take(fb);
+  L.H = take(Fp * Bn * 4);
+  L.P = take((size_t)ksplit * 2 * Rp * Bn * 4);
+  L.cc3 = take((size_t)NS * 2 * Rp * Bn * 2);
+  L.e3 = take(Fp * NS * Bn * 2);
+  L.red = take((size_t)Bn * 2 * Rp * 8);
+  L.part_dot = take((size_t)bg::MAX_EW_BLOCKS * Bn * 8);
+  L.part_s = take((size_t)bg::MAX_EW_BLOCKS * Bn * 8);
+  L.part_kl = take((size_t)bg::MAX_EW_BLOCKS * KL_N * Bn * 8);
+  L.ctl = take((size_t)Bn * sizeof(bg::BCtl));
+  L.ctl_init = take((size_t)Bn * sizeof(bg::BCtl));
+  L.records = take((size_t)bg::RB * Bn * sizeof(JaxentLossRecord));
+  L.avg = take((size_t)Bn * 2 * R * 4);
+  L.logpf = take((size_t)Bn * R * 4);
+  L.uptake = take((size_t)Bn * T * R * 4);
+  L.gsel = take(4);
+  L.counter = take(4);
+  for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
+    L.blob[i] = 0;
+    L.blob_words[i] = 0;
+    if (i < pb->n_slots && pb->slots[i].kind <= JAXENT_LOSS_PF_L2) {
+      const JaxentLossSlot& sl = pb->slots[i];
+      L.blob_words[i] = blob_words(pb->R, pb->uptake ? pb->T : 0, sl.train.n_pep, sl.train.nnz, sl.val.n_pep, sl.val.nnz);
+      L.blob[i] = take((size_t)L.blob_words[i] * 4);
+    }
+  }
+  L.total = o;
+  return L;
+}
+
+int b_check(const JaxentBvProblem* pb, int n_replicas, int NS) {
+  if (!pb || pb->R <= 0 || pb->F <= 0) { set_error("batched plan: invalid problem"); return JAXENT_E_INVALID; }
+  if (n_replicas < 1 || n_replicas > 256 || n_replicas % 16 != 0) { set_error("batched plan: replicas must be a multiple of 16 in 16..256 (pad by repeating the last)"); return JAXENT_E_INVALID; }
+  if (NS < 1 || NS > 3) { set_error("batched plan: 1..3 bf16 pieces"); return JAXENT_E_INVALID; }
+  if (pb->R > TAIL_THREADS) { set_error("batched plan: n_residues=%d exceeds %d", pb->R, TAIL_THREADS); return JAXENT_E_UNSUPPORTED; }
+  if (pb->feature_format != 2) { set_error("batched plan: features must be in the bf16 GEMM layout (jaxent_bg_pack_features, feature_format = 2)"); return JAXENT_E_INVALID; }
+  return JAXENT_OK;
+}
+int b_ksplit(const JaxentBvProblem* pb, int sm) {
+  const int Rp = (pb->R + 127) / 128 * 128, n_mt = 2 * Rp / 128;
+  const long long n_hb = 2 * ((pb->F + 127) / 128);
+  long long ks = sm / n_mt;
+  if (ks < 1) ks = 1;
+  if (ks > n_hb) ks = n_hb;
+  return (int)ks;
+}
+}  // namespace
+
+extern "C" size_t jaxent_bg_workspace_bytes(const JaxentBvProblem* pb, int32_t n_replicas, int32_t n_pieces, int32_t sm_count) {
+  if (b_check(pb, n_replicas, n_pieces)) return 0;
+  if (sm_count <= 0) sm_count = 148;
+  return b_layout(pb, n_replicas, n_pieces, b_ksplit(pb, sm_count)).total;
+}
+
+extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptConfig* cfg, int32_t n_replicas, int32_t n_pieces,
+                                     void* workspace, size_t workspace_bytes, int32_t sm_count, JaxentBatchPlan** out) {
+  if (!out) { set_error("batched plan: NULL output"); return JAXENT_E_INVALID; }
+  *out = nullptr;
+  int rc = b_check(pb, n_replicas, n_pieces);
+  if (rc) return rc;
+  if (!cfg || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) { set_error("batched plan: config / 256-byte aligned workspace required"); return JAXENT_E_INVALID; }
+  if (sm_count <= 0) sm_count = 148;
+  const int ksplit = b_ksplit(pb, sm_count);
+  const BLayout L = b_layout(pb, n_replicas, n_pieces, ksplit);
+  if (workspace_bytes < L.total) { set_error("batched plan: workspace too small: %zu < %zu", workspace_bytes, L.total); return JAXENT_E_WORKSPACE; }
+  int n_kl = 0;
+  bool general = false;
+  for (int i = 0; i < pb->n_slots; ++i) {
+    const int k = pb->slots[i].kind;
+    if (k == JAXENT_LOSS_MAXENT_CONVEX_KL) {
+      if (!pb->prior || !(pb->prior_norm > 0.0)) { set_error("batched plan: maxent_convexKL_loss needs prior and prior_norm"); return JAXENT_E_INVALID; }
+      ++n_kl;
+    }
+    if (k < 0 || k > JAXENT_LOSS_PARAMS_L2) { set_error("batched plan: unsupported loss kind %d", k); return JAXENT_E_UNSUPPORTED; }
+    if ((k <= JAXENT_LOSS_UPTAKE_SIGMA_MSE) != (pb->uptake != 0) && k <= JAXENT_LOSS_PF_L2) { set_error("batched plan: slot %d does not match the forward model", i); return JAXENT_E_UNSUPPORTED; }
+    general = general || k == JAXENT_LOSS_UPTAKE_MC_EYE_MSE || k == JAXENT_LOSS_UPTAKE_SIGMA_MSE;
+  }
+  if (n_kl > 1) { set_error("batched plan: at most one maxent_convexKL_loss slot"); return JAXENT_E_UNSUPPORTED; }
+  JaxentBatchPlan* p = new (std::nothrow) JaxentBatchPlan();
+  if (!p) { set_error("out of host memory"); return JAXENT_E_INVALID; }
+  memset(p, 0, sizeof(*p));
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  p->ws = ws;
+  bg::BatchArgs& a = p->a;
+  a.prob = *pb;
+  a.cfg = *cfg;
+  a.Bn = n_replicas;
+  a.NS = n_pieces;
+  a.Rp = (pb->R + 127) / 128 * 128;
+  a.n_rg = a.Rp / 8;
+  a.n_fb = (int)((pb->F + 127) / 128);
+  a.ksplit = ksplit;
+  a.F = pb->F;
+  a.z = (float*)(ws + L.z); a.m = (float*)(ws + L.m); a.v = (float*)(ws + L.v); a.e = (float*)(ws + L.e);
+  a.g[0] = (float*)(ws + L.g0); a.g[1] = (float*)(ws + L.g1);
+  a.H = (float*)(ws + L.H);
+  a.P = (float*)(ws + L.P);
+  a.cc3 = ws + L.cc3;
+  a.e3 = ws + L.e3;
+  a.red = (double*)(ws + L.red);
+  a.part_dot = (double*)(ws + L.part_dot);
+  a.part_s = (double*)(ws + L.part_s);
+  a.part_kl = (double*)(ws + L.part_kl);
+  a.ctl = (bg::BCtl*)(ws + L.ctl);
+  a.records = (JaxentLossRecord*)(ws + L.records);
+  a.avg = (float*)(ws + L.avg);
+  a.logpf = (float*)(ws + L.logpf);
+  a.uptake = (float*)(ws + L.uptake);
+  a.gsel = (unsigned*)(ws + L.gsel);
+  a.counter = (unsigned*)(ws + L.counter);
+  p->off_ctl_init = L.ctl_init;
+  for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
+    a.blobs.words[i] = L.blob_words[i];
+    a.blobs.blob[i] = L.blob_words[i] ? (int*)(ws + L.blob[i]) : nullptr;
+  }
+  int p_tr = 1, p_va = 1;
+  for (int i = 0; i < pb->n_slots; ++i)
+    if (pb->slots[i].kind <= JAXENT_LOSS_PF_L2) {
+      if (pb->slots[i].train.n_pep > p_tr) p_tr = pb->slots[i].train.n_pep;
+      if (pb->slots[i].val.n_pep > p_va) p_va = pb->slots[i].val.n_pep;
+      if (pb->slots[i].train.n_pep <= 0) { delete p; set_error("batched plan: slot %d has an empty training set", i); return JAXENT_E_INVALID; }
+    }
+  a.p_max_tr = p_tr;
+  a.p_max_va = p_va;
+  a.eps_kl = (float)(1e-10 / (double)pb->F_total);
+  // elementwise geometry: blocks of Bn x fy threads
+  a.fy = 1024 / n_replicas;
+  long long blocks = ((long long)pb->F + a.fy - 1) / a.fy;
+  const long long want = (long long)sm_count * 2;
+  if (blocks > want) blocks = want;
+  if (blocks > bg::MAX_EW_BLOCKS) blocks = bg::MAX_EW_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  a.ew_blocks = (int)blocks;
+  {
+    int nnz_tr = 1, nnz_va = 1;
+    for (int i = 0; i < pb->n_slots; ++i)
+      if (pb->slots[i].kind <= JAXENT_LOSS_PF_L2) {
+        if (pb->slots[i].train.nnz > nnz_tr) nnz_tr = pb->slots[i].train.nnz;
+        if (pb->slots[i].val.nnz > nnz_va) nnz_va = pb->slots[i].val.nnz;
+      }
+    const int T = pb->uptake ? pb->T : 0;
+    a.blob_words_max = blob_words(pb->R, T, p_tr, nnz_tr, p_va, nnz_va);
+    p->tail_smem = tail_smem_bytes(pb->R, T, p_tr, p_va, nnz_tr, nnz_va) + (size_t)2 * a.Rp * 4 + 64;
+  }
+  if (p->tail_smem > 220 * 1024) { delete p; set_error("batched plan: tail needs %zu bytes of shared memory", p->tail_smem); return JAXENT_E_UNSUPPORTED; }
+  p->general = general;
+  p->sm_count = sm_count;
+  *out = p;
+  return JAXENT_OK;
+}
+
+extern "C" void jaxent_bg_plan_destroy(JaxentBatchPlan* p) { delete p; }
+
+static int bg_err(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s launch: %s", what, cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}
+
+static int bg_forward(JaxentBatchPlan* p, cudaStream_t s) {
+  const bg::BatchArgs& a = p->a;
+  int rc = jaxent_bg_gemm2(a.prob.packed, a.e3, a.P, a.n_fb, a.n_rg, a.Bn, a.NS, a.ksplit, s);
+  if (rc) return rc;
+  dim3 grid((2 * a.Rp + 31) / 32, (a.Bn + 31) / 32);
+  bg::bt_reduce2_kernel<<<grid, 1024, 0, s>>>(a);
+  if ((rc = bg_err("bt_reduce2"))) return rc;
+  static size_t configured[2] = {0, 0};
+  if (p->tail_smem > configured[p->general]) {
+    cudaError_t e = p->general ? cudaFuncSetAttribute(bg::bt_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tail_smem)
+                               : cudaFuncSetAttribute(bg::bt_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tail_smem);
+    if (e != cudaSuccess) { set_error("bt_tail: %zu bytes of shared memory: %s", p->tail_smem, cudaGetErrorString(e)); return JAXENT_E_UNSUPPORTED; }
+    configured[p->general] = p->tail_smem;
+  }
+  if (p->general) bg::bt_tail_kernel<true><<<a.Bn, TAIL_THREADS, p->tail_smem, s>>>(a);
+  else bg::bt_tail_kernel<false><<<a.Bn, TAIL_THREADS, p->tail_smem, s>>>(a);
+  if ((rc = bg_err("bt_tail"))) return rc;
+  bg::bt_kl_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * KL_N * a.Bn * 8, s>>>(a);
+  return bg_err("bt_kl");
+}
+
+extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float zmax, float bc, float bh, const float* fw_host,
+                                    const float* fs_host, const float* lr_host, jaxent_stream_t stream) {
+  if (!p || !z0 || !fw_host || !fs_host) { set_error("bg_state_init: NULL argument"); return JAXENT_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  bg::BatchArgs& a = p->a;
+  std::vector<bg::BCtl> init((size_t)a.Bn);
+  for (int b = 0; b < a.Bn; ++b) {
+    bg::BCtl c;
+    memset(&c, 0, sizeof(c));
+    c.lr = a.cfg.initial_learning_rate;
+    c.model_lr = a.cfg.initial_learning_rate * a.cfg.model_parameters_lr_scale;
+    c.cfg_lr = lr_host ? lr_host[b] : a.cfg.learning_rate;
+    c.lse = zmax;
+    c.bc = bc;
+    c.bh = bh;
+    c.kl_slot = -1;
+    c.lr_eff = c.lr;
+    c.bc1 = c.bc2 = 1.f;
+    c.mask_frame = 1.f;
+    c.S = 1.0;
+    for (int i = 0; i < a.prob.n_slots; ++i) {
+      c.fw[i] = fw_host[(size_t)b * JAXENT_MAX_SLOTS + i];
+      c.fs[i] = fs_host[(size_t)b * JAXENT_MAX_SLOTS + i];
+      if (a.prob.slots[i].kind == JAXENT_LOSS_MAXENT_CONVEX_KL) {
+        c.kl_slot = i;
+        c.kl_scale = c.fw[i] * c.fs[i];
+      }
+    }
+    init[b] = c;
+  }
+  bg::BCtl* dinit = reinterpret_cast<bg::BCtl*>(p->ws + p->off_ctl_init);
+  cudaError_t e = cudaMemcpyAsync(dinit, init.data(), init.size() * sizeof(bg::BCtl), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // `init` is pageable host memory: set-up time only
+  if (e != cudaSuccess) { set_error("bg_state_init: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  bg::bt_init_kernel<<<592, 256, 0, s>>>(a, z0, dinit);
+  int rc = bg_err("bt_init");
+  if (rc) return rc;
+  if ((rc = launch_build_blobs(a.prob, a.blobs, s))) return rc;
+  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a, 0);
+  if ((rc = bg_err("bt_adam(init)"))) return rc;
+  rc = bg_forward(p, s);
+  if (rc) return rc;
+  p->initialised = 1;
+  p->steps = 0;
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bg_step(JaxentBatchPlan* p, jaxent_stream_t stream) {
+  if (!p || !p->initialised) { set_error("bg_step: jaxent_bg_state_init has not been called"); return JAXENT_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const bg::BatchArgs& a = p->a;
+  int rc = jaxent_bg_gemm1(a.prob.packed, a.cc3, a.H, a.n_fb, a.n_rg, a.Bn, a.NS, p->sm_count, s);
+  if (rc) return rc;
+  bg::bt_grad_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a);
+  if ((rc = bg_err("bt_grad"))) return rc;
+  bg::bt_decide_kernel<<<(a.Bn + 63) / 64, 64, 0, s>>>(a);
+  if ((rc = bg_err("bt_decide"))) return rc;
+  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a, 1);
+  if ((rc = bg_err("bt_adam"))) return rc;
+  rc = bg_forward(p, s);
+  if (rc) return rc;
+  p->steps += 1;
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bg_plan_buffer(const JaxentBatchPlan* p, int32_t which, void** ptr, size_t* bytes) {
+  if (!p || !ptr || !bytes) { set_error("bg_plan_buffer: NULL argument"); return JAXENT_E_INVALID; }
+  const bg::BatchArgs& a = p->a;
+  const size_t fb = (size_t)a.F * a.Bn * 4;
+  switch (which) {
+    case 0: *ptr = a.z; *bytes = fb; break;                                             /* logits  [F][Bn]      */
+    case 1: *ptr = a.e; *bytes = fb; break;                                             /* exp(z - lse) [F][Bn] */
+    case 2: *ptr = a.records; *bytes = (size_t)bg::RB * a.Bn * sizeof(JaxentLossRecord); break;
+    case 3: *ptr = a.ctl; *bytes = (size_t)a.Bn * sizeof(bg::BCtl); break;
+    case 4: *ptr = a.logpf; *bytes = (size_t)a.Bn * a.prob.R * 4; break;
+    case 5: *ptr = a.uptake; *bytes = (size_t)a.Bn * (a.prob.uptake ? a.prob.T : 1) * a.prob.R * 4; break;
+    case 6: *ptr = a.H; *bytes = (size_t)a.n_fb * 128 * a.Bn * 4; break;
+    case 7: *ptr = a.red; *bytes = (size_t)a.Bn * 2 * a.Rp * 8; break;
+    default: set_error("bg_plan_buffer: unknown buffer id %d", which); return JAXENT_E_INVALID;
+  }
+  return JAXENT_OK;
+}
+
+extern "C" int jaxent_bg_ctl_sizeof(void) { return (int)sizeof(bg::BCtl); }
+
+extern "C" int jaxent_bg_ctl_offset(int32_t field) {
+  switch (field) {
+    case 0: return (int)offsetof(bg::BCtl, S);
+    case 1: return (int)offsetof(bg::BCtl, bc);
+    case 2: return (int)offsetof(bg::BCtl, bh);
+    case 3: return (int)offsetof(bg::BCtl, step);
+    case 4: return (int)offsetof(bg::BCtl, lse);
+    default: return -1;
+  }
+}

@@ -126,14 +126,14 @@ class BvEngine:
         self._keep = []  # device tensors referenced by raw pointer from the plan
 
         R, F = int(heavy.shape[0]), int(heavy.shape[1])
-        if not isinstance(heavy, PackedFeatures) and tuple(acceptor.shape) != (R, F):
+        if not hasattr(heavy, "packed") and tuple(acceptor.shape) != (R, F):
             raise ValueError("Input features have different shapes")  # reference models/core.py:61-62
         self.R, self.F = R, F
         self.F_total = int(F_total) if F_total is not None else F
         self.T = int(np.asarray(timepoints).reshape(-1).shape[0]) if self.uptake else 0
 
         with torch.cuda.device(self.device):
-            if isinstance(heavy, PackedFeatures):
+            if isinstance(heavy, PackedFeatures) or hasattr(heavy, "packed"):
                 self.features = heavy
             else:
                 self.features = self._pack(heavy, acceptor, feature_dtype)
@@ -174,14 +174,20 @@ class BvEngine:
                     self._fill_map(prob.slots[i].train, s.S_train, s.y_train, s.W_train, s.kind)
                     self._fill_map(prob.slots[i].val, s.S_val, s.y_val, s.W_val, s.kind)
             self.prob = prob
+            cfg = settings.to_c()
+            sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            if getattr(self, "_batched", False):  # BatchedBvEngine (batch_engine.py): same problem description, batched plan
+                self.plan = self._create_plan(prob, cfg, sm)
+                self.steps_done = 0
+                self.launches = 0
+                self.peer, self.exchange, self.fused = None, "none", False
+                return
             nbytes = self.lib.jaxent_bv_workspace_bytes(C.byref(prob))
             if nbytes == 0:
                 raise L.JaxentError(L.E_INVALID, "workspace size query failed")
             self.ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
             self._ws_off = (-self.ws.data_ptr()) % 256
-            cfg = settings.to_c()
             plan = C.c_void_p()
-            sm = torch.cuda.get_device_properties(self.device).multi_processor_count
             L.check(
                 self.lib.jaxent_bv_plan_create(
                     C.byref(prob), C.byref(cfg), self.ws.data_ptr() + self._ws_off, nbytes, sm, C.byref(plan)

@@ -1,0 +1,102 @@
+"""Batched (tensor-core) optimise step against the sequential CUDA engine and the oracle.
+
+Reference behaviour being checked: batch_optimise == sequential runs (modules/optimise/test_module_batch_optimise.py:163-229,
+loss rtol 1e-4, frame weights atol 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from jaxent_b200 import _lib as L
+from oracle import bv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _batched(case, cfg, B, n_pieces=3):
+    from jaxent_b200.batch_engine import BatchedBvEngine
+    from jaxent_b200.engine import OptSettings, SlotSpec
+
+    pb = case["problem"]
+    specs = [SlotSpec(H.KIND_TO_C[s.kind], s.S_train, s.y_train, s.S_val, s.y_val, s.W_train, s.W_val, s.prior_bc, s.prior_bh) for s in pb.slots]
+    st = OptSettings(cfg.learning_rate, cfg.initial_learning_rate, cfg.initial_steps, cfg.plateau_denominator, cfg.model_parameters_lr_scale,
+                     cfg.clip_value, cfg.optimise_frame_weights, cfg.optimise_model_parameters, cfg.b1, cfg.b2, cfg.eps)
+    return BatchedBvEngine(pb.heavy, pb.acceptor, pb.k_ints, pb.timepoints, specs, pb.uptake, st, B, prior=case["prior"], device="cuda:0",
+                           n_pieces=n_pieces)
+
+
+def _hparams(B, n, seed):
+    rng = np.random.default_rng(seed)
+    fw = rng.uniform(0.1, 1.0, (B, n)).astype(np.float32)
+    fw /= fw.sum(1, keepdims=True)
+    fs = np.full((B, n), 100.0, np.float32) * rng.uniform(0.5, 2.0, (B, 1)).astype(np.float32)
+    lr = rng.choice([0.05, 0.1, 0.2, 0.5], B).astype(np.float32)
+    return fw, fs, lr
+
+
+@pytest.mark.parametrize("kind,extra,opt_model,F,R,T,B", [
+    (O.UPTAKE_EYE_MSE, (), False, 777, 53, 3, 5),
+    (O.UPTAKE_EYE_MSE, (O.PARAMS_L2,), True, 2000, 130, 5, 20),
+    (O.PF_L2, (), True, 1500, 64, 0, 16),
+    (O.UPTAKE_MC_EYE_MSE, (), False, 900, 40, 4, 3),
+])
+def test_batched_step_matches_sequential_engine(kind, extra, opt_model, F, R, T, B):
+    case = H.make_case(F, R, max(T, 1), kind, extra=extra, seed=11, prior="random")
+    n = len(case["problem"].slots)
+    fw, fs, lr = _hparams(B, n, 5)
+    cfg = O.OptConfig(learning_rate=0.1, initial_learning_rate=1.0, initial_steps=2, clip_value=None, optimise_model_parameters=opt_model)
+    eng = _batched(case, cfg, B)
+    p = case["params"]
+    z0 = np.asarray(p.z, np.float32) * np.float32(F)
+    eng.init_state(z0, p.bc, p.bh, fw, fs, lr)
+    n_steps = 12
+    eng.step(n_steps)
+    torch.cuda.synchronize()
+    recs = [eng.records_at(k) for k in range(n_steps + 1)]
+    W = eng.weights_all().cpu().numpy()
+    bcs = eng.ctl_field(1, np.float32)
+    for b in range(B):
+        cfg_b = O.OptConfig(learning_rate=float(lr[b]), initial_learning_rate=1.0, initial_steps=2, clip_value=None, optimise_model_parameters=opt_model)
+        ref = H.make_engine(case, cfg_b, device="cuda:0")
+        ref.init_state(z0, p.bc, p.bh, fw[b], fs[b])
+        ref.step(n_steps)
+        ref.finish_record()
+        torch.cuda.synchronize()
+        rrecs = ref.records(0, n_steps + 1)
+        for k in range(n_steps + 1):
+            a, r = recs[k][b], rrecs[k]
+            assert a.step == r.step == k and a.complete == 1
+            assert a.branch == r.branch, (b, k)
+            np.testing.assert_allclose(a.total_train, r.total_train, rtol=1e-4)
+            np.testing.assert_allclose(a.total_val, r.total_val, rtol=1e-4)
+            np.testing.assert_allclose(a.lr, r.lr, rtol=1e-6)
+        np.testing.assert_allclose(W[:, b], ref.weights.cpu().numpy(), atol=1e-4 / F, rtol=2e-3)
+        np.testing.assert_allclose(bcs[b], ref.export_state(())[1]["bc"], rtol=1e-4)
+        assert abs(W[:, b].sum() - 1.0) < 1e-5
+
+
+def test_batched_first_step_matches_oracle():
+    F, R, T, B = 1200, 53, 3, 4
+    case = H.make_case(F, R, T, O.UPTAKE_EYE_MSE, extra=(O.PARAMS_L2,), seed=3, prior="random")
+    n = len(case["problem"].slots)
+    fw, fs, lr = _hparams(B, n, 9)
+    cfg = O.OptConfig(learning_rate=0.2, clip_value=None, optimise_model_parameters=True)
+    eng = _batched(case, cfg, B)
+    p = case["params"]
+    eng.init_state(np.asarray(p.z, np.float32) * np.float32(F), p.bc, p.bh, fw, fs, lr)
+    torch.cuda.synchronize()
+    recs = eng.records_at(0)
+    for b in range(B):
+        par = O.Params(p.z, p.frame_mask, p.bc, p.bh, fw[b], fs[b], p.nlf)
+        st = O.optimizer_initialise(par, cfg, np.float64)
+        losses, _, _ = O.compute_loss(case["problem"], st.params, np.float64)
+        np.testing.assert_allclose(recs[b].total_train, losses.total_train_loss, rtol=1e-5)
+        np.testing.assert_allclose(recs[b].total_val, losses.total_val_loss, rtol=1e-5)
+
+
+def test_batched_rejects_fractional_features():
+    from jaxent_b200.batch_engine import pack_gemm_features
+
+    x = torch.rand(8, 64, device="cuda") * 3.0 + 0.123456
+    with pytest.raises(ValueError, match="bf16"):
+        pack_gemm_features(x, x, "cuda:0")
