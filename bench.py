@@ -30,8 +30,151 @@ WORKLOADS = {
     "cfg4": dict(F=1_000_000, R=500, T=8, name="synthetic 1M frames x 500 residues x 8 timepoints (BASELINE config 4)"),
     "cfg1": dict(F=500, R=53, T=3, name="BPTI-shaped 500 frames x 53 residues x 3 timepoints (BASELINE config 1 shape)"),
     "cfg2": dict(F=1000, R=130, T=1, name="aSyn-shaped 1000 frames x 130 residues (BASELINE config 2 shape)"),
+    "cfg5": dict(F=100_000, R=500, T=8, B=256, name="batched sweep: 256 replicas (MaxEnt strengths) on 100k frames x 500 residues x 8 timepoints, tensor-core GEMM path (BASELINE config 5)"),
 }
 N_BLOCKS = 8  # features are generated in 8 frame blocks so that shards are identical for N = 1, 2, 4, 8
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 1500.0, "fallback (B200_PROFILING.md)"
+
+
+def run_batched(args, wl):
+    """BASELINE config 5: B replicas advanced together; the two feature sweeps are tcgen05 GEMMs (single GPU)."""
+    import torch
+
+    from jaxent_b200 import _lib as L
+    from jaxent_b200.batch_engine import BatchedBvEngine
+    from jaxent_b200.engine import BvEngine, OptSettings, SlotSpec
+
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        if int(os.environ.get("RANK", 0)) == 0:
+            sys.stderr.write("config 5 is a single-GPU workload (replicas only): run with --gpus 1\n")
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    F, R, T, B = wl["F"], wl["R"], wl["T"], wl["B"]
+    NS = args.pieces
+    small = small_problem(R, T)
+    heavy, acc, _, _ = gen_features(R, F, 0, 1, dev)
+    slots = [SlotSpec(L.LOSS_UPTAKE_EYE_MSE, small.S_train, small.y_train, small.S_val, small.y_val), SlotSpec(L.LOSS_MAXENT_CONVEX_KL)]
+    settings = OptSettings(learning_rate=1.0, initial_learning_rate=1.0, initial_steps=0, clip_value=None)
+    prior = torch.full((F,), 1.0 / F, device=dev)
+    gam = np.logspace(0, 3, B).astype(np.float32)  # MaxEnt strengths: fw = [gamma, 1] normalised (examples/common/optimization.py:169-188)
+    fw = np.stack([gam / (gam + 1), 1 / (gam + 1)], 1).astype(np.float32)
+    fs = np.full((B, 2), 1000.0, np.float32)
+    host_h = torch.empty((R, F), dtype=torch.float32, pin_memory=True)
+    host_a = torch.empty((R, F), dtype=torch.float32, pin_memory=True)
+    host_h.copy_(heavy)
+    host_a.copy_(acc)
+    eng = BatchedBvEngine(heavy, acc, small.k_ints, small.timepoints, slots, True, settings, B, prior=prior, device=dev, n_pieces=NS)
+    eng.init_state(torch.ones(F, device=dev), 0.35, 2.0, fw, fs, None)
+    eng.step(max(3, args.warmup))
+    torch.cuda.synchronize()
+    K = args.steps
+    sp = torch.cuda.current_stream().cuda_stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(K):
+        ev[k][0].record()
+        L.check(eng.lib.jaxent_bg_step_phase(eng.plan, 0, sp))
+        ev[k][1].record()
+        L.check(eng.lib.jaxent_bg_step_phase(eng.plan, 1, sp))
+        ev[k][2].record()
+        L.check(eng.lib.jaxent_bg_step_phase(eng.plan, 2, sp))
+        ev[k][3].record()
+        L.check(eng.lib.jaxent_bg_step_phase(eng.plan, 3, sp))
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    eng.steps_done += K
+    ms_step = e0.elapsed_time(e1) / K
+    g1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    g2_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    rec = eng.records_at(eng.steps_done)
+    wsum = float(eng.weights_all().double().sum(0).mean())
+
+    # e2e: whole sweep from pinned host features through the engine API, per-step loss records read back
+    import ctypes
+
+    del eng
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    eng2 = BatchedBvEngine(host_h, host_a, small.k_ints, small.timepoints, slots, True, settings, B, prior=prior, device=dev, n_pieces=NS)
+    eng2.init_state(torch.ones(F, device=dev), 0.35, 2.0, fw, fs, None)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    sz = ctypes.sizeof(L.LossRecord)
+    pinned = torch.empty(B * sz, dtype=torch.uint8, pin_memory=True)
+    for k in range(K):
+        eng2.step(1)
+        row = ((k + 1) % 256) * eng2.Bn * sz
+        pinned.copy_(eng2._brecords[row : row + B * sz], non_blocking=True)  # every replica's loss record of this step
+        torch.cuda.current_stream().synchronize()
+    last = [L.LossRecord.from_buffer_copy(pinned.numpy()[:sz].tobytes())]
+    w_host = eng2.weights_all().cpu()
+    t_steps = time.perf_counter() - t1
+    rec_bytes = ctypes.sizeof(L.LossRecord) * B
+    e2e = {"value": B * K / (t_setup + t_steps), "unit": "replica-steps/s", "h2d_bytes_per_step": (2 * R * F * 4 + F * 4) / K,
+           "d2h_bytes_per_step": rec_bytes + F * B * 4 / K, "steady_value": B * K / t_steps, "setup_s": t_setup,
+           "note": "whole K-step sweep of all replicas from pinned host features (upload + bf16 pack + init inside the timed region), every replica's loss "
+                   "record read back and host-synchronised every step, final weights of all replicas read back",
+           "last_loss_replica0": float(last[0].total_train)}
+    del eng2, w_host
+
+    # sequential baseline on the same GPU: the single-ensemble engine, one replica after the other (measured on 4 replicas)
+    seq = None
+    try:
+        heavy, acc, _, _ = gen_features(R, F, 0, 1, dev)
+        one = BvEngine(heavy, acc, small.k_ints, small.timepoints, slots, True, settings, prior=prior, device=dev)
+        del heavy, acc
+        one.init_state(torch.ones(F, device=dev), 0.35, 2.0, fw[0], fs[0])
+        one.step(5)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        one.step(50)
+        s1.record()
+        torch.cuda.synchronize()
+        seq = 50 * 1e3 / s0.elapsed_time(s1)
+        del one
+    except Exception as ex:  # pragma: no cover
+        sys.stderr.write(f"sequential comparison skipped: {ex}\n")
+
+    peak, peak_src = tensor_peak()
+    alg_flops = 4 * R * F * B  # per GEMM launch: 2 flops x (2 arrays x R) x F x B
+    gemm_ms = 0.5 * (g1_ms + g2_ms)
+    achieved = alg_flops / (gemm_ms * 1e-3) / 1e12
+    line = {
+        "metric": "optimise steps/sec", "value": B * 1e3 / ms_step, "unit": "replica-steps/s", "n_gpus": 1, "steps": K, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 x%d pieces, fp32 accumulate" % NS,
+        "data": "synthetic", "batched_steps_per_s": 1e3 / ms_step, "frame_residue_timepoint_per_s": B * 1e3 / ms_step * F * R * T,
+        "config": {"workload": wl["name"], "frames": F, "residues": R, "timepoints": T, "replicas": B, "bf16_pieces": NS,
+                   "parallelism": "single GPU, replicas only", "l2": "state arrays 6 x 102 MB + features 205 MB per step >> 126 MB L2, no flush needed",
+                   "losses": ["hdx_uptake_eye_MSE_loss", "maxent_convexKL_loss"], "optimizer": "adam lr=1.0, plateau 1.005"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "bg_gemm_kernel<1>/<2> (mean of the backward and forward product)", "algorithmic_flops_per_launch": alg_flops,
+                     "kernel_ms": gemm_ms, "gemm1_ms": g1_ms, "gemm2_ms": g2_ms, "executed_tflops": NS * achieved,
+                     "executed_frac": NS * achieved / peak, "peak_source": peak_src, "step_frac": 2 * gemm_ms / ms_step,
+                     "note": "achieved counts the algorithmic 2*(2R)*F*B flops per product; the fp32 operand is split into bf16 pieces, so the tensor "
+                             "pipe executes `bf16_pieces` times that (executed_tflops)"},
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": 9 * K, "clocks": sampler.result(),
+        "sequential_replica_steps_per_s": seq, "speedup_vs_sequential_engine": (B * 1e3 / ms_step / seq) if seq else None,
+        "check": {"mean_sum_weights": wsum, "final_loss_replica0": float(rec[0].total_train), "final_step": int(rec[0].step)},
+    }
+    print(json.dumps(line), flush=True)
 
 
 def peaks():
@@ -462,12 +605,15 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvlink", "nccl"])
     ap.add_argument("--event-every", type=int, default=8)
+    ap.add_argument("--pieces", type=int, default=3, help="cfg5: bf16 pieces of the fp32 operand (2 or 3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif "B" in wl:
+        run_batched(args, wl)
     else:
         run_ours(args, wl)
 

@@ -302,6 +302,8 @@ void jaxent_bg_plan_destroy(JaxentBatchPlan* plan);
 int jaxent_bg_state_init(JaxentBatchPlan* plan, const float* z0, float zmax, float bc, float bh, const float* fw_host,
                          const float* fs_host, const float* lr_host, jaxent_stream_t stream);
 int jaxent_bg_step(JaxentBatchPlan* plan, jaxent_stream_t stream);
+/* the four phases of jaxent_bg_step, for timing: 0 gemm1, 1 grad + decide + adam, 2 gemm2, 3 reduce + tails + MaxEnt terms */
+int jaxent_bg_step_phase(JaxentBatchPlan* plan, int32_t phase, jaxent_stream_t stream);
 int jaxent_bg_plan_buffer(const JaxentBatchPlan* plan, int32_t which, void** ptr, size_t* bytes);
 int jaxent_bg_ctl_sizeof(void);
 int jaxent_bg_ctl_offset(int32_t field); /* 0: double S, 1: float bc, 2: float bh, 3: int step, 4: float lse */

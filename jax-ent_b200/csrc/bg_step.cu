@@ -65,6 +65,7 @@ struct BatchArgs {
   float* avg;             // [Bn][2R]
   float* logpf;           // [Bn][R]
   float* uptake;          // [Bn][T*R]
+  float* pnorm;           // [F] normalised prior p_f = (|prior_f| + eps) / sum (fp32, as frame_terms forms it)
   unsigned* gsel;         // which g buffer holds the current masked gradients
   unsigned* counter;      // ticket of bt_kl
   int p_max_tr, p_max_va;
@@ -82,18 +83,22 @@ __device__ __forceinline__ void split3(float x, int NS, __nv_bfloat16& p0, __nv_
   p2 = (NS > 2) ? __float2bfloat16_rn(r) : __float2bfloat16_rn(0.f);
 }
 
-// kappa (= d KL / d w, scaled) and the normalised weight of one (frame, replica); same arithmetic as frame_terms (bv_tail.cu)
-__device__ __forceinline__ void weight_terms(float e, float Sf, float prior_f, bool has_kl, float eps, double inv_pnorm, float lam, float& w,
-                                             float& kap, float& q, float& p, double& ratio) {
+// kappa (= d KL / d w, scaled) and the normalised weight of one (frame, replica).  Same quantities as frame_terms
+// (bv_tail.cu), but p/q is carried as an unevaluated fp32 pair r0 + corr (r0 = fl(p/q), corr = fl((p - r0*q)/q) with the
+// exact FMA residual) instead of an fp64 quotient: 256 replicas x 1e5 frames of fp64 division and log would make this
+// kernel arithmetic bound.  1 - p/q = (1 - r0) - corr keeps full relative accuracy when p/q is close to 1.
+__device__ __forceinline__ void weight_terms(float e, float Sf, float p, bool has_kl, float eps, float lam, float& w, float& kap, float& q,
+                                             float& r0, float& corr) {
   w = e / Sf;
   kap = 0.f;
-  q = p = 0.f;
-  ratio = 1.0;
+  q = 0.f;
+  r0 = 1.f;
+  corr = 0.f;
   if (has_kl) {
     q = fabsf(w) + eps;
-    p = (float)(((double)fabsf(prior_f) + (double)eps) * inv_pnorm);
-    ratio = (double)p * __drcp_rn((double)q);
-    const float G_ = (float)(1.0 - ratio);
+    r0 = p / q;
+    corr = fmaf(-r0, q, p) / q;
+    const float G_ = (1.0f - r0) - corr;
     kap = (w > 0.f) ? lam * G_ : 0.f;
   }
 }
@@ -112,13 +117,11 @@ __global__ void __launch_bounds__(1024) bt_grad_kernel(const BatchArgs a) {
   const int have_prev = c->have_prev;
   const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
   const bool active = !c->stop;
-  const double inv_pnorm = has_kl ? __drcp_rn(a.prob.prior_norm) : 0.0;
   double dot = 0.0;
   for (long long f = (long long)blockIdx.x * a.fy + fy; f < a.F; f += (long long)gridDim.x * a.fy) {
     const size_t i = (size_t)f * Bn + b;
-    float w, kap, q, p;
-    double ratio;
-    weight_terms(a.e[i], Sf, has_kl ? a.prob.prior[f] : 0.f, has_kl, a.eps_kl, inv_pnorm, lam, w, kap, q, p, ratio);
+    float w, kap, q, r0, corr;
+    weight_terms(a.e[i], Sf, has_kl ? a.pnorm[f] : 0.f, has_kl, a.eps_kl, lam, w, kap, q, r0, corr);
     const float gf = active ? maskf * (w * ((a.H[i] + kap) - hbar)) : 0.f;
     const float gpv = have_prev ? gprev[i] : gf;
     dot += (double)(gpv * gf);
@@ -136,14 +139,17 @@ __global__ void __launch_bounds__(1024) bt_grad_kernel(const BatchArgs a) {
 // ------------------------------------------------------------------------------------------ bt_decide
 // one thread per replica: plateau rule, BV-parameter Adam (optax adam + keep_params_nonnegative), counters
 __global__ void bt_decide_kernel(const BatchArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) *a.gsel = *a.gsel ^ 1u;  // bt_grad wrote the other buffer: it now holds the current gradients
+  // one warp per replica: the per-block partials are summed lane-strided, then across lanes (fixed order)
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.gsel = *a.gsel ^ 1u;  // bt_grad wrote the other buffer: it now holds the current gradients
   if (b >= a.Bn) return;
   BCtl* c = a.ctl + b;
   if (c->stop) return;
   const JaxentOptConfig& cfg = a.cfg;
   double gdot = 0.0;
-  for (int k = 0; k < a.ew_blocks; ++k) gdot += a.part_dot[(size_t)k * a.Bn + b];
+  for (int k = lane; k < a.ew_blocks; k += 32) gdot += a.part_dot[(size_t)k * a.Bn + b];
+  gdot = wsum(gdot);
+  if (lane != 0) return;
   const float g0 = c->gb[0], g1 = c->gb[1];
   const float p0 = c->have_prev ? c->gb_prev[0] : g0, p1 = c->have_prev ? c->gb_prev[1] : g1;
   const double dot = gdot + (double)p0 * (double)g0 + (double)p1 * (double)g1;
@@ -249,8 +255,10 @@ __global__ void __launch_bounds__(1024) bt_reduce2_kernel(const BatchArgs a) {
   {
     const int row = row0 + ty, b = b0 + tx;
     double s = 0.0;
-    if (row < R2 && b < Bn)
-      for (int ks = 0; ks < a.ksplit; ++ks) s += (double)a.P[((size_t)ks * R2 + row) * Bn + b];
+    if (row < R2 && b < Bn) {
+#pragma unroll 8
+      for (int ks = 0; ks < a.ksplit; ++ks) s += (double)__ldcg(&a.P[((size_t)ks * R2 + row) * Bn + b]);
+    }
     tile[ty][tx] = s;
   }
   __syncthreads();
@@ -381,17 +389,17 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
   const BCtl* c = a.ctl + b;
   const float Sf = (float)c->S, lam = c->kl_scale;
   const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
-  const double inv_pnorm = has_kl ? __drcp_rn(a.prob.prior_norm) : 0.0;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (!c->stop) {
     for (long long f = (long long)blockIdx.x * a.fy + fy; f < a.F; f += (long long)gridDim.x * a.fy) {
-      float w, kap, q, p;
-      double ratio;
-      weight_terms(a.e[(size_t)f * Bn + b], Sf, has_kl ? a.prob.prior[f] : 0.f, has_kl, a.eps_kl, inv_pnorm, lam, w, kap, q, p, ratio);
+      float w, kap, q, r0, corr;
+      const float p = has_kl ? a.pnorm[f] : 0.f;
+      weight_terms(a.e[(size_t)f * Bn + b], Sf, p, has_kl, a.eps_kl, lam, w, kap, q, r0, corr);
       if (has_kl) {
-        s0 += (double)w * (double)kap;
-        if (p > 0.f) s1 += (double)p * dlog(ratio);
-        s2 += (double)q - (double)p;
+        s0 += (double)(w * kap);
+        // log(p/q) = log(r0 + corr) = log r0 + log1p(corr / r0)
+        if (p > 0.f) s1 += (double)p * ((double)logf(r0) + (double)(corr / r0));
+        s2 += (double)(q - p);
       }
       s3 += (double)w;
     }
@@ -448,6 +456,11 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
 
 // ------------------------------------------------------------------------------------------ init
 __global__ void bt_init_kernel(const BatchArgs a, const float* __restrict__ z0, const BCtl* __restrict__ init) {
+  if (a.prob.prior != nullptr) {
+    const double inv_pnorm = 1.0 / a.prob.prior_norm;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < a.F; f += (long long)gridDim.x * blockDim.x)
+      a.pnorm[f] = (float)(((double)fabsf(a.prob.prior[f]) + (double)a.eps_kl) * inv_pnorm);
+  }
   const long long n = (long long)a.F * a.Bn;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   for (long long i = i0; i < n; i += stride) {
@@ -486,7 +499,7 @@ struct JaxentBatchPlan {
 
 namespace {
 struct BLayout {
-  size_t z, m, v, e, g0, g1, H, P, cc3, e3, red, part_dot, part_s, part_kl, ctl, ctl_init, records, avg, logpf, uptake, gsel, counter;
+  size_t z, m, v, e, g0, g1, pnorm, H, P, cc3, e3, red, part_dot, part_s, part_kl, ctl, ctl_init, records, avg, logpf, uptake, gsel, counter;
   size_t blob[JAXENT_MAX_SLOTS];
   int blob_words[JAXENT_MAX_SLOTS];
   size_t total;
@@ -501,6 +514,7 @@ BLayout b_layout(const JaxentBvProblem* pb, int Bn, int NS, int ksplit) {
   auto take = [&](size_t bytes) { size_t r = o; o = up(o + bytes); return r; };
   const size_t fb = F * Bn * 4;
   L.z = take(fb); L.m = take(fb); L.v = take(fb); L.e = take(fb); L.g0 = take(fb); L.g1 = take(fb);
+  L.pnorm = take(F * 4);
   L.H = take(Fp * Bn * 4);
   L.P = take((size_t)ksplit * 2 * Rp * Bn * 4);
   L.cc3 = take((size_t)NS * 2 * Rp * Bn * 2);
@@ -595,6 +609,7 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   a.F = pb->F;
   a.z = (float*)(ws + L.z); a.m = (float*)(ws + L.m); a.v = (float*)(ws + L.v); a.e = (float*)(ws + L.e);
   a.g[0] = (float*)(ws + L.g0); a.g[1] = (float*)(ws + L.g1);
+  a.pnorm = (float*)(ws + L.pnorm);
   a.H = (float*)(ws + L.H);
   a.P = (float*)(ws + L.P);
   a.cc3 = ws + L.cc3;
@@ -659,10 +674,14 @@ static int bg_err(const char* what) {
   return JAXENT_OK;
 }
 
-static int bg_forward(JaxentBatchPlan* p, cudaStream_t s) {
+static int bg_gemm2_phase(JaxentBatchPlan* p, cudaStream_t s) {
   const bg::BatchArgs& a = p->a;
-  int rc = jaxent_bg_gemm2(a.prob.packed, a.e3, a.P, a.n_fb, a.n_rg, a.Bn, a.NS, a.ksplit, s);
-  if (rc) return rc;
+  return jaxent_bg_gemm2(a.prob.packed, a.e3, a.P, a.n_fb, a.n_rg, a.Bn, a.NS, a.ksplit, s);
+}
+
+static int bg_tail_phase(JaxentBatchPlan* p, cudaStream_t s) {
+  const bg::BatchArgs& a = p->a;
+  int rc;
   dim3 grid((2 * a.Rp + 31) / 32, (a.Bn + 31) / 32);
   bg::bt_reduce2_kernel<<<grid, 1024, 0, s>>>(a);
   if ((rc = bg_err("bt_reduce2"))) return rc;
@@ -678,6 +697,28 @@ static int bg_forward(JaxentBatchPlan* p, cudaStream_t s) {
   if ((rc = bg_err("bt_tail"))) return rc;
   bg::bt_kl_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * KL_N * a.Bn * 8, s>>>(a);
   return bg_err("bt_kl");
+}
+
+static int bg_forward(JaxentBatchPlan* p, cudaStream_t s) {
+  int rc = bg_gemm2_phase(p, s);
+  if (rc) return rc;
+  return bg_tail_phase(p, s);
+}
+
+static int bg_gemm1_phase(JaxentBatchPlan* p, cudaStream_t s) {
+  const bg::BatchArgs& a = p->a;
+  return jaxent_bg_gemm1(a.prob.packed, a.cc3, a.H, a.n_fb, a.n_rg, a.Bn, a.NS, p->sm_count, s);
+}
+
+static int bg_update_phase(JaxentBatchPlan* p, cudaStream_t s) {
+  const bg::BatchArgs& a = p->a;
+  int rc;
+  bg::bt_grad_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a);
+  if ((rc = bg_err("bt_grad"))) return rc;
+  bg::bt_decide_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a);
+  if ((rc = bg_err("bt_decide"))) return rc;
+  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a, 1);
+  return bg_err("bt_adam");
 }
 
 extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float zmax, float bc, float bh, const float* fw_host,
@@ -727,20 +768,25 @@ extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float z
   return JAXENT_OK;
 }
 
-extern "C" int jaxent_bg_step(JaxentBatchPlan* p, jaxent_stream_t stream) {
+// phases of one batched step: 0 gemm1 (backward product), 1 grad + decide + adam, 2 gemm2 (forward product),
+// 3 reduce + per-replica tails + MaxEnt terms.  jaxent_bg_step runs all four.
+extern "C" int jaxent_bg_step_phase(JaxentBatchPlan* p, int32_t phase, jaxent_stream_t stream) {
   if (!p || !p->initialised) { set_error("bg_step: jaxent_bg_state_init has not been called"); return JAXENT_E_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
-  const bg::BatchArgs& a = p->a;
-  int rc = jaxent_bg_gemm1(a.prob.packed, a.cc3, a.H, a.n_fb, a.n_rg, a.Bn, a.NS, p->sm_count, s);
-  if (rc) return rc;
-  bg::bt_grad_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a);
-  if ((rc = bg_err("bt_grad"))) return rc;
-  bg::bt_decide_kernel<<<(a.Bn + 63) / 64, 64, 0, s>>>(a);
-  if ((rc = bg_err("bt_decide"))) return rc;
-  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a, 1);
-  if ((rc = bg_err("bt_adam"))) return rc;
-  rc = bg_forward(p, s);
-  if (rc) return rc;
+  switch (phase) {
+    case 0: return bg_gemm1_phase(p, s);
+    case 1: return bg_update_phase(p, s);
+    case 2: return bg_gemm2_phase(p, s);
+    case 3: return bg_tail_phase(p, s);
+    default: set_error("bg_step_phase: phase must be 0..3"); return JAXENT_E_INVALID;
+  }
+}
+
+extern "C" int jaxent_bg_step(JaxentBatchPlan* p, jaxent_stream_t stream) {
+  for (int ph = 0; ph < 4; ++ph) {
+    const int rc = jaxent_bg_step_phase(p, ph, stream);
+    if (rc) return rc;
+  }
   p->steps += 1;
   return JAXENT_OK;
 }
