@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(1024) bt_grad_kernel(const BatchArgs a) {
   const float* __restrict__ gprev = a.g[sel];
   float* __restrict__ gout = a.g[sel ^ 1u];
   const float Sf = (float)c->S, lam = c->kl_scale, maskf = c->mask_frame;
-  const float hbar = (float)(c->hbar_data + c->klsum[0]);
+  const float hbar = (float)c->hbar_data;  // the MaxEnt part of hbar is O(1e-10 lambda): see bv_pass.cu, finish_previous_record
   const int have_prev = c->have_prev;
   const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
   const bool active = !c->stop;

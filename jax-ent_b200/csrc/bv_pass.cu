@@ -293,14 +293,15 @@ __device__ __forceinline__ void phase_b(const TileRegs<RPT>& d, const float* s_e
   }
 }
 
-// Adam warp, once per launch: the MaxEnt sums of the tail that preceded this pass (all ranks; spins on the peers'
-// words when frame-sharded) -> hbar = sum_j w_j h_j; CTA 0 also completes that step's loss record.  Kept out of line
-// so that its registers do not weigh on the per-tile loop.
-__device__ __noinline__ float adam_prologue(const Xchg x, unsigned ep, const Ctl* __restrict__ ctl, JaxentLossRecord* records, int lane) {
+// CTA 0's Adam warp, once per launch, AFTER its tile loop: the MaxEnt sums of the tail that preceded this pass (all
+// ranks; by now every peer's words have long landed, so nothing waits) complete that step's loss record.
+// The MaxEnt part of hbar = sum_j w_j h_j is sum_j w_j kappa_j = lambda * eps * sum_j p_j / q_j = O(1e-10 lambda)
+// analytically (both distributions sum to one); its numerical value is rounding noise seven orders below kappa_f, so
+// the gradient uses hbar = sum_r c_r lnPF_r only and the frame-sharded step needs no second exchange on its critical path.
+__device__ __noinline__ void finish_previous_record(const Xchg x, unsigned ep, const Ctl* __restrict__ ctl, JaxentLossRecord* records, int lane) {
   double kl[KL_N];
   kl_gather_warp(x, ep, lane, kl);
-  if (lane == 0 && blockIdx.x == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
-  return (float)(ctl->hbar_data + kl[0]);
+  if (lane == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
 }
 
 template <int RPT, int FMT>
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
     // ================================================================== Adam warp
     const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
     // MaxEnt sums of the tail that preceded this pass (all ranks; waits on the peers' flags when frame-sharded)
-    const float hbar = mode ? adam_prologue(a.x, ep, ctl, a.records, lane) : 0.f;
+    const float hbar = (float)ctl->hbar_data;
     if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 42);
     const int in_set = ep & 1u, out_set = in_set ^ 1;
     const int in_br = ctl->branch;
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
       gdot += __shfl_xor_sync(0xffffffffu, gdot, o);
     }
     if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 43);
+    if (blockIdx.x == 0 && mode == 1) finish_previous_record(a.x, ep, ctl, a.records, lane);
     if (lane == 0) {
       part[4 * R + 0] = sumA;
       part[4 * R + 1] = sumB;
