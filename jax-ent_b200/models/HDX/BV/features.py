@@ -27,6 +27,22 @@ class BV_input_features:
     def feat_pred(self):
         return (self.heavy_contacts, self.acceptor_contacts)
 
+    # .npz round trip in the reference's key layout (custom_types/features.py:91-286)
+    def save(self, filepath: str) -> None:
+        from ....utils.io import save_features_npz
+
+        save_features_npz(self, filepath)
+
+    save_features = save
+
+    @classmethod
+    def load(cls, filepath):
+        from ....utils.io import load_features_npz
+
+        return load_features_npz(str(filepath))
+
+    load_features = load
+
 
 @dataclass(frozen=True, slots=True)
 class BV_output_features:
