@@ -305,6 +305,13 @@ int jaxent_bg_step(JaxentBatchPlan* plan, jaxent_stream_t stream);
 /* the four phases of jaxent_bg_step, for timing: 0 gemm1, 1 grad + decide + adam, 2 gemm2, 3 reduce + tails + MaxEnt terms */
 int jaxent_bg_step_phase(JaxentBatchPlan* plan, int32_t phase, jaxent_stream_t stream);
 int jaxent_bg_plan_buffer(const JaxentBatchPlan* plan, int32_t which, void** ptr, size_t* bytes);
+/* on-device loop of every replica (the ConvergenceTracker of _optimise_pure, opt/run.py:141-232): call before
+ * jaxent_bg_state_init.  convergence: n (<= 8) relative thresholds in descending order, NOT yet multiplied by the learning
+ * rate (each replica uses convergence[i] * its own learning rate, opt/track.py:12-21).  ema_w: float[F][Bn]; snap_w, snap_ema:
+ * float[n+1][F][Bn]; snaps: JaxentTrackSnapshot[n+1][Bn].  A replica whose loop has ended is frozen; the others continue. */
+int jaxent_bg_track_init(JaxentBatchPlan* plan, const float* convergence, int32_t n, float ema_alpha, int32_t min_steps_per_threshold,
+                         float tolerance, float* ema_w, float* snap_w, float* snap_ema, JaxentTrackSnapshot* snaps);
+int jaxent_bg_track_status(JaxentBatchPlan* plan, JaxentTrackStatus* status, jaxent_stream_t stream);
 int jaxent_bg_ctl_sizeof(void);
 int jaxent_bg_ctl_offset(int32_t field); /* 0: double S, 1: float bc, 2: float bh, 3: int step, 4: float lse */
 

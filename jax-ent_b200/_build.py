@@ -21,43 +21,67 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found; libjaxent_b200.so cannot be built (there is no CPU fallback)")
 
 
+HASH = LIB + ".srchash"
+
+
+def _flags() -> list:
+    flags = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"]
+    extra = os.environ.get("JAXENT_NVCC_FLAGS")
+    return (extra.split() if extra else []) + flags
+
+
+def source_hash() -> str:
+    """content hash of every source / header and of the compile flags: decides whether the in-tree .so is current
+    (file times are not preserved when the tree is copied to another box)"""
+    import hashlib
+
+    h = hashlib.sha256()
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(_flags()).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(HASH):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(HASH) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles into a temporary file and renames it into place under an exclusive lock, so concurrent processes
+    (one per GPU under torchrun) never load a half-written library."""
+    import fcntl
+
     if not force and not needs_build():
         return LIB
-    cmd = [
-        nvcc_path(),
-        "-shared",
-        "-Xcompiler",
-        "-fPIC",
-        "-gencode",
-        "arch=compute_100a,code=sm_100a",
-        "-lineinfo",
-        "-O3",
-        "-std=c++17",
-        "-I",
-        os.path.join(ROOT, "include"),
-        "-o",
-        LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
-    extra = os.environ.get("JAXENT_NVCC_FLAGS")
-    if extra:
-        cmd[1:1] = extra.split()
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while we waited
+                return LIB
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            cmd = [nvcc_path()] + _flags() + ["-I", os.path.join(ROOT, "include"), "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+            if verbose:
+                print(res.stderr, file=sys.stderr)
+            os.replace(tmp, LIB)
+            with open(HASH, "w") as f:
+                f.write(source_hash())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

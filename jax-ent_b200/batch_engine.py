@@ -135,6 +135,63 @@ class BatchedBvEngine(BvEngine):
         self.log_pf_b = self._bview(4, torch.float32).view(self.Bn, self.R)
         self.uptake_b = self._bview(5, torch.float32).view(self.Bn, max(self.T, 1), self.R) if self.uptake else None
 
+    # ------------------------------------------------------------------ on-device loop of every replica
+    def enable_tracking(self, convergence, ema_alpha: float = 0.5, min_steps_per_threshold: int = 2, tolerance: float = 1e-10) -> None:
+        """Arm the per-replica ConvergenceTracker (reference opt/track.py:128-197); call before init_state().  The
+        thresholds are sorted descending here and scaled by each replica's learning rate on the device side."""
+        conv = np.sort(np.atleast_1d(np.asarray(convergence, np.float32)))[::-1].copy()
+        n = int(conv.shape[0])
+        if n < 1 or n > L.TRACK_MAX_THRESHOLDS:
+            raise ValueError(f"between 1 and {L.TRACK_MAX_THRESHOLDS} convergence thresholds are supported on the device")
+        with torch.cuda.device(self.device):
+            self._trk_ema = torch.zeros((self.F, self.Bn), dtype=torch.float32, device=self.device)
+            self._trk_snap_w = torch.zeros((n + 1, self.F, self.Bn), dtype=torch.float32, device=self.device)
+            self._trk_snap_ema = torch.zeros((n + 1, self.F, self.Bn), dtype=torch.float32, device=self.device)
+            self._trk_snaps = torch.zeros((n + 1) * self.Bn * C.sizeof(L.TrackSnapshot), dtype=torch.uint8, device=self.device)
+            self._trk_status = torch.zeros(self.Bn * C.sizeof(L.TrackStatus), dtype=torch.uint8, device=self.device)
+        arr = (C.c_float * n)(*[float(t) for t in conv])
+        L.check(self.lib.jaxent_bg_track_init(self.plan, arr, n, float(ema_alpha), int(min_steps_per_threshold), float(tolerance),
+                                              self._trk_ema.data_ptr(), self._trk_snap_w.data_ptr(), self._trk_snap_ema.data_ptr(),
+                                              self._trk_snaps.data_ptr()))
+        self._trk_n = n
+        self.tracking = True
+
+    def track_status(self):
+        """[TrackStatus] per replica (device -> host read: the only host synchronisation of the loop)."""
+        with torch.cuda.device(self.device):
+            L.check(self.lib.jaxent_bg_track_status(self.plan, self._trk_status.data_ptr(), _stream_ptr()))
+            host = self._trk_status.cpu().numpy().tobytes()
+        sz = C.sizeof(L.TrackStatus)
+        return [L.TrackStatus.from_buffer_copy(host[i * sz : (i + 1) * sz]) for i in range(self.B)]
+
+    def track_snapshots(self, b: int, n: int):
+        """[(TrackSnapshot, weights[F] view, ema_weights[F] view or None)] for the first n snapshots of replica b."""
+        sz = C.sizeof(L.TrackSnapshot)
+        if getattr(self, "_trk_snaps_host", None) is None:
+            self._trk_snaps_host = self._trk_snaps.cpu().numpy()
+        out = []
+        for i in range(n):
+            off = (i * self.Bn + b) * sz
+            sn = L.TrackSnapshot.from_buffer_copy(self._trk_snaps_host[off : off + sz].tobytes())
+            out.append((sn, self._trk_snap_w[i, :, b], self._trk_snap_ema[i, :, b] if sn.have_ema else None))
+        return out
+
+    def run(self, n_steps: int, chunk: int = 32):
+        """Up to n_steps steps; replicas whose loop has ended are frozen on the device, the host looks at the status every
+        `chunk` steps and stops when every replica has ended.  Returns [TrackStatus]."""
+        if not getattr(self, "tracking", False):
+            raise RuntimeError("enable_tracking() has not been called")
+        done, st = 0, None
+        self._trk_snaps_host = None
+        while done < n_steps:
+            m = min(chunk, n_steps - done)
+            self.step(m)
+            done += m
+            st = self.track_status()
+            if all(s.stop for s in st):
+                break
+        return st if st is not None else self.track_status()
+
     def step(self, n: int = 1) -> None:
         with torch.cuda.device(self.device):
             s = _stream_ptr()

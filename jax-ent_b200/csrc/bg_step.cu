@@ -42,6 +42,14 @@ struct alignas(16) BCtl {
   double S, hbar_data;
   double klsum[KL_N];
   float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
+  // ---- per-replica ConvergenceTracker (reference opt/track.py:128-197, opt/run.py:285-348); see derive_scalars (bv_tail.cu)
+  int stopping;           // the loop of this replica ended at this step: the update is still applied and the new state
+                          // evaluated (snapshot of the post-update weights), then `stop` freezes the replica
+  int trk_reason, trk_stop_step, trk_have_prev, trk_have_ema, trk_steps_since, trk_idx, trk_nsnap;
+  int snap_now, ema_update, ema_first, loop_step;
+  float trk_ema_bc, trk_ema_bh, trk_pad[2];
+  float thr[JAXENT_TRACK_MAX_THRESHOLDS];  // descending, already multiplied by this replica's learning rate
+  double trk_prev_loss, trk_ema;
 };
 static_assert(sizeof(BCtl) % 16 == 0, "BCtl is copied with 16-byte loads");
 
@@ -72,6 +80,13 @@ struct BatchArgs {
   int blob_words_max;     // words reserved for the blob image in the tail's shared memory
   int ew_blocks, fy;      // elementwise grid / frames per block iteration
   float eps_kl;
+  // on-device loop (jaxent_bg_track_init)
+  int trk_on, trk_n_thr, trk_min_steps;
+  float trk_alpha, trk_tolerance;
+  float* ema_w;                // [F][Bn] EMA of the softmax weights
+  float* snap_w;               // [n_thr + 1][F][Bn]
+  float* snap_ema;             // [n_thr + 1][F][Bn]
+  JaxentTrackSnapshot* snaps;  // [n_thr + 1][Bn]
 };
 
 // fp32 -> NS bf16 pieces (round to nearest at every level): x ~= p0 + p1 + p2
@@ -186,6 +201,69 @@ __global__ void bt_decide_kernel(const BatchArgs a) {
   c->bc2 = 1.0f - fpow(b2, (float)cf);
   c->last_dot = (float)dot;
   c->last_branch = d;
+
+  // ---- ConvergenceTracker for loop step k = state.step before this update (same logic as derive_scalars, bv_tail.cu)
+  c->snap_now = -1;
+  c->ema_update = 0;
+  c->ema_first = 0;
+  if (a.trk_on) {
+    const int k = c->step - 1;
+    c->loop_step = k;
+    const double loss = (double)a.records[(size_t)(k % RB) * a.Bn + b].total_train;
+    const double alpha = (double)a.trk_alpha;
+    if (c->trk_have_prev) {  // tracker.update
+      const double raw = fabs(c->trk_prev_loss - loss);
+      if (!c->trk_have_ema) {
+        c->trk_ema = raw;
+        c->trk_have_ema = 1;
+        c->ema_first = 1;
+      } else {
+        c->trk_ema = alpha * raw + (1.0 - alpha) * c->trk_ema;
+      }
+      c->ema_update = 1;
+      c->trk_ema_bc = c->ema_first ? c->bc : (float)(alpha * (double)c->bc + (1.0 - alpha) * (double)c->trk_ema_bc);
+      c->trk_ema_bh = c->ema_first ? c->bh : (float)(alpha * (double)c->bh + (1.0 - alpha) * (double)c->trk_ema_bh);
+    }
+    c->trk_steps_since += 1;
+    c->trk_prev_loss = loss;
+    c->trk_have_prev = 1;
+    const double gd = (k > 0) ? dot : 0.0;  // check_gradient_oscillation: zeros before the first step
+    if (gd < 0.0) c->trk_steps_since = 0;
+    if (loss < (double)a.trk_tolerance || isnan(loss) || isinf(loss)) {
+      c->stopping = 1;
+      c->trk_reason = 2;
+      c->trk_stop_step = k;
+    } else {
+      const double rel = (c->trk_have_ema && loss > 0.0) ? c->trk_ema / loss : 0.0;
+      const int ti = c->trk_idx < a.trk_n_thr ? c->trk_idx : a.trk_n_thr - 1;
+      const bool met = c->trk_steps_since >= a.trk_min_steps && c->trk_have_ema && rel < (double)c->thr[ti] && k > cfg.initial_steps;
+      if (k == 0 || met) {
+        c->snap_now = c->trk_nsnap;
+        c->trk_nsnap += 1;
+        if (k > 0) {
+          c->trk_idx += 1;
+          c->trk_steps_since = 0;
+          if (c->trk_idx >= a.trk_n_thr) {
+            c->stopping = 1;
+            c->trk_reason = 1;
+            c->trk_stop_step = k;
+          }
+        }
+      }
+    }
+    if (c->snap_now >= 0 && a.snaps != nullptr) {
+      JaxentTrackSnapshot* sn = a.snaps + (size_t)c->snap_now * a.Bn + b;
+      sn->loop_step = k;
+      sn->state_step = c->step;
+      sn->have_ema = c->trk_have_ema;
+      sn->threshold_idx = c->trk_idx;
+      sn->bc = c->bc;
+      sn->bh = c->bh;
+      sn->ema_bc = c->trk_ema_bc;
+      sn->ema_bh = c->trk_ema_bh;
+      sn->losses = a.records[(size_t)(k % RB) * a.Bn + b];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ bt_adam
@@ -390,6 +468,7 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
   const float Sf = (float)c->S, lam = c->kl_scale;
   const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int snap = a.trk_on ? c->snap_now : -1, ema_update = a.trk_on ? c->ema_update : 0, ema_first = c->ema_first;
   if (!c->stop) {
     for (long long f = (long long)blockIdx.x * a.fy + fy; f < a.F; f += (long long)gridDim.x * a.fy) {
       float w, kap, q, r0, corr;
@@ -402,6 +481,15 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
         s2 += (double)(q - p);
       }
       s3 += (double)w;
+      if (a.trk_on) {  // tracker.ema_params (opt/track.py:160-165) and the history snapshot of the post-update weights
+        const size_t i = (size_t)f * Bn + b;
+        if (ema_update) {
+          const float em = ema_first ? w : a.trk_alpha * w + (1.0f - a.trk_alpha) * a.ema_w[i];
+          a.ema_w[i] = em;
+          if (snap >= 0) a.snap_ema[(size_t)snap * a.F * Bn + i] = em;
+        }
+        if (snap >= 0) a.snap_w[(size_t)snap * a.F * Bn + i] = w;
+      }
     }
   }
   double* mine = sh_d + ((size_t)fy * KL_N) * Bn + b;
@@ -427,6 +515,12 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
   if (fy == 0) {
     BCtl* cw = a.ctl + b;
     if (cw->stop) return;
+    if (cw->stopping) {  // this was the last evaluation of the replica: freeze it
+      cw->stop = 1;
+      cw->stopping = 0;
+    }
+    cw->snap_now = -1;
+    cw->ema_update = 0;
     double kl[KL_N];
     for (int k = 0; k < KL_N; ++k) {
       double t = 0.0;
@@ -488,6 +582,7 @@ using namespace jx;
 
 struct JaxentBatchPlan {
   bg::BatchArgs a;
+  float conv[JAXENT_TRACK_MAX_THRESHOLDS];
   unsigned char* ws;
   size_t off_ctl_init;
   size_t tail_smem;
@@ -741,6 +836,8 @@ extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float z
     c.bc1 = c.bc2 = 1.f;
     c.mask_frame = 1.f;
     c.S = 1.0;
+    c.snap_now = -1;
+    for (int i = 0; i < a.trk_n_thr; ++i) c.thr[i] = p->conv[i] * c.cfg_lr;  // create_convergence_thresholds, opt/track.py:12-21
     for (int i = 0; i < a.prob.n_slots; ++i) {
       c.fw[i] = fw_host[(size_t)b * JAXENT_MAX_SLOTS + i];
       c.fs[i] = fs_host[(size_t)b * JAXENT_MAX_SLOTS + i];
@@ -820,4 +917,55 @@ extern "C" int jaxent_bg_ctl_offset(int32_t field) {
     case 4: return (int)offsetof(bg::BCtl, lse);
     default: return -1;
   }
+}
+
+// ---- on-device loop of every replica (reference _optimise_pure / ConvergenceTracker, opt/run.py:141-232, opt/track.py:128-197)
+extern "C" int jaxent_bg_track_init(JaxentBatchPlan* p, const float* convergence, int32_t n, float ema_alpha, int32_t min_steps,
+                                    float tolerance, float* ema_w, float* snap_w, float* snap_ema, JaxentTrackSnapshot* snaps) {
+  if (!p) { set_error("bg_track_init: plan is NULL"); return JAXENT_E_INVALID; }
+  if (!convergence || n < 1 || n > JAXENT_TRACK_MAX_THRESHOLDS || !ema_w || !snap_w || !snap_ema || !snaps) {
+    set_error("bg_track_init: need 1..%d thresholds and the EMA / snapshot buffers", JAXENT_TRACK_MAX_THRESHOLDS);
+    return JAXENT_E_INVALID;
+  }
+  if (!(ema_alpha >= 0.f && ema_alpha <= 1.f) || min_steps < 0) { set_error("bg_track_init: invalid ema_alpha / min_steps"); return JAXENT_E_INVALID; }
+  for (int i = 1; i < n; ++i)
+    if (convergence[i] > convergence[i - 1]) { set_error("bg_track_init: thresholds must be in descending order"); return JAXENT_E_INVALID; }
+  bg::BatchArgs& a = p->a;
+  a.trk_on = 1;
+  a.trk_n_thr = n;
+  a.trk_min_steps = min_steps;
+  a.trk_alpha = ema_alpha;
+  a.trk_tolerance = tolerance;
+  a.ema_w = ema_w;
+  a.snap_w = snap_w;
+  a.snap_ema = snap_ema;
+  a.snaps = snaps;
+  for (int i = 0; i < n; ++i) p->conv[i] = convergence[i];
+  p->initialised = 0;  // the tracker state lives in the control blocks: jaxent_bg_state_init must follow
+  return JAXENT_OK;
+}
+
+namespace jx {
+namespace bg {
+__global__ void bt_status_kernel(const BatchArgs a, JaxentTrackStatus* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.Bn) return;
+  const BCtl* c = a.ctl + b;
+  out[b].stop = c->stop;
+  out[b].reason = c->trk_reason;
+  out[b].stop_step = c->trk_stop_step;
+  out[b].n_snapshots = c->trk_nsnap;
+  out[b].steps_done = c->step;
+  out[b].threshold_idx = c->trk_idx;
+  out[b].last_loss = (float)c->trk_prev_loss;
+  out[b].ema_loss_delta = (float)c->trk_ema;
+}
+}  // namespace bg
+}  // namespace jx
+
+// one JaxentTrackStatus per replica written to `status` (device memory, n_replicas entries)
+extern "C" int jaxent_bg_track_status(JaxentBatchPlan* p, JaxentTrackStatus* status, jaxent_stream_t stream) {
+  if (!p || !p->initialised || !status) { set_error("bg_track_status: invalid argument"); return JAXENT_E_INVALID; }
+  bg::bt_status_kernel<<<(p->a.Bn + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p->a, status);
+  return bg_err("bt_status");
 }

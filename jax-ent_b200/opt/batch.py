@@ -1,11 +1,13 @@
 """batch_optimise (reference jaxent/src/opt/batch.py:51-192): sweeps over (forward_model_weights,
 forward_model_scaling, learning_rate) that share the features, the data and the starting point.
 
-The reference vmaps `_optimise_pure` over the hyper-parameter batch.  Here every run uses the on-device loop
-(`_optimise_device`) on an engine that shares ONE packed copy of the features, so the sweep costs no extra
-feature memory and no host synchronisation inside a run.  Runs are issued back to back on the device; the
-tensor-core formulation that advances all replicas in one (R x F)(F x B) GEMM per step (BASELINE config 5) is
-the planned replacement for this loop and is described in DESIGN.md section 8."""
+The reference vmaps `_optimise_pure` over the hyper-parameter batch.  Here a batch of replicas is advanced by ONE fused
+step on the tensor cores (BatchedBvEngine: the two feature sweeps are tcgen05 GEMMs over all replicas, DESIGN.md
+section 6) with the per-replica ConvergenceTracker, history snapshots and stop decision evaluated on the device; replicas
+whose loop has ended are frozen while the others continue -- the semantics of a vmapped `lax.while_loop`.  The
+tensor-core path needs features that are exact in bf16 (hard-cutoff contact counts); otherwise (`engine="sequential"`,
+or "auto" on other features) every run uses the single-ensemble on-device loop (`_optimise_device`) on shared packed
+features, one replica after the other."""
 from __future__ import annotations
 
 from typing import NamedTuple, Optional, Sequence
@@ -35,9 +37,62 @@ class BatchOptimisationResult(NamedTuple):
     hparam_batch: HParamBatch
 
 
+def _batch_optimise_gemm(simulation: Simulation, fw, fs, lrs, batch_size: int, data_to_fit, config: OptimiserSettings, indexes,
+                         loss_functions, optimizer: OptaxOptimizer, optimisable_funcs):
+    """the tensor-core path: batches of up to 256 replicas on one BatchedBvEngine"""
+    from .. import _lib as L
+    from .._arrays import scalar, to_device
+    from ..batch_engine import MAX_REPLICAS, BatchedBvEngine, pack_gemm_features
+    from ..interfaces.simulation import Simulation_Parameters
+    from .optimiser import B200OptState, _losses_from_record, _slot_specs
+
+    feats = simulation.__dict__.get("_gemm_features")
+    if feats is None:
+        f0 = simulation.input_features[0]
+        feats = pack_gemm_features(f0.heavy_contacts, f0.acceptor_contacts, simulation.device)  # raises ValueError if not bf16-exact
+        simulation.__dict__["_gemm_features"] = feats
+    data_targets, losses_t, idx_t = tuple(data_to_fit), tuple(loss_functions), tuple(indexes)
+    specs, prior = _slot_specs(simulation, data_targets, losses_t, idx_t)
+    state0 = optimizer.initialise(simulation, optimisable_funcs)
+    params = state0.params
+    mp = params.model_parameters[0]
+    z0 = to_device(params.frame_weights, simulation.device).reshape(-1)
+    n_h, n_l = fw.shape[0], len(losses_t)
+    convergence = [config.convergence] if isinstance(config.convergence, float) else list(config.convergence)
+    histories, best_states, conv_steps = [], [], []
+    per = max(1, min(int(batch_size), MAX_REPLICAS))
+    for lo in range(0, n_h, per):
+        hi = min(lo + per, n_h)
+        eng = BatchedBvEngine(feats, None, simulation._k_ints, simulation._timepoints, specs, simulation._uptake, optimizer._settings(),
+                              hi - lo, prior=prior, device=simulation.device)
+        eng.enable_tracking(convergence, config.ema_alpha, config.min_steps_per_threshold, config.tolerance)
+        lr = lrs[lo:hi] if lrs is not None else np.full(hi - lo, config.learning_rate, np.float32)
+        eng.init_state(z0, scalar(mp.bv_bc), scalar(mp.bv_bh), fw[lo:hi], fs[lo:hi], lr)
+        status = eng.run(config.n_steps)
+        for b in range(hi - lo):
+            st = status[b]
+            hist = OptimizationHistory()
+            for sn, w, _ema in eng.track_snapshots(b, st.n_snapshots):
+                mp_s = type(mp)(bv_bc=torch.tensor([sn.bc], device=eng.device), bv_bh=torch.tensor([sn.bh], device=eng.device),
+                                temperature=mp.temperature, timepoints=mp.timepoints)
+                sp = _replace(Simulation_Parameters.normalize_weights(params), frame_weights=w.clone(), model_parameters=[mp_s],
+                              forward_model_weights=fw[lo + b].astype(np.float32), forward_model_scaling=fs[lo + b].astype(np.float32))
+                rec = torch.frombuffer(bytearray(bytes(sn.losses)), dtype=torch.float32).to(eng.device)
+                hist.add_state(OptimizationState(sp, B200OptState(None, sn.state_step), sn.state_step, _losses_from_record(rec, n_l), None))
+            if hist.states:
+                hist.best_state = hist.get_best_state()
+            histories.append(hist)
+            best_states.append(hist.best_state if hist.states else state0)
+            conv_steps.append(int(st.steps_done))
+        del eng
+    return histories, best_states, conv_steps
+
+
 def batch_optimise(simulation: Simulation, hparam_batch: HParamBatch, batch_size: int, data_to_fit: Sequence,
                    config: OptimiserSettings, indexes: Sequence[int], loss_functions: Sequence,
-                   optimizer: Optional[OptaxOptimizer] = None, optimisable_funcs=None) -> BatchOptimisationResult:
+                   optimizer: Optional[OptaxOptimizer] = None, optimisable_funcs=None, engine: str = "auto") -> BatchOptimisationResult:
+    if engine not in ("auto", "gemm", "sequential"):
+        raise ValueError("engine must be 'auto', 'gemm' or 'sequential'")
     if batch_size <= 0:
         raise ValueError("batch_size must be > 0")
     fw = to_numpy(hparam_batch.forward_model_weights)
@@ -52,6 +107,16 @@ def batch_optimise(simulation: Simulation, hparam_batch: HParamBatch, batch_size
             raise ValueError("Failed to initialise simulation before batch optimisation")
     if optimizer is None:
         optimizer = OptaxOptimizer(learning_rate=config.learning_rate, optimizer=config.optimiser_type)
+
+    result_hparams = HParamBatch(hparam_batch.forward_model_weights, hparam_batch.forward_model_scaling, hparam_batch.learning_rate)
+    if engine in ("auto", "gemm"):
+        try:
+            histories, best_states, conv_steps = _batch_optimise_gemm(simulation, fw, fs, lrs, batch_size, data_to_fit, config, indexes,
+                                                                      loss_functions, optimizer, optimisable_funcs)
+            return BatchOptimisationResult(tuple(histories), tuple(best_states), np.asarray(conv_steps, np.int32), result_hparams)
+        except ValueError as e:
+            if engine == "gemm" or "bf16" not in str(e):
+                raise
 
     histories, best_states, conv_steps = [], [], []
     base_params = simulation.params

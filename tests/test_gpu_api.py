@@ -168,7 +168,8 @@ def test_on_device_loop_matches_host_loop():
         assert torch.equal(eng.export_state(("z",))[0]["z"], z0) and eng.track_status().steps_done == st.steps_done
 
 
-def test_batch_optimise_equals_sequential_runs():
+@pytest.mark.parametrize("engine", ["gemm", "sequential"])
+def test_batch_optimise_equals_sequential_runs(engine):
     """reference modules/optimise/test_module_batch_optimise.py:163-229: batch == sequential (loss rtol 1e-4, weights atol 1e-4)."""
     case, sim, data, losses, opt, cfg = _setup(lr=0.1, scaling=100.0)
     sim.initialise()
@@ -177,7 +178,7 @@ def test_batch_optimise_equals_sequential_runs():
     fs = np.full((3, 3), 100.0, np.float32)
     lr = np.array([0.1, 0.05, 0.2], np.float32)
     res = J.batch_optimise(sim, J.HParamBatch(fw, fs, lr), batch_size=2, data_to_fit=data, config=settings, indexes=[0, 0, 0],
-                           loss_functions=list(losses), optimizer=opt)
+                           loss_functions=list(losses), optimizer=opt, engine=engine)
     assert len(res.histories) == 3 and res.convergence_steps.shape == (3,)
     for i in range(3):
         o = J.OptaxOptimizer(learning_rate=float(lr[i]), parameter_partition_masks=set(opt.parameter_partition_masks), clip_value=None,
