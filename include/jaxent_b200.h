@@ -81,7 +81,8 @@ typedef struct {
 typedef struct {
   int32_t R;            /* residues */
   int32_t T;            /* time points (uptake mode) */
-  int32_t uptake;       /* 1: BV_uptake_ForwardPass, 0: BV_ForwardPass (log_Pf) */
+  int32_t uptake;       /* 1: BV_uptake_ForwardPass, 0: BV_ForwardPass (log_Pf), 2: BV_uptake_ForwardPass with
+                           average_first = False (uptake per frame, then frame-averaged; models/core.py:302-304) */
   int32_t n_slots;
   int64_t F;            /* frames held by this rank */
   int64_t F_total;      /* frames of the whole ensemble (eps = 1e-10 / F_total, opt/losses.py:308) */
@@ -213,6 +214,8 @@ int jaxent_bv_plan_buffer(const JaxentPlan* plan, int32_t which, void** ptr, siz
 #define JAXENT_MAX_RANKS 8
 #define JAXENT_IPC_HANDLE_BYTES 64
 size_t jaxent_bv_exchange_bytes(int32_t R, int32_t world);
+/* same, for any forward mode of `problem` (the per-frame uptake mode exchanges 2*T*R + 4 doubles instead of 4*R + 4) */
+size_t jaxent_bv_exchange_bytes_for(const JaxentBvProblem* problem, int32_t world);
 int jaxent_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle);
 int jaxent_peer_open(const unsigned char* handle, void** dev_ptr);
 int jaxent_peer_close(void* dev_ptr);

@@ -157,6 +157,7 @@ SYMBOLS = {
     "jaxent_bv_plan_destroy": (None, [_VP]),
     "jaxent_bv_plan_buffer": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_SZ)]),
     "jaxent_bv_exchange_bytes": (_SZ, [_I32, _I32]),
+    "jaxent_bv_exchange_bytes_for": (_SZ, [C.POINTER(BvProblem), _I32]),
     "jaxent_peer_alloc": (C.c_int, [_SZ, C.POINTER(_VP), C.c_char_p]),
     "jaxent_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
     "jaxent_peer_close": (C.c_int, [_VP]),

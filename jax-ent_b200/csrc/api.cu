@@ -23,7 +23,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
-  size_t off_w, off_kappa, off_cc, off_ch, off_logpf, off_uptake, off_avg;
+  size_t off_w, off_kappa, off_cc, off_ch, off_logpf, off_uptake, off_avg, off_pfG;
   size_t off_partials, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_ticket, off_records;
   size_t off_cl_scratch;
   size_t off_blob[JAXENT_MAX_SLOTS];
@@ -60,8 +60,10 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_logpf = take((size_t)R * 4);
   L.off_uptake = take((size_t)(T > 0 ? T : 1) * R * 4);
   L.off_avg = take((size_t)2 * R * 4);
-  L.off_partials = take((size_t)MAX_PASS_CTAS * (4 * R + 4) * sizeof(double));
-  L.off_xchg = take(xchg_bytes(4 * R + 4, 1));  // single-rank exchange buffer (red / kl inbox of world = 1)
+  L.off_pfG = take((size_t)(T > 0 ? T : 1) * R * 4);
+  const int part_n = pass_part_n(R, T, pb->uptake);
+  L.off_partials = take((size_t)MAX_PASS_CTAS * part_n * sizeof(double));
+  L.off_xchg = take(xchg_bytes(part_n, 1));  // single-rank exchange buffer (red / kl inbox of world = 1)
   L.off_klpart = take((size_t)MAX_TAIL_CTAS * KL_N * sizeof(double));
   L.off_ctl = take(2 * sizeof(Ctl));
   L.off_epoch = take(sizeof(unsigned));
@@ -187,6 +189,11 @@ static int validate_problem(const JaxentBvProblem* p) {
     set_error("uptake mode needs T>0, k_ints and timepoints");
     return JAXENT_E_INVALID;
   }
+  if (p->uptake != 0 && p->uptake != 1 && p->uptake != 2) { set_error("uptake must be 0 (log_Pf), 1 (uptake) or 2 (per-frame uptake)"); return JAXENT_E_INVALID; }
+  if (p->uptake == 2 && (p->R > PASS_THREADS_MAX || p->T > 8 || p->feature_format != 0)) {
+    set_error("per-frame uptake mode (average_first=False) needs n_residues <= %d, <= 8 time points and fp32 features", PASS_THREADS_MAX);
+    return JAXENT_E_UNSUPPORTED;
+  }
   int n_kl = 0;
   for (int i = 0; i < p->n_slots; ++i) {
     const JaxentLossSlot& s = p->slots[i];
@@ -265,6 +272,11 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
     return JAXENT_E_INVALID;
   }
   const int R = problem->R, T = problem->uptake ? problem->T : 0;
+  if (problem->uptake == 2 && cfg->optimise_model_parameters) {
+    set_error("per-frame uptake mode (average_first=False) optimises the frame weights only: the BV-parameter gradient of step k "
+              "would be needed before the same sweep's forward half can start (set optimise_model_parameters = 0)");
+    return JAXENT_E_UNSUPPORTED;
+  }
   Layout L = make_layout(problem);
   if (workspace_bytes < L.total) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, L.total);
@@ -298,7 +310,7 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   p->subtile_bytes = (uint32_t)(FT * R * 2 * (problem->feature_format == 1 ? 1 : sizeof(float)));
   p->tile_bytes = p->subtile_bytes * p->sub_tiles;
   p->stage_stride = (uint32_t)align_up(p->tile_bytes, 128);
-  const size_t smem_budget = (p->rpt == 1 ? 108 : 216) * 1024;
+  const size_t smem_budget = ((p->rpt == 1 && problem->uptake != 2) ? 108 : 216) * 1024;
   const size_t fixed = MAX_STAGES * 8 + 2 * 16 * FT * 4 + 2 * 2 * FT * 4 + 128;
   int stages = (int)((smem_budget - fixed) / p->stage_stride);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -307,7 +319,7 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   p->pass_smem = (size_t)stages * p->stage_stride + fixed;
   p->n_tiles = (problem->F + FT - 1) / FT;
   p->n_stage_units = (p->n_tiles + p->sub_tiles - 1) / p->sub_tiles;
-  const int per_sm = (p->rpt == 1) ? 2 : 1;
+  const int per_sm = (p->rpt == 1 && problem->uptake != 2) ? 2 : 1;
   long long ctas = (long long)device_sm_count * per_sm;
   if (ctas > p->n_stage_units) ctas = p->n_stage_units;
   if (ctas > MAX_PASS_CTAS) ctas = MAX_PASS_CTAS;
@@ -340,7 +352,7 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   memset(&p->x, 0, sizeof(p->x));
   p->x.world = 1;
   p->x.rank = 0;
-  p->x.part_n = 4 * R + 4;
+  p->x.part_n = pass_part_n(R, T, problem->uptake);
   p->x.base[0] = p->ws + L.off_xchg;
   p->x.local = p->x.base[0];
   p->initialised = 0;
@@ -356,7 +368,7 @@ extern "C" int jaxent_bv_plan_buffer(const JaxentPlan* p, int32_t which, void** 
   const int R = p->prob.R, T = p->prob.uptake ? p->prob.T : 0;
   switch (which) {
     case JAXENT_BUF_RED:  // plain doubles; meaningful when the exchange is not fused (one rank, or NCCL between the phases)
-      *ptr = p->x.local + xchg_plain_red_off(p->x); *bytes = (size_t)(4 * R + 4) * 8; break;
+      *ptr = p->x.local + xchg_plain_red_off(p->x); *bytes = (size_t)p->x.part_n * 8; break;
     case JAXENT_BUF_KLSUM: *ptr = p->x.local + xchg_plain_kl_off(p->x); *bytes = KL_N * 8; break;
     case JAXENT_BUF_XCHG_ERR: *ptr = p->x.local + xchg_err_off(p->x); *bytes = 8; break;
     case JAXENT_BUF_WEIGHTS: *ptr = p->ws + p->lay.off_w; *bytes = (size_t)p->prob.F * 4; break;
@@ -430,8 +442,14 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.R = p->prob.R;
   a.mode = mode;
   a.stages = p->stages;
-  a.part_n = 4 * p->prob.R + 4;
+  a.part_n = p->x.part_n;
   a.format = p->prob.feature_format;
+  if (p->prob.uptake == 2) {
+    a.pf_T = p->prob.T;
+    a.pf_G = reinterpret_cast<const float*>(p->ws + p->lay.off_pfG);
+    a.pf_k = p->prob.k_ints;
+    a.pf_tp = p->prob.timepoints;
+  }
   a.sub_tiles = p->sub_tiles;
   a.subtile_bytes = p->subtile_bytes;
   a.n_stage_units = p->n_stage_units;
@@ -470,7 +488,7 @@ extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t stream) {
   a.ticket = reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket);
   a.dbg = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
   a.n_part = p->pass_ctas;
-  a.part_n = 4 * p->prob.R + 4;
+  a.part_n = p->x.part_n;
   return launch_reduce(a, (cudaStream_t)stream);
 }
 
@@ -494,6 +512,8 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.logpf = reinterpret_cast<float*>(p->ws + p->lay.off_logpf);
   a.uptake = reinterpret_cast<float*>(p->ws + p->lay.off_uptake);
   a.avg = reinterpret_cast<float*>(p->ws + p->lay.off_avg);
+  a.pf_G = reinterpret_cast<float*>(p->ws + p->lay.off_pfG);
+  a.part_n = p->x.part_n;
   a.klpart = reinterpret_cast<double*>(p->ws + p->lay.off_klpart);
   a.records = reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records);
   for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
@@ -542,6 +562,11 @@ extern "C" int jaxent_bv_step(JaxentPlan* p, jaxent_stream_t stream) {
 extern "C" size_t jaxent_bv_exchange_bytes(int32_t R, int32_t world) {
   if (R <= 0 || world < 1 || world > JAXENT_MAX_RANKS) return 0;
   return xchg_bytes(4 * R + 4, world);
+}
+
+extern "C" size_t jaxent_bv_exchange_bytes_for(const JaxentBvProblem* pb, int32_t world) {
+  if (!pb || pb->R <= 0 || world < 1 || world > JAXENT_MAX_RANKS) return 0;
+  return xchg_bytes(pass_part_n(pb->R, pb->uptake ? pb->T : 0, pb->uptake), world);
 }
 
 extern "C" int jaxent_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle) {
@@ -595,7 +620,7 @@ extern "C" int jaxent_bv_plan_set_exchange(JaxentPlan* p, int32_t rank, int32_t 
   memset(&p->x, 0, sizeof(p->x));
   p->x.world = world;
   p->x.rank = rank;
-  p->x.part_n = 4 * p->prob.R + 4;
+  p->x.part_n = pass_part_n(p->prob.R, p->prob.uptake ? p->prob.T : 0, p->prob.uptake);
   for (int r = 0; r < world; ++r) p->x.base[r] = static_cast<unsigned char*>(peers[r]);
   p->x.local = p->x.base[rank];
   p->initialised = 0;  // state_init clears the local flags; it must follow

@@ -304,8 +304,133 @@ __device__ __noinline__ void finish_previous_record(const Xchg x, unsigned ep, c
   if (lane == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
 }
 
-template <int RPT, int FMT>
-__global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_pass_kernel(const PassArgs a) {
+// ------------------------------------------------------------------------------------------ per-frame uptake mode
+// ForwardPass.average_first = False (reference models/core.py:302-304, BV_uptake_ForwardPass models/HDX/forward.py:57-74):
+// the uptake is evaluated per (time point, residue, frame) and THEN frame-averaged, so the pass carries the non-linearity:
+//   u[t,r,f] = 1 - exp(-k_r tau_t exp(-(bc Nc[r,f] + bh Nh[r,f])))
+//   phase A  H_f = sum_{t,r} G[t,r] u[t,r,f]            G = dL/d<uptake> from the tail
+//   phase B  acc[branch][t][r] += e'_f u[t,r,f]
+// F*R*(T+1) exponentials per step make this mode special-function bound rather than HBM bound.  The BV parameters are
+// frozen in this mode (their gradient would be needed before the same sweep's forward half could start).
+constexpr int PF_TMAX = 8;
+
+// 1 - exp(-x) for x >= 0: series below 0.25 (relative error < 4e-7), 1 - ex2(-x log2 e) above (absolute error < 2.4e-7)
+__device__ __forceinline__ float uptake_of(float x) {
+  const float e = exp2f(-1.4426950408889634f * x);
+  const float small = x * (1.f - x * (0.5f - x * (0.16666667f - x * (0.041666668f - x * 0.0083333338f))));
+  return x < 0.25f ? small : 1.f - e;
+}
+
+template <int TM>
+__device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ring, uint64_t* bars, float* s_part, const float* s_e,
+                                             double* part, int n, int mode, float bc, float bh) {
+  const int R = a.R, T = a.pf_T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbar = blockDim.x;
+  const bool ok = tid < R;
+  const int rc = ok ? tid : R - 1;
+  const uint32_t rowoff = (uint32_t)rc * 16u, rstride = (uint32_t)R * 16u;
+  float kt[TM], G[TM];
+  const float kr = a.pf_k[rc];
+#pragma unroll
+  for (int t = 0; t < TM; ++t) {
+    kt[t] = (t < T) ? kr * a.pf_tp[t] : 0.f;
+    G[t] = (ok && mode && t < T) ? a.pf_G[(size_t)t * R + rc] : 0.f;
+  }
+  if (ok)
+    for (int k = 0; k < 2 * T; ++k) part[(size_t)k * R + rc] = 0.0;
+  float acc[2][TM];
+#pragma unroll
+  for (int t = 0; t < TM; ++t) acc[0][t] = acc[1][t] = 0.f;
+  const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const float nlog2e_bc = -1.4426950408889634f * bc, nlog2e_bh = -1.4426950408889634f * bh;
+  int slot = 0;
+  uint32_t parity = 0;
+  int since = 0;
+  for (int it = 0; it < n; ++it) {
+    const int b = it & 1;
+    mbar_wait(smem_u32(&bars[slot]), parity);
+    const unsigned char* sub = ring + (size_t)slot * a.stage_stride + rowoff;
+    const float4 c0 = *reinterpret_cast<const float4*>(sub), h0 = *reinterpret_cast<const float4*>(sub + rstride);
+    const float4 c1 = *reinterpret_cast<const float4*>(sub + 2 * rstride), h1 = *reinterpret_cast<const float4*>(sub + 3 * rstride);
+    if (++slot == a.stages) {
+      slot = 0;
+      parity ^= 1u;
+    }
+    const float nc[FT] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float nh[FT] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    float u[FT][TM];
+    float p[FT];
+#pragma unroll
+    for (int j = 0; j < FT; ++j) {
+      const float pinv = exp2f(fmaf(nlog2e_bc, nc[j], nlog2e_bh * nh[j]));  // exp(-lnPF)
+      float hj = 0.f;
+#pragma unroll
+      for (int t = 0; t < TM; ++t) {
+        u[j][t] = uptake_of(kt[t] * pinv);
+        hj = fmaf(G[t], u[j][t], hj);
+      }
+      p[j] = hj;
+    }
+    // transposing warp reduction of the 8 per-frame partials (same scheme as phase_a)
+    {
+      const bool hi = lane & 16;
+      float q4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = hi ? p[i] : p[i + 4];
+        const float keep = hi ? p[i + 4] : p[i];
+        q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+      const bool b3 = lane & 8;
+      float r2[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? q4[i] : q4[i + 2];
+        const float keep = b3 ? q4[i + 2] : q4[i];
+        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      const bool b2_ = lane & 4;
+      const float send = b2_ ? r2[0] : r2[1];
+      const float keep = b2_ ? r2[1] : r2[0];
+      float sres = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      sres += __shfl_xor_sync(0xffffffffu, sres, 2);
+      sres += __shfl_xor_sync(0xffffffffu, sres, 1);
+      if ((lane & 3) == 0) s_part[b * 16 * FT + warp * FT + jred] = sres;
+    }
+    bar_arrive(BAR_PART0 + b, nbar);
+    bar_sync(BAR_E0 + b, nbar);  // e'(it) of both branches from the Adam warp
+    const float4* e4 = reinterpret_cast<const float4*>(s_e + b * 2 * FT);
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      const float4 e0 = e4[2 * br], e1 = e4[2 * br + 1];
+      const float ev[FT] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+      for (int t = 0; t < TM; ++t) {
+        float s_ = 0.f;
+#pragma unroll
+        for (int j = 0; j < FT; ++j) s_ = fmaf(ev[j], u[j][t], s_);
+        acc[br][t] += s_;
+      }
+    }
+    if (++since >= FLUSH_TILES || it == n - 1) {
+      since = 0;
+      if (ok) {
+#pragma unroll
+        for (int br = 0; br < 2; ++br)
+#pragma unroll
+          for (int t = 0; t < TM; ++t)
+            if (t < T) {
+              atomicAdd(&part[(size_t)(br * T + t) * R + rc], (double)acc[br][t]);  // single writer per address: deterministic
+              acc[br][t] = 0.f;
+            }
+      }
+    }
+  }
+}
+
+template <int RPT, int FMT, int PF>
+__global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1 && PF == 0) ? 2 : 1) bv_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -471,15 +596,21 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1) ? 2 : 1) bv_
     if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 43);
     if (blockIdx.x == 0 && mode == 1) finish_previous_record(a.x, ep, ctl, a.records, lane);
     if (lane == 0) {
-      part[4 * R + 0] = sumA;
-      part[4 * R + 1] = sumB;
-      part[4 * R + 2] = gdot;
-      part[4 * R + 3] = 0.0;
+      part[a.part_n - 4] = sumA;
+      part[a.part_n - 3] = sumB;
+      part[a.part_n - 2] = gdot;
+      part[a.part_n - 1] = 0.0;
     }
     return;
   }
 
   // ==================================================================== consumers
+  if (PF != 0) {
+    const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
+    if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_part, s_e, part, n, mode, ctl->bc, ctl->bh);
+    else pf_consumer<PF_TMAX>(a, ring, bars, s_part, s_e, part, n, mode, ctl->bc, ctl->bh);
+    return;
+  }
   float ccr[RPT], chr[RPT];
   uint32_t rowoff[RPT];
   int row[RPT];
@@ -629,25 +760,31 @@ __global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, cons
 // ------------------------------------------------------------------------------------------ launchers
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(bv_pass_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<1,0>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  e = cudaFuncSetAttribute(bv_pass_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<2,0>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  e = cudaFuncSetAttribute(bv_pass_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<1,1>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  e = cudaFuncSetAttribute(bv_pass_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pass<2,1>): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+#define JX_CFG(K, BYTES)                                                                                       \
+  e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);                              \
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(" #K "): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  JX_CFG((bv_pass_kernel<1, 0, 0>), 111 * 1024)
+  JX_CFG((bv_pass_kernel<2, 0, 0>), 220 * 1024)
+  JX_CFG((bv_pass_kernel<1, 1, 0>), 111 * 1024)
+  JX_CFG((bv_pass_kernel<2, 1, 0>), 220 * 1024)
+  JX_CFG((bv_pass_kernel<1, 0, 1>), 220 * 1024)
+#undef JX_CFG
   return JAXENT_OK;
 }
 
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s) {
   cudaError_t le = cudaSuccess;
-  switch (rpt * 2 + (a.format ? 1 : 0)) {
-    case 2: le = launch_pdl(bv_pass_kernel<1, 0>, ctas, threads, smem, s, a); break;
-    case 3: le = launch_pdl(bv_pass_kernel<1, 1>, ctas, threads, smem, s, a); break;
-    case 4: le = launch_pdl(bv_pass_kernel<2, 0>, ctas, threads, smem, s, a); break;
-    case 5: le = launch_pdl(bv_pass_kernel<2, 1>, ctas, threads, smem, s, a); break;
-    default: set_error("unsupported rows-per-thread %d", rpt); return JAXENT_E_UNSUPPORTED;
+  if (a.pf_T > 0) {
+    if (rpt != 1 || a.format != 0 || a.pf_T > PF_TMAX) { set_error("per-frame uptake mode needs n_residues <= 512, fp32 features and <= %d time points", PF_TMAX); return JAXENT_E_UNSUPPORTED; }
+    le = launch_pdl(bv_pass_kernel<1, 0, 1>, ctas, threads, smem, s, a);
+  } else {
+    switch (rpt * 2 + (a.format ? 1 : 0)) {
+      case 2: le = launch_pdl(bv_pass_kernel<1, 0, 0>, ctas, threads, smem, s, a); break;
+      case 3: le = launch_pdl(bv_pass_kernel<1, 1, 0>, ctas, threads, smem, s, a); break;
+      case 4: le = launch_pdl(bv_pass_kernel<2, 0, 0>, ctas, threads, smem, s, a); break;
+      case 5: le = launch_pdl(bv_pass_kernel<2, 1, 0>, ctas, threads, smem, s, a); break;
+      default: set_error("unsupported rows-per-thread %d", rpt); return JAXENT_E_UNSUPPORTED;
+    }
   }
   cudaError_t e = (le != cudaSuccess) ? le : cudaGetLastError();
   if (e != cudaSuccess) { set_error("bv_pass_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }

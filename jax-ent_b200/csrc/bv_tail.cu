@@ -463,11 +463,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
 
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (warp == 0) {
-    const double SA = red_total(a.x, ep, 4 * R + 0), SB = red_total(a.x, ep, 4 * R + 1), gdot = red_total(a.x, ep, 4 * R + 2);
+    const double SA = red_total(a.x, ep, a.part_n - 4), SB = red_total(a.x, ep, a.part_n - 3), gdot = red_total(a.x, ep, a.part_n - 2);
     derive_scalars(&s_sc, &s_old, SA, SB, gdot, a.cfg, a.trk, a.records);
   }
+  const bool pfm = pb.uptake == 2;
   if (tail_cta) {
-    if (tid < R) {
+    if (tid < R && !pfm) {
       accA0 = red_total(a.x, ep, 0 * R + tid);
       accA1 = red_total(a.x, ep, 1 * R + tid);
       accB0 = red_total(a.x, ep, 2 * R + tid);
@@ -488,9 +489,20 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     io.avg = a.avg;
     io.logpf = a.logpf;
     io.uptake = a.uptake;
+    io.pf_G = a.pf_G;
+    io.pf_mode = pfm ? 1 : 0;
+    if (pfm) {  // per-frame uptake mode: <u>[t,r] = acc[branch d][t][r] / S straight from the reduced pass sums
+      const double invS = __drcp_rn(S);
+#pragma unroll 1
+      for (int it = tid; it < R * T; it += nt) {
+        const double uv = red_total(a.x, ep, d * T * R + it) * invS;
+        tsm.sU[it] = uv;
+        a.uptake[it] = (float)uv;
+      }
+    }
     tail_body<GENERAL>(pb, a.blobs, first_data, tsm, d ? accB0 : accA0, d ? accB1 : accA1, S, bc, bh, s_old.fw, s_old.fs, io, s_red, s_fin,
                        my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg);
-    if (tid < R) {  // row coefficients of the next pass
+    if (tid < R && !pfm) {  // row coefficients of the next pass
       a.cc[tid] = (float)(my_c * bc);
       a.ch[tid] = (float)(my_c * bh);
     }

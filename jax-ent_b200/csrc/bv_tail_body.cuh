@@ -89,6 +89,8 @@ struct TailIO {
   float* avg;     // [2R] frame-averaged contacts
   float* logpf;   // [R]
   float* uptake;  // [T*R]
+  float* pf_G;    // per-frame uptake mode: [T*R] dL/d<uptake>[t,r] for the next pass (else unused)
+  int pf_mode;    // 1: per-frame uptake mode -- the caller has filled sm.sU with the frame-averaged uptake already
 };
 
 // Whole-CTA function.  In: acc0/acc1 = un-normalised weighted row sums of this thread's residue (tid < R), S = sum of the
@@ -110,7 +112,9 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
   int* s_blob = sm.s_blob;
   {
     my_a = 0, my_b = 0, my_lp = 0, my_c = 0;
-    if (tid < R) {
+    const bool pfm = io.pf_mode != 0;
+    double pf_hbar = 0.0;  // per-frame mode: sum_t G[t,r] <u>[t,r] of this thread's residue
+    if (!pfm && tid < R) {
       const double invS = __drcp_rn(S);
       my_a = acc0 * invS;
       my_b = acc1 * invS;
@@ -121,7 +125,7 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
       io.logpf[tid] = (float)my_lp;
       if (T > 0) sxe[tid] = dexp(-my_lp);
     }
-    if (T > 0) {
+    if (T > 0 && !pfm) {
       __syncthreads();  // exp(-lnPF) visible
 #pragma unroll 1
       for (int it = tid; it < R * T; it += nt) {
@@ -337,7 +341,7 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
             if (t < Tm) {
               double back = bk[k];
               if (centre) back -= colsum * smean[2 * T + t];  // centred gradient: minus mean_p(gp) through the column
-              if (!pf) {
+              if (!pf && !pfm) {
                 const double x = (double)s_k[r] * (double)s_tp[t] * sxe[r];
                 back *= -x * (1.0 - sU[(size_t)t * R + r]);  // du/dlnPF = -x exp(-x)
               }
@@ -348,8 +352,20 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
       }
       __syncthreads();  // (4) items visible
       if (tid < R) {
+        if (pfm) {
+          // per-frame mode: the items ARE G[t,r] = dL/d<uptake>[t,r]; accumulate them over the data slots in global memory
+          // (this thread owns residue tid) and form the data part of hbar = sum_{t,r} G <u>
 #pragma unroll 1
-        for (int t = 0; t < Tm; ++t) my_c += sc_rt[(size_t)t * R + tid];
+          for (int t = 0; t < Tm; ++t) {
+            const double gv = sc_rt[(size_t)t * R + tid];
+            float* gdst = io.pf_G + (size_t)t * R + tid;
+            *gdst = (i == first_data) ? (float)gv : *gdst + (float)gv;
+            pf_hbar += gv * sU[(size_t)t * R + tid];
+          }
+        } else {
+#pragma unroll 1
+          for (int t = 0; t < Tm; ++t) my_c += sc_rt[(size_t)t * R + tid];
+        }
       }
     }
 
@@ -357,7 +373,7 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
     {
       double v12 = 0.0, v13 = 0.0, v14 = 0.0;
       if (tid < R) {
-        v12 = my_c * my_lp;  // hbar (data part) = sum_r c_r lnPF_r = sum_j w_j h_j
+        v12 = pfm ? pf_hbar : my_c * my_lp;  // hbar (data part) = sum_r c_r lnPF_r = sum_j w_j h_j
         v13 = my_c * my_a;   // dL/dbc
         v14 = my_c * my_b;   // dL/dbh
       }

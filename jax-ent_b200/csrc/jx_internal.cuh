@@ -200,6 +200,11 @@ struct PassArgs {
   const float* kappa;
   const float* cc;
   const float* ch;
+  // per-frame uptake mode (ForwardPass.average_first = False): pf_T > 0
+  int pf_T;                 // time points
+  const float* pf_G;        // [T][R] dL/d<uptake>[t,r] from the tail
+  const float* pf_k;        // [R] intrinsic rates
+  const float* pf_tp;       // [T] time points
   double* partials;
   Xchg x;
   const Ctl* ctl;
@@ -252,6 +257,8 @@ struct TailArgs {
   float* logpf;
   float* uptake;
   float* avg;
+  float* pf_G;         // per-frame uptake mode: [T][R] dL/d<uptake> for the next pass
+  int part_n;          // length of the reduced vector (4R+4, or 2TR+4 in per-frame uptake mode)
   double* klpart;
   JaxentLossRecord* records;
   BlobSet blobs;
@@ -292,6 +299,8 @@ inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, c
 }
 
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s);
+// number of doubles every pass CTA contributes: row sums (+ sum e for both branches, grad-dot, pad)
+__host__ __device__ inline int pass_part_n(int R, int T, int uptake_mode) { return uptake_mode == 2 ? 2 * T * R + 4 : 4 * R + 4; }
 int launch_reduce(const ReduceArgs& a, cudaStream_t s);
 int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
 int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const Xchg& x, JaxentLossRecord* rec, int n_slots, cudaStream_t s);

@@ -113,6 +113,7 @@ class BvEngine:
         group=None,
         feature_dtype: str = "f32",
         exchange: str = "auto",
+        average_first: bool = True,
     ):
         if not torch.cuda.is_available():
             raise RuntimeError("jaxent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -123,6 +124,8 @@ class BvEngine:
         self.sharded = self.comm.active
         self.settings = settings
         self.uptake = bool(uptake)
+        # ForwardPass.average_first (reference models/core.py:299): False = uptake per frame, then frame-averaged
+        self.average_first = bool(average_first) or not self.uptake
         self._keep = []  # device tensors referenced by raw pointer from the plan
 
         R, F = int(heavy.shape[0]), int(heavy.shape[1])
@@ -139,7 +142,8 @@ class BvEngine:
                 self.features = self._pack(heavy, acceptor, feature_dtype)
             self.packed = self.features.packed
             prob = L.BvProblem()
-            prob.R, prob.T, prob.uptake, prob.n_slots = R, self.T, int(self.uptake), len(slots)
+            prob.R, prob.T, prob.n_slots = R, self.T, len(slots)
+            prob.uptake = (1 if self.average_first else 2) if self.uptake else 0
             prob.F, prob.F_total = F, self.F_total
             prob.packed = self.packed.data_ptr()
             prob.feature_format = self.features.format
@@ -204,7 +208,7 @@ class BvEngine:
                 self.exchange = "nccl"
                 if exchange in ("auto", "nvlink"):
                     try:
-                        self.peer = PeerExchange(self.lib, group, R, self.device)
+                        self.peer = PeerExchange(self.lib, group, prob, self.device)
                         self.peer.attach(self.plan)
                         self.exchange = "nvlink"
                     except RuntimeError:

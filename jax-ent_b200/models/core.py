@@ -57,8 +57,6 @@ class Simulation:
         if len(self.forward_models) != 1 or not isinstance(self.input_features[0], BV_input_features):
             raise NotImplementedError("the fused B200 path covers exactly one BV forward model per Simulation")
         fp = self.forwardpass[0]
-        if not getattr(fp, "average_first", True):
-            raise NotImplementedError("average_first=False (per-frame uptake) is not on the fused path yet (SURVEY.md 8f.2)")
         if not hasattr(fp, "uptake"):
             raise NotImplementedError(f"forward pass {type(fp).__name__} is not a BV forward pass of the fused path")
         if not torch.cuda.is_available():
@@ -73,6 +71,9 @@ class Simulation:
         if tuple(np.shape(feat.heavy_contacts)) != tuple(np.shape(feat.acceptor_contacts)) or len(np.shape(feat.heavy_contacts)) != 2:
             raise ValueError("BV features must be two (n_residues, n_frames) arrays of equal shape")
         self._uptake = bool(fp.uptake)
+        # average_first=False: the uptake is evaluated per frame and the outputs are frame-averaged (reference :302-304);
+        # for the linear log_Pf forward pass the two orders coincide, so only the uptake pass has a per-frame kernel
+        self._average_first = bool(getattr(fp, "average_first", True)) or not self._uptake
         mp = self.params.model_parameters[0]
         self._timepoints = to_numpy(mp.timepoints).reshape(-1) if self._uptake else None
         self._k_ints = to_numpy(feat.k_ints).reshape(-1) if (self._uptake and feat.k_ints is not None) else None
@@ -80,7 +81,8 @@ class Simulation:
             raise ValueError("Failed to apply forward models without JIT: BV_uptake_ForwardPass needs k_ints")
         try:
             self._fwd_engine = BvEngine(feat.heavy_contacts, feat.acceptor_contacts, self._k_ints, self._timepoints,
-                                        [SlotSpec(L.LOSS_PARAMS_L2)], self._uptake, OptSettings(), device=self.device)
+                                        [SlotSpec(L.LOSS_PARAMS_L2)], self._uptake, OptSettings(optimise_model_parameters=False),
+                                        device=self.device, average_first=self._average_first)
         except Exception as e:
             raise ValueError(f"Failed to apply forward models without JIT: {e}")
         self._features = self._fwd_engine.features

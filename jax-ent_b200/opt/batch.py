@@ -109,6 +109,10 @@ def batch_optimise(simulation: Simulation, hparam_batch: HParamBatch, batch_size
         optimizer = OptaxOptimizer(learning_rate=config.learning_rate, optimizer=config.optimiser_type)
 
     result_hparams = HParamBatch(hparam_batch.forward_model_weights, hparam_batch.forward_model_scaling, hparam_batch.learning_rate)
+    if not getattr(simulation, "_average_first", True):
+        if engine == "gemm":
+            raise NotImplementedError("the tensor-core sweep covers average_first=True forward passes")
+        engine = "sequential"
     if engine in ("auto", "gemm"):
         try:
             histories, best_states, conv_steps = _batch_optimise_gemm(simulation, fw, fs, lrs, batch_size, data_to_fit, config, indexes,

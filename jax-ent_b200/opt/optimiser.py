@@ -76,7 +76,7 @@ def _build_engine(simulation: Simulation, data_targets, loss_functions, indexes,
         raise RuntimeError("Simulation must be initialised first")
     specs, prior = _slot_specs(simulation, data_targets, loss_functions, indexes)
     return BvEngine(simulation._features, None, simulation._k_ints, simulation._timepoints, specs, simulation._uptake,
-                    settings, prior=prior, device=simulation.device)
+                    settings, prior=prior, device=simulation.device, average_first=getattr(simulation, "_average_first", True))
 
 
 def _record_view(eng: BvEngine, step: int) -> torch.Tensor:

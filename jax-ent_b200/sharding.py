@@ -89,7 +89,7 @@ class PeerExchange:
     fused in-kernel all-reduce.  Set-up only; raises if any rank cannot map its peers (the caller then
     falls back to NCCL collectives on all ranks together)."""
 
-    def __init__(self, lib, group, n_residues: int, device: torch.device):
+    def __init__(self, lib, group, problem, device: torch.device):
         import ctypes as C
 
         from . import _lib as L
@@ -101,7 +101,7 @@ class PeerExchange:
         self.ptrs = [None] * self.world
         if self.world > L.MAX_RANKS:
             raise RuntimeError(f"the fused exchange supports at most {L.MAX_RANKS} ranks")
-        nbytes = lib.jaxent_bv_exchange_bytes(int(n_residues), self.world)
+        nbytes = lib.jaxent_bv_exchange_bytes_for(C.byref(problem), self.world)
         ok, err = 1, ""
         handle = C.create_string_buffer(L.IPC_HANDLE_BYTES)
         ptr = C.c_void_p()

@@ -68,6 +68,9 @@ class Problem:
     timepoints: Optional[np.ndarray]  # (T,) static field of BV_Model_Parameters
     slots: Sequence[LossSlot]
     uptake: bool = True  # BV_uptake_ForwardPass (True) or BV_ForwardPass (False)
+    # ForwardPass.average_first (models/core.py:299): True = frame-average the features, then the forward pass;
+    # False = forward pass per frame, then frame-average the outputs (uptake only; BV_uptake_ForwardPass_frames)
+    average_first: bool = True
 
 
 @dataclass
@@ -219,15 +222,22 @@ def convex_kl_divergence(log_predictions, targets, dtype=np.float32):
 
 # ----------------------------------------------------------------------------- forward + losses
 def forward(problem: Problem, params: Params, dtype=np.float32):
-    """Simulation.forward + forward_pure, average_first=True (models/core.py:131-163,270-307).
+    """Simulation.forward + forward_pure (models/core.py:131-163,270-307), both branches of `average_first`.
     Returns (normalised params, outputs dict)."""
     npar = normalize_weights(params, dtype)
     a = frame_average(problem.heavy, npar.z, dtype)
     b = frame_average(problem.acceptor, npar.z, dtype)
     log_pf = bv_log_pf(a, b, npar.bc, npar.bh, dtype)
     out = {"avg_heavy": a, "avg_acceptor": b, "log_Pf": log_pf}
-    if problem.uptake:
+    if problem.uptake and problem.average_first:
         out["uptake"] = bv_uptake(log_pf, problem.k_ints, problem.timepoints, dtype)
+    elif problem.uptake:
+        # models/core.py:302-304: output = single_pass(fp, feat, param); output = frame_average_features(output, w)
+        lp_f = bv_log_pf(problem.heavy, problem.acceptor, npar.bc, npar.bh, dtype)  # (R,F)
+        u_f = bv_uptake(lp_f, problem.k_ints, problem.timepoints, dtype)  # (T,R,F)
+        out["log_Pf_frames"] = lp_f
+        out["uptake_frames"] = u_f
+        out["uptake"] = (u_f @ np.asarray(npar.z, dtype)).astype(dtype)  # sum(x * w, axis=-1), utils/jax_fn.py:30-38
     return npar, out
 
 
@@ -334,6 +344,9 @@ def loss_and_grads(problem: Problem, params: Params, dtype=np.float32):
     R = a.shape[0]
     c = np.zeros(R, dtype)  # dL/d log_Pf_r
     hw = np.zeros_like(w)  # explicit dL/dw_f terms (KL)
+    per_frame = problem.uptake and not problem.average_first
+    hpf = np.zeros_like(w)  # per-frame mode: sum_{t,r} G[t,r] u[t,r,f]
+    Gtot = None
     gbc = dtype(0)
     gbh = dtype(0)
     for i, s in enumerate(problem.slots):
@@ -343,6 +356,18 @@ def loss_and_grads(problem: Problem, params: Params, dtype=np.float32):
             centre = k == UPTAKE_MC_EYE_MSE
             W = s.W_train if k == UPTAKE_SIGMA_MSE else None
             du = _dpred_uptake(s.S_train, s.y_train, W, out["uptake"], centre, sc, dtype)
+            if per_frame:
+                # uptake[t,r] = sum_f w_f u[t,r,f]: dL/dw_f = sum_{t,r} G[t,r] u[t,r,f]; d u/d lnPF[r,f] = -x exp(-x)
+                u_f, lp_f = out["uptake_frames"], out["log_Pf_frames"]
+                hpf += np.einsum("tr,trf->f", du, u_f).astype(dtype)
+                kk3 = np.asarray(problem.k_ints, dtype)[None, :, None]
+                tt3 = np.asarray(problem.timepoints, dtype).reshape(-1, 1, 1)
+                x3 = kk3 * tt3 * np.exp(-lp_f)[None, :, :]
+                dl = np.einsum("tr,trf->rf", du, -x3 * np.exp(-x3)) * w[None, :]  # dL/d lnPF[r,f]
+                gbc += dtype((dl * problem.heavy).sum())
+                gbh += dtype((dl * problem.acceptor).sum())
+                Gtot = du if Gtot is None else Gtot + du
+                continue
             kk = np.asarray(problem.k_ints, dtype)[None, :]
             tt = np.asarray(problem.timepoints, dtype).reshape(-1, 1)
             x = kk * tt * np.exp(-lp)[None, :]
@@ -373,12 +398,12 @@ def loss_and_grads(problem: Problem, params: Params, dtype=np.float32):
             raise ValueError(k)
     heavy = problem.heavy.astype(dtype, copy=False)
     acc = problem.acceptor.astype(dtype, copy=False)
-    h = heavy.T @ (c * dtype(npar.bc)) + acc.T @ (c * dtype(npar.bh)) + hw
+    h = heavy.T @ (c * dtype(npar.bc)) + acc.T @ (c * dtype(npar.bh)) + hw + hpf
     hbar = np.dot(w, h)
     gz = (w * (h - hbar)).astype(dtype)
     gbc = dtype(gbc + np.dot(c, a))
     gbh = dtype(gbh + np.dot(c, b))
-    aux = {"w": w, "c": c, "h": h, "hbar": hbar, "out": out}
+    aux = {"w": w, "c": c, "h": h, "hbar": hbar, "out": out, "G": Gtot}
     return losses, Grads(gz, gbc, gbh), aux
 
 

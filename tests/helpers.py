@@ -65,7 +65,7 @@ def make_engine(case, cfg: O.OptConfig, device=None, frames=None, F_total=None, 
                      cfg.b1, cfg.b2, cfg.eps)
     eng = BvEngine(np.ascontiguousarray(pb.heavy[:, sl]), np.ascontiguousarray(pb.acceptor[:, sl]), pb.k_ints, pb.timepoints, specs,
                    pb.uptake, st, prior=case["prior"][sl], device=device, F_total=F_total, group=group, feature_dtype=feature_dtype,
-                   exchange=exchange)
+                   exchange=exchange, average_first=getattr(pb, "average_first", True))
     return eng
 
 

@@ -31,7 +31,7 @@ def _oracle_params(case, z, sc):
     return O.Params(np.asarray(z, np.float64), p.frame_mask, sc["bc"], sc["bh"], p.fw, p.fs, p.nlf)
 
 
-def _check_steps(case, cfg, n_steps, check_adam=True):
+def _check_steps(case, cfg, n_steps, check_adam=True, STEP_RTOL=STEP_RTOL):
     eng = H.make_engine(case, cfg)
     H.init_engine(eng, case)
     pb = case["problem"]

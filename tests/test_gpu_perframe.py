@@ -1,0 +1,71 @@
+"""Per-frame BV uptake mode (ForwardPass.average_first = False): uptake per (time point, residue, frame),
+then the frame average -- reference models/core.py:302-304, models/HDX/forward.py:57-74.
+
+The pass evaluates F*R*(T+1) exponentials per step with the fast special-function unit (ex2.approx + a series below
+x = 0.25), so the per-step tolerance is 5e-5 (loss) / 2e-4 (gradients, max-abs relative) against the fp64 oracle instead
+of the 1e-5 of the average-first path; frame weights after a long run still agree to 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import bv_oracle as O
+from test_gpu_parity import _check_steps
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(F, R, T, kind=O.UPTAKE_EYE_MSE, seed=4, **kw):
+    case = H.make_case(F, R, T, kind, seed=seed, **kw)
+    case["problem"].average_first = False
+    return case
+
+
+@pytest.mark.parametrize("kind,F,R,T,clip", [
+    (O.UPTAKE_EYE_MSE, 777, 97, 5, None),
+    (O.UPTAKE_MC_EYE_MSE, 1000, 53, 3, 1.0),
+    (O.UPTAKE_SIGMA_MSE, 515, 64, 8, None),
+    (O.UPTAKE_EYE_MSE, 4099, 500, 8, None),
+])
+def test_per_frame_step_parity(kind, F, R, T, clip):
+    case = _case(F, R, T, kind, gamma=2.0, prior="random")
+    cfg = O.OptConfig(learning_rate=1.0, initial_learning_rate=1.0, initial_steps=0, clip_value=clip, optimise_model_parameters=False)
+    _, wl, wg = _check_steps(case, cfg, 6, STEP_RTOL=2e-4)
+    assert wl < 5e-5, wl
+
+
+def test_per_frame_forward_outputs_and_difference_to_average_first():
+    case = _case(1500, 64, 4)
+    cfg = O.OptConfig(learning_rate=0.5, clip_value=None, optimise_model_parameters=False)
+    eng = H.make_engine(case, cfg)
+    H.init_engine(eng, case)
+    torch.cuda.synchronize()
+    st = O.optimizer_initialise(case["params"], cfg, np.float64)
+    _, out = O.forward(case["problem"], st.params, np.float64)
+    np.testing.assert_allclose(eng.uptake_out.cpu().numpy(), out["uptake"], rtol=5e-6, atol=1e-7)
+    case["problem"].average_first = True
+    _, out_af = O.forward(case["problem"], st.params, np.float64)
+    assert np.abs(out_af["uptake"] - out["uptake"]).max() > 1e-4  # the two orders differ for a non-linear forward pass
+
+
+def test_per_frame_weights_after_500_steps():
+    case = _case(600, 53, 3, seed=9)
+    cfg = O.OptConfig(learning_rate=0.05, initial_learning_rate=1.0, initial_steps=2, clip_value=None, optimise_model_parameters=False)
+    eng = H.make_engine(case, cfg)
+    H.init_engine(eng, case)
+    eng.step(500)
+    torch.cuda.synchronize()
+    st = O.optimizer_initialise(case["params"], cfg, np.float64)
+    for _ in range(500):
+        st, _, _ = O.step_with_rates(case["problem"], st, cfg, np.float64)
+    w_ref = O.softmax(st.params.z, np.float64)
+    np.testing.assert_allclose(eng.weights.cpu().numpy(), w_ref, atol=1e-4)
+
+
+def test_per_frame_rejects_model_parameter_optimisation():
+    from jaxent_b200 import _lib as L
+
+    case = _case(300, 32, 3)
+    cfg = O.OptConfig(learning_rate=0.5, clip_value=None, optimise_model_parameters=True)
+    with pytest.raises(L.JaxentError, match="frame weights only"):
+        H.make_engine(case, cfg)

@@ -72,7 +72,12 @@ def _torch_loss(case, z, bc, bh):
         sc = float(par.fw[i]) * float(par.fs[i])
         if s.kind in O.UPTAKE_KINDS:
             k, tp = torch.tensor(pb.k_ints, dtype=f64), torch.tensor(pb.timepoints, dtype=f64)
-            u = 1 - torch.exp(-k[None, :] * tp[:, None] / torch.exp(lp)[None, :])
+            if pb.average_first:
+                u = 1 - torch.exp(-k[None, :] * tp[:, None] / torch.exp(lp)[None, :])
+            else:  # per-frame forward pass, then the frame average of the outputs (reference models/core.py:302-304)
+                lpf = bc * Nc + bh * Nh
+                uf = 1 - torch.exp(-k[None, :, None] * tp[:, None, None] / torch.exp(lpf)[None, :, :])
+                u = (uf * w[None, None, :]).sum(-1)
             S, y = torch.tensor(s.S_train, dtype=f64), torch.tensor(s.y_train, dtype=f64)
             W = torch.tensor(s.W_train, dtype=f64) if s.kind == O.UPTAKE_SIGMA_MSE else torch.eye(y.shape[0], dtype=f64)
             tot = 0.0
@@ -117,6 +122,29 @@ def test_closed_form_gradients_match_autograd(kind):
     np.testing.assert_allclose(float(tot.detach()), float(L.total_train_loss), rtol=1e-12)
     np.testing.assert_allclose(g.z, tz.grad.numpy(), rtol=0, atol=1e-12 * np.abs(g.z).max())
     np.testing.assert_allclose([g.bc, g.bh], [float(tbc.grad), float(tbh.grad)], rtol=1e-10)
+
+
+@pytest.mark.parametrize("kind", [O.UPTAKE_EYE_MSE, O.UPTAKE_MC_EYE_MSE, O.UPTAKE_SIGMA_MSE])
+def test_per_frame_uptake_gradients_match_autograd(kind):
+    """average_first=False: closed-form backward of the per-frame uptake mode vs torch.autograd fp64"""
+    case = H.make_case(150, 13, 4, kind, extra=(O.PARAMS_L2,), seed=8, n_pep=7, prior="random", gamma=2.0, scaling=30.0)
+    case["problem"].average_first = False
+    rng = np.random.default_rng(2)
+    z = rng.normal(size=150) * 1.5
+    par = O.Params(z, np.ones(150), 0.1, 0.6, case["params"].fw, case["params"].fs, case["params"].nlf)
+    L, g, aux = O.loss_and_grads(case["problem"], par, np.float64)
+    tz = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+    tbc = torch.tensor(0.1, dtype=torch.float64, requires_grad=True)
+    tbh = torch.tensor(0.6, dtype=torch.float64, requires_grad=True)
+    tot = _torch_loss(case, tz, tbc, tbh)
+    tot.backward()
+    np.testing.assert_allclose(float(tot.detach()), float(L.total_train_loss), rtol=1e-12)
+    np.testing.assert_allclose(g.z, tz.grad.numpy(), rtol=0, atol=1e-11 * np.abs(g.z).max())
+    np.testing.assert_allclose([g.bc, g.bh], [float(tbc.grad), float(tbh.grad)], rtol=1e-9)
+    # the two modes differ (the average of a non-linear function is not the function of the average)
+    case["problem"].average_first = True
+    L2, _, _ = O.loss_and_grads(case["problem"], par, np.float64)
+    assert abs(float(L2.total_train_loss) - float(L.total_train_loss)) > 1e-6 * abs(float(L.total_train_loss))
 
 
 def test_finite_difference_bv_parameters():
