@@ -409,7 +409,7 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     eng = BvEngine(heavy, acc, small.k_ints, small.timepoints, slots, True, settings, prior=prior, device=dev, F_total=F, group=group,
-                   exchange=args.exchange)
+                   exchange=args.exchange, average_first=not args.per_frame)
     del heavy, acc
     eng.init_state(torch.ones(Fl, device=dev), 0.35, 2.0, fw, fs)
     torch.cuda.synchronize()
@@ -503,7 +503,7 @@ def run_ours(args, wl):
         barrier()
         t0 = time.perf_counter()
         eng2 = BvEngine(host_h, host_a, small.k_ints, small.timepoints, slots, True, settings, prior=prior, device=dev, F_total=F, group=group,
-                        exchange=args.exchange)
+                        exchange=args.exchange, average_first=not args.per_frame)
         eng2.init_state(torch.ones(Fl, device=dev), 0.35, 2.0, fw, fs)
         torch.cuda.synchronize()
         t_setup = time.perf_counter() - t0
@@ -578,6 +578,8 @@ def run_ours(args, wl):
                        "exchange": {"nvlink": "fused in-kernel all-reduce over NVLink peer memory (no collective launches)",
                                     "nccl": "two NCCL all-reduces per step", "none": "none (single GPU)"}[exchange_kind],
                        "pass_events": f"CUDA events around every {EV}th pass kernel of the timed region",
+                       "forward_mode": "per-frame uptake (average_first=False): F*R*(T+1) exponentials per step, special-function bound; "
+                                       "roofline.achieved still counts the 8*R*F + 28*F bytes" if args.per_frame else "average_first=True",
                        "l2": f"inputs {8 * R * Fl / 1e9:.2f} GB per GPU per step >> 126 MB L2, no flush needed" if 8 * R * Fl > 4e8 else "inputs fit in L2 (latency-bound config; steps/s only)",
                        "losses": ["hdx_uptake_eye_MSE_loss", "maxent_convexKL_loss"], "optimizer": "adam lr=1.0, plateau 1.005"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -606,6 +608,7 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvlink", "nccl"])
     ap.add_argument("--event-every", type=int, default=8)
     ap.add_argument("--pieces", type=int, default=3, help="cfg5: bf16 pieces of the fp32 operand (2 or 3)")
+    ap.add_argument("--per-frame", action="store_true", help="BV uptake per frame, then frame-averaged (average_first=False)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
