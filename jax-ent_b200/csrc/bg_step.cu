@@ -39,7 +39,7 @@ struct alignas(16) BCtl {
   float bc, bh, mb[2], vb[2], gb_prev[2], gb[2];
   float lrA, lrB, mlrA, mlrB, mask_frame, mask_model;
   float lr_eff, bc1, bc2, kl_scale, last_dot, pad0;
-  double S, hbar_data;
+  double S, hbar_data, zp;  // zp = sum_f p_f z_f of the current logits
   double klsum[KL_N];
   float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
   // ---- per-replica ConvergenceTracker (reference opt/track.py:128-197, opt/run.py:285-348); see derive_scalars (bv_tail.cu)
@@ -74,6 +74,7 @@ struct BatchArgs {
   float* logpf;           // [Bn][R]
   float* uptake;          // [Bn][T*R]
   float* pnorm;           // [F] normalised prior p_f = (|prior_f| + eps) / sum (fp32, as frame_terms forms it)
+  double* kl_const;       // [2] sum_f p_f log p_f, sum_f p_f
   unsigned* gsel;         // which g buffer holds the current masked gradients
   unsigned* counter;      // ticket of bt_kl
   int p_max_tr, p_max_va;
@@ -102,17 +103,22 @@ __device__ __forceinline__ void split3(float x, int NS, __nv_bfloat16& p0, __nv_
 // (bv_tail.cu), but p/q is carried as an unevaluated fp32 pair r0 + corr (r0 = fl(p/q), corr = fl((p - r0*q)/q) with the
 // exact FMA residual) instead of an fp64 quotient: 256 replicas x 1e5 frames of fp64 division and log would make this
 // kernel arithmetic bound.  1 - p/q = (1 - r0) - corr keeps full relative accuracy when p/q is close to 1.
-__device__ __forceinline__ void weight_terms(float e, float Sf, float p, bool has_kl, float eps, float lam, float& w, float& kap, float& q,
-                                             float& r0, float& corr) {
-  w = e / Sf;
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// invS = 1 / S_b.  The quotient p/q only has to be *some* fp32 approximation r0: the FMA residual p - r0*q is exact, so
+// r0 + corr carries p/q to ~1e-14 whatever the error of the approximate reciprocal.
+__device__ __forceinline__ void weight_terms(float e, float invS, float p, bool has_kl, float eps, float lam, float& w, float& kap, float& q) {
+  w = e * invS;
   kap = 0.f;
   q = 0.f;
-  r0 = 1.f;
-  corr = 0.f;
   if (has_kl) {
     q = fabsf(w) + eps;
-    r0 = p / q;
-    corr = fmaf(-r0, q, p) / q;
+    const float rq = rcp_approx(q);
+    const float r0 = p * rq;
+    const float corr = fmaf(-r0, q, p) * rq;
     const float G_ = (1.0f - r0) - corr;
     kap = (w > 0.f) ? lam * G_ : 0.f;
   }
@@ -127,20 +133,41 @@ __global__ void __launch_bounds__(1024) bt_grad_kernel(const BatchArgs a) {
   const unsigned sel = *a.gsel;
   const float* __restrict__ gprev = a.g[sel];
   float* __restrict__ gout = a.g[sel ^ 1u];
-  const float Sf = (float)c->S, lam = c->kl_scale, maskf = c->mask_frame;
+  const float invS = (float)(1.0 / c->S), lam = c->kl_scale, maskf = c->mask_frame;
   const float hbar = (float)c->hbar_data;  // the MaxEnt part of hbar is O(1e-10 lambda): see bv_pass.cu, finish_previous_record
   const int have_prev = c->have_prev;
   const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
   const bool active = !c->stop;
   double dot = 0.0;
-  for (long long f = (long long)blockIdx.x * a.fy + fy; f < a.F; f += (long long)gridDim.x * a.fy) {
-    const size_t i = (size_t)f * Bn + b;
-    float w, kap, q, r0, corr;
-    weight_terms(a.e[i], Sf, has_kl ? a.pnorm[f] : 0.f, has_kl, a.eps_kl, lam, w, kap, q, r0, corr);
-    const float gf = active ? maskf * (w * ((a.H[i] + kap) - hbar)) : 0.f;
-    const float gpv = have_prev ? gprev[i] : gf;
-    dot += (double)(gpv * gf);
-    gout[i] = gf;
+  const float* __restrict__ ep = a.e;
+  const float* __restrict__ Hp = a.H;
+  const float* __restrict__ pn = a.pnorm;
+  // 4 frames per iteration with all loads issued first: one 4-byte load per thread in flight cannot cover the HBM latency
+  const long long fstep = (long long)gridDim.x * a.fy;
+  for (long long f0 = (long long)blockIdx.x * a.fy + fy; f0 < a.F; f0 += 4 * fstep) {
+    float ev[4], hv[4], gv[4], pv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long f = f0 + k * fstep;
+      const bool in = f < a.F;
+      const size_t i = (size_t)(in ? f : f0) * Bn + b;
+      ev[k] = ep[i];
+      hv[k] = Hp[i];
+      gv[k] = gprev[i];
+      pv[k] = has_kl ? pn[in ? f : f0] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long f = f0 + k * fstep;
+      if (f < a.F) {
+        float w, kap, q;
+        weight_terms(ev[k], invS, pv[k], has_kl, a.eps_kl, lam, w, kap, q);
+        const float gf = active ? maskf * (w * ((hv[k] + kap) - hbar)) : 0.f;
+        const float gpv = have_prev ? gv[k] : gf;
+        dot += (double)(gpv * gf);
+        gout[(size_t)f * Bn + b] = gf;
+      }
+    }
   }
   sh_d[fy * Bn + b] = dot;
   __syncthreads();
@@ -274,13 +301,15 @@ __global__ void __launch_bounds__(1024) bt_adam_kernel(const BatchArgs a, int up
   const int Bn = a.Bn, b = threadIdx.x % Bn, cy = threadIdx.x / Bn, ncy = blockDim.x / Bn;
   const BCtl* c = a.ctl + b;
   const float* __restrict__ g = a.g[*a.gsel];
-  const float lr = c->lr_eff, bc1 = c->bc1, bc2 = c->bc2, lse = c->lse;
+  const float lr = c->lr_eff, lse = c->lse;
+  const float ibc1 = 1.0f / c->bc1, ibc2 = 1.0f / c->bc2;  // bias corrections applied as reciprocal multiplies
+  const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
   const bool active = update && !c->stop;
   const float b1 = (float)a.cfg.b1, b2 = (float)a.cfg.b2, eps = (float)a.cfg.eps, clip = a.cfg.clip_value;
   const float om_b1 = (float)(1.0 - a.cfg.b1), om_b2 = (float)(1.0 - a.cfg.b2);
   const int NS = a.NS;
   const long long n_chunks = (long long)a.n_fb * 16;
-  double sum = 0.0;
+  double sum = 0.0, zp = 0.0;  // sum_f e'_f and sum_f p_f z'_f (the MaxEnt loss needs sum_f p_f log q_f = sum_f p_f z_f - lse + ...)
   for (long long ch = (long long)blockIdx.x * ncy + cy; ch < n_chunks; ch += (long long)gridDim.x * ncy) {
     __nv_bfloat16 p0[8], p1[8], p2[8];
 #pragma unroll
@@ -296,14 +325,15 @@ __global__ void __launch_bounds__(1024) bt_adam_kernel(const BatchArgs a, int up
           if (clip > 0.f) s = fminf(fmaxf(s, -clip), clip);
           const float m1 = om_b1 * s + b1 * m_;
           const float v1 = om_b2 * (s * s) + b2 * v_;
-          z_ = z_ - (m1 / bc1) / (sqrtf(v1 / bc2) + eps);
+          z_ = z_ - (m1 * ibc1) / (sqrtf(v1 * ibc2) + eps);
           a.z[i] = z_;
           a.m[i] = m1;
           a.v[i] = v1;
         }
-        en = expf(z_ - lse);
+        en = __expf(z_ - lse);
         a.e[i] = en;
         sum += (double)en;
+        if (has_kl) zp += (double)a.pnorm[f] * (double)z_;
       }
       split3(en, NS, p0[k], p1[k], p2[k]);
     }
@@ -315,11 +345,16 @@ __global__ void __launch_bounds__(1024) bt_adam_kernel(const BatchArgs a, int up
     if (NS > 2) dst[(((size_t)fb * NS + 2) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p2);
   }
   sh_d[cy * Bn + b] = sum;
+  sh_d[(ncy + cy) * Bn + b] = zp;
   __syncthreads();
   if (cy == 0) {
-    double t = 0.0;
-    for (int k = 0; k < ncy; ++k) t += sh_d[k * Bn + b];
+    double t = 0.0, tz = 0.0;
+    for (int k = 0; k < ncy; ++k) {
+      t += sh_d[k * Bn + b];
+      tz += sh_d[(ncy + k) * Bn + b];
+    }
     a.part_s[(size_t)blockIdx.x * Bn + b] = t;
+    a.part_s[(size_t)(MAX_EW_BLOCKS + blockIdx.x) * Bn + b] = tz;
   }
 }
 
@@ -344,12 +379,21 @@ __global__ void __launch_bounds__(1024) bt_reduce2_kernel(const BatchArgs a) {
     const int b = b0 + ty, row = row0 + tx;
     if (row < R2 && b < Bn) a.red[(size_t)b * R2 + row] = tile[tx][ty];
   }
-  if (blockIdx.x == 0 && ty == 0) {
+  if (blockIdx.x == 0) {  // S_b = sum_f e' and sum_f p_f z_f: block partials summed ty-strided, then over ty (fixed order)
     const int b = b0 + tx;
-    if (b < Bn) {
+    for (int which = 0; which < 2; ++which) {
+      __syncthreads();
       double s = 0.0;
-      for (int k = 0; k < a.ew_blocks; ++k) s += a.part_s[(size_t)k * Bn + b];
-      a.ctl[b].S = s;
+      if (b < Bn)
+        for (int k = ty; k < a.ew_blocks; k += 32) s += a.part_s[(size_t)(which * MAX_EW_BLOCKS + k) * Bn + b];
+      tile[ty][tx] = s;
+      __syncthreads();
+      if (ty == 0 && b < Bn) {
+        double t = 0.0;
+        for (int k = 0; k < 32; ++k) t += tile[k][tx];
+        if (which == 0) a.ctl[b].S = t;
+        else a.ctl[b].zp = t;
+      }
     }
   }
 }
@@ -388,6 +432,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArg
   io.avg = a.avg + (size_t)b * 2 * R;
   io.logpf = a.logpf + (size_t)b * R;
   io.uptake = a.uptake + (size_t)b * (T > 0 ? T : 1) * R;
+  io.pf_G = nullptr;
+  io.pf_mode = 0;
   tail_body<GENERAL>(pb, a.blobs, first_data, tsm, acc0, acc1, S, bc, bh, s_c.fw, s_c.fs, io, s_red, s_fin, my_c, my_a, my_b, my_lp, gbc_reg,
                      gbh_reg);
   if (tid < R) {
@@ -465,20 +511,39 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
   __shared__ int s_last;
   const int Bn = a.Bn, b = threadIdx.x % Bn, fy = threadIdx.x / Bn;
   const BCtl* c = a.ctl + b;
-  const float Sf = (float)c->S, lam = c->kl_scale;
+  // maxent_convexKL_loss = sum_f p_f (log p_f - log q_f) + sum_f (q_f - p_f),  q_f = w_f + eps,  w_f = e_f / S = exp(z_f - lse_new):
+  //   sum_f p_f log q_f = sum_f p_f z_f - lse_new * sum_f p_f + sum_f p_f log1p(eps / w_f)
+  // sum p z comes from bt_adam (fp64), sum p log p and sum p are constants of the prior (a.kl_const), and log1p(eps / w)
+  // only matters for frames whose weight has collapsed to the order of eps = 1e-10 / F: those are evaluated here,
+  // every other frame contributes less than 1e-9 * p_f and is skipped.  No logarithm per (frame, replica).
+  const float invS = (float)(1.0 / c->S);
   const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   const int snap = a.trk_on ? c->snap_now : -1, ema_update = a.trk_on ? c->ema_update : 0, ema_first = c->ema_first;
   if (!c->stop) {
-    for (long long f = (long long)blockIdx.x * a.fy + fy; f < a.F; f += (long long)gridDim.x * a.fy) {
-      float w, kap, q, r0, corr;
-      const float p = has_kl ? a.pnorm[f] : 0.f;
-      weight_terms(a.e[(size_t)f * Bn + b], Sf, p, has_kl, a.eps_kl, lam, w, kap, q, r0, corr);
+    const float* __restrict__ ep = a.e;
+    const float* __restrict__ pn = a.pnorm;
+    const long long fstep = (long long)gridDim.x * a.fy;
+    for (long long f0 = (long long)blockIdx.x * a.fy + fy; f0 < a.F; f0 += 4 * fstep) {
+      float ev[4], pv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long fk = f0 + k * fstep;
+        const long long fc = fk < a.F ? fk : f0;
+        ev[k] = ep[(size_t)fc * Bn + b];
+        pv[k] = has_kl ? pn[fc] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+      const long long f = f0 + k * fstep;
+      if (f >= a.F) break;
+      const float p = pv[k];
+      const float w = ev[k] * invS;
       if (has_kl) {
-        s0 += (double)(w * kap);
-        // log(p/q) = log(r0 + corr) = log r0 + log1p(corr / r0)
-        if (p > 0.f) s1 += (double)p * ((double)logf(r0) + (double)(corr / r0));
+        const float q = w + a.eps_kl;
         s2 += (double)(q - p);
+        const float x = a.eps_kl * rcp_approx(fmaxf(w, 1e-38f));
+        if (x > 1e-9f) s1 += (double)p * (double)((w > 0.f) ? log1pf(a.eps_kl / w) : (logf(a.eps_kl) - (a.z[(size_t)f * Bn + b] - c->lse)));
       }
       s3 += (double)w;
       if (a.trk_on) {  // tracker.ema_params (opt/track.py:160-165) and the history snapshot of the post-update weights
@@ -489,6 +554,7 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
           if (snap >= 0) a.snap_ema[(size_t)snap * a.F * Bn + i] = em;
         }
         if (snap >= 0) a.snap_w[(size_t)snap * a.F * Bn + i] = w;
+      }
       }
     }
   }
@@ -530,7 +596,9 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
     }
     if (cw->kl_slot >= 0) {
       JaxentLossRecord* rec = a.records + (size_t)(cw->step % RB) * Bn + b;
-      const float klv = (float)(kl[1] + kl[2]);
+      // kl[1] holds the rare-frame corrections sum p log1p(eps / w)
+      const double plogq = cw->zp - (double)cw->lse * a.kl_const[1] + kl[1];
+      const float klv = (float)((a.kl_const[0] - plogq) + kl[2]);
       const int i = cw->kl_slot;
       rec->train[i] = klv;
       rec->val[i] = klv;
@@ -548,13 +616,31 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
   }
 }
 
+// normalised prior and its two constants (one block, fixed order)
+__global__ void __launch_bounds__(1024) bt_prior_kernel(const BatchArgs a) {
+  __shared__ double sh[2][32];
+  const double inv_pnorm = 1.0 / a.prob.prior_norm;
+  double s_plogp = 0.0, s_p = 0.0;
+  for (long long f = threadIdx.x; f < a.F; f += blockDim.x) {
+    const float p = (float)(((double)fabsf(a.prob.prior[f]) + (double)a.eps_kl) * inv_pnorm);
+    a.pnorm[f] = p;
+    s_p += (double)p;
+    if (p > 0.f) s_plogp += (double)p * log((double)p);
+  }
+  s_plogp = wsum(s_plogp);
+  s_p = wsum(s_p);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s_plogp; sh[1][threadIdx.x >> 5] = s_p; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sh[threadIdx.x][i];
+    a.kl_const[threadIdx.x] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ init
 __global__ void bt_init_kernel(const BatchArgs a, const float* __restrict__ z0, const BCtl* __restrict__ init) {
-  if (a.prob.prior != nullptr) {
-    const double inv_pnorm = 1.0 / a.prob.prior_norm;
-    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < a.F; f += (long long)gridDim.x * blockDim.x)
-      a.pnorm[f] = (float)(((double)fabsf(a.prob.prior[f]) + (double)a.eps_kl) * inv_pnorm);
-  }
+
   const long long n = (long long)a.F * a.Bn;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   for (long long i = i0; i < n; i += stride) {
@@ -594,7 +680,7 @@ struct JaxentBatchPlan {
 
 namespace {
 struct BLayout {
-  size_t z, m, v, e, g0, g1, pnorm, H, P, cc3, e3, red, part_dot, part_s, part_kl, ctl, ctl_init, records, avg, logpf, uptake, gsel, counter;
+  size_t z, m, v, e, g0, g1, pnorm, kl_const, H, P, cc3, e3, red, part_dot, part_s, part_kl, ctl, ctl_init, records, avg, logpf, uptake, gsel, counter;
   size_t blob[JAXENT_MAX_SLOTS];
   int blob_words[JAXENT_MAX_SLOTS];
   size_t total;
@@ -616,7 +702,8 @@ BLayout b_layout(const JaxentBvProblem* pb, int Bn, int NS, int ksplit) {
   L.e3 = take(Fp * NS * Bn * 2);
   L.red = take((size_t)Bn * 2 * Rp * 8);
   L.part_dot = take((size_t)bg::MAX_EW_BLOCKS * Bn * 8);
-  L.part_s = take((size_t)bg::MAX_EW_BLOCKS * Bn * 8);
+  L.part_s = take((size_t)2 * bg::MAX_EW_BLOCKS * Bn * 8);
+  L.kl_const = take(2 * 8);
   L.part_kl = take((size_t)bg::MAX_EW_BLOCKS * KL_N * Bn * 8);
   L.ctl = take((size_t)Bn * sizeof(bg::BCtl));
   L.ctl_init = take((size_t)Bn * sizeof(bg::BCtl));
@@ -705,6 +792,7 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   a.z = (float*)(ws + L.z); a.m = (float*)(ws + L.m); a.v = (float*)(ws + L.v); a.e = (float*)(ws + L.e);
   a.g[0] = (float*)(ws + L.g0); a.g[1] = (float*)(ws + L.g1);
   a.pnorm = (float*)(ws + L.pnorm);
+  a.kl_const = (double*)(ws + L.kl_const);
   a.H = (float*)(ws + L.H);
   a.P = (float*)(ws + L.P);
   a.cc3 = ws + L.cc3;
@@ -812,7 +900,7 @@ static int bg_update_phase(JaxentBatchPlan* p, cudaStream_t s) {
   if ((rc = bg_err("bt_grad"))) return rc;
   bg::bt_decide_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a);
   if ((rc = bg_err("bt_decide"))) return rc;
-  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a, 1);
+  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 1);
   return bg_err("bt_adam");
 }
 
@@ -855,8 +943,12 @@ extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float z
   bg::bt_init_kernel<<<592, 256, 0, s>>>(a, z0, dinit);
   int rc = bg_err("bt_init");
   if (rc) return rc;
+  if (a.prob.prior != nullptr) {
+    bg::bt_prior_kernel<<<1, 1024, 0, s>>>(a);
+    if ((rc = bg_err("bt_prior"))) return rc;
+  }
   if ((rc = launch_build_blobs(a.prob, a.blobs, s))) return rc;
-  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a, 0);
+  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 0);
   if ((rc = bg_err("bt_adam(init)"))) return rc;
   rc = bg_forward(p, s);
   if (rc) return rc;
