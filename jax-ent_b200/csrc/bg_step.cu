@@ -578,6 +578,13 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x == 0) *a.counter = 0u;
+  // fold of the per-block sums: block index strided over the fy lanes of a replica, then over fy (fixed order)
+  for (int k = 0; k < KL_N; ++k) {
+    double t = 0.0;
+    for (unsigned blk = fy; blk < gridDim.x; blk += a.fy) t += __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]);
+    sh_d[((size_t)fy * KL_N + k) * Bn + b] = t;
+  }
+  __syncthreads();
   if (fy == 0) {
     BCtl* cw = a.ctl + b;
     if (cw->stop) return;
@@ -590,7 +597,7 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
     double kl[KL_N];
     for (int k = 0; k < KL_N; ++k) {
       double t = 0.0;
-      for (unsigned blk = 0; blk < gridDim.x; ++blk) t += __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]);
+      for (int y = 0; y < a.fy; ++y) t += sh_d[((size_t)y * KL_N + k) * Bn + b];
       kl[k] = t;
       cw->klsum[k] = t;
     }
