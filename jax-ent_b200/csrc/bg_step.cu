@@ -581,7 +581,17 @@ __global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
   // fold of the per-block sums: block index strided over the fy lanes of a replica, then over fy (fixed order)
   for (int k = 0; k < KL_N; ++k) {
     double t = 0.0;
-    for (unsigned blk = fy; blk < gridDim.x; blk += a.fy) t += __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]);
+    // independent loads, 8 in flight (a dependent chain of L2 round trips would dominate this kernel)
+    for (unsigned blk0 = fy; blk0 < gridDim.x; blk0 += 8 * a.fy) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned blk = blk0 + u * a.fy;
+        v[u] = blk < gridDim.x ? __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
     sh_d[((size_t)fy * KL_N + k) * Bn + b] = t;
   }
   __syncthreads();
