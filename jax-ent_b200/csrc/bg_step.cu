@@ -125,53 +125,82 @@ __device__ __forceinline__ void weight_terms(float e, float invS, float p, bool 
 }
 
 // ------------------------------------------------------------------------------------------ bt_grad
-// thread = (replica b = tid % Bn, frame lane fy = tid / Bn); frames strided over the grid
-__global__ void __launch_bounds__(1024) bt_grad_kernel(const BatchArgs a) {
+// thread = (4 consecutive replicas bq = tid % (Bn/4), frame lane fy = tid / (Bn/4)): 16-byte loads / stores, per-replica
+// constants in registers; frames strided over the grid, two frames (6 vector loads) in flight per thread
+__global__ void __launch_bounds__(512) bt_grad_kernel(const BatchArgs a) {
   extern __shared__ double sh_d[];  // [fy][Bn]
-  const int Bn = a.Bn, b = threadIdx.x % Bn, fy = threadIdx.x / Bn;
-  const BCtl* c = a.ctl + b;
+  const int Bn = a.Bn, Bq = Bn >> 2, bq = threadIdx.x % Bq, fy = threadIdx.x / Bq, b0 = 4 * bq;
   const unsigned sel = *a.gsel;
-  const float* __restrict__ gprev = a.g[sel];
-  float* __restrict__ gout = a.g[sel ^ 1u];
-  const float invS = (float)(1.0 / c->S), lam = c->kl_scale, maskf = c->mask_frame;
-  const float hbar = (float)c->hbar_data;  // the MaxEnt part of hbar is O(1e-10 lambda): see bv_pass.cu, finish_previous_record
-  const int have_prev = c->have_prev;
-  const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
-  const bool active = !c->stop;
-  double dot = 0.0;
-  const float* __restrict__ ep = a.e;
-  const float* __restrict__ Hp = a.H;
+  const float4* __restrict__ gprev = reinterpret_cast<const float4*>(a.g[sel]);
+  float4* __restrict__ gout = reinterpret_cast<float4*>(a.g[sel ^ 1u]);
+  const float4* __restrict__ ep = reinterpret_cast<const float4*>(a.e);
+  const float4* __restrict__ Hp = reinterpret_cast<const float4*>(a.H);
   const float* __restrict__ pn = a.pnorm;
-  // 4 frames per iteration with all loads issued first: one 4-byte load per thread in flight cannot cover the HBM latency
-  const long long fstep = (long long)gridDim.x * a.fy;
-  for (long long f0 = (long long)blockIdx.x * a.fy + fy; f0 < a.F; f0 += 4 * fstep) {
-    float ev[4], hv[4], gv[4], pv[4];
+  // per-replica constants: one thread per replica reads its control block, everybody else takes them from shared memory
+  // (a strided control-block read per thread costs more than the whole frame loop)
+  __shared__ float s_f[4][256];
+  __shared__ int s_i[256];
+  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {
+    const BCtl* c = a.ctl + b;
+    s_f[0][b] = (float)(1.0 / c->S);
+    s_f[1][b] = c->kl_scale;
+    s_f[2][b] = c->mask_frame;
+    s_f[3][b] = (float)c->hbar_data;  // the MaxEnt part of hbar is O(1e-10 lambda): see bv_pass.cu, finish_previous_record
+    s_i[b] = (c->have_prev ? 1 : 0) | ((c->kl_slot >= 0 && a.prob.prior != nullptr) ? 2 : 0) | (c->stop ? 0 : 4);
+  }
+  __syncthreads();
+  float invS[4], lam[4], maskf[4], hbar[4];
+  int have_prev[4];
+  bool has_kl[4], active[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+  for (int j = 0; j < 4; ++j) {
+    invS[j] = s_f[0][b0 + j];
+    lam[j] = s_f[1][b0 + j];
+    maskf[j] = s_f[2][b0 + j];
+    hbar[j] = s_f[3][b0 + j];
+    const int fl = s_i[b0 + j];
+    have_prev[j] = fl & 1;
+    has_kl[j] = fl & 2;
+    active[j] = fl & 4;
+  }
+  double dot[4] = {0.0, 0.0, 0.0, 0.0};
+  const long long fstep = (long long)gridDim.x * a.fy;
+  for (long long f0 = (long long)blockIdx.x * a.fy + fy; f0 < a.F; f0 += 2 * fstep) {
+    float4 ev[2], hv[2], gv[2];
+    float pv[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
       const long long f = f0 + k * fstep;
-      const bool in = f < a.F;
-      const size_t i = (size_t)(in ? f : f0) * Bn + b;
-      ev[k] = ep[i];
-      hv[k] = Hp[i];
-      gv[k] = gprev[i];
-      pv[k] = has_kl ? pn[in ? f : f0] : 0.f;
+      const long long fc = f < a.F ? f : f0;
+      ev[k] = ep[(size_t)fc * Bq + bq];
+      hv[k] = Hp[(size_t)fc * Bq + bq];
+      gv[k] = gprev[(size_t)fc * Bq + bq];
+      pv[k] = pn ? pn[fc] : 0.f;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 2; ++k) {
       const long long f = f0 + k * fstep;
       if (f < a.F) {
-        float w, kap, q;
-        weight_terms(ev[k], invS, pv[k], has_kl, a.eps_kl, lam, w, kap, q);
-        const float gf = active ? maskf * (w * ((hv[k] + kap) - hbar)) : 0.f;
-        const float gpv = have_prev ? gv[k] : gf;
-        dot += (double)(gpv * gf);
-        gout[(size_t)f * Bn + b] = gf;
+        const float e4[4] = {ev[k].x, ev[k].y, ev[k].z, ev[k].w}, h4[4] = {hv[k].x, hv[k].y, hv[k].z, hv[k].w};
+        const float g4[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float w, kap, q;
+          weight_terms(e4[j], invS[j], pv[k], has_kl[j], a.eps_kl, lam[j], w, kap, q);
+          const float gf = active[j] ? maskf[j] * (w * ((h4[j] + kap) - hbar[j])) : 0.f;
+          const float gpv = have_prev[j] ? g4[j] : gf;
+          dot[j] += (double)(gpv * gf);
+          o[j] = gf;
+        }
+        gout[(size_t)f * Bq + bq] = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
   }
-  sh_d[fy * Bn + b] = dot;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sh_d[fy * Bn + b0 + j] = dot[j];
   __syncthreads();
-  if (fy == 0) {
+  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {
     double t = 0.0;
     for (int k = 0; k < a.fy; ++k) t += sh_d[k * Bn + b];
     a.part_dot[(size_t)blockIdx.x * Bn + b] = t;
@@ -294,60 +323,103 @@ __global__ void bt_decide_kernel(const BatchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ bt_adam
-// thread = (replica b, chunk lane cy); a chunk is 8 consecutive frames: z, m, v updated in place, e' written, and the
-// bf16 pieces of e' stored as 16-byte K-chunks of the gemm2 B operand.  update = 0: initial forward (no Adam).
-__global__ void __launch_bounds__(1024) bt_adam_kernel(const BatchArgs a, int update) {
-  extern __shared__ double sh_d[];  // [cy][Bn]
-  const int Bn = a.Bn, b = threadIdx.x % Bn, cy = threadIdx.x / Bn, ncy = blockDim.x / Bn;
-  const BCtl* c = a.ctl + b;
-  const float* __restrict__ g = a.g[*a.gsel];
-  const float lr = c->lr_eff, lse = c->lse;
-  const float ibc1 = 1.0f / c->bc1, ibc2 = 1.0f / c->bc2;  // bias corrections applied as reciprocal multiplies
-  const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
-  const bool active = update && !c->stop;
+// thread = (4 consecutive replicas, chunk lane cy); a chunk is 8 consecutive frames: z, m, v updated in place, e' written
+// (16-byte loads / stores), and the bf16 pieces of e' stored as 16-byte K-chunks of the gemm2 B operand.
+// update = 0: initial forward (no Adam).
+__global__ void __launch_bounds__(512) bt_adam_kernel(const BatchArgs a, int update) {
+  extern __shared__ double sh_d[];  // [2][cy][Bn]
+  const int Bn = a.Bn, Bq = Bn >> 2, bq = threadIdx.x % Bq, cy = threadIdx.x / Bq, ncy = blockDim.x / Bq, b0 = 4 * bq;
+  const float4* __restrict__ g4p = reinterpret_cast<const float4*>(a.g[*a.gsel]);
+  float4* __restrict__ z4p = reinterpret_cast<float4*>(a.z);
+  float4* __restrict__ m4p = reinterpret_cast<float4*>(a.m);
+  float4* __restrict__ v4p = reinterpret_cast<float4*>(a.v);
+  float4* __restrict__ e4p = reinterpret_cast<float4*>(a.e);
+  __shared__ float s_f[4][256];
+  __shared__ int s_i[256];
+  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {  // per-replica constants through shared memory (see bt_grad)
+    const BCtl* c = a.ctl + b;
+    s_f[0][b] = c->lr_eff;
+    s_f[1][b] = c->lse;
+    s_f[2][b] = 1.0f / c->bc1;  // bias corrections applied as reciprocal multiplies
+    s_f[3][b] = 1.0f / c->bc2;
+    s_i[b] = ((update && !c->stop) ? 1 : 0) | ((c->kl_slot >= 0 && a.prob.prior != nullptr) ? 2 : 0);
+  }
+  __syncthreads();
+  float lr[4], lse[4], ibc1[4], ibc2[4];
+  bool active[4], has_kl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lr[j] = s_f[0][b0 + j];
+    lse[j] = s_f[1][b0 + j];
+    ibc1[j] = s_f[2][b0 + j];
+    ibc2[j] = s_f[3][b0 + j];
+    active[j] = s_i[b0 + j] & 1;
+    has_kl[j] = s_i[b0 + j] & 2;
+  }
   const float b1 = (float)a.cfg.b1, b2 = (float)a.cfg.b2, eps = (float)a.cfg.eps, clip = a.cfg.clip_value;
   const float om_b1 = (float)(1.0 - a.cfg.b1), om_b2 = (float)(1.0 - a.cfg.b2);
   const int NS = a.NS;
   const long long n_chunks = (long long)a.n_fb * 16;
-  double sum = 0.0, zp = 0.0;  // sum_f e'_f and sum_f p_f z'_f (the MaxEnt loss needs sum_f p_f log q_f = sum_f p_f z_f - lse + ...)
+  double sum[4] = {0.0, 0.0, 0.0, 0.0}, zp[4] = {0.0, 0.0, 0.0, 0.0};  // sum_f e'_f and sum_f p_f z'_f (MaxEnt loss)
   for (long long ch = (long long)blockIdx.x * ncy + cy; ch < n_chunks; ch += (long long)gridDim.x * ncy) {
-    __nv_bfloat16 p0[8], p1[8], p2[8];
+    __nv_bfloat16 p0[4][8], p1[4][8], p2[4][8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const long long f = ch * 8 + k;
-      float en = 0.f;
+      float en[4] = {0.f, 0.f, 0.f, 0.f};
       if (f < a.F) {
-        const size_t i = (size_t)f * Bn + b;
-        float z_ = a.z[i];
-        if (active) {
-          const float m_ = a.m[i], v_ = a.v[i];
-          float s = g[i] * lr;
-          if (clip > 0.f) s = fminf(fmaxf(s, -clip), clip);
-          const float m1 = om_b1 * s + b1 * m_;
-          const float v1 = om_b2 * (s * s) + b2 * v_;
-          z_ = z_ - (m1 * ibc1) / (sqrtf(v1 * ibc2) + eps);
-          a.z[i] = z_;
-          a.m[i] = m1;
-          a.v[i] = v1;
+        const size_t i = (size_t)f * Bq + bq;
+        const float4 zv = z4p[i];
+        float z_[4] = {zv.x, zv.y, zv.z, zv.w};
+        if (update) {
+          const float4 gv = g4p[i], mv = m4p[i], vv = v4p[i];
+          const float g_[4] = {gv.x, gv.y, gv.z, gv.w}, m_[4] = {mv.x, mv.y, mv.z, mv.w}, v_[4] = {vv.x, vv.y, vv.z, vv.w};
+          float mo[4], vo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mo[j] = m_[j];
+            vo[j] = v_[j];
+            if (active[j]) {
+              float sg = g_[j] * lr[j];
+              if (clip > 0.f) sg = fminf(fmaxf(sg, -clip), clip);
+              mo[j] = om_b1 * sg + b1 * m_[j];
+              vo[j] = om_b2 * (sg * sg) + b2 * v_[j];
+              z_[j] = z_[j] - (mo[j] * ibc1[j]) / (sqrtf(vo[j] * ibc2[j]) + eps);
+            }
+          }
+          z4p[i] = make_float4(z_[0], z_[1], z_[2], z_[3]);
+          m4p[i] = make_float4(mo[0], mo[1], mo[2], mo[3]);
+          v4p[i] = make_float4(vo[0], vo[1], vo[2], vo[3]);
         }
-        en = __expf(z_ - lse);
-        a.e[i] = en;
-        sum += (double)en;
-        if (has_kl) zp += (double)a.pnorm[f] * (double)z_;
+        const float pf = a.prob.prior != nullptr ? a.pnorm[f] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          en[j] = __expf(z_[j] - lse[j]);
+          sum[j] += (double)en[j];
+          if (has_kl[j]) zp[j] += (double)pf * (double)z_[j];
+        }
+        e4p[i] = make_float4(en[0], en[1], en[2], en[3]);
       }
-      split3(en, NS, p0[k], p1[k], p2[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split3(en[j], NS, p0[j][k], p1[j][k], p2[j][k]);
     }
     const long long fb = ch >> 4;
     const int kc = (int)(ch & 15);
     uint4* dst = reinterpret_cast<uint4*>(a.e3);
-    dst[(((size_t)fb * NS + 0) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p0);
-    if (NS > 1) dst[(((size_t)fb * NS + 1) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p1);
-    if (NS > 2) dst[(((size_t)fb * NS + 2) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dst[(((size_t)fb * NS + 0) * 16 + kc) * Bn + b0 + j] = *reinterpret_cast<const uint4*>(p0[j]);
+      if (NS > 1) dst[(((size_t)fb * NS + 1) * 16 + kc) * Bn + b0 + j] = *reinterpret_cast<const uint4*>(p1[j]);
+      if (NS > 2) dst[(((size_t)fb * NS + 2) * 16 + kc) * Bn + b0 + j] = *reinterpret_cast<const uint4*>(p2[j]);
+    }
   }
-  sh_d[cy * Bn + b] = sum;
-  sh_d[(ncy + cy) * Bn + b] = zp;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh_d[cy * Bn + b0 + j] = sum[j];
+    sh_d[(ncy + cy) * Bn + b0 + j] = zp[j];
+  }
   __syncthreads();
-  if (cy == 0) {
+  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {
     double t = 0.0, tz = 0.0;
     for (int k = 0; k < ncy; ++k) {
       t += sh_d[k * Bn + b];
@@ -506,111 +578,124 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArg
 // ------------------------------------------------------------------------------------------ bt_kl
 // MaxEnt terms per (frame, replica); the last block folds the per-block sums (fixed order) into the control blocks
 // and completes the loss records of this step
-__global__ void __launch_bounds__(1024) bt_kl_kernel(const BatchArgs a) {
+__global__ void __launch_bounds__(512) bt_kl_kernel(const BatchArgs a) {
   extern __shared__ double sh_d[];  // [fy][KL_N][Bn]
-  __shared__ int s_last;
-  const int Bn = a.Bn, b = threadIdx.x % Bn, fy = threadIdx.x / Bn;
-  const BCtl* c = a.ctl + b;
+  const int Bn = a.Bn, Bq = Bn >> 2, bq = threadIdx.x % Bq, fy = threadIdx.x / Bq, b0 = 4 * bq;
   // maxent_convexKL_loss = sum_f p_f (log p_f - log q_f) + sum_f (q_f - p_f),  q_f = w_f + eps,  w_f = e_f / S = exp(z_f - lse_new):
   //   sum_f p_f log q_f = sum_f p_f z_f - lse_new * sum_f p_f + sum_f p_f log1p(eps / w_f)
   // sum p z comes from bt_adam (fp64), sum p log p and sum p are constants of the prior (a.kl_const), and log1p(eps / w)
   // only matters for frames whose weight has collapsed to the order of eps = 1e-10 / F: those are evaluated here,
   // every other frame contributes less than 1e-9 * p_f and is skipped.  No logarithm per (frame, replica).
-  const float invS = (float)(1.0 / c->S);
-  const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  const int snap = a.trk_on ? c->snap_now : -1, ema_update = a.trk_on ? c->ema_update : 0, ema_first = c->ema_first;
-  if (!c->stop) {
-    const float* __restrict__ ep = a.e;
-    const float* __restrict__ pn = a.pnorm;
-    const long long fstep = (long long)gridDim.x * a.fy;
-    for (long long f0 = (long long)blockIdx.x * a.fy + fy; f0 < a.F; f0 += 4 * fstep) {
-      float ev[4], pv[4];
+  // thread = (4 consecutive replicas, frame lane): 16-byte loads, 4 frames in flight.
+  __shared__ float s_f[2][256];
+  __shared__ int s_i[2][256];
+  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {  // per-replica constants through shared memory (see bt_grad)
+    const BCtl* c = a.ctl + b;
+    s_f[0][b] = (float)(1.0 / c->S);
+    s_f[1][b] = c->lse;
+    s_i[0][b] = ((c->kl_slot >= 0 && a.prob.prior != nullptr) ? 1 : 0) | (c->stop ? 0 : 2) | ((a.trk_on && c->ema_update) ? 4 : 0) | (c->ema_first ? 8 : 0);
+    s_i[1][b] = a.trk_on ? c->snap_now : -1;
+  }
+  __syncthreads();
+  float invS[4], lse[4];
+  bool has_kl[4], run[4];
+  int snap[4], ema_update[4], ema_first[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long long fk = f0 + k * fstep;
-        const long long fc = fk < a.F ? fk : f0;
-        ev[k] = ep[(size_t)fc * Bn + b];
-        pv[k] = has_kl ? pn[fc] : 0.f;
-      }
+  for (int j = 0; j < 4; ++j) {
+    invS[j] = s_f[0][b0 + j];
+    lse[j] = s_f[1][b0 + j];
+    const int fl = s_i[0][b0 + j];
+    has_kl[j] = fl & 1;
+    run[j] = fl & 2;
+    ema_update[j] = (fl & 4) ? 1 : 0;
+    ema_first[j] = (fl & 8) ? 1 : 0;
+    snap[j] = s_i[1][b0 + j];
+  }
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0}, s3[4] = {0.0, 0.0, 0.0, 0.0};
+  const float4* __restrict__ ep = reinterpret_cast<const float4*>(a.e);
+  const float* __restrict__ pn = a.pnorm;
+  const long long fstep = (long long)gridDim.x * a.fy;
+  for (long long f0 = (long long)blockIdx.x * a.fy + fy; f0 < a.F; f0 += 4 * fstep) {
+    float4 ev[4];
+    float pv[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k) {
+      const long long fk = f0 + k * fstep;
+      const long long fc = fk < a.F ? fk : f0;
+      ev[k] = ep[(size_t)fc * Bq + bq];
+      pv[k] = a.prob.prior != nullptr ? pn[fc] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
       const long long f = f0 + k * fstep;
       if (f >= a.F) break;
-      const float p = pv[k];
-      const float w = ev[k] * invS;
-      if (has_kl) {
-        const float q = w + a.eps_kl;
-        s2 += (double)(q - p);
-        const float x = a.eps_kl * rcp_approx(fmaxf(w, 1e-38f));
-        if (x > 1e-9f) s1 += (double)p * (double)((w > 0.f) ? log1pf(a.eps_kl / w) : (logf(a.eps_kl) - (a.z[(size_t)f * Bn + b] - c->lse)));
-      }
-      s3 += (double)w;
-      if (a.trk_on) {  // tracker.ema_params (opt/track.py:160-165) and the history snapshot of the post-update weights
-        const size_t i = (size_t)f * Bn + b;
-        if (ema_update) {
-          const float em = ema_first ? w : a.trk_alpha * w + (1.0f - a.trk_alpha) * a.ema_w[i];
-          a.ema_w[i] = em;
-          if (snap >= 0) a.snap_ema[(size_t)snap * a.F * Bn + i] = em;
+      const float e4[4] = {ev[k].x, ev[k].y, ev[k].z, ev[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!run[j]) continue;
+        const float p = pv[k];
+        const float w = e4[j] * invS[j];
+        if (has_kl[j]) {
+          const float q = w + a.eps_kl;
+          s2[j] += (double)(q - p);
+          const float x = a.eps_kl * rcp_approx(fmaxf(w, 1e-38f));
+          if (x > 1e-9f)
+            s1[j] += (double)p * (double)((w > 0.f) ? log1pf(a.eps_kl / w) : (logf(a.eps_kl) - (a.z[(size_t)f * Bn + b0 + j] - lse[j])));
         }
-        if (snap >= 0) a.snap_w[(size_t)snap * a.F * Bn + i] = w;
-      }
+        s3[j] += (double)w;
+        if (a.trk_on) {  // tracker.ema_params (opt/track.py:160-165) and the history snapshot of the post-update weights
+          const size_t i = (size_t)f * Bn + b0 + j;
+          if (ema_update[j]) {
+            const float em = ema_first[j] ? w : a.trk_alpha * w + (1.0f - a.trk_alpha) * a.ema_w[i];
+            a.ema_w[i] = em;
+            if (snap[j] >= 0) a.snap_ema[(size_t)snap[j] * a.F * Bn + i] = em;
+          }
+          if (snap[j] >= 0) a.snap_w[(size_t)snap[j] * a.F * Bn + i] = w;
+        }
       }
     }
   }
-  double* mine = sh_d + ((size_t)fy * KL_N) * Bn + b;
-  mine[0 * Bn] = s0;
-  mine[1 * Bn] = s1;
-  mine[2 * Bn] = s2;
-  mine[3 * Bn] = s3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double* mine = sh_d + ((size_t)fy * KL_N) * Bn + b0 + j;
+    mine[0 * Bn] = 0.0;
+    mine[1 * Bn] = s1[j];
+    mine[2 * Bn] = s2[j];
+    mine[3 * Bn] = s3[j];
+  }
   __syncthreads();
-  if (fy == 0) {
+  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {
     for (int k = 0; k < KL_N; ++k) {
       double t = 0.0;
       for (int y = 0; y < a.fy; ++y) t += sh_d[((size_t)y * KL_N + k) * Bn + b];
       a.part_kl[((size_t)blockIdx.x * KL_N + k) * Bn + b] = t;
     }
-    __threadfence();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x == 0) *a.counter = 0u;
-  // fold of the per-block sums: block index strided over the fy lanes of a replica, then over fy (fixed order)
-  for (int k = 0; k < KL_N; ++k) {
-    double t = 0.0;
-    // independent loads, 8 in flight (a dependent chain of L2 round trips would dominate this kernel)
-    for (unsigned blk0 = fy; blk0 < gridDim.x; blk0 += 8 * a.fy) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const unsigned blk = blk0 + u * a.fy;
-        v[u] = blk < gridDim.x ? __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) t += v[u];
-    }
-    sh_d[((size_t)fy * KL_N + k) * Bn + b] = t;
-  }
-  __syncthreads();
-  if (fy == 0) {
+}
+
+// fold of the per-block MaxEnt sums, one warp per replica (block index lane-strided, then a shuffle reduction: fixed order),
+// and completion of this step's loss record
+__global__ void __launch_bounds__(256) bt_klfold_kernel(const BatchArgs a, int n_blocks) {
+  const int Bn = a.Bn;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= Bn) return;
+  {
     BCtl* cw = a.ctl + b;
     if (cw->stop) return;
+    double kl[KL_N];
+    for (int k = 0; k < KL_N; ++k) {
+      double t = 0.0;
+      for (int blk = lane; blk < n_blocks; blk += 32) t += __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]);
+      kl[k] = wsum(t);
+    }
+    if (lane != 0) return;
     if (cw->stopping) {  // this was the last evaluation of the replica: freeze it
       cw->stop = 1;
       cw->stopping = 0;
     }
     cw->snap_now = -1;
     cw->ema_update = 0;
-    double kl[KL_N];
-    for (int k = 0; k < KL_N; ++k) {
-      double t = 0.0;
-      for (int y = 0; y < a.fy; ++y) t += sh_d[((size_t)y * KL_N + k) * Bn + b];
-      kl[k] = t;
-      cw->klsum[k] = t;
-    }
+    for (int k = 0; k < KL_N; ++k) cw->klsum[k] = kl[k];
     if (cw->kl_slot >= 0) {
       JaxentLossRecord* rec = a.records + (size_t)(cw->step % RB) * Bn + b;
       // kl[1] holds the rare-frame corrections sum p log1p(eps / w)
@@ -841,7 +926,7 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   a.p_max_va = p_va;
   a.eps_kl = (float)(1e-10 / (double)pb->F_total);
   // elementwise geometry: blocks of Bn x fy threads
-  a.fy = 1024 / n_replicas;
+  a.fy = 512 / (n_replicas / 4);  // elementwise kernels: Bn/4 threads (4 replicas each) per frame, fy frames per 512-thread block
   long long blocks = ((long long)pb->F + a.fy - 1) / a.fy;
   const long long want = (long long)sm_count * 2;
   if (blocks > want) blocks = want;
@@ -895,8 +980,18 @@ static int bg_tail_phase(JaxentBatchPlan* p, cudaStream_t s) {
   if (p->general) bg::bt_tail_kernel<true><<<a.Bn, TAIL_THREADS, p->tail_smem, s>>>(a);
   else bg::bt_tail_kernel<false><<<a.Bn, TAIL_THREADS, p->tail_smem, s>>>(a);
   if ((rc = bg_err("bt_tail"))) return rc;
-  bg::bt_kl_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * KL_N * a.Bn * 8, s>>>(a);
-  return bg_err("bt_kl");
+  {
+    static bool kl_configured = false;
+    if (!kl_configured) {
+      cudaError_t e = cudaFuncSetAttribute(bg::bt_kl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) { set_error("bt_kl: shared memory: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+      kl_configured = true;
+    }
+  }
+  bg::bt_kl_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)a.fy * KL_N * a.Bn * 8, s>>>(a);
+  if ((rc = bg_err("bt_kl"))) return rc;
+  bg::bt_klfold_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a, a.ew_blocks);
+  return bg_err("bt_klfold");
 }
 
 static int bg_forward(JaxentBatchPlan* p, cudaStream_t s) {
@@ -913,11 +1008,11 @@ static int bg_gemm1_phase(JaxentBatchPlan* p, cudaStream_t s) {
 static int bg_update_phase(JaxentBatchPlan* p, cudaStream_t s) {
   const bg::BatchArgs& a = p->a;
   int rc;
-  bg::bt_grad_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a);
+  bg::bt_grad_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a);
   if ((rc = bg_err("bt_grad"))) return rc;
   bg::bt_decide_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a);
   if ((rc = bg_err("bt_decide"))) return rc;
-  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 1);
+  bg::bt_adam_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 1);
   return bg_err("bt_adam");
 }
 
@@ -965,7 +1060,7 @@ extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float z
     if ((rc = bg_err("bt_prior"))) return rc;
   }
   if ((rc = launch_build_blobs(a.prob, a.blobs, s))) return rc;
-  bg::bt_adam_kernel<<<a.ew_blocks, a.Bn * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 0);
+  bg::bt_adam_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 0);
   if ((rc = bg_err("bt_adam(init)"))) return rc;
   rc = bg_forward(p, s);
   if (rc) return rc;
