@@ -268,6 +268,12 @@ int jaxent_bv_track_status(JaxentPlan* plan, JaxentTrackStatus* status, jaxent_s
 int jaxent_bv_export_state(JaxentPlan* plan, float* z, float* m, float* v, float* g, float* scalars,
                            jaxent_stream_t stream);
 
+/* ---- per-frame forward pass (Simulation.predict, models/core.py:181-208): the forward pass on the un-averaged features.
+ * packed: fp32 tile layout (jaxent_bv_pack_features_f32).  T = 0: out = log_Pf float[R][F] (BV_ForwardPass);
+ * T > 0: out = uptake float[T][R][F] (BV_uptake_ForwardPass).  Row-major, frame axis last, as in the reference. */
+int jaxent_bv_predict_frames(const float* packed, int32_t R, int64_t F, int32_t T, const float* k_ints, const float* timepoints,
+                             float bc, float bh, float* out, jaxent_stream_t stream);
+
 /* ---- batched (replicate / hyper-parameter sweep) mode: tensor-core building blocks (csrc/bg_gemm.cu) ----
  * With B replicas sharing the features (reference opt/batch.py:51-192 vmaps _optimise_pure over the hyper-parameter
  * batch) the two sweeps of a step are dense GEMMs on the tcgen05 tensor cores:

@@ -634,6 +634,44 @@ extern "C" int jaxent_bv_exchange_error(JaxentPlan* p, uint64_t* out, jaxent_str
   return JAXENT_OK;
 }
 
+// ---- per-frame forward pass (Simulation.predict, reference models/core.py:181-208): no frame average
+namespace jx {
+// one thread per (quad of 4 frames, residue): reads the packed tile layout, writes row-major (R, F) / (T, R, F)
+__global__ void predict_frames_kernel(const float* __restrict__ packed, int R, long long F, int T, const float* __restrict__ k_ints,
+                                      const float* __restrict__ tp, float bc, float bh, float* __restrict__ out) {
+  const long long n_quads = (F + 3) / 4;
+  const long long n = n_quads * R;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < n; it += (long long)gridDim.x * blockDim.x) {
+    const long long q = it / R;
+    const int r = (int)(it - q * R);
+    const float4 c = reinterpret_cast<const float4*>(packed)[(q * 2 + 0) * R + r];
+    const float4 h = reinterpret_cast<const float4*>(packed)[(q * 2 + 1) * R + r];
+    const float nc[4] = {c.x, c.y, c.z, c.w}, nh[4] = {h.x, h.y, h.z, h.w};
+    for (int j = 0; j < 4; ++j) {
+      const long long f = 4 * q + j;
+      if (f >= F) break;
+      const float lp = bc * nc[j] + bh * nh[j];  // BV_ForwardPass, models/HDX/forward.py:30-35
+      if (T == 0) {
+        out[(long long)r * F + f] = lp;
+      } else {
+        const float pf = expf(lp);  // BV_uptake_ForwardPass, models/HDX/forward.py:57-74
+        for (int t = 0; t < T; ++t) out[((long long)t * R + r) * F + f] = 1.0f - expf(-k_ints[r] * tp[t] / pf);
+      }
+    }
+  }
+}
+}  // namespace jx
+
+extern "C" int jaxent_bv_predict_frames(const float* packed, int32_t R, int64_t F, int32_t T, const float* k_ints, const float* timepoints,
+                                        float bc, float bh, float* out, jaxent_stream_t stream) {
+  if (!packed || !out || R <= 0 || F <= 0 || T < 0 || (T > 0 && (!k_ints || !timepoints))) { set_error("predict_frames: invalid argument"); return JAXENT_E_INVALID; }
+  if (reinterpret_cast<uintptr_t>(packed) & 15u) { set_error("predict_frames: packed features must be 16-byte aligned"); return JAXENT_E_INVALID; }
+  predict_frames_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(packed, R, F, T, k_ints, timepoints, bc, bh, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("predict_frames launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
+}
+
 extern "C" int jaxent_bv_track_init(JaxentPlan* p, const float* thresholds, int32_t n, float ema_alpha, int32_t min_steps,
                                     float tolerance, float* ema_w, float* snap_w, float* snap_ema, JaxentTrackSnapshot* snaps) {
   if (!p) { set_error("track_init: plan is NULL"); return JAXENT_E_INVALID; }

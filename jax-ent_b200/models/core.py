@@ -121,7 +121,28 @@ class Simulation:
         return new_sim, outputs
 
     def predict(self, params):
-        raise NotImplementedError("per-frame prediction (Simulation.predict) is not on the fused path (SURVEY.md 8f.2)")
+        """Forward passes on the un-averaged (frame-wise) features: every output keeps the frame axis last
+        (reference models/core.py:181-208).  log_Pf (R, F) or uptake (T, R, F)."""
+        if self._fwd_engine is None:
+            raise RuntimeError("Simulation must be initialized before calling predict")
+        model_parameters = params.model_parameters if isinstance(params, Simulation_Parameters) else params
+        if len(model_parameters) != len(self.forwardpass):
+            raise ValueError(f"Number of model parameters ({len(model_parameters)}) must match number of forward models ({len(self.forwardpass)})")
+        feats = self._features
+        if getattr(feats, "format", 0) != 0:
+            raise NotImplementedError("Simulation.predict reads the fp32 feature layout")
+        mp = model_parameters[0]
+        eng = self._fwd_engine
+        R, F, T = eng.R, eng.F, (eng.T if self._uptake else 0)
+        with torch.cuda.device(self.device):
+            out = torch.empty((T, R, F) if T else (R, F), dtype=torch.float32, device=self.device)
+            L.check(eng.lib.jaxent_bv_predict_frames(feats.packed.data_ptr(), R, F, T,
+                                                     eng.k_ints.data_ptr() if T else None, eng.timepoints.data_ptr() if T else None,
+                                                     scalar(mp.bv_bc), scalar(mp.bv_bh), out.data_ptr(),
+                                                     int(torch.cuda.current_stream().cuda_stream)))
+        if T:
+            return [uptake_BV_output_features(uptake=out)]
+        return [BV_output_features(log_Pf=out, k_ints=None)]
 
     @property
     def outputs_by_key(self) -> dict:

@@ -196,3 +196,63 @@ def test_batch_optimise_equals_sequential_runs(engine):
         J.batch_optimise(sim, J.HParamBatch(fw, fs), 0, data, settings, [0, 0, 0], list(losses))
     with pytest.raises(ValueError, match="same n_hparams"):
         J.batch_optimise(sim, J.HParamBatch(fw, fs[:2]), 2, data, settings, [0, 0, 0], list(losses))
+
+
+@pytest.mark.parametrize("kind", [O.UPTAKE_EYE_MSE, O.PF_L2])
+def test_simulation_predict_keeps_the_frame_axis(kind):
+    """Simulation.predict (reference models/core.py:181-208): forward pass on the un-averaged features."""
+    case, sim, *_ = _setup(F=333, R=41, T=4 if kind != O.PF_L2 else 1, kind=kind)
+    with pytest.raises(RuntimeError, match="initiali"):
+        sim.predict(sim.params)
+    sim.initialise()
+    pb = case["problem"]
+    out = sim.predict(sim.params)[0]
+    lp = O.bv_log_pf(pb.heavy, pb.acceptor, 0.35, 2.0, np.float64)
+    if kind == O.PF_L2:
+        assert tuple(out.log_Pf.shape) == (41, 333)
+        np.testing.assert_allclose(out.log_Pf.cpu().numpy(), lp, rtol=1e-6)
+    else:
+        assert tuple(out.uptake.shape) == (4, 41, 333)  # reference unit/models/test_bv_forward_pass.py:179-196 shape (T,R,F)
+        np.testing.assert_allclose(out.uptake.cpu().numpy(), O.bv_uptake(lp, pb.k_ints, pb.timepoints, np.float64), rtol=2e-5, atol=1e-7)
+    out2 = sim.predict(sim.params.model_parameters)[0]  # a bare list of model parameters is accepted as well
+    a, b = (out.log_Pf, out2.log_Pf) if kind == O.PF_L2 else (out.uptake, out2.uptake)
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError, match="must match"):
+        sim.predict([])
+
+
+def test_per_frame_forward_pass_through_the_api():
+    """A BV_uptake_ForwardPass with average_first=False (BV_uptake_ForwardPass_frames of the examples) runs the per-frame
+    kernel: Simulation.forward == frame average of Simulation.predict, and run_optimise lowers the loss."""
+    case, sim, data, losses, opt, cfg = _setup(F=500, R=41, T=4)
+    fp = J.BV_uptake_ForwardPass()
+    fp.average_first = False
+    sim = J.Simulation(input_features=sim.input_features, forward_models=(_Model(fp),), params=sim.params)
+    assert sim.initialise() is True
+    w = sim.params.frame_weights
+    per_frame = sim.predict(sim.params)[0].uptake  # (T,R,F)
+    np.testing.assert_allclose(sim.outputs[0].uptake.cpu().numpy(), (per_frame * w[None, None, :]).sum(-1).cpu().numpy(), rtol=2e-5, atol=1e-7)
+    opt = J.OptaxOptimizer(learning_rate=0.02, parameter_partition_masks={J.Optimisable_Parameters.frame_weights}, clip_value=None,
+                           initial_learning_rate=0.02, initial_steps=0)
+    state = opt.initialise(sim)
+    n_steps = 25
+    sim2, opt2 = J._optimise_device(sim, data, n_steps, 1e-10, [1e-9], [0, 0, 0], list(losses), state, opt)
+    recs = opt2._engine.records(0, n_steps + 1)
+    assert recs[n_steps].step == n_steps
+    # the same trajectory on the oracle (per-frame mode), started from the parameters the Simulation was initialised to
+    pb = case["problem"]
+    pb.average_first = False
+    ocfg = O.OptConfig(learning_rate=0.02, initial_learning_rate=0.02, initial_steps=0, clip_value=None, optimise_model_parameters=False)
+    par = case["params"]
+    par = O.Params(par.z, par.frame_mask, par.bc, par.bh, O.normalize_masked_loss_scalingweights([2.0, 1.0, 1.0], np.ones(3)), par.fs, par.nlf)
+    st = O.optimizer_initialise(par, ocfg, np.float64)
+    for k in range(n_steps + 1):
+        l, _, _ = O.compute_loss(pb, st.params, np.float64)
+        np.testing.assert_allclose(recs[k].total_train, l.total_train_loss, rtol=2e-4)
+        st, _, _ = O.step_with_rates(pb, st, ocfg, np.float64)
+    # model-parameter optimisation is rejected in this mode
+    opt_bad = J.OptaxOptimizer(learning_rate=0.5, parameter_partition_masks={J.Optimisable_Parameters.frame_weights, J.Optimisable_Parameters.model_parameters},
+                               clip_value=None)
+    st = opt_bad.initialise(sim)
+    with pytest.raises(Exception, match="frame weights only"):
+        J._optimise_device(sim, data, 5, 1e-10, [1e-6], [0, 0, 0], list(losses), st, opt_bad)
