@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, F, R, T, n_steps, exchange, out):
+def _worker(rank, world, port, F, R, T, n_steps, exchange, out, per_frame=False):
     import torch.distributed as dist
 
     from jaxent_b200.sharding import frame_shard
@@ -30,7 +30,8 @@ def _worker(rank, world, port, F, R, T, n_steps, exchange, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         case = H.make_case(F, R, T, O.UPTAKE_EYE_MSE, extra=(O.PARAMS_L2,), seed=6, prior="random")
-        cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=True)
+        case["problem"].average_first = not per_frame
+        cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=not per_frame)
         sh = frame_shard(F, rank, world)
         eng = H.make_engine(case, cfg, device=f"cuda:{rank}", frames=sh.slice(), F_total=F, group=dist.group.WORLD, exchange=exchange)
         assert eng.exchange == exchange
@@ -89,4 +90,14 @@ def test_sharded_matches_single_gpu(world, exchange):
         pytest.skip("not enough GPUs")
     out = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), 5003, 97, 5, 6, exchange, out), nprocs=world, join=True)
+    assert out.get("ok") == 1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_per_frame_uptake_matches_single_gpu():
+    """the per-frame uptake mode exchanges 2*T*R + 4 doubles per step through the same fused NVLink inbox"""
+    import torch.multiprocessing as mp
+
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), 3001, 64, 4, 6, "nvlink", out, True), nprocs=2, join=True)
     assert out.get("ok") == 1
