@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(1024) bt_reduce2_kernel(const BatchArgs a) {
 // ------------------------------------------------------------------------------------------ bt_tail
 template <bool GENERAL>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* const smem_raw = jx_dyn_smem;
   __shared__ double s_red[32][16];
   __shared__ double s_fin[16];
   __shared__ __align__(16) BCtl s_c;
@@ -506,6 +506,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArg
   io.uptake = a.uptake + (size_t)b * (T > 0 ? T : 1) * R;
   io.pf_G = nullptr;
   io.pf_mode = 0;
+  io.p_max_tr = a.p_max_tr;
+  io.p_max_va = a.p_max_va;
   tail_body<GENERAL>(pb, a.blobs, first_data, tsm, acc0, acc1, S, bc, bh, s_c.fw, s_c.fs, io, s_red, s_fin, my_c, my_a, my_b, my_lp, gbc_reg,
                      gbh_reg);
   if (tid < R) {

@@ -50,12 +50,15 @@ struct StepScalars {
   double trk_prev_loss, trk_ema;
 };
 
-// warp 0 only.  Reads the previous control block straight from global memory (one round trip that
-// overlaps the staging done by the other warps); the four powf and two log evaluations run on
-// separate lanes behind single call sites.
-__device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restrict__ old, double SA, double SB, double gdot,
-                                            const JaxentOptConfig cfg, const TrackConfig trk,
-                                            const JaxentLossRecord* __restrict__ records) {
+// The step scalars are derived in two parts by one warp each:
+//   derive_critical : everything the R x T tail and the per-frame terms wait for -- plateau branch d, S, the BV-parameter Adam
+//                     update (bc, bh), counters.  Runs before the block-wide barrier (1).
+//   derive_rest     : the learning rates / masks / bias corrections / log-sum-exp of the COMING update and the convergence
+//                     tracker.  In the tail CTA it is executed by the last warp while the (smaller) peptide-map phase keeps
+//                     only the first warps busy, i.e. off the critical path; the frame CTAs run it right after the critical part.
+// The powf / log evaluations run on separate lanes behind single call sites.
+__device__ __noinline__ void derive_critical(StepScalars* out, const Ctl* __restrict__ old, double SA, double SB, double gdot,
+                                             const JaxentOptConfig cfg) {
   const int lane = threadIdx.x & 31;
   StepScalars s;
   s.pending = old->pending;
@@ -77,14 +80,10 @@ __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restr
   const float gp0 = old->gb_prev[0], gp1 = old->gb_prev[1];
   const float olrA = old->lrA, olrB = old->lrB, omlrA = old->mlrA, omlrB = old->mlrB;
   const int cm1 = s.cm + (s.pending ? 1 : 0), cf1 = s.cf + (s.pending ? 1 : 0);
-  // lanes 0..3: b1^cm1, b2^cm1, b1^(cf1+1), b2^(cf1+1);  lanes 4,5: log S_A, log S_B
+  // lanes 0,1: b1^cm1, b2^cm1 (bias corrections of the BV-parameter Adam update)
   float pw = 0.f;
-  double lg = 0.0;
-  if (lane < 4) pw = fpow((lane & 1) ? (float)cfg.b2 : (float)cfg.b1, (float)(lane < 2 ? cm1 : cf1 + 1));
-  if (lane == 4 || lane == 5) lg = dlog(lane == 4 ? SA : SB);
+  if (lane < 2) pw = fpow((lane & 1) ? (float)cfg.b2 : (float)cfg.b1, (float)cm1);
   const float pw0 = __shfl_sync(0xffffffffu, pw, 0), pw1 = __shfl_sync(0xffffffffu, pw, 1);
-  const float pw2 = __shfl_sync(0xffffffffu, pw, 2), pw3 = __shfl_sync(0xffffffffu, pw, 3);
-  const double lgA = __shfl_sync(0xffffffffu, lg, 4), lgB = __shfl_sync(0xffffffffu, lg, 5);
   if (lane != 0) return;
   s.d = 0;
   s.dot = 0.0;
@@ -120,6 +119,28 @@ __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restr
     s.step += 1;
   }
   s.S = s.d ? SB : SA;
+  s.loop_step = old->step;
+  // the fields of derive_rest start from their carried values
+  s.trk_stop = old->trk_stop;
+  s.snap_now = -1;
+  s.ema_update = 0;
+  s.ema_first = 0;
+  *out = s;
+}
+
+// second half: reads the critical part from *sc (shared memory), completes it in place.  One whole warp.
+__device__ __noinline__ void derive_rest(StepScalars* sc, const Ctl* __restrict__ old, const JaxentOptConfig cfg, const TrackConfig trk,
+                                         const JaxentLossRecord* __restrict__ records) {
+  const int lane = threadIdx.x & 31;
+  StepScalars s = *sc;
+  // lanes 0,1: b1^(cf+1), b2^(cf+1) (bias corrections of the coming frame Adam update);  lane 2: log S
+  float pw = 0.f;
+  double lg = 0.0;
+  if (lane < 2) pw = fpow((lane & 1) ? (float)cfg.b2 : (float)cfg.b1, (float)(s.cf + 1));
+  if (lane == 2) lg = dlog(s.S);
+  const float pw2 = __shfl_sync(0xffffffffu, pw, 0), pw3 = __shfl_sync(0xffffffffu, pw, 1);
+  const double lgS = __shfl_sync(0xffffffffu, lg, 2);
+  if (lane != 0) return;
   // speculative rates of the NEXT update (state.step == step): opt/optimiser.py:365-381,403-413
   const bool switched = s.step >= cfg.initial_steps;
   const int mi = switched ? 1 : s.mask_idx;
@@ -133,7 +154,7 @@ __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restr
   s.mask_model = (mi == 0) ? 0.f : (cfg.optimise_model_parameters ? 1.f : 0.f);
   s.bc1 = 1.0f - pw2;
   s.bc2 = 1.0f - pw3;
-  s.lse_new = (float)((double)s.lse_old + (s.d ? lgB : lgA));
+  s.lse_new = (float)((double)s.lse_old + lgS);
 
   // ---- ConvergenceTracker for loop step k = old->step (reference opt/run.py:285-348, opt/track.py:150-197)
   s.trk_stop = old->trk_stop;
@@ -151,7 +172,6 @@ __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restr
   s.snap_now = -1;
   s.ema_update = 0;
   s.ema_first = 0;
-  s.loop_step = old->step;
   if (trk.on && s.pending && !s.trk_stop) {
     const int k = old->step;
     const double loss = (double)records[k % JAXENT_RECORD_RING].total_train;
@@ -197,7 +217,7 @@ __device__ __noinline__ void derive_scalars(StepScalars* out, const Ctl* __restr
       }
     }
   }
-  *out = s;
+  *sc = s;
 }
 
 // ------------------------------------------------------------------------------------------ blobs
@@ -424,7 +444,7 @@ __device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep,
 // common eye-MSE / PF-L2 configuration executes the shortest possible instruction stream.
 template <bool GENERAL>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* const smem_raw = jx_dyn_smem;
   __shared__ double s_red[32][16];  // per-warp partials of the multi-value reductions
   __shared__ double s_fin[16];
   __shared__ __align__(16) Ctl s_ctl2[2];  // both control blocks, fetched before the epoch is known
@@ -464,7 +484,13 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (warp == 0) {
     const double SA = red_total(a.x, ep, a.part_n - 4), SB = red_total(a.x, ep, a.part_n - 3), gdot = red_total(a.x, ep, a.part_n - 2);
-    derive_scalars(&s_sc, &s_old, SA, SB, gdot, a.cfg, a.trk, a.records);
+    derive_critical(&s_sc, &s_old, SA, SB, gdot, a.cfg);
+    // the per-frame CTAs need the tracker's decisions (snapshot slot, EMA update) before their frame loop;
+    // the tail CTA defers this half to an otherwise idle warp of the peptide-map phase (see tail_body's `side`)
+    if (!tail_cta || gridDim.x == 1) {
+      __syncwarp();
+      derive_rest(&s_sc, &s_old, a.cfg, a.trk, a.records);
+    }
   }
   const bool pfm = pb.uptake == 2;
   if (tail_cta) {
@@ -491,6 +517,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     io.uptake = a.uptake;
     io.pf_G = a.pf_G;
     io.pf_mode = pfm ? 1 : 0;
+    io.p_max_tr = a.p_max_tr;
+    io.p_max_va = a.p_max_va;
     if (pfm) {  // per-frame uptake mode: <u>[t,r] = acc[branch d][t][r] / S straight from the reduced pass sums
       const double invS = __drcp_rn(S);
 #pragma unroll 1
@@ -500,8 +528,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
         a.uptake[it] = (float)uv;
       }
     }
+    const bool defer_rest = gridDim.x > 1;
+    auto side = [&]() {
+      if (defer_rest) derive_rest(&s_sc, &s_old, a.cfg, a.trk, a.records);
+    };
     tail_body<GENERAL>(pb, a.blobs, first_data, tsm, d ? accB0 : accA0, d ? accB1 : accA1, S, bc, bh, s_old.fw, s_old.fs, io, s_red, s_fin,
-                       my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg);
+                       my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg, side);
+    if (defer_rest && first_data < 0) {  // no data slot: nothing called `side`
+      if (warp == 0) derive_rest(&s_sc, &s_old, a.cfg, a.trk, a.records);
+      __syncthreads();
+    }
     if (tid < R && !pfm) {  // row coefficients of the next pass
       a.cc[tid] = (float)(my_c * bc);
       a.ch[tid] = (float)(my_c * bh);

@@ -39,6 +39,11 @@ __host__ __device__ inline BlobLayout blob_layout(int R, int Tm, int p_tr, int n
   return b;
 }
 
+// The dynamic shared memory of the tail kernels.  Declared at namespace scope and re-derived inside tail_body() so that the
+// compiler keeps the shared address space of every pointer (pointers that travel through a struct degrade to generic
+// loads, LD.E instead of LDS, in the sparse-map loops).
+extern __shared__ __align__(16) unsigned char jx_dyn_smem[];
+
 // shared-memory carve-up of the tail body
 struct TailSmem {
   double *slp, *sxe, *sc_rt, *sU, *res_tr, *gp_tr, *res_va, *smean;
@@ -91,6 +96,7 @@ struct TailIO {
   float* uptake;  // [T*R]
   float* pf_G;    // per-frame uptake mode: [T*R] dL/d<uptake>[t,r] for the next pass (else unused)
   int pf_mode;    // 1: per-frame uptake mode -- the caller has filled sm.sU with the frame-averaged uptake already
+  int p_max_tr, p_max_va;  // carve-up parameters (carve_tail_smem)
 };
 
 // Whole-CTA function.  In: acc0/acc1 = un-normalised weighted row sums of this thread's residue (tid < R), S = sum of the
@@ -98,18 +104,26 @@ struct TailIO {
 // [6..11] val losses, [12] sum_r c_r lnPF_r, [13] dL/dbc, [14] dL/dbh (data part); my_c = c_r of this thread's residue;
 // gbc_reg / gbh_reg = regulariser gradients.  s_red must be zeroed ([warp][0..15]) by the caller before the call and a
 // __syncthreads() must separate that and the staging from the call.
-template <bool GENERAL>
+struct NoSide {
+  __device__ void operator()() const {}
+};
+
+// `side` is called once by the LAST warp at the start of the first data slot's peptide-map phase (a phase that usually keeps
+// only the first warps busy): the caller can park latency-tolerant scalar work there.
+template <bool GENERAL, class Side = NoSide>
 __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobSet& blobs, int first_data, const TailSmem& sm,
                                           double acc0, double acc1, double S, double bc, double bh, const float* fw, const float* fs,
                                           const TailIO io, double (*s_red)[16], double* s_fin, double& my_c, double& my_a, double& my_b,
-                                          double& my_lp, double& gbc_reg_out, double& gbh_reg_out) {
+                                          double& my_lp, double& gbc_reg_out, double& gbh_reg_out, Side side = Side()) {
   const int R = pb.R, T = pb.uptake ? pb.T : 0, Tm = T > 0 ? T : 1;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const float invR = 1.0f / (float)R, invTm = 1.0f / (float)Tm;
-  double *slp = sm.slp, *sxe = sm.sxe, *sc_rt = sm.sc_rt, *sU = sm.sU, *res_tr = sm.res_tr, *gp_tr = sm.gp_tr, *res_va = sm.res_va,
-         *smean = sm.smean;
-  float *s_k = sm.s_k, *s_tp = sm.s_tp;
-  int* s_blob = sm.s_blob;
+  const TailSmem smx = carve_tail_smem(jx_dyn_smem, R, T, io.p_max_tr, io.p_max_va);  // == sm, with the address space intact
+  (void)sm;
+  double *slp = smx.slp, *sxe = smx.sxe, *sc_rt = smx.sc_rt, *sU = smx.sU, *res_tr = smx.res_tr, *gp_tr = smx.gp_tr, *res_va = smx.res_va,
+         *smean = smx.smean;
+  float *s_k = smx.s_k, *s_tp = smx.s_tp;
+  int* s_blob = smx.s_blob;
   {
     my_a = 0, my_b = 0, my_lp = 0, my_c = 0;
     const bool pfm = io.pf_mode != 0;
@@ -172,6 +186,7 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
       // indices / values are read once per 4 products and the 4 accumulation chains are independent.  The eye / PF
       // kinds finish residual + loss here.
       {
+        if (i == first_data && warp == nw - 1) side();
         const int nch = (Tm + 3) >> 2;
         const float inv_nch = 1.0f / (float)nch;
         const int items = (Ptr + Pva) * nch;

@@ -70,5 +70,39 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(JaxentBvPack, BvPackImpl,
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>());
+
+// batched sweep (batch_optimise): one call advances every replica of a JaxentBatchPlan
+static ffi::Error BgStepImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> workspace, int64_t plan,
+                             ffi::Result<ffi::Buffer<ffi::U8>> workspace_out) {
+  (void)workspace;
+  (void)workspace_out;
+  return Check(jaxent_bg_step(reinterpret_cast<JaxentBatchPlan*>(plan), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JaxentBgStep, BgStepImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int64_t>("plan")
+                                  .Ret<ffi::Buffer<ffi::U8>>());
+
+// Simulation.predict: per-frame forward pass on the packed features (T = 0: log_Pf (R,F); T > 0: uptake (T,R,F))
+static ffi::Error BvPredictImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> packed, ffi::Buffer<ffi::F32> k_ints,
+                                ffi::Buffer<ffi::F32> timepoints, int64_t n_residues, int64_t n_frames, int64_t n_timepoints, float bc,
+                                float bh, ffi::Result<ffi::Buffer<ffi::F32>> out) {
+  return Check(jaxent_bv_predict_frames(packed.typed_data(), (int32_t)n_residues, n_frames, (int32_t)n_timepoints, k_ints.typed_data(),
+                                        timepoints.typed_data(), bc, bh, out->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JaxentBvPredict, BvPredictImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int64_t>("n_residues")
+                                  .Attr<int64_t>("n_frames")
+                                  .Attr<int64_t>("n_timepoints")
+                                  .Attr<float>("bc")
+                                  .Attr<float>("bh")
+                                  .Ret<ffi::Buffer<ffi::F32>>());
 #endif
 #endif

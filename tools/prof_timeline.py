@@ -9,7 +9,7 @@ torch.cuda.set_device(rank); dev = torch.device("cuda", rank)
 dist.init_process_group("nccl", device_id=dev)
 mode = sys.argv[1] if len(sys.argv) > 1 else "nvlink"
 R, T = 500, 8
-Fl = 500_000
+Fl = int(os.environ.get("FRAMES_PER_RANK", 500_000))
 F = Fl * world
 use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
 g = torch.Generator(device=dev); g.manual_seed(rank)
