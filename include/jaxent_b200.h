@@ -268,6 +268,16 @@ int jaxent_bv_track_status(JaxentPlan* plan, JaxentTrackStatus* status, jaxent_s
 int jaxent_bv_export_state(JaxentPlan* plan, float* z, float* m, float* v, float* g, float* scalars,
                            jaxent_stream_t stream);
 
+/* ---- BV featuriser (calc_BV_contacts_universe, models/func/contacts.py:125-243; BV_model.featurise,
+ * models/HDX/BV/forwardmodel.py:214-300): per frame, for every target atom the number of contact atoms within `radius`
+ * (use_switch = 0) or the sum of the rational switch 1/(1 + (r/r0)^6) over the atoms within the radius (use_switch = 1),
+ * skipping contact atoms whose residue id is in [target_resid + ignore_lo, target_resid + ignore_hi] (default -2..2).
+ * coords: float[F][A][3] positions (Angstrom); target_idx / contact_idx: atom indices into a frame; box: float[F][3]
+ * orthorhombic box lengths for the minimum-image convention, or NULL; out: float[Nt][F] (frame axis last).  All device memory. */
+int jaxent_bv_contacts(const float* coords, int64_t F, int32_t A, const int32_t* target_idx, const int32_t* target_resid, int32_t Nt,
+                       const int32_t* contact_idx, const int32_t* contact_resid, int32_t Nc, int32_t ignore_lo, int32_t ignore_hi,
+                       float radius, int32_t use_switch, const float* box, float* out, jaxent_stream_t stream);
+
 /* ---- per-frame forward pass (Simulation.predict, models/core.py:181-208): the forward pass on the un-averaged features.
  * packed: fp32 tile layout (jaxent_bv_pack_features_f32).  T = 0: out = log_Pf float[R][F] (BV_ForwardPass);
  * T > 0: out = uptake float[T][R][F] (BV_uptake_ForwardPass).  Row-major, frame axis last, as in the reference. */
