@@ -79,7 +79,8 @@ struct BatchArgs {
   unsigned* counter;      // ticket of bt_kl
   int p_max_tr, p_max_va;
   int blob_words_max;     // words reserved for the blob image in the tail's shared memory
-  int ew_blocks, fy;      // elementwise grid / frames per block iteration
+  int ew_blocks, fy;      // elementwise grid (2 blocks of 512 threads per SM) / frames per block iteration
+  int adam_blocks;        // bt_adam keeps 128 registers per thread: one 512-thread block per SM, one wave
   float eps_kl;
   // on-device loop (jaxent_bg_track_init)
   int trk_on, trk_n_thr, trk_min_steps;
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(1024) bt_reduce2_kernel(const BatchArgs a) {
       __syncthreads();
       double s = 0.0;
       if (b < Bn)
-        for (int k = ty; k < a.ew_blocks; k += 32) s += a.part_s[(size_t)(which * MAX_EW_BLOCKS + k) * Bn + b];
+        for (int k = ty; k < a.adam_blocks; k += 32) s += a.part_s[(size_t)(which * MAX_EW_BLOCKS + k) * Bn + b];
       tile[ty][tx] = s;
       __syncthreads();
       if (ty == 0 && b < Bn) {
@@ -687,7 +688,16 @@ __global__ void __launch_bounds__(256) bt_klfold_kernel(const BatchArgs a, int n
     double kl[KL_N];
     for (int k = 0; k < KL_N; ++k) {
       double t = 0.0;
-      for (int blk = lane; blk < n_blocks; blk += 32) t += __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]);
+      for (int blk0 = lane; blk0 < n_blocks; blk0 += 32 * 8) {  // 8 independent loads in flight per lane
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int blk = blk0 + 32 * u;
+          v[u] = blk < n_blocks ? __ldcg(&a.part_kl[((size_t)blk * KL_N + k) * Bn + b]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += v[u];
+      }
       kl[k] = wsum(t);
     }
     if (lane != 0) return;
@@ -935,6 +945,7 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   if (blocks > bg::MAX_EW_BLOCKS) blocks = bg::MAX_EW_BLOCKS;
   if (blocks < 1) blocks = 1;
   a.ew_blocks = (int)blocks;
+  a.adam_blocks = a.ew_blocks < sm_count ? a.ew_blocks : sm_count;
   {
     int nnz_tr = 1, nnz_va = 1;
     for (int i = 0; i < pb->n_slots; ++i)
@@ -1014,7 +1025,7 @@ static int bg_update_phase(JaxentBatchPlan* p, cudaStream_t s) {
   if ((rc = bg_err("bt_grad"))) return rc;
   bg::bt_decide_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a);
   if ((rc = bg_err("bt_decide"))) return rc;
-  bg::bt_adam_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 1);
+  bg::bt_adam_kernel<<<a.adam_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 1);
   return bg_err("bt_adam");
 }
 
@@ -1062,7 +1073,7 @@ extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float z
     if ((rc = bg_err("bt_prior"))) return rc;
   }
   if ((rc = launch_build_blobs(a.prob, a.blobs, s))) return rc;
-  bg::bt_adam_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 0);
+  bg::bt_adam_kernel<<<a.adam_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 0);
   if ((rc = bg_err("bt_adam(init)"))) return rc;
   rc = bg_forward(p, s);
   if (rc) return rc;
