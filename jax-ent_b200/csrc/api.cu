@@ -311,7 +311,8 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   p->tile_bytes = p->subtile_bytes * p->sub_tiles;
   p->stage_stride = (uint32_t)align_up(p->tile_bytes, 128);
   const size_t smem_budget = ((p->rpt == 1 && problem->uptake != 2) ? 108 : 216) * 1024;
-  const size_t fixed = MAX_STAGES * 8 + 2 * 16 * FT * 4 + 2 * 2 * FT * 4 + 128;
+  // per-frame mode adds per-thread slots {k tau, G}: [4 pairs of time points][512] float4, and the row partials [2 quads][512] float4
+  const size_t fixed = MAX_STAGES * 8 + 2 * 16 * FT * 4 + 2 * 2 * FT * 4 + 128 + (problem->uptake == 2 ? (4 + 2) * PASS_THREADS_MAX * 16 : 0);
   int stages = (int)((smem_budget - fixed) / p->stage_stride);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { delete p; set_error("tile of %u bytes does not fit a 2-stage ring", p->tile_bytes); return JAXENT_E_UNSUPPORTED; }

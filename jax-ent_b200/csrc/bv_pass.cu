@@ -309,7 +309,7 @@ __device__ __noinline__ void finish_previous_record(const Xchg x, unsigned ep, c
 // the uptake is evaluated per (time point, residue, frame) and THEN frame-averaged, so the pass carries the non-linearity:
 //   u[t,r,f] = 1 - exp(-k_r tau_t exp(-(bc Nc[r,f] + bh Nh[r,f])))
 //   phase A  H_f = sum_{t,r} G[t,r] u[t,r,f]            G = dL/d<uptake> from the tail
-//   phase B  acc[branch][t][r] += e'_f u[t,r,f]
+//   phase B  acc[branch][t][r] += e'_f (1 - u[t,r,f])  (the tail forms <u> = 1 - acc / S in double precision)
 // F*R*(T+1) exponentials per step make this mode special-function bound rather than HBM bound.  The BV parameters are
 // frozen in this mode (their gradient would be needed before the same sweep's forward half could start).
 constexpr int PF_TMAX = 8;
@@ -323,116 +323,148 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ float uptake_of(float x) { return 1.f - ex2_approx(-1.4426950408889634f * x); }
 
+constexpr int PF_FU = 4;  // frames per unit of work in this mode: a tile is handled as its two quads (see pf_consumer)
+
+__device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
+
+// One consumer thread owns one residue row.  A tile (8 frames) is processed as its two quads of 4 frames so that TWO units
+// are in flight per thread: phase A of unit h+1 (the exponentials) is issued before phase B of unit h waits for the Adam
+// warp, which hides the H_f -> Adam -> e' latency behind special-function work.  The uptake values of a unit stay in
+// registers between its two phases (4 frames x TM time points, as packed pairs: fma.rn.f32x2 halves the issue slots of the
+// multiply / accumulate instructions around each ex2).  -log2(e) k_r tau_t and G[t][r] live in per-thread slots of shared
+// memory (each thread reads back only what it wrote: no barrier).  The special-function unit shares its issue queue with
+// shared-memory and shuffle instructions, so the reduction of H_f over the rows is NOT done here: every thread stores its
+// four per-frame partials (one 16-byte store) and the Adam warp, which has time to spare, sums them.
 template <int TM>
-__device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ring, uint64_t* bars, float* s_part, const float* s_e,
-                                             double* part, int n, int mode, float bc, float bh) {
+__device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ring, uint64_t* bars, float4* s_rows, const float* s_e,
+                                             float4* s_tab, double* part, int n, int mode, float bc, float bh, int NTc, int nbar) {
+  constexpr int TP = TM / 2;
   const int R = a.R, T = a.pf_T;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nbar = blockDim.x;
+  const int tid = threadIdx.x;
   const bool ok = tid < R;
   const int rc = ok ? tid : R - 1;
   const uint32_t rowoff = (uint32_t)rc * 16u, rstride = (uint32_t)R * 16u;
-  float kt[TM], G[TM];
-  const float kr = a.pf_k[rc];
+  float4* my_tab = s_tab + tid;  // [TP][NTc] {kt(2 tp), kt(2 tp + 1), G(2 tp), G(2 tp + 1)}
+  float Gsum = 0.f;
+  {
+    const float kr = -1.4426950408889634f * a.pf_k[rc];
 #pragma unroll
-  for (int t = 0; t < TM; ++t) {
-    kt[t] = (t < T) ? -1.4426950408889634f * (kr * a.pf_tp[t]) : 0.f;  // -log2(e) k_r tau_t
-    G[t] = (ok && mode && t < T) ? a.pf_G[(size_t)t * R + rc] : 0.f;
+    for (int tp = 0; tp < TP; ++tp) {
+      const int t0_ = 2 * tp, t1_ = 2 * tp + 1;
+      const float2 g2 = make_float2((ok && mode && t0_ < T) ? a.pf_G[(size_t)t0_ * R + rc] : 0.f,
+                                    (ok && mode && t1_ < T) ? a.pf_G[(size_t)t1_ * R + rc] : 0.f);
+      my_tab[tp * NTc] = make_float4(t0_ < T ? kr * a.pf_tp[t0_] : 0.f, t1_ < T ? kr * a.pf_tp[t1_] : 0.f, g2.x, g2.y);  // kt = -log2(e) k_r tau_t
+      Gsum += g2.x + g2.y;
+    }
   }
   if (ok)
     for (int k = 0; k < 2 * T; ++k) part[(size_t)k * R + rc] = 0.0;
-  float acc[2][TM];
+  float2 acc[2][TP];
 #pragma unroll
-  for (int t = 0; t < TM; ++t) acc[0][t] = acc[1][t] = 0.f;
-  const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  for (int tp = 0; tp < TP; ++tp) acc[0][tp] = acc[1][tp] = make_float2(0.f, 0.f);
   const float nlog2e_bc = -1.4426950408889634f * bc, nlog2e_bh = -1.4426950408889634f * bh;
+  JCLK_DECL(clk_ring);
+  JCLK_DECL(clk_a);
+  JCLK_DECL(clk_e);
+  JCLK_DECL(clk_b);
   int slot = 0;
   uint32_t parity = 0;
-  int since = 0;
-  for (int it = 0; it < n; ++it) {
-    const int b = it & 1;
-    mbar_wait(smem_u32(&bars[slot]), parity);
-    const unsigned char* sub = ring + (size_t)slot * a.stage_stride + rowoff;
-    const float4 c0 = *reinterpret_cast<const float4*>(sub), h0 = *reinterpret_cast<const float4*>(sub + rstride);
-    const float4 c1 = *reinterpret_cast<const float4*>(sub + 2 * rstride), h1 = *reinterpret_cast<const float4*>(sub + 3 * rstride);
-    if (++slot == a.stages) {
-      slot = 0;
-      parity ^= 1u;
-    }
-    const float nc[FT] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    const float nh[FT] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    float u[FT][TM];
-    float p[FT];
-#pragma unroll
-    for (int j = 0; j < FT; ++j) {
-      const float pinv = ex2_approx(fmaf(nlog2e_bc, nc[j], nlog2e_bh * nh[j]));  // exp(-lnPF)
-      float hj = 0.f;
-#pragma unroll
-      for (int t = 0; t < TM; ++t) {
-        u[j][t] = 1.f - ex2_approx(kt[t] * pinv);  // 1 - exp(-k tau / PF)
-        hj = fmaf(G[t], u[j][t], hj);
+
+  // phase A of one quad: u[j][tp] = exp(-k tau / PF) = 1 - uptake; per-frame partial sums of G.(1 - u) to the Adam warp
+  auto phase_a_pf = [&](int half, float2 (&u)[PF_FU][TP]) {
+    JCLK_TIC(tm0);
+    if (half == 0) mbar_wait(smem_u32(&bars[slot]), parity);
+    JCLK_TOC(clk_ring, tm0);
+    JCLK_TIC(ta0);
+    const unsigned char* sub = ring + (size_t)slot * a.stage_stride + rowoff + (half ? 2 * rstride : 0u);
+    const float4 c4 = *reinterpret_cast<const float4*>(sub), h4 = *reinterpret_cast<const float4*>(sub + rstride);
+    if (half) {
+      if (++slot == a.stages) {
+        slot = 0;
+        parity ^= 1u;
       }
-      p[j] = hj;
     }
-    // transposing warp reduction of the 8 per-frame partials (same scheme as phase_a)
-    {
-      const bool hi = lane & 16;
-      float q4[4];
+    const float nc[PF_FU] = {c4.x, c4.y, c4.z, c4.w}, nh[PF_FU] = {h4.x, h4.y, h4.z, h4.w};
+    float2 pinv[PF_FU], p2[PF_FU];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float send = hi ? p[i] : p[i + 4];
-        const float keep = hi ? p[i + 4] : p[i];
-        q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
-      const bool b3 = lane & 8;
-      float r2[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float send = b3 ? q4[i] : q4[i + 2];
-        const float keep = b3 ? q4[i + 2] : q4[i];
-        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-      const bool b2_ = lane & 4;
-      const float send = b2_ ? r2[0] : r2[1];
-      const float keep = b2_ ? r2[1] : r2[0];
-      float sres = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      sres += __shfl_xor_sync(0xffffffffu, sres, 2);
-      sres += __shfl_xor_sync(0xffffffffu, sres, 1);
-      if ((lane & 3) == 0) s_part[b * 16 * FT + warp * FT + jred] = sres;
+    for (int j = 0; j < PF_FU; ++j) {
+      pinv[j] = bcast2(ex2_approx(fmaf(nlog2e_bc, nc[j], nlog2e_bh * nh[j])));  // exp(-lnPF)
+      p2[j] = make_float2(0.f, 0.f);
     }
-    bar_arrive(BAR_PART0 + b, nbar);
-    bar_sync(BAR_E0 + b, nbar);  // e'(it) of both branches from the Adam warp
-    const float4* e4 = reinterpret_cast<const float4*>(s_e + b * 2 * FT);
+#pragma unroll
+    for (int tp = 0; tp < TP; ++tp) {
+      const float4 kg = my_tab[tp * NTc];
+      const float2 kt2 = make_float2(kg.x, kg.y), G2 = make_float2(kg.z, kg.w);
+#pragma unroll
+      for (int j = 0; j < PF_FU; ++j) {
+        const float2 x2 = __fmul2_rn(kt2, pinv[j]);
+        const float2 e2 = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
+        u[j][tp] = e2;
+        p2[j] = __ffma2_rn(G2, e2, p2[j]);
+      }
+    }
+    // per-row partials of H_f for the 4 frames: the Adam warp of this quad sums them over the rows
+    s_rows[half * NTc + tid] = make_float4(Gsum - (p2[0].x + p2[0].y), Gsum - (p2[1].x + p2[1].y), Gsum - (p2[2].x + p2[2].y),
+                                           Gsum - (p2[3].x + p2[3].y));
+    bar_arrive(BAR_PART0 + half, nbar);
+    JCLK_TOC(clk_a, ta0);
+  };
+  // phase B of one quad: acc[branch][t] += e'_f exp(-k tau / PF)
+  auto phase_b_pf = [&](int half, const float2 (&u)[PF_FU][TP]) {
+    JCLK_TIC(te0);
+    bar_sync(BAR_E0 + half, nbar);  // e' of both branches from the Adam warp
+    JCLK_TOC(clk_e, te0);
+    JCLK_TIC(tb0);
+    const float4* e4 = reinterpret_cast<const float4*>(s_e + half * 2 * PF_FU);
 #pragma unroll
     for (int br = 0; br < 2; ++br) {
-      const float4 e0 = e4[2 * br], e1 = e4[2 * br + 1];
-      const float ev[FT] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      const float4 e = e4[br];
+      const float2 ev[PF_FU] = {bcast2(e.x), bcast2(e.y), bcast2(e.z), bcast2(e.w)};
 #pragma unroll
-      for (int t = 0; t < TM; ++t) {
-        float s_ = 0.f;
+      for (int tp = 0; tp < TP; ++tp)
 #pragma unroll
-        for (int j = 0; j < FT; ++j) s_ = fmaf(ev[j], u[j][t], s_);
-        acc[br][t] += s_;
-      }
+        for (int j = 0; j < PF_FU; ++j) acc[br][tp] = __ffma2_rn(ev[j], u[j][tp], acc[br][tp]);
     }
-    if (++since >= FLUSH_TILES || it == n - 1) {
+    JCLK_TOC(clk_b, tb0);
+  };
+  auto flush = [&]() {
+    if (ok) {
+#pragma unroll
+      for (int br = 0; br < 2; ++br)
+#pragma unroll
+        for (int tp = 0; tp < TP; ++tp) {
+          // single writer per address: deterministic
+          if (2 * tp < T) atomicAdd(&part[(size_t)(br * T + 2 * tp) * R + rc], (double)acc[br][tp].x);
+          if (2 * tp + 1 < T) atomicAdd(&part[(size_t)(br * T + 2 * tp + 1) * R + rc], (double)acc[br][tp].y);
+          acc[br][tp] = make_float2(0.f, 0.f);
+        }
+    }
+  };
+
+  float2 U0[PF_FU][TP], U1[PF_FU][TP];
+  phase_a_pf(0, U0);
+  int since = 0;
+  for (int it = 0; it < n; ++it) {
+    phase_a_pf(1, U1);
+    phase_b_pf(0, U0);
+    if (it + 1 < n) phase_a_pf(0, U0);
+    phase_b_pf(1, U1);
+    if (++since >= FLUSH_TILES) {
       since = 0;
-      if (ok) {
-#pragma unroll
-        for (int br = 0; br < 2; ++br)
-#pragma unroll
-          for (int t = 0; t < TM; ++t)
-            if (t < T) {
-              atomicAdd(&part[(size_t)(br * T + t) * R + rc], (double)acc[br][t]);  // single writer per address: deterministic
-              acc[br][t] = 0.f;
-            }
-      }
+      flush();
     }
+  }
+  flush();
+  if (blockIdx.x == 0 && tid == 0) {
+    JCLK_OUT(a.dbg, 56, clk_ring);
+    JCLK_OUT(a.dbg, 57, clk_a);
+    JCLK_OUT(a.dbg, 58, clk_e);
+    JCLK_OUT(a.dbg, 59, clk_b);
   }
 }
 
-template <int RPT, int FMT, int PF>
-__global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1 && PF == 0) ? 2 : 1) bv_pass_kernel(const PassArgs a) {
+template <int RPT, int FMT>
+__global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -607,12 +639,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1 && PF == 0) ?
   }
 
   // ==================================================================== consumers
-  if (PF != 0) {
-    const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
-    if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_part, s_e, part, n, mode, ctl->bc, ctl->bh);
-    else pf_consumer<PF_TMAX>(a, ring, bars, s_part, s_e, part, n, mode, ctl->bc, ctl->bh);
-    return;
-  }
   float ccr[RPT], chr[RPT];
   uint32_t rowoff[RPT];
   int row[RPT];
@@ -705,6 +731,255 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, (RPT == 1 && PF == 0) ?
   flush();
 }
 
+// ------------------------------------------------------------------------------------------ per-frame mode: Adam warps, kernel
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr int BAR_ADAM = 5;  // the two Adam warps of the per-frame kernel, once, at the end
+
+// One invocation of the Adam code is a ~1500-cycle dependent chain on a single warp whatever the number of frames it carries
+// (measured with clock64: it, not the special-function unit, bounded the first version of this mode).  A quad has to be
+// turned around in ~1150 cycles, so: two Adam warps (warp q owns quad q of every tile), 2-ulp reciprocal / square root /
+// exponential instead of the IEEE sequences, and the per-frame state fetched 8 tiles ahead, one frame per lane.
+__device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __restrict__ ctl, unsigned ep, int q, int lane, int NWc, int nbar,
+                                             unsigned char* ring, uint64_t* bars, const float4* s_rows, float* s_e, double* s_x,
+                                             long long t0, long long s0, int ns, int n, double* part) {
+  const int mode = a.mode;
+  const float hbar = (float)ctl->hbar_data;
+  const int in_set = ep & 1u, out_set = in_set ^ 1;
+  const int in_br = ctl->branch;
+  const float* __restrict__ zin = a.st.z[in_set][in_br];
+  const float* __restrict__ min_ = a.st.m[in_set][in_br];
+  const float* __restrict__ vin = a.st.v[in_set][in_br];
+  const float* __restrict__ gprev = a.st.g[in_set];
+  float* __restrict__ gout = a.st.g[out_set];
+  float* __restrict__ zA = a.st.z[out_set][0];
+  float* __restrict__ mA = a.st.m[out_set][0];
+  float* __restrict__ vA = a.st.v[out_set][0];
+  float* __restrict__ zB = a.st.z[out_set][1];
+  float* __restrict__ mB = a.st.m[out_set][1];
+  float* __restrict__ vB = a.st.v[out_set][1];
+  const float nlse2 = -1.4426950408889634f * ctl->lse;
+  const float lrA = ctl->lrA, lrB = ctl->lrB;
+  const float maskf = ctl->mask_frame;
+  const float rbc1 = 1.f / ctl->bc1, rbc2 = 1.f / ctl->bc2;
+  const int have_prev = ctl->have_prev;
+  const float b1 = a.b1, b2 = a.b2, om_b1 = a.om_b1, om_b2 = a.om_b2, eps = a.eps, clip = a.clip;
+  const int fk = lane >> 2;                                   // prefetch batch: lane (fk, lane & 3) holds frame lane & 3 of tile i0 + fk
+  const int fj = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);   // frame this lane ends up with after the transposing reduction
+  const bool lead = (lane & 7) == 0;                          // lanes 0, 8, 16, 24 carry frames 0..3
+  const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
+  double sumA = 0.0, sumB = 0.0, gdot = 0.0;
+  JCLK_DECL(clk_wait);
+  JCLK_DECL(clk_work);
+  JCLK_DECL(clk_s1);
+  JCLK_DECL(clk_s2);
+  JCLK_DECL(clk_s3);
+
+  // lane (k, fj) holds frame fj of quad q of tile i0 + k
+  float cz, cm, cv, cw, ck, cg, nz, nm, nv, nw, nk, ng;
+  auto load_batch = [&](int i0, float& z, float& m, float& v, float& w, float& k, float& g) {
+    const long long f = (t0 + i0 + fk) * FT + q * PF_FU + (lane & 3);
+    z = m = v = w = k = g = 0.f;
+    if (i0 + fk < n && f < a.F) {
+      z = zin[f];
+      m = min_[f];
+      v = vin[f];
+      if (mode) {
+        w = a.w[f];
+        k = a.kappa[f];
+        g = gprev[f];
+      }
+    }
+  };
+  load_batch(0, cz, cm, cv, cw, ck, cg);
+  load_batch(8, nz, nm, nv, nw, nk, ng);
+  const float4* sr = s_rows + q * (NWc * 32);
+  for (int i = 0; i < n; ++i) {
+    const int kb = i & 7;
+    if (kb == 0 && i > 0) {
+      cz = nz, cm = nm, cv = nv, cw = nw, ck = nk, cg = ng;
+      load_batch(i + 8, nz, nm, nv, nw, nk, ng);
+    }
+    const int src = kb * PF_FU + fj;
+    const float z_ = __shfl_sync(0xffffffffu, cz, src), m_ = __shfl_sync(0xffffffffu, cm, src), v_ = __shfl_sync(0xffffffffu, cv, src);
+    const float w_ = __shfl_sync(0xffffffffu, cw, src), k_ = __shfl_sync(0xffffffffu, ck, src), gp_ = __shfl_sync(0xffffffffu, cg, src);
+    const long long f = (t0 + i) * FT + q * PF_FU + fj;
+    const bool valid = lead && (f < a.F);
+    JCLK_TIC(tw0);
+    bar_sync(BAR_PART0 + q, nbar);  // partials of this quad visible, every consumer has it in registers
+    JCLK_TOC(clk_wait, tw0);
+    JCLK_TIC(tc0);
+    if (q == 1) {  // second quad: the tile's slot is free (one tile per stage in this mode)
+      const int slot = i % a.stages;
+      if (lane == 0 && i + a.stages < ns) {
+        const uint32_t bar = smem_u32(&bars[slot]);
+        mbar_expect_tx(bar, a.tile_bytes);
+        bulk_g2s(smem_u32(ring + (size_t)slot * a.stage_stride), gsrc + (size_t)(s0 + i + a.stages) * a.tile_bytes, a.tile_bytes, bar);
+      }
+    }
+    // H_f = sum over the rows of the consumers' partials: lane-strided, then a transposing butterfly (fixed order)
+    float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int wv = 0; wv < NWc; ++wv) {
+      const float4 t = sr[wv * 32 + lane];
+      h4.x += t.x, h4.y += t.y, h4.z += t.z, h4.w += t.w;
+    }
+    float H;
+    {
+      const bool hi = lane & 16, b3 = lane & 8;
+      const float q0 = (hi ? h4.z : h4.x) + __shfl_xor_sync(0xffffffffu, hi ? h4.x : h4.z, 16);
+      const float q1 = (hi ? h4.w : h4.y) + __shfl_xor_sync(0xffffffffu, hi ? h4.y : h4.w, 16);
+      H = (b3 ? q1 : q0) + __shfl_xor_sync(0xffffffffu, b3 ? q0 : q1, 8);
+      H += __shfl_xor_sync(0xffffffffu, H, 4);
+      H += __shfl_xor_sync(0xffffffffu, H, 2);
+      H += __shfl_xor_sync(0xffffffffu, H, 1);
+    }
+    JCLK_TOC(clk_s1, tc0);
+    float eA = 0.f, eB = 0.f;
+    if (valid) {
+      if (mode) {
+        const float gf = maskf * (w_ * ((H + k_) - hbar));
+        const float gpv = have_prev ? gp_ : gf;
+        gdot += (double)(gpv * gf);
+        gout[f] = gf;
+        float sA = gf * lrA, sB = gf * lrB;
+        if (clip > 0.f) {
+          sA = fminf(fmaxf(sA, -clip), clip);
+          sB = fminf(fmaxf(sB, -clip), clip);
+        }
+        const float m1 = om_b1 * sA + b1 * m_;
+        const float m2 = om_b1 * sB + b1 * m_;
+        const float v1 = om_b2 * (sA * sA) + b2 * v_;
+        const float v2 = om_b2 * (sB * sB) + b2 * v_;
+        const float z1 = z_ - (m1 * rbc1) * rcp_approx(sqrt_approx(v1 * rbc2) + eps);
+        const float z2 = z_ - (m2 * rbc1) * rcp_approx(sqrt_approx(v2 * rbc2) + eps);
+        eA = ex2_approx(fmaf(1.4426950408889634f, z1, nlse2));
+        eB = ex2_approx(fmaf(1.4426950408889634f, z2, nlse2));
+        JCLK_TOC(clk_s2, tc0);
+        zA[f] = z1;
+        mA[f] = m1;
+        vA[f] = v1;
+        zB[f] = z2;
+        mB[f] = m2;
+        vB[f] = v2;
+      } else {
+        eA = eB = ex2_approx(fmaf(1.4426950408889634f, z_, nlse2));
+        zA[f] = z_;
+        mA[f] = m_;
+        vA[f] = v_;
+      }
+      sumA += (double)eA;
+      sumB += (double)eB;
+    }
+    JCLK_TOC(clk_s3, tc0);
+    if (lead) {
+      s_e[q * 2 * PF_FU + fj] = eA;
+      s_e[q * 2 * PF_FU + PF_FU + fj] = eB;
+    }
+    bar_arrive(BAR_E0 + q, nbar);  // e' of this quad visible to the consumers
+    JCLK_TOC(clk_work, tc0);
+  }
+  if (blockIdx.x == 0 && lane == 0) {
+    JCLK_OUT(a.dbg, 48 + 3 * q, clk_wait);
+    JCLK_OUT(a.dbg, 49 + 3 * q, clk_work);
+    JCLK_OUT(a.dbg, 50 + 3 * q, (long long)n);
+    if (q == 0) {
+      JCLK_OUT(a.dbg, 60, clk_s1);
+      JCLK_OUT(a.dbg, 61, clk_s2);
+      JCLK_OUT(a.dbg, 62, clk_s3);
+    }
+  }
+  for (int o = 16; o >= 8; o >>= 1) {  // lanes 0, 8, 16, 24 carry the sums
+    sumA += __shfl_xor_sync(0xffffffffu, sumA, o);
+    sumB += __shfl_xor_sync(0xffffffffu, sumB, o);
+    gdot += __shfl_xor_sync(0xffffffffu, gdot, o);
+  }
+  if (q == 1 && lane == 0) {
+    s_x[0] = sumA;
+    s_x[1] = sumB;
+    s_x[2] = gdot;
+  }
+  bar_sync(BAR_ADAM, 64);
+  if (q == 0) {
+    if (blockIdx.x == 0 && mode == 1) finish_previous_record(a.x, ep, ctl, a.records, lane);
+    if (lane == 0) {
+      part[a.part_n - 4] = sumA + s_x[0];
+      part[a.part_n - 3] = sumB + s_x[1];
+      part[a.part_n - 2] = gdot + s_x[2];
+      part[a.part_n - 1] = 0.0;
+    }
+  }
+}
+
+// 16 consumer warps + 2 Adam warps: 5 warps on two of the four sub-partitions, i.e. at most 96 registers per thread
+__global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(const PassArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NTc = blockDim.x - 64, NWc = NTc >> 5;  // consumer threads / warps
+  const int nbar = NTc + 32;                          // a named barrier joins the consumers and ONE Adam warp
+  const bool is_adam = warp >= NWc;
+  const int q = warp - NWc;
+
+  unsigned char* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * a.stage_stride);
+  float* s_part = reinterpret_cast<float*>(bars + MAX_STAGES);            // (main-mode layout kept) here: 3 doubles of Adam warp 1
+  double* s_x = reinterpret_cast<double*>(s_part);
+  float* s_e = s_part + 2 * 16 * FT;                                      // [2 quads][2 branches][4 frames]
+  float4* s_tab = reinterpret_cast<float4*>(s_e + 2 * 2 * FT);            // per-thread slots: [4 pairs of time points][512 threads]
+  float4* s_rows = s_tab + (PF_TMAX / 2) * PASS_THREADS_MAX;              // [2 quads][consumer threads] per-row partials of H
+
+  // static, deterministic tile partition (one tile per bulk-copy stage in this mode)
+  const long long G = gridDim.x, cta = blockIdx.x;
+  const long long s0 = a.n_stage_units * cta / G, s1 = a.n_stage_units * (cta + 1) / G;
+  const int ns = (int)(s1 - s0);
+  const long long t0 = s0;
+  const int n = ns;
+  const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
+  double* part = a.partials + (size_t)blockIdx.x * a.part_n;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (is_adam && q == 0 && lane == 0) {  // the first tiles only need the (constant) features: start them before the PDL wait
+    const int pre = ns < a.stages ? ns : a.stages;
+    for (int s = 0; s < pre; ++s) {
+      const uint32_t bar = smem_u32(&bars[s]);
+      mbar_expect_tx(bar, a.tile_bytes);
+      bulk_g2s(smem_u32(ring + (size_t)s * a.stage_stride), gsrc + (size_t)(s0 + s) * a.tile_bytes, a.tile_bytes, bar);
+    }
+  }
+  if (blockIdx.x == 0 && tid == NTc) JPROF(a.dbg, 40);
+  pdl_wait();
+  pdl_launch_dependents();
+  if (blockIdx.x == 0 && tid == NTc) JPROF(a.dbg, 41);
+
+  const unsigned ep = *a.epoch;
+  const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
+  if (ctl->trk_stop) {  // the on-device loop has ended: drain the prefetched tiles and leave everything untouched
+    if (is_adam && q == 0 && lane == 0) {
+      const int pre = ns < a.stages ? ns : a.stages;
+      for (int s = 0; s < pre; ++s) mbar_wait(smem_u32(&bars[s]), 0);
+    }
+    return;
+  }
+  if (is_adam) {
+    pf_adam_warp(a, ctl, ep, q, lane, NWc, nbar, ring, bars, s_rows, s_e, s_x, t0, s0, ns, n, part);
+    return;
+  }
+  if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, part, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, part, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+}
+
 // ------------------------------------------------------------------------------------------ reduce
 // sum_cta partials[cta][j] in CTA order (deterministic), stored into the red inbox of EVERY rank (slot = this rank);
 // the last block to finish advances the epoch.
@@ -765,11 +1040,11 @@ int configure_kernels() {
 #define JX_CFG(K, BYTES)                                                                                       \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);                              \
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(" #K "): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  JX_CFG((bv_pass_kernel<1, 0, 0>), 111 * 1024)
-  JX_CFG((bv_pass_kernel<2, 0, 0>), 220 * 1024)
-  JX_CFG((bv_pass_kernel<1, 1, 0>), 111 * 1024)
-  JX_CFG((bv_pass_kernel<2, 1, 0>), 220 * 1024)
-  JX_CFG((bv_pass_kernel<1, 0, 1>), 220 * 1024)
+  JX_CFG((bv_pass_kernel<1, 0>), 111 * 1024)
+  JX_CFG((bv_pass_kernel<2, 0>), 220 * 1024)
+  JX_CFG((bv_pass_kernel<1, 1>), 111 * 1024)
+  JX_CFG((bv_pass_kernel<2, 1>), 220 * 1024)
+  JX_CFG(bv_pass_kernel_pf, 220 * 1024)
 #undef JX_CFG
   return JAXENT_OK;
 }
@@ -778,13 +1053,13 @@ int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, 
   cudaError_t le = cudaSuccess;
   if (a.pf_T > 0) {
     if (rpt != 1 || a.format != 0 || a.pf_T > PF_TMAX) { set_error("per-frame uptake mode needs n_residues <= 512, fp32 features and <= %d time points", PF_TMAX); return JAXENT_E_UNSUPPORTED; }
-    le = launch_pdl(bv_pass_kernel<1, 0, 1>, ctas, threads, smem, s, a);
+    le = launch_pdl(bv_pass_kernel_pf, ctas, threads + 32, smem, s, a);  // a second Adam warp
   } else {
     switch (rpt * 2 + (a.format ? 1 : 0)) {
-      case 2: le = launch_pdl(bv_pass_kernel<1, 0, 0>, ctas, threads, smem, s, a); break;
-      case 3: le = launch_pdl(bv_pass_kernel<1, 1, 0>, ctas, threads, smem, s, a); break;
-      case 4: le = launch_pdl(bv_pass_kernel<2, 0, 0>, ctas, threads, smem, s, a); break;
-      case 5: le = launch_pdl(bv_pass_kernel<2, 1, 0>, ctas, threads, smem, s, a); break;
+      case 2: le = launch_pdl(bv_pass_kernel<1, 0>, ctas, threads, smem, s, a); break;
+      case 3: le = launch_pdl(bv_pass_kernel<1, 1>, ctas, threads, smem, s, a); break;
+      case 4: le = launch_pdl(bv_pass_kernel<2, 0>, ctas, threads, smem, s, a); break;
+      case 5: le = launch_pdl(bv_pass_kernel<2, 1>, ctas, threads, smem, s, a); break;
       default: set_error("unsupported rows-per-thread %d", rpt); return JAXENT_E_UNSUPPORTED;
     }
   }

@@ -519,11 +519,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     io.pf_mode = pfm ? 1 : 0;
     io.p_max_tr = a.p_max_tr;
     io.p_max_va = a.p_max_va;
-    if (pfm) {  // per-frame uptake mode: <u>[t,r] = acc[branch d][t][r] / S straight from the reduced pass sums
+    if (pfm) {  // per-frame uptake mode: <u>[t,r] = 1 - acc[branch d][t][r] / S, acc = sum_f e'_f exp(-k tau / PF_f) from the pass
       const double invS = __drcp_rn(S);
 #pragma unroll 1
       for (int it = tid; it < R * T; it += nt) {
-        const double uv = red_total(a.x, ep, d * T * R + it) * invS;
+        const double uv = 1.0 - red_total(a.x, ep, d * T * R + it) * invS;
         tsm.sU[it] = uv;
         a.uptake[it] = (float)uv;
       }

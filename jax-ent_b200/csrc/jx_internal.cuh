@@ -271,8 +271,16 @@ struct TailArgs {
 #ifdef JX_PROFILE
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define JPROF(buf, i) do { reinterpret_cast<long long*>(buf)[i] = jx::gtime(); } while (0)
+#define JCLK_DECL(v) long long v = 0
+#define JCLK_TIC(t) const long long t = clock64()
+#define JCLK_TOC(acc, t) acc += clock64() - t
+#define JCLK_OUT(buf, i, v) do { reinterpret_cast<long long*>(buf)[i] = (v); } while (0)
 #else
 #define JPROF(buf, i) do {} while (0)
+#define JCLK_DECL(v) do {} while (0)
+#define JCLK_TIC(t) do {} while (0)
+#define JCLK_TOC(acc, t) do {} while (0)
+#define JCLK_OUT(buf, i, v) do {} while (0)
 #endif
 
 void set_error(const char* fmt, ...);
