@@ -742,6 +742,22 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (range reduction with the 1.5 * 2^23 trick, degree-6 polynomial, exponent insertion): 2.4e-7 relative.
+// The Adam warps use it because their special-function instructions would queue behind the consumers' (the MUFU / shared-memory
+// issue queue of a sub-partition is kept full by design in this kernel) and e' is on the critical path of every quad.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.f);
+  const float y = x + 12582912.f;
+  const float f = x - (y - 12582912.f);  // [-0.5, 0.5]
+  float p = 0.00015403530393381608f;
+  p = fmaf(p, f, 0.0013333558146428443f);
+  p = fmaf(p, f, 0.009618129107628477f);
+  p = fmaf(p, f, 0.05550410866482158f);
+  p = fmaf(p, f, 0.2402265069591007f);
+  p = fmaf(p, f, 0.6931471805599453f);
+  p = fmaf(p, f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
+}
 constexpr int BAR_ADAM = 5;  // the two Adam warps of the per-frame kernel, once, at the end
 
 // One invocation of the Adam code is a ~1500-cycle dependent chain on a single warp whatever the number of frames it carries
@@ -802,6 +818,7 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
   load_batch(0, cz, cm, cv, cw, ck, cg);
   load_batch(8, nz, nm, nv, nw, nk, ng);
   const float4* sr = s_rows + q * (NWc * 32);
+  int ring_slot = 0;
   for (int i = 0; i < n; ++i) {
     const int kb = i & 7;
     if (kb == 0 && i > 0) {
@@ -818,7 +835,8 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
     JCLK_TOC(clk_wait, tw0);
     JCLK_TIC(tc0);
     if (q == 1) {  // second quad: the tile's slot is free (one tile per stage in this mode)
-      const int slot = i % a.stages;
+      const int slot = ring_slot;
+      if (++ring_slot == a.stages) ring_slot = 0;
       if (lane == 0 && i + a.stages < ns) {
         const uint32_t bar = smem_u32(&bars[slot]);
         mbar_expect_tx(bar, a.tile_bytes);
@@ -827,10 +845,13 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
     }
     // H_f = sum over the rows of the consumers' partials: lane-strided, then a transposing butterfly (fixed order)
     float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int wv = 0; wv < NWc; ++wv) {
-      const float4 t = sr[wv * 32 + lane];
-      h4.x += t.x, h4.y += t.y, h4.z += t.z, h4.w += t.w;
+#pragma unroll 1
+    for (int w0 = 0; w0 < NWc; w0 += 8) {  // 8 loads in flight: one trip through the shared-memory queue per 256 rows
+      float4 t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = (w0 + k < NWc) ? sr[(w0 + k) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h4.x += t[k].x, h4.y += t[k].y, h4.z += t[k].z, h4.w += t[k].w;
     }
     float H;
     {
@@ -861,8 +882,8 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
         const float v2 = om_b2 * (sB * sB) + b2 * v_;
         const float z1 = z_ - (m1 * rbc1) * rcp_approx(sqrt_approx(v1 * rbc2) + eps);
         const float z2 = z_ - (m2 * rbc1) * rcp_approx(sqrt_approx(v2 * rbc2) + eps);
-        eA = ex2_approx(fmaf(1.4426950408889634f, z1, nlse2));
-        eB = ex2_approx(fmaf(1.4426950408889634f, z2, nlse2));
+        eA = exp2_fma(fmaf(1.4426950408889634f, z1, nlse2));
+        eB = exp2_fma(fmaf(1.4426950408889634f, z2, nlse2));
         JCLK_TOC(clk_s2, tc0);
         zA[f] = z1;
         mA[f] = m1;
@@ -871,7 +892,7 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
         mB[f] = m2;
         vB[f] = v2;
       } else {
-        eA = eB = ex2_approx(fmaf(1.4426950408889634f, z_, nlse2));
+        eA = eB = exp2_fma(fmaf(1.4426950408889634f, z_, nlse2));
         zA[f] = z_;
         mA[f] = m_;
         vA[f] = v_;
