@@ -283,13 +283,22 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_steps(F, R, T, heavy, acc, small, budget_s, max_steps, warm=1):
-    """times the oracle port (NumPy fp32, multi-threaded BLAS) on the full-size workload."""
+PF_CPU_FRAMES = 50_000  # per-frame mode: the oracle materialises (T, R, F) arrays, so the CPU arms time a frame sample
+
+
+def cpu_steps(F, R, T, heavy, acc, small, budget_s, max_steps, warm=1, average_first=True):
+    """times the oracle port (NumPy fp32, multi-threaded BLAS) on the full-size workload; per-frame mode (average_first False):
+    on the first PF_CPU_FRAMES frames, steps/s scaled by the frame ratio (the cost is linear in the number of frames)."""
     from oracle import bv_oracle as O
+
+    scale = 1.0
+    if not average_first and F > PF_CPU_FRAMES:
+        scale = PF_CPU_FRAMES / F
+        heavy, acc, F = np.ascontiguousarray(heavy[:, :PF_CPU_FRAMES]), np.ascontiguousarray(acc[:, :PF_CPU_FRAMES]), PF_CPU_FRAMES
 
     slots = [O.LossSlot(O.UPTAKE_EYE_MSE, small.S_train, small.y_train, small.S_val, small.y_val),
              O.LossSlot(O.MAXENT_CONVEX_KL, prior=np.full(F, 1.0 / F, np.float32))]
-    pb = O.Problem(heavy, acc, small.k_ints, small.timepoints, slots, True)
+    pb = O.Problem(heavy, acc, small.k_ints, small.timepoints, slots, True, average_first)
     fw = O.normalize_masked_loss_scalingweights(np.array([1.0, 1.0]), np.ones(2))
     par = O.Params(np.full(F, 1.0 / F, np.float32), np.ones(F, np.float32), 0.35, 2.0, fw, np.full(2, 1000.0, np.float32), np.ones(2))
     cfg = O.OptConfig(learning_rate=1.0, clip_value=None)
@@ -302,7 +311,7 @@ def cpu_steps(F, R, T, heavy, acc, small, budget_s, max_steps, warm=1):
         st, loss, _ = O.step_with_rates(pb, st, cfg, np.float32)
         n += 1
     dt = time.perf_counter() - t0
-    return n / dt, n, dt, float(loss)
+    return scale * n / dt, n, dt, float(loss)
 
 
 def host_threads():
@@ -338,7 +347,8 @@ def run_reference(args, wl):
     small = small_problem(R, T)
     heavy, acc = host_features(F, R)
     budget = min(60.0, max(5.0, 0.5 * args.steps))
-    sps, n, dt, loss = cpu_steps(F, R, T, heavy, acc, small, budget_s=budget, max_steps=max(2, args.steps), warm=max(1, min(args.warmup, 2)))
+    sps, n, dt, loss = cpu_steps(F, R, T, heavy, acc, small, budget_s=budget, max_steps=max(2, args.steps), warm=max(1, min(args.warmup, 2)),
+                                 average_first=not args.per_frame)
     cores = host_threads()
     line = {
         "impl": "reference",
@@ -357,7 +367,9 @@ def run_reference(args, wl):
         "frame_residue_timepoint_per_s": sps * F * R * T,
         "config": {"workload": wl["name"], "frames": F, "residues": R, "timepoints": T},
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} full-size optimise steps of the NumPy fp32 oracle port (oracle/bv_oracle.py), {dt:.1f} s; "
+                         "sample": f"{n} " + (f"optimise steps on the first {PF_CPU_FRAMES} frames (per-frame mode; steps/s scaled by {PF_CPU_FRAMES}/{F})"
+                                               if args.per_frame and F > PF_CPU_FRAMES else "full-size optimise steps") +
+                                   f" of the NumPy fp32 oracle port (oracle/bv_oracle.py), {dt:.1f} s; "
                                    "the reference's JAX loop itself cannot run here (no jax/optax in the image)"},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_loss": loss,
@@ -556,9 +568,18 @@ def run_ours(args, wl):
                 hh, aa = host_h.numpy(), host_a.numpy()
             else:
                 hh, aa = host_features(F, R)
-            c_sps, c_n, c_dt, _ = cpu_steps(F, R, T, hh, aa, small, budget_s=15.0, max_steps=50)
+            c_sps, c_n, c_dt, _ = cpu_steps(F, R, T, hh, aa, small, budget_s=15.0, max_steps=50, average_first=not args.per_frame)
+            what = (f"optimise steps on the first {PF_CPU_FRAMES} frames (per-frame mode; steps/s scaled by {PF_CPU_FRAMES}/{F})"
+                    if args.per_frame and F > PF_CPU_FRAMES else "full-size optimise steps")
             cpu = {"value": c_sps, "unit": "steps/s", "cores": host_threads(), "kind": "port",
-                   "sample": f"{c_n} full-size optimise steps of the NumPy fp32 oracle port in {c_dt:.1f} s (oracle restatement, not the reference's JAX loop)"}
+                   "sample": f"{c_n} {what} of the NumPy fp32 oracle port in {c_dt:.1f} s (oracle restatement, not the reference's JAX loop)"}
+        sfu = None
+        if args.per_frame:  # the bound that matters in this mode: 16 special-function results per clock per SM
+            clk = sampler.result().get("sm_mhz") or 1900.0
+            sf_peak = 16 * 148 * clk * 1e6 / 1e9
+            sf_ach = Fl * R * (T + 1) / (pass_ms * 1e-3) / 1e9
+            sfu = {"achieved": sf_ach, "peak": sf_peak, "unit": "G ex2/s", "frac": sf_ach / sf_peak,
+                   "note": "F*R*(T+1) ex2.approx per launch against 16/clk/SM at the sampled SM clock"}
         line = {
             "metric": "optimise steps/sec",
             "value": sps,
@@ -584,7 +605,8 @@ def run_ours(args, wl):
                        "losses": ["hdx_uptake_eye_MSE_loss", "maxent_convexKL_loss"], "optimizer": "adam lr=1.0, plateau 1.005"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "bv_pass_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": pass_ms, "peak_source": peak_src, "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                         "kernel_ms": pass_ms, "peak_source": peak_src, "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                         **({"special_function": sfu} if sfu else {})},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": 3 * K,
