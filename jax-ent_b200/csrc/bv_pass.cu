@@ -795,6 +795,7 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
   double sumA = 0.0, sumB = 0.0, gdot = 0.0;
   JCLK_DECL(clk_wait);
   JCLK_DECL(clk_work);
+  JCLK_DECL(clk_s0);
   JCLK_DECL(clk_s1);
   JCLK_DECL(clk_s2);
   JCLK_DECL(clk_s3);
@@ -853,6 +854,7 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
 #pragma unroll
       for (int k = 0; k < 8; ++k) h4.x += t[k].x, h4.y += t[k].y, h4.z += t[k].z, h4.w += t[k].w;
     }
+    JCLK_TOC(clk_s0, tc0);
     float H;
     {
       const bool hi = lane & 16, b3 = lane & 8;
@@ -864,27 +866,40 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
       H += __shfl_xor_sync(0xffffffffu, H, 1);
     }
     JCLK_TOC(clk_s1, tc0);
-    float eA = 0.f, eB = 0.f;
+    // critical path first: e' of both branches -> shared memory -> barrier; the global stores and the fp64 sums follow
+    float eA = 0.f, eB = 0.f, gf = 0.f, m1 = 0.f, m2 = 0.f, v1 = 0.f, v2 = 0.f, z1 = 0.f, z2 = 0.f;
     if (valid) {
       if (mode) {
-        const float gf = maskf * (w_ * ((H + k_) - hbar));
-        const float gpv = have_prev ? gp_ : gf;
-        gdot += (double)(gpv * gf);
-        gout[f] = gf;
+        gf = maskf * (w_ * ((H + k_) - hbar));
         float sA = gf * lrA, sB = gf * lrB;
         if (clip > 0.f) {
           sA = fminf(fmaxf(sA, -clip), clip);
           sB = fminf(fmaxf(sB, -clip), clip);
         }
-        const float m1 = om_b1 * sA + b1 * m_;
-        const float m2 = om_b1 * sB + b1 * m_;
-        const float v1 = om_b2 * (sA * sA) + b2 * v_;
-        const float v2 = om_b2 * (sB * sB) + b2 * v_;
-        const float z1 = z_ - (m1 * rbc1) * rcp_approx(sqrt_approx(v1 * rbc2) + eps);
-        const float z2 = z_ - (m2 * rbc1) * rcp_approx(sqrt_approx(v2 * rbc2) + eps);
+        m1 = om_b1 * sA + b1 * m_;
+        m2 = om_b1 * sB + b1 * m_;
+        v1 = om_b2 * (sA * sA) + b2 * v_;
+        v2 = om_b2 * (sB * sB) + b2 * v_;
+        z1 = z_ - (m1 * rbc1) * rcp_approx(sqrt_approx(v1 * rbc2) + eps);
+        z2 = z_ - (m2 * rbc1) * rcp_approx(sqrt_approx(v2 * rbc2) + eps);
         eA = exp2_fma(fmaf(1.4426950408889634f, z1, nlse2));
         eB = exp2_fma(fmaf(1.4426950408889634f, z2, nlse2));
-        JCLK_TOC(clk_s2, tc0);
+      } else {
+        eA = eB = exp2_fma(fmaf(1.4426950408889634f, z_, nlse2));
+      }
+    }
+    JCLK_TOC(clk_s2, tc0);
+    if (lead) {
+      s_e[q * 2 * PF_FU + fj] = eA;
+      s_e[q * 2 * PF_FU + PF_FU + fj] = eB;
+    }
+    bar_arrive(BAR_E0 + q, nbar);  // e' of this quad visible to the consumers
+    JCLK_TOC(clk_s3, tc0);
+    if (valid) {
+      if (mode) {
+        const float gpv = have_prev ? gp_ : gf;
+        gdot += (double)(gpv * gf);
+        gout[f] = gf;
         zA[f] = z1;
         mA[f] = m1;
         vA[f] = v1;
@@ -892,7 +907,6 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
         mB[f] = m2;
         vB[f] = v2;
       } else {
-        eA = eB = exp2_fma(fmaf(1.4426950408889634f, z_, nlse2));
         zA[f] = z_;
         mA[f] = m_;
         vA[f] = v_;
@@ -900,12 +914,6 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
       sumA += (double)eA;
       sumB += (double)eB;
     }
-    JCLK_TOC(clk_s3, tc0);
-    if (lead) {
-      s_e[q * 2 * PF_FU + fj] = eA;
-      s_e[q * 2 * PF_FU + PF_FU + fj] = eB;
-    }
-    bar_arrive(BAR_E0 + q, nbar);  // e' of this quad visible to the consumers
     JCLK_TOC(clk_work, tc0);
   }
   if (blockIdx.x == 0 && lane == 0) {
@@ -913,6 +921,7 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
     JCLK_OUT(a.dbg, 49 + 3 * q, clk_work);
     JCLK_OUT(a.dbg, 50 + 3 * q, (long long)n);
     if (q == 0) {
+      JCLK_OUT(a.dbg, 63, clk_s0);
       JCLK_OUT(a.dbg, 60, clk_s1);
       JCLK_OUT(a.dbg, 61, clk_s2);
       JCLK_OUT(a.dbg, 62, clk_s3);

@@ -31,4 +31,4 @@ if len(sys.argv) > 4:
         n = float(dbg[50])
         print(f"  per tile: adam0 wait {dbg[48]/n:.0f} work {dbg[49]/n:.0f} | adam1 wait {dbg[51]/n:.0f} work {dbg[52]/n:.0f} | "
               f"consumer ring {dbg[56]/n:.0f} A {dbg[57]/n:.0f} waitE {dbg[58]/n:.0f} B {dbg[59]/n:.0f} | "
-              f"adam0 since sync: H {dbg[60]/n:.0f} math {dbg[61]/n:.0f} stores {dbg[62]/n:.0f}", flush=True)
+              f"adam0 since sync: row sums {dbg[63]/n:.0f} H {dbg[60]/n:.0f} math {dbg[61]/n:.0f} arrive {dbg[62]/n:.0f}", flush=True)
