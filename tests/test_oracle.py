@@ -245,3 +245,62 @@ def test_bpti_fixture_optimise_runs_and_recovers():
     assert np.all(np.isfinite(tr)) and min(tr[20:]) < tr[1]
     assert len(res["history"]) >= 1 and res["best"] is not None
     np.testing.assert_allclose(res["history"][-1]["weights"].sum(), 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("clip", [None, 0.05])
+def test_trajectory_matches_torch_optim_adam(clip):
+    """The optax pieces are not importable here (oracle header: parity unpinned).  This pins the oracle's update rule against an
+    INDEPENDENT implementation of the same published algorithm: torch.optim.Adam(lr=1) fed the LR-pre-scaled, clipped
+    gradients of a torch.autograd fp64 loss (opt/optimiser.py:124-148,403-424), with the plateau rule and
+    keep_params_nonnegative applied by hand."""
+    case = H.make_case(160, 11, 4, O.UPTAKE_EYE_MSE, extra=(O.PARAMS_L2,), seed=12, n_pep=6, prior="random", gamma=2.0, scaling=40.0)
+    cfg = O.OptConfig(learning_rate=0.3, initial_learning_rate=0.3, clip_value=clip, optimise_model_parameters=True, model_parameters_lr_scale=0.5)
+    st = O.optimizer_initialise(case["params"], cfg, np.float64)
+    tz = torch.tensor(st.params.z, dtype=torch.float64, requires_grad=True)
+    tb = torch.tensor([st.params.bc, st.params.bh], dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([tz, tb], lr=1.0, betas=(cfg.b1, cfg.b2), eps=cfg.eps)
+    prev = None
+    reduced = 0
+    for k in range(25):
+        st, loss, _ = O.step_with_rates(case["problem"], st, cfg, np.float64)
+        opt.zero_grad()
+        tot = _torch_loss(case, tz, tb[0], tb[1])
+        tot.backward()
+        np.testing.assert_allclose(float(tot.detach()), float(loss), rtol=1e-10)
+        g = [tz.grad.clone(), tb.grad.clone()]
+        dot = float(sum((a * b).sum() for a, b in zip(prev if prev is not None else g, g)))
+        prev = g
+        red = dot < 0 and k > 1
+        reduced += red
+        lr = cfg.learning_rate / (cfg.plateau_denominator if red else 1.0)
+        tz.grad.mul_(lr)
+        tb.grad.mul_(lr * cfg.model_parameters_lr_scale)
+        if clip is not None:
+            tz.grad.clamp_(-clip, clip)
+            tb.grad.clamp_(-clip, clip)
+        opt.step()
+        with torch.no_grad():
+            tb.clamp_(min=0.0)  # where(p + u < 0, -p, u)
+        np.testing.assert_allclose(st.params.z, tz.detach().numpy(), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose([st.params.bc, st.params.bh], tb.detach().numpy(), rtol=1e-9)
+    assert reduced > 0  # the plateau branch was exercised
+
+
+def test_convex_kl_matches_torch_kl_div():
+    """maxent_convexKL_loss (opt/losses.py:304-322) = KL(p || q) + sum(q - p): against torch.nn.functional.kl_div"""
+    rng = np.random.default_rng(3)
+    F = 500
+    z = rng.normal(size=F) * 3
+    prior = rng.random(F) + 0.01
+    prior /= prior.sum()
+    w = O.softmax(z, np.float64)
+    eps = 1e-10 / F
+    q = torch.tensor((np.abs(w) + eps) / (np.abs(w) + eps).sum())
+    p = torch.tensor((np.abs(prior) + eps) / (np.abs(prior) + eps).sum())
+    want = float(torch.nn.functional.kl_div(q.log(), p, reduction="sum") + (q - p).sum())
+    case = H.make_case(F, 5, 3, O.UPTAKE_EYE_MSE, seed=1, n_pep=3)
+    slot = O.LossSlot(O.MAXENT_CONVEX_KL, prior=prior)
+    pb = O.Problem(case["problem"].heavy, case["problem"].acceptor, case["problem"].k_ints, case["problem"].timepoints, [slot], True)
+    par = O.Params(z, np.ones(F), 0.35, 2.0, np.ones(1), np.ones(1), np.zeros(1))
+    L, _, _ = O.loss_and_grads(pb, par, np.float64)
+    np.testing.assert_allclose(float(L.train_losses[0]), want, rtol=1e-10)
