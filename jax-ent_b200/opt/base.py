@@ -57,3 +57,20 @@ class OptimizationHistory:
     def get_best_state(self):
         self.best_state = self._pick_best_state(self.states)
         return self.best_state
+
+
+class HParamBatch(NamedTuple):
+    """Batch of hyper-parameter values for `batch_optimise` (reference opt/base.py:212-217)."""
+
+    forward_model_weights: Any  # (n_hparams, n_losses)
+    forward_model_scaling: Any  # (n_hparams, n_losses)
+    learning_rate: Optional[Any] = None  # (n_hparams,)
+
+
+class BatchOptimisationResult(NamedTuple):
+    """Structured output of `batch_optimise` (reference opt/base.py:220-227)."""
+
+    histories: tuple
+    best_states: tuple
+    convergence_steps: Any
+    hparam_batch: HParamBatch

@@ -10,7 +10,7 @@ or "auto" on other features) every run uses the single-ensemble on-device loop (
 features, one replica after the other."""
 from __future__ import annotations
 
-from typing import NamedTuple, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -19,22 +19,9 @@ from .._arrays import to_numpy
 from ..custom_types.config import OptimiserSettings
 from ..interfaces.simulation import Simulation_Parameters, _replace
 from ..models.core import Simulation
-from .base import OptimizationHistory, OptimizationState
+from .base import BatchOptimisationResult, HParamBatch, OptimizationHistory, OptimizationState  # noqa: F401 (re-exported)
 from .optimiser import OptaxOptimizer
 from .run import _optimise_device
-
-
-class HParamBatch(NamedTuple):
-    forward_model_weights: object  # (n_hparams, n_losses)
-    forward_model_scaling: object  # (n_hparams, n_losses)
-    learning_rate: Optional[object] = None  # (n_hparams,)
-
-
-class BatchOptimisationResult(NamedTuple):
-    histories: tuple
-    best_states: tuple
-    convergence_steps: object
-    hparam_batch: HParamBatch
 
 
 def _batch_optimise_gemm(simulation: Simulation, fw, fs, lrs, batch_size: int, data_to_fit, config: OptimiserSettings, indexes,
