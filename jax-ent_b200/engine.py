@@ -14,6 +14,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import _lib as L
 from .sharding import PeerExchange, ShardComm
@@ -228,15 +229,25 @@ class BvEngine:
         self.launches = 0
 
     # ------------------------------------------------------------------ plumbing
+    def close(self, barrier: bool = True) -> None:
+        """Releases the plan and the peer-mapped exchange buffers.  Frame-sharded engines: call this on EVERY rank (it is a
+        collective when `barrier` is true) -- a rank must not free its inbox while a slower peer's last tail kernel may still
+        store its MaxEnt words into it, so the ranks synchronise their devices and meet at a barrier first."""
+        peer = getattr(self, "peer", None)
+        if peer is not None:
+            torch.cuda.synchronize(self.device)
+            if barrier and self.group is not None and dist.is_available() and dist.is_initialized():
+                dist.barrier(group=self.group)
+        if getattr(self, "plan", None):
+            self.lib.jaxent_bv_plan_destroy(self.plan)
+            self.plan = None
+        if peer is not None:
+            peer.close()
+            self.peer = None
+
     def __del__(self):
-        try:
-            if getattr(self, "plan", None):
-                self.lib.jaxent_bv_plan_destroy(self.plan)
-                self.plan = None
-            if getattr(self, "peer", None) is not None:
-                torch.cuda.synchronize(self.device)
-                self.peer.close()
-                self.peer = None
+        try:  # best effort, never a collective: an explicit close() is the safe path for sharded engines
+            self.close(barrier=False)
         except Exception:
             pass
 
