@@ -46,7 +46,7 @@ def backend() -> str:
 def save_array_to_hdf5(h5file, path: str, array, **kwargs) -> None:
     """reference :29-50 -- scalars are stored without chunking / compression"""
     a = to_numpy(array)
-    if a.shape == () or a.size == 1:
+    if a.shape == () or a.size <= 1:  # h5py cannot chunk scalars (nor empty arrays)
         kwargs = {k: v for k, v in kwargs.items() if k not in ("compression", "compression_opts", "chunks")}
     h5file.create_dataset(path, data=a, **kwargs)
 

@@ -203,3 +203,43 @@ def test_empty_history_and_missing_losses(tmp_path):
     h.states[0] = h.states[0]._replace(losses=None)
     hdf.save_optimization_history_to_file(path, h)
     assert hdf.load_optimization_history_from_file(path).states[0].losses is None
+
+
+def test_random_trees_round_trip(tmp_path):
+    """seeded random group trees: names that sort differently as bytes / numbers, all supported dtypes, attributes everywhere"""
+    rng = np.random.default_rng(7)
+    dtypes = [np.float32, np.float64, np.int8, np.int32, np.int64, np.uint16, np.uint64, np.bool_]
+
+    def fill(g, depth):
+        spec = {}
+        for k in range(int(rng.integers(0, 12))):
+            name = f"{'n' if rng.random() < 0.5 else ''}{int(rng.integers(0, 1000))}_{k}"
+            if depth < 3 and rng.random() < 0.3:
+                spec[name] = fill(g.create_group(name), depth + 1)
+            else:
+                dt = dtypes[int(rng.integers(len(dtypes)))]
+                shape = tuple(int(x) for x in rng.integers(0, 5, size=int(rng.integers(0, 4))))
+                a = (rng.random(shape) * 100).astype(dt)
+                g.create_dataset(name, data=a)
+                spec[name] = a
+        g.attrs["depth"] = depth
+        g.attrs["label"] = f"level-{depth}-é"
+        g.attrs["vals"] = rng.random(3)
+        return spec
+
+    def check(g, spec, depth):
+        assert sorted(g.keys()) == sorted(spec) and int(g.attrs["depth"]) == depth and g.attrs["label"] == f"level-{depth}-é"
+        assert g.attrs["vals"].shape == (3,)
+        for name, want in spec.items():
+            if isinstance(want, dict):
+                check(g[name], want, depth + 1)
+            else:
+                got = g[name][()]
+                assert np.asarray(got).dtype == want.dtype and np.asarray(got).shape == want.shape
+                np.testing.assert_array_equal(got, want)
+
+    for trial in range(5):
+        path = str(tmp_path / f"r{trial}.h5")
+        with _h5mini.File(path, "w") as f:
+            spec = fill(f, 0)
+        check(_h5mini.File(path, "r"), spec, 0)
