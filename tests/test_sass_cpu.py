@@ -13,6 +13,12 @@ cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 pytestmark = pytest.mark.skipif(shutil.which(cuobjdump) is None, reason="cuobjdump not available")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if _build.needs_build():
+        _build.build()
+
+
 @pytest.fixture(scope="module")
 def resources():
     out = subprocess.run([cuobjdump, "--dump-resource-usage", _build.LIB], capture_output=True, text=True, check=True).stdout
