@@ -1,0 +1,38 @@
+"""bench.py contract checks that need no GPU: the reference arm's JSON line, and that our arm fails loudly (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = _run("--impl", "reference", "--workload", "cfg1", "--steps", "3", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "optimise steps/sec" and d["unit"] == "steps/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] >= 2 and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["config"]["frames"] == 500 and d["config"]["residues"] == 53 and d["config"]["timepoints"] == 3
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--gpus", "2", "--steps", "2"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_our_arm_has_no_cpu_fallback():
+    r = _run("--workload", "cfg1", "--steps", "2", "--warmup", "1")
+    assert r.returncode != 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
