@@ -1,5 +1,10 @@
-"""m_key / m_id (reference jaxent/src/custom_types/key.py)."""
-from typing import NewType
+"""String tags used as dictionary keys for forward-model outputs and identifiers (same names and call behaviour as the
+reference's `custom_types/key.py`: `m_key("HDX_peptide")` returns the plain string, statically typed as its own kind)."""
+import typing
 
-m_key = NewType("m_key", str)
-m_id = NewType("m_id", str)
+
+def _string_tag(name: str):
+    return typing.NewType(name, str)
+
+
+m_key, m_id = _string_tag("m_key"), _string_tag("m_id")
