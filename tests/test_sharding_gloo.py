@@ -100,3 +100,44 @@ def test_sharded_protocol_matches_unsharded_oracle(world, F):
     out = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, port, F, 23, 3, out), nprocs=world, join=True)
     assert sorted(out.keys()) == list(range(world))
+
+
+def _worker_per_frame(rank, world, port, F, R, T, out):
+    """per-frame uptake mode (average_first=False): the reduced vector is 2*T*R + 4 doubles holding sum_f e_f exp(-k tau / PF_f)
+    for both branches; every rank forms <u> = 1 - acc / S from it (tail of the per-frame mode)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = ShardComm(dist.group.WORLD)
+        from dataclasses import replace
+
+        case = H.make_case(F, R, T, O.UPTAKE_EYE_MSE, seed=6, prior="random")
+        pb, par = replace(case["problem"], average_first=False), case["params"]
+        sh = frame_shard(F, rank, world)
+        z = np.random.default_rng(11).normal(size=F) * 2.0
+        zl = z[sh.slice()]
+        Nc, Nh = pb.heavy[:, sh.slice()].astype(np.float64), pb.acceptor[:, sh.slice()].astype(np.float64)
+        zmax = comm.max_(torch.tensor([zl.max()], dtype=torch.float64))
+        e = np.exp(zl - float(zmax))
+        pinv = np.exp(-(par.bc * Nc + par.bh * Nh))  # (R, Fl)
+        E = np.exp(-pb.k_ints[None, :, None] * pb.timepoints[:, None, None] * pinv[None, :, :])  # (T, R, Fl)
+        acc = (E * e[None, None, :]).sum(-1).reshape(-1)
+        red = np.concatenate([acc, acc, [e.sum(), e.sum(), 0.0, 0.0]])
+        assert red.shape[0] == 2 * T * R + 4
+        red = comm.sum_(torch.from_numpy(red)).numpy()
+        S = red[2 * T * R]
+        u = 1.0 - red[: T * R].reshape(T, R) / S
+        full = O.Params(z, par.frame_mask, par.bc, par.bh, par.fw, par.fs, par.nlf)
+        _, _, outp = O.compute_loss(pb, full, np.float64)
+        np.testing.assert_allclose(u, outp["uptake"], rtol=1e-11, atol=1e-13)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_per_frame_protocol_matches_unsharded_oracle():
+    port = _free_port()
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker_per_frame, args=(2, port, 600, 19, 4, out), nprocs=2, join=True)
+    assert sorted(out.keys()) == [0, 1]
