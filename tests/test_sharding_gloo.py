@@ -121,7 +121,8 @@ def _worker_per_frame(rank, world, port, F, R, T, out):
         zmax = comm.max_(torch.tensor([zl.max()], dtype=torch.float64))
         e = np.exp(zl - float(zmax))
         pinv = np.exp(-(par.bc * Nc + par.bh * Nh))  # (R, Fl)
-        E = np.exp(-pb.k_ints[None, :, None] * pb.timepoints[:, None, None] * pinv[None, :, :])  # (T, R, Fl)
+        k, tp = pb.k_ints.astype(np.float64), pb.timepoints.astype(np.float64)
+        E = np.exp(-k[None, :, None] * tp[:, None, None] * pinv[None, :, :])  # (T, R, Fl)
         acc = (E * e[None, None, :]).sum(-1).reshape(-1)
         red = np.concatenate([acc, acc, [e.sum(), e.sum(), 0.0, 0.0]])
         assert red.shape[0] == 2 * T * R + 4
