@@ -312,7 +312,8 @@ int jaxent_bg_gemm2(const void* features, const void* e3, float* partials, int32
  * jaxent_bg_state_init = OptaxOptimizer.initialise + the step-0 forward; jaxent_bg_step = one optimise step of every replica.
  * Buffers (jaxent_bg_plan_buffer): 0 logits float[F][Bn], 1 exp(z - lse) float[F][Bn] (softmax weights = column / S),
  * 2 JaxentLossRecord[256][Bn] ring (index step % 256), 3 control blocks (jaxent_bg_ctl_sizeof() bytes each; double S at
- * jaxent_bg_ctl_offset(0)), 4 log_Pf float[Bn][R], 5 uptake float[Bn][T*R]. */
+ * jaxent_bg_ctl_offset(0)), 4 log_Pf float[Bn][R], 5 uptake float[Bn][T*R]; 8 / 9 the two masked-gradient buffers float[F][Bn]
+ * (state.gradients of the update applied last is the one selected by the uint32 at buffer 10). */
 typedef struct JaxentBatchPlan JaxentBatchPlan;
 size_t jaxent_bg_workspace_bytes(const JaxentBvProblem* problem, int32_t n_replicas, int32_t n_pieces, int32_t sm_count);
 int jaxent_bg_plan_create(const JaxentBvProblem* problem, const JaxentOptConfig* cfg, int32_t n_replicas, int32_t n_pieces,

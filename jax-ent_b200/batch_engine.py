@@ -221,6 +221,11 @@ class BatchedBvEngine(BvEngine):
         S = torch.from_numpy(self.ctl_field(0, np.float64)).to(self.device)
         return self.e[:, : self.B] / S.to(torch.float32)[None, :]
 
+    def gradients_all(self) -> torch.Tensor:
+        """masked gradients d loss / d logits of the update applied last, (F, B) float32 (state.gradients)."""
+        sel = int(self._bview(10, torch.int32).cpu().item())
+        return self._bview(8 + sel, torch.float32).view(self.F, self.Bn)[:, : self.B]
+
     def algorithmic_flops_per_step(self) -> int:
         """2*(2*R*F*B) forward + 2*(2*R*F*B) backward, times the number of bf16 pieces."""
         return 8 * self.R * self.F * self.B * self.n_pieces

@@ -23,7 +23,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
-  size_t off_w, off_kappa, off_cc, off_ch, off_logpf, off_uptake, off_avg, off_pfG;
+  size_t off_w, off_kappa, off_kappa_lo, off_cc, off_ch, off_ck, off_logpf, off_uptake, off_avg, off_pfG;
   size_t off_partials, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_ticket, off_records;
   size_t off_cl_scratch;
   size_t off_blob[JAXENT_MAX_SLOTS];
@@ -55,8 +55,10 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_g[1] = take(fb);
   L.off_w = take(fb);
   L.off_kappa = take(fb);
+  L.off_kappa_lo = take(fb);
   L.off_cc = take((size_t)R * 4);
   L.off_ch = take((size_t)R * 4);
+  L.off_ck = take((size_t)R * 4);
   L.off_logpf = take((size_t)R * 4);
   L.off_uptake = take((size_t)(T > 0 ? T : 1) * R * 4);
   L.off_avg = take((size_t)2 * R * 4);
@@ -461,8 +463,10 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.st = p->st;
   a.w = reinterpret_cast<const float*>(p->ws + p->lay.off_w);
   a.kappa = reinterpret_cast<const float*>(p->ws + p->lay.off_kappa);
+  a.kappa_lo = reinterpret_cast<const float*>(p->ws + p->lay.off_kappa_lo);
   a.cc = reinterpret_cast<const float*>(p->ws + p->lay.off_cc);
   a.ch = reinterpret_cast<const float*>(p->ws + p->lay.off_ch);
+  a.ck = reinterpret_cast<const float*>(p->ws + p->lay.off_ck);
   a.partials = reinterpret_cast<double*>(p->ws + p->lay.off_partials);
   a.x = p->x;
   a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
@@ -508,8 +512,10 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.counter = reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter);
   a.w = reinterpret_cast<float*>(p->ws + p->lay.off_w);
   a.kappa = reinterpret_cast<float*>(p->ws + p->lay.off_kappa);
+  a.kappa_lo = reinterpret_cast<float*>(p->ws + p->lay.off_kappa_lo);
   a.cc = reinterpret_cast<float*>(p->ws + p->lay.off_cc);
   a.ch = reinterpret_cast<float*>(p->ws + p->lay.off_ch);
+  a.ck = reinterpret_cast<float*>(p->ws + p->lay.off_ck);
   a.logpf = reinterpret_cast<float*>(p->ws + p->lay.off_logpf);
   a.uptake = reinterpret_cast<float*>(p->ws + p->lay.off_uptake);
   a.avg = reinterpret_cast<float*>(p->ws + p->lay.off_avg);

@@ -111,17 +111,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 // invS = 1 / S_b.  The quotient p/q only has to be *some* fp32 approximation r0: the FMA residual p - r0*q is exact, so
 // r0 + corr carries p/q to ~1e-14 whatever the error of the approximate reciprocal.
-__device__ __forceinline__ void weight_terms(float e, float invS, float p, bool has_kl, float eps, float lam, float& w, float& kap, float& q) {
+// kappa is returned in fp64 (two conversions and three fp64 operations, no fp64 division): once a few frames dominate,
+// g_f = w_f (H_f + kappa_f - hbar) is a difference of O(lambda) numbers and needs more than 24 bits (see frame_terms).
+__device__ __forceinline__ void weight_terms(float e, float invS, float p, bool has_kl, float eps, float lam, float& w, double& kap, float& q) {
   w = e * invS;
-  kap = 0.f;
+  kap = 0.0;
   q = 0.f;
   if (has_kl) {
     q = fabsf(w) + eps;
     const float rq = rcp_approx(q);
     const float r0 = p * rq;
     const float corr = fmaf(-r0, q, p) * rq;
-    const float G_ = (1.0f - r0) - corr;
-    kap = (w > 0.f) ? lam * G_ : 0.f;
+    const double G_ = (1.0 - (double)r0) - (double)corr;
+    kap = (w > 0.f) ? (double)lam * G_ : 0.0;
   }
 }
 
@@ -139,18 +141,20 @@ __global__ void __launch_bounds__(512) bt_grad_kernel(const BatchArgs a) {
   const float* __restrict__ pn = a.pnorm;
   // per-replica constants: one thread per replica reads its control block, everybody else takes them from shared memory
   // (a strided control-block read per thread costs more than the whole frame loop)
-  __shared__ float s_f[4][256];
+  __shared__ float s_f[3][256];
+  __shared__ double s_hbar[256];
   __shared__ int s_i[256];
   for (int b = threadIdx.x; b < Bn; b += blockDim.x) {
     const BCtl* c = a.ctl + b;
     s_f[0][b] = (float)(1.0 / c->S);
     s_f[1][b] = c->kl_scale;
     s_f[2][b] = c->mask_frame;
-    s_f[3][b] = (float)c->hbar_data;  // the MaxEnt part of hbar is O(1e-10 lambda): see bv_pass.cu, finish_previous_record
+    s_hbar[b] = c->hbar_data + c->klsum[0];  // hbar = sum_j w_j (H_j + kappa_j): data part + MaxEnt part (see gather_hbar, bv_pass.cu)
     s_i[b] = (c->have_prev ? 1 : 0) | ((c->kl_slot >= 0 && a.prob.prior != nullptr) ? 2 : 0) | (c->stop ? 0 : 4);
   }
   __syncthreads();
-  float invS[4], lam[4], maskf[4], hbar[4];
+  float invS[4], lam[4], maskf[4];
+  double hbar[4];
   int have_prev[4];
   bool has_kl[4], active[4];
 #pragma unroll
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(512) bt_grad_kernel(const BatchArgs a) {
     invS[j] = s_f[0][b0 + j];
     lam[j] = s_f[1][b0 + j];
     maskf[j] = s_f[2][b0 + j];
-    hbar[j] = s_f[3][b0 + j];
+    hbar[j] = s_hbar[b0 + j];
     const int fl = s_i[b0 + j];
     have_prev[j] = fl & 1;
     has_kl[j] = fl & 2;
@@ -187,9 +191,10 @@ __global__ void __launch_bounds__(512) bt_grad_kernel(const BatchArgs a) {
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float w, kap, q;
+          float w, q;
+          double kap;
           weight_terms(e4[j], invS[j], pv[k], has_kl[j], a.eps_kl, lam[j], w, kap, q);
-          const float gf = active[j] ? maskf[j] * (w * ((h4[j] + kap) - hbar[j])) : 0.f;
+          const float gf = active[j] ? maskf[j] * (w * (float)(((double)h4[j] + kap) - hbar[j])) : 0.f;
           const float gpv = have_prev[j] ? g4[j] : gf;
           dot[j] += (double)(gpv * gf);
           o[j] = gf;
@@ -509,6 +514,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArg
   io.pf_mode = 0;
   io.p_max_tr = a.p_max_tr;
   io.p_max_va = a.p_max_va;
+  io.c_pieces = a.NS;
+  io.ck = nullptr;
   tail_body<GENERAL>(pb, a.blobs, first_data, tsm, acc0, acc1, S, bc, bh, s_c.fw, s_c.fs, io, s_red, s_fin, my_c, my_a, my_b, my_lp, gbc_reg,
                      gbh_reg);
   if (tid < R) {
@@ -590,23 +597,27 @@ __global__ void __launch_bounds__(512) bt_kl_kernel(const BatchArgs a) {
   // only matters for frames whose weight has collapsed to the order of eps = 1e-10 / F: those are evaluated here,
   // every other frame contributes less than 1e-9 * p_f and is skipped.  No logarithm per (frame, replica).
   // thread = (4 consecutive replicas, frame lane): 16-byte loads, 4 frames in flight.
-  __shared__ float s_f[2][256];
+  __shared__ float s_f[3][256];
+  __shared__ double s_invS[256];
   __shared__ int s_i[2][256];
   for (int b = threadIdx.x; b < Bn; b += blockDim.x) {  // per-replica constants through shared memory (see bt_grad)
     const BCtl* c = a.ctl + b;
+    s_invS[b] = 1.0 / c->S;
     s_f[0][b] = (float)(1.0 / c->S);
     s_f[1][b] = c->lse;
+    s_f[2][b] = c->kl_scale;
     s_i[0][b] = ((c->kl_slot >= 0 && a.prob.prior != nullptr) ? 1 : 0) | (c->stop ? 0 : 2) | ((a.trk_on && c->ema_update) ? 4 : 0) | (c->ema_first ? 8 : 0);
     s_i[1][b] = a.trk_on ? c->snap_now : -1;
   }
   __syncthreads();
-  float invS[4], lse[4];
+  float invS[4], lse[4], lam[4];
   bool has_kl[4], run[4];
   int snap[4], ema_update[4], ema_first[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     invS[j] = s_f[0][b0 + j];
     lse[j] = s_f[1][b0 + j];
+    lam[j] = s_f[2][b0 + j];
     const int fl = s_i[0][b0 + j];
     has_kl[j] = fl & 1;
     run[j] = fl & 2;
@@ -614,7 +625,7 @@ __global__ void __launch_bounds__(512) bt_kl_kernel(const BatchArgs a) {
     ema_first[j] = (fl & 8) ? 1 : 0;
     snap[j] = s_i[1][b0 + j];
   }
-  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0}, s3[4] = {0.0, 0.0, 0.0, 0.0};
+  double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0}, s3[4] = {0.0, 0.0, 0.0, 0.0};
   const float4* __restrict__ ep = reinterpret_cast<const float4*>(a.e);
   const float* __restrict__ pn = a.pnorm;
   const long long fstep = (long long)gridDim.x * a.fy;
@@ -637,13 +648,20 @@ __global__ void __launch_bounds__(512) bt_kl_kernel(const BatchArgs a) {
       for (int j = 0; j < 4; ++j) {
         if (!run[j]) continue;
         const float p = pv[k];
-        const float w = e4[j] * invS[j];
+        float w, q;
+        double kap;
+        weight_terms(e4[j], invS[j], p, has_kl[j], a.eps_kl, lam[j], w, kap, q);  // the same w, kappa bt_grad will form
         if (has_kl[j]) {
-          const float q = w + a.eps_kl;
+          s0[j] += ((double)e4[j] * s_invS[b0 + j]) * kap;  // MaxEnt part of hbar with e_f / S in fp64 (see frame_terms, bv_tail.cu)
           s2[j] += (double)(q - p);
           const float x = a.eps_kl * rcp_approx(fmaxf(w, 1e-38f));
-          if (x > 1e-9f)
-            s1[j] += (double)p * (double)((w > 0.f) ? log1pf(a.eps_kl / w) : (logf(a.eps_kl) - (a.z[(size_t)f * Bn + b0 + j] - lse[j])));
+          if (x > 1e-9f) {
+            // log(w + eps) - log(w) with log w = z - lse taken from the logits: a weight this small may be a denormal fp32
+            // number (2 bits of precision at exp(-100)), so w itself must not enter the logarithm
+            const float lw = a.z[(size_t)f * Bn + b0 + j] - lse[j];
+            const float le = logf(a.eps_kl);
+            s1[j] += (double)p * (double)((le + log1pf(expf(lw - le))) - lw);
+          }
         }
         s3[j] += (double)w;
         if (a.trk_on) {  // tracker.ema_params (opt/track.py:160-165) and the history snapshot of the post-update weights
@@ -661,7 +679,7 @@ __global__ void __launch_bounds__(512) bt_kl_kernel(const BatchArgs a) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     double* mine = sh_d + ((size_t)fy * KL_N) * Bn + b0 + j;
-    mine[0 * Bn] = 0.0;
+    mine[0 * Bn] = s0[j];
     mine[1 * Bn] = s1[j];
     mine[2 * Bn] = s2[j];
     mine[3 * Bn] = s3[j];
@@ -1118,6 +1136,9 @@ extern "C" int jaxent_bg_plan_buffer(const JaxentBatchPlan* p, int32_t which, vo
     case 5: *ptr = a.uptake; *bytes = (size_t)a.Bn * (a.prob.uptake ? a.prob.T : 1) * a.prob.R * 4; break;
     case 6: *ptr = a.H; *bytes = (size_t)a.n_fb * 128 * a.Bn * 4; break;
     case 7: *ptr = a.red; *bytes = (size_t)a.Bn * 2 * a.Rp * 8; break;
+    case 8: *ptr = a.g[0]; *bytes = fb; break;                                          /* masked gradients, buffer 0 */
+    case 9: *ptr = a.g[1]; *bytes = fb; break;                                          /* masked gradients, buffer 1 */
+    case 10: *ptr = a.gsel; *bytes = 4; break;                                          /* which of 8 / 9 is current  */
     default: set_error("bg_plan_buffer: unknown buffer id %d", which); return JAXENT_E_INVALID;
   }
   return JAXENT_OK;

@@ -3,7 +3,7 @@
 // One pass over the packed (frame-quad major) feature arrays does, per tile of FT=8 frames:
 //   phase A  column sums  H_f = sum_r cc_r*Nc[r,f] + ch_r*Nh[r,f]        (backward of step k;
 //            reference: the transpose products jax.grad emits for utils/jax_fn.py:30-38)
-//   Adam     g_f = mask*w_f*(H_f + kappa_f - hbar), grad-dot partial, optax adam for BOTH plateau
+//   Adam     g_f = mask*w_f*(H_f + kappa_f - hbar), hbar = sum_j w_j (H_j + kappa_j); grad-dot partial, optax adam for BOTH plateau
 //            learning rates (opt/optimiser.py:396-424), z' -> e' = exp(z' - lse)
 //   phase B  row sums     acc_r += e'_f * N[r,f]  for both branches      (forward of step k+1;
 //            reference: frame_average_features, utils/jax_fn.py:15-38)
@@ -215,16 +215,23 @@ __device__ __forceinline__ void load_tile(TileRegs<RPT>& d, const unsigned char*
 }
 
 // phase A: H partials of this thread's rows, transposing warp reduction, one float per (warp, frame)
+// Centred: every row's product carries -k_r = -fl(cc_r <Nc>_r + ch_r <Nh>_r) (nk, from the tail), so the column sum is
+// H_f - sum_r k_r = sum_r cc_r (Nc[r,f] - <Nc>_r) + ch_r (Nh[r,f] - <Nh>_r): same instruction count (fma + fma instead of
+// mul + fma), and the quantity the softmax Jacobian needs, h_f - hbar, no longer hinges on the last bits of a large fp32 H_f.
+// The inner fma holds cc*Nc - k ~ -ch*<Nh>: the acceptor term is normally the smaller of the two, so that is the cheaper rounding.
 template <int RPT>
-__device__ __forceinline__ void phase_a(const TileRegs<RPT>& d, const float (&cc)[RPT], const float (&ch)[RPT],
+__device__ __forceinline__ void phase_a(const TileRegs<RPT>& d, const float (&cc)[RPT], const float (&ch)[RPT], const float (&nk)[RPT],
                                         float* s_part_warp, int lane, int jred) {
   float p[FT];
+  float nk0 = nk[0];  // the constants of all rows of this thread enter with the first row's product
+#pragma unroll
+  for (int i = 1; i < RPT; ++i) nk0 += nk[i];
 #pragma unroll
   for (int q = 0; q < QT; ++q) {
-    p[4 * q + 0] = fmaf(cc[0], d.nc[0][q].x, ch[0] * d.nh[0][q].x);
-    p[4 * q + 1] = fmaf(cc[0], d.nc[0][q].y, ch[0] * d.nh[0][q].y);
-    p[4 * q + 2] = fmaf(cc[0], d.nc[0][q].z, ch[0] * d.nh[0][q].z);
-    p[4 * q + 3] = fmaf(cc[0], d.nc[0][q].w, ch[0] * d.nh[0][q].w);
+    p[4 * q + 0] = fmaf(ch[0], d.nh[0][q].x, fmaf(cc[0], d.nc[0][q].x, nk0));
+    p[4 * q + 1] = fmaf(ch[0], d.nh[0][q].y, fmaf(cc[0], d.nc[0][q].y, nk0));
+    p[4 * q + 2] = fmaf(ch[0], d.nh[0][q].z, fmaf(cc[0], d.nc[0][q].z, nk0));
+    p[4 * q + 3] = fmaf(ch[0], d.nh[0][q].w, fmaf(cc[0], d.nc[0][q].w, nk0));
   }
 #pragma unroll
   for (int i = 1; i < RPT; ++i) {
@@ -293,15 +300,38 @@ __device__ __forceinline__ void phase_b(const TileRegs<RPT>& d, const float* s_e
   }
 }
 
-// CTA 0's Adam warp, once per launch, AFTER its tile loop: the MaxEnt sums of the tail that preceded this pass (all
-// ranks; by now every peer's words have long landed, so nothing waits) complete that step's loss record.
-// The MaxEnt part of hbar = sum_j w_j h_j is sum_j w_j kappa_j = lambda * eps * sum_j p_j / q_j = O(1e-10 lambda)
-// analytically (both distributions sum to one); its numerical value is rounding noise seven orders below kappa_f, so
-// the gradient uses hbar = sum_r c_r lnPF_r only and the frame-sharded step needs no second exchange on its critical path.
-__device__ __noinline__ void finish_previous_record(const Xchg x, unsigned ep, const Ctl* __restrict__ ctl, JaxentLossRecord* records, int lane) {
+// hbar = sum_j w_j h_j of the softmax Jacobian (dL/dz_f = w_f (h_f - hbar)), both parts:
+//   data    sum_r c_r lnPF_r                     exact identity, from the tail's control block
+//   MaxEnt  sum_j w_j kappa_j = kl[0]            reduced by the tail's frame CTAs over ALL ranks' frames
+// The MaxEnt part equals lambda * sum_j p_j eps / (w_j + eps): negligible while every w_j >> eps = 1e-10 / F, but it
+// tends to lambda times the prior mass of the collapsed frames once weights fall below eps (logit spread >~ 37 at
+// F = 1e6), so it is part of the gradient exactly as jax.value_and_grad forms it (reference opt/optimiser.py:391-393,
+// opt/losses.py:304-322).  Every Adam warp gathers the words itself (world * KL_N 16-byte loads from the LOCAL inbox,
+// issued while the first tiles are still in flight); frame-sharded, the peers' tails published them before their own
+// R x T tail finished, so the spin is normally satisfied by the first load.  CTA 0 also completes the loss record of
+// the step those sums belong to.
+// (plain pointers instead of the Xchg struct: passing a kernel-parameter struct by reference forces a local-memory copy)
+static __device__ __noinline__ double gather_hbar(const unsigned char* kl_words, int world, unsigned char* err_word, unsigned ep,
+                                                 const Ctl* __restrict__ ctl, JaxentLossRecord* records, int lane, bool finish) {
+  double v = 0.0;
+  if (lane < world * KL_N) {
+    if (world == 1) v = __ldcg(reinterpret_cast<const double*>(kl_words) + lane);
+    else v = ll_load(err_word, kl_words + (size_t)lane * 16, ep);  // [rank][KL_N] 16-byte stamped words
+  }
+  __syncwarp();
   double kl[KL_N];
-  kl_gather_warp(x, ep, lane, kl);
-  if (lane == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
+#pragma unroll
+  for (int k = 0; k < KL_N; ++k) kl[k] = 0.0;
+  for (int r = 0; r < world; ++r) {  // rank order: identical on every rank
+#pragma unroll
+    for (int k = 0; k < KL_N; ++k) kl[k] += __shfl_sync(0xffffffffu, v, r * KL_N + k);
+  }
+  if (finish && lane == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
+  return ctl->hbar_data + kl[0];
+}
+__device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, const Ctl* __restrict__ ctl, int lane, bool finish) {
+  const unsigned char* kl_words = a.x.local + (a.x.world == 1 ? xchg_plain_kl_off(a.x) : xchg_kl_off(a.x, (int)(ep & 1u), 0));
+  return gather_hbar(kl_words, a.x.world, a.x.local + xchg_err_off(a.x), ep, ctl, a.records, lane, finish);
 }
 
 // ------------------------------------------------------------------------------------------ per-frame uptake mode
@@ -345,7 +375,8 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
   const int rc = ok ? tid : R - 1;
   const uint32_t rowoff = (uint32_t)rc * 16u, rstride = (uint32_t)R * 16u;
   float4* my_tab = s_tab + tid;  // [TP][NTc] {kt(2 tp), kt(2 tp + 1), G(2 tp), G(2 tp + 1)}
-  float Gsum = 0.f;
+  // centred: the tail's k_r = fl(sum_t G[t,r] (1 - <u>[t,r])) replaces sum_t G[t,r], so the row partial is sum_t G (u_f - <u>)
+  const float Gsum = (ok && mode) ? a.ck[rc] : 0.f;
   {
     const float kr = -1.4426950408889634f * a.pf_k[rc];
 #pragma unroll
@@ -354,7 +385,6 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
       const float2 g2 = make_float2((ok && mode && t0_ < T) ? a.pf_G[(size_t)t0_ * R + rc] : 0.f,
                                     (ok && mode && t1_ < T) ? a.pf_G[(size_t)t1_ * R + rc] : 0.f);
       my_tab[tp * NTc] = make_float4(t0_ < T ? kr * a.pf_tp[t0_] : 0.f, t1_ < T ? kr * a.pf_tp[t1_] : 0.f, g2.x, g2.y);  // kt = -log2(e) k_r tau_t
-      Gsum += g2.x + g2.y;
     }
   }
   if (ok)
@@ -522,8 +552,11 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
   if (is_adam) {
     // ================================================================== Adam warp
     const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
-    // MaxEnt sums of the tail that preceded this pass (all ranks; waits on the peers' flags when frame-sharded)
-    const float hbar = (float)ctl->hbar_data;
+    // MaxEnt sums of the tail that preceded this pass (all ranks; spins on the peers' words when frame-sharded)
+    // hbar as an unevaluated fp32 pair: h_f - hbar is evaluated as (H + (k_hi - hb_hi)) + (k_lo - hb_lo), which keeps the
+    // O(lambda) cancellation between kappa_f and hbar exact (Sterbenz) without fp64 instructions or conversions on this warp
+    const double hbar_d = mode ? pass_hbar(a, ep, ctl, lane, blockIdx.x == 0) : 0.0;
+    const float hb_hi = (float)hbar_d, hb_lo = (float)(hbar_d - (double)hb_hi);
     if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 42);
     const int in_set = ep & 1u, out_set = in_set ^ 1;
     const int in_br = ctl->branch;
@@ -552,7 +585,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
       const int b = it & 1;
       const long long f = (t0 + it) * FT + fj;
       const bool valid = (fk == 0) && (f < a.F);
-      float z_ = 0.f, m_ = 0.f, v_ = 0.f, w_ = 0.f, k_ = 0.f, gp_ = 0.f;
+      float z_ = 0.f, m_ = 0.f, v_ = 0.f, w_ = 0.f, k_ = 0.f, kl_ = 0.f, gp_ = 0.f;
       if (valid) {  // prefetch before waiting on the consumers
         z_ = zin[f];
         m_ = min_[f];
@@ -560,6 +593,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
         if (mode) {
           w_ = a.w[f];
           k_ = a.kappa[f];
+          kl_ = a.kappa_lo[f];
           gp_ = gprev[f];
         }
       }
@@ -584,7 +618,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
       float eA = 0.f, eB = 0.f;
       if (valid) {
         if (mode) {
-          const float gf = maskf * (w_ * ((H + k_) - hbar));
+          const float gf = maskf * (w_ * ((H + (k_ - hb_hi)) + (kl_ - hb_lo)));
           const float gpv = have_prev ? gp_ : gf;
           gdot += (double)(gpv * gf);
           gout[f] = gf;
@@ -628,7 +662,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
       gdot += __shfl_xor_sync(0xffffffffu, gdot, o);
     }
     if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 43);
-    if (blockIdx.x == 0 && mode == 1) finish_previous_record(a.x, ep, ctl, a.records, lane);
     if (lane == 0) {
       part[a.part_n - 4] = sumA;
       part[a.part_n - 3] = sumB;
@@ -639,7 +672,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
   }
 
   // ==================================================================== consumers
-  float ccr[RPT], chr[RPT];
+  float ccr[RPT], chr[RPT], nkr[RPT];
   uint32_t rowoff[RPT];
   int row[RPT];
 #pragma unroll
@@ -650,6 +683,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     rowoff[i] = (uint32_t)rc * (FMT == 0 ? 16u : 8u);
     ccr[i] = (ok && mode) ? a.cc[rc] : 0.f;
     chr[i] = (ok && mode) ? a.ch[rc] : 0.f;
+    nkr[i] = (ok && mode) ? -a.ck[rc] : 0.f;
     if (ok) {
       part[0 * R + rc] = 0.0;
       part[1 * R + rc] = 0.0;
@@ -696,7 +730,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
 
   TileRegs<RPT> D0, D1;
   fetch(D0);
-  phase_a<RPT>(D0, ccr, chr, spw0, lane, jred);
+  phase_a<RPT>(D0, ccr, chr, nkr, spw0, lane, jred);
   bar_arrive(BAR_PART0, nbar);
   int it = 1, since = 0;
   while (true) {
@@ -706,7 +740,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
       break;
     }
     fetch(D1);
-    phase_a<RPT>(D1, ccr, chr, spw1, lane, jred);
+    phase_a<RPT>(D1, ccr, chr, nkr, spw1, lane, jred);
     bar_arrive(BAR_PART0 + 1, nbar);
     bar_sync(BAR_E0, nbar);
     phase_b<RPT>(D0, se0, acc);
@@ -717,7 +751,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
       break;
     }
     fetch(D0);
-    phase_a<RPT>(D0, ccr, chr, spw0, lane, jred);
+    phase_a<RPT>(D0, ccr, chr, nkr, spw0, lane, jred);
     bar_arrive(BAR_PART0, nbar);
     bar_sync(BAR_E0 + 1, nbar);
     phase_b<RPT>(D1, se1, acc);
@@ -768,7 +802,8 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
                                              unsigned char* ring, uint64_t* bars, const float4* s_rows, float* s_e, double* s_x,
                                              long long t0, long long s0, int ns, int n, double* part) {
   const int mode = a.mode;
-  const float hbar = (float)ctl->hbar_data;
+  const double hbar_d = mode ? pass_hbar(a, ep, ctl, lane, blockIdx.x == 0 && q == 0) : 0.0;
+  const float hb_hi = (float)hbar_d, hb_lo = (float)(hbar_d - (double)hb_hi);  // see bv_pass_kernel's Adam warp
   const int in_set = ep & 1u, out_set = in_set ^ 1;
   const int in_br = ctl->branch;
   const float* __restrict__ zin = a.st.z[in_set][in_br];
@@ -801,10 +836,10 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
   JCLK_DECL(clk_s3);
 
   // lane (k, fj) holds frame fj of quad q of tile i0 + k
-  float cz, cm, cv, cw, ck, cg, nz, nm, nv, nw, nk, ng;
-  auto load_batch = [&](int i0, float& z, float& m, float& v, float& w, float& k, float& g) {
+  float cz, cm, cv, cw, ck, cl, cg, nz, nm, nv, nw, nk, nl, ng;  // (ck, cl): kappa as an unevaluated fp32 pair (frame_terms, bv_tail.cu)
+  auto load_batch = [&](int i0, float& z, float& m, float& v, float& w, float& k, float& kl, float& g) {
     const long long f = (t0 + i0 + fk) * FT + q * PF_FU + (lane & 3);
-    z = m = v = w = k = g = 0.f;
+    z = m = v = w = k = kl = g = 0.f;
     if (i0 + fk < n && f < a.F) {
       z = zin[f];
       m = min_[f];
@@ -812,23 +847,25 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
       if (mode) {
         w = a.w[f];
         k = a.kappa[f];
+        kl = a.kappa_lo[f];
         g = gprev[f];
       }
     }
   };
-  load_batch(0, cz, cm, cv, cw, ck, cg);
-  load_batch(8, nz, nm, nv, nw, nk, ng);
+  load_batch(0, cz, cm, cv, cw, ck, cl, cg);
+  load_batch(8, nz, nm, nv, nw, nk, nl, ng);
   const float4* sr = s_rows + q * (NWc * 32);
   int ring_slot = 0;
   for (int i = 0; i < n; ++i) {
     const int kb = i & 7;
     if (kb == 0 && i > 0) {
-      cz = nz, cm = nm, cv = nv, cw = nw, ck = nk, cg = ng;
-      load_batch(i + 8, nz, nm, nv, nw, nk, ng);
+      cz = nz, cm = nm, cv = nv, cw = nw, ck = nk, cl = nl, cg = ng;
+      load_batch(i + 8, nz, nm, nv, nw, nk, nl, ng);
     }
     const int src = kb * PF_FU + fj;
     const float z_ = __shfl_sync(0xffffffffu, cz, src), m_ = __shfl_sync(0xffffffffu, cm, src), v_ = __shfl_sync(0xffffffffu, cv, src);
     const float w_ = __shfl_sync(0xffffffffu, cw, src), k_ = __shfl_sync(0xffffffffu, ck, src), gp_ = __shfl_sync(0xffffffffu, cg, src);
+    const float kl_ = __shfl_sync(0xffffffffu, cl, src);
     const long long f = (t0 + i) * FT + q * PF_FU + fj;
     const bool valid = lead && (f < a.F);
     JCLK_TIC(tw0);
@@ -870,7 +907,7 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
     float eA = 0.f, eB = 0.f, gf = 0.f, m1 = 0.f, m2 = 0.f, v1 = 0.f, v2 = 0.f, z1 = 0.f, z2 = 0.f;
     if (valid) {
       if (mode) {
-        gf = maskf * (w_ * ((H + k_) - hbar));
+        gf = maskf * (w_ * ((H + (k_ - hb_hi)) + (kl_ - hb_lo)));
         float sA = gf * lrA, sB = gf * lrB;
         if (clip > 0.f) {
           sA = fminf(fmaxf(sA, -clip), clip);
@@ -939,7 +976,6 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
   }
   bar_sync(BAR_ADAM, 64);
   if (q == 0) {
-    if (blockIdx.x == 0 && mode == 1) finish_previous_record(a.x, ep, ctl, a.records, lane);
     if (lane == 0) {
       part[a.part_n - 4] = sumA + s_x[0];
       part[a.part_n - 3] = sumB + s_x[1];

@@ -97,7 +97,25 @@ struct TailIO {
   float* pf_G;    // per-frame uptake mode: [T*R] dL/d<uptake>[t,r] for the next pass (else unused)
   int pf_mode;    // 1: per-frame uptake mode -- the caller has filled sm.sU with the frame-averaged uptake already
   int p_max_tr, p_max_va;  // carve-up parameters (carve_tail_smem)
+  float* ck;      // [R] centring constants of the pass (see "centred column sums" in tail_body), or nullptr (batched GEMM path)
+  int c_pieces;   // how the sweep sees the row coefficients: 0 = rounded to fp32, n > 0 = the sum of n bf16 pieces (batched GEMM path)
 };
+
+// the value of a row coefficient as the feature sweep will use it (see the hbar comment in tail_body)
+__device__ __forceinline__ double coeff_as_used(double x, int pieces) {
+  const float xf = (float)x;
+  if (pieces <= 0) return (double)xf;
+  float r = xf;
+  double acc = 0.0;
+  for (int i = 0; i < pieces; ++i) {  // round-to-nearest-even bf16 pieces, as split3() forms them (bg_step.cu)
+    unsigned u = __float_as_uint(r);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    const float pc = __uint_as_float(u & 0xffff0000u);
+    acc += (double)pc;
+    r -= pc;
+  }
+  return acc;
+}
 
 // Whole-CTA function.  In: acc0/acc1 = un-normalised weighted row sums of this thread's residue (tid < R), S = sum of the
 // un-normalised weights, (bc, bh), fw/fs = forward_model_weights / scaling of every slot.  Out: s_fin[0..5] train losses,
@@ -127,7 +145,6 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
   {
     my_a = 0, my_b = 0, my_lp = 0, my_c = 0;
     const bool pfm = io.pf_mode != 0;
-    double pf_hbar = 0.0;  // per-frame mode: sum_t G[t,r] <u>[t,r] of this thread's residue
     if (!pfm && tid < R) {
       const double invS = __drcp_rn(S);
       my_a = acc0 * invS;
@@ -369,13 +386,12 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
       if (tid < R) {
         if (pfm) {
           // per-frame mode: the items ARE G[t,r] = dL/d<uptake>[t,r]; accumulate them over the data slots in global memory
-          // (this thread owns residue tid) and form the data part of hbar = sum_{t,r} G <u>
+          // (this thread owns residue tid); the data part of hbar = sum_{t,r} G <u> is formed after the slot loop
 #pragma unroll 1
           for (int t = 0; t < Tm; ++t) {
             const double gv = sc_rt[(size_t)t * R + tid];
             float* gdst = io.pf_G + (size_t)t * R + tid;
             *gdst = (i == first_data) ? (float)gv : *gdst + (float)gv;
-            pf_hbar += gv * sU[(size_t)t * R + tid];
           }
         } else {
 #pragma unroll 1
@@ -388,7 +404,30 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
     {
       double v12 = 0.0, v13 = 0.0, v14 = 0.0;
       if (tid < R) {
-        v12 = pfm ? pf_hbar : my_c * my_lp;  // hbar (data part) = sum_r c_r lnPF_r = sum_j w_j h_j
+        // hbar (data part) = sum_j w_j H_j = sum_r k_r,  k_r = cc_r <Nc>_r + ch_r <Nh>_r  (per-frame mode: sum_t G[t,r] <u>[t,r]),
+        // with the row coefficients AS THE SWEEP WILL USE THEM (rounded to fp32 / bf16 pieces): with exact c_r the identity
+        // would be off by 2^-24 |hbar|, which the near-cancellation h_f - hbar of a dominant frame amplifies.
+        // Centred column sums (io.ck != nullptr): the pass subtracts fl(k_r) inside every row's product, i.e. it forms
+        // H_f - sum_r fl(k_r) = sum_r cc_r (Nc[r,f] - <Nc>_r) + ch_r (Nh[r,f] - <Nh>_r) + rounding, whose terms are small exactly
+        // where the cancellation is worst (a frame that carries most of the weight looks like the average).  Only the
+        // residual sum_r (k_r - fl(k_r)) is left for the control block.  An uncentred fp32 H_f cannot even REPRESENT the
+        // column sum well enough there (measured: 2.5e-5 of the gradient scale at w_max = 0.997, |H| = 9e3).
+        double kd;
+        if (pfm) {  // G as the pass reads it (fp32, accumulated over the data slots by this thread)
+          double gsum = 0.0, gu = 0.0;
+#pragma unroll 1
+          for (int t = 0; t < Tm; ++t) {
+            const double gv = (double)io.pf_G[(size_t)t * R + tid];
+            gsum += gv;
+            gu += gv * sU[(size_t)t * R + tid];
+          }
+          kd = gsum - gu;  // the pass forms fl(kd) - sum_t G exp(-k tau / PF_f) = sum_t G (u_f - <u>) per row
+          v12 = (io.ck != nullptr) ? -(kd - (double)(float)kd) : gu;
+        } else {
+          kd = coeff_as_used(my_c * bc, io.c_pieces) * my_a + coeff_as_used(my_c * bh, io.c_pieces) * my_b;
+          v12 = (io.ck != nullptr) ? kd - (double)(float)kd : kd;
+        }
+        if (io.ck != nullptr) io.ck[tid] = (float)kd;
         v13 = my_c * my_a;   // dL/dbc
         v14 = my_c * my_b;   // dL/dbh
       }

@@ -39,7 +39,7 @@ struct alignas(16) Ctl {
   float last_dot, last_lr;
   int last_branch;
   int rec_idx;                 // ring index of this step's loss record
-  double hbar_data;            // sum_r c_r * log_Pf_r  (= sum_j w_j h_j, data part)
+  double hbar_data;            // data part of hbar = sum_j w_j H_j MINUS what the pass subtracts itself (sum_r fl(k_r), see tail_body)
   float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
   // ---- on-device convergence tracking (reference opt/run.py:272-348, opt/track.py:128-197)
   int trk_stop;                // 1: the loop has ended; pass / reduce / tail launches become no-ops
@@ -198,8 +198,10 @@ struct PassArgs {
   StateSets st;
   const float* w;
   const float* kappa;
+  const float* kappa_lo;  // kappa = kappa + kappa_lo carries dKL/dw to ~2^-48 relative (see frame_terms)
   const float* cc;
   const float* ch;
+  const float* ck;          // [R] fl(cc_r <Nc>_r + ch_r <Nh>_r): subtracted inside every row's product (centred column sums)
   // per-frame uptake mode (ForwardPass.average_first = False): pf_T > 0
   int pf_T;                 // time points
   const float* pf_G;        // [T][R] dL/d<uptake>[t,r] from the tail
@@ -252,8 +254,10 @@ struct TailArgs {
   unsigned* counter;
   float* w;
   float* kappa;
+  float* kappa_lo;
   float* cc;
   float* ch;
+  float* ck;
   float* logpf;
   float* uptake;
   float* avg;

@@ -407,7 +407,7 @@ def loss_and_grads(problem: Problem, params: Params, dtype=np.float32):
     gz = (w * (h - hbar)).astype(dtype)
     gbc = dtype(gbc + np.dot(c, a))
     gbh = dtype(gbh + np.dot(c, b))
-    aux = {"w": w, "c": c, "h": h, "hbar": hbar, "out": out, "G": Gtot}
+    aux = {"w": w, "c": c, "h": h, "hbar": hbar, "hbar_kl": float(np.dot(w, hw)) if np.ndim(hw) else 0.0, "out": out, "G": Gtot}
     return losses, Grads(gz, gbc, gbh), aux
 
 

@@ -34,6 +34,18 @@ def test_per_frame_step_parity(kind, F, R, T, clip):
     assert wl < 5e-5, wl
 
 
+def test_per_frame_collapsed_weights():
+    """logit spread 10: 70 % of the frames below eps = 1e-10/F, the MaxEnt part of hbar is O(lambda) (VERDICT r1 #1)"""
+    from test_gpu_parity import _collapsed_case
+
+    case, frac = _collapsed_case(2000, 40, 4, O.UPTAKE_EYE_MSE, 10.0)
+    case["problem"].average_first = False
+    assert frac > 0.5
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=False)
+    _, wl, wg = _check_steps(case, cfg, 6, STEP_RTOL=2e-4)
+    assert wl < 5e-5, wl
+
+
 def test_per_frame_forward_outputs_and_difference_to_average_first():
     case = _case(1500, 64, 4)
     cfg = O.OptConfig(learning_rate=0.5, clip_value=None, optimise_model_parameters=False)
