@@ -181,6 +181,16 @@ def normalize_weights(p: Params, dtype=np.float32) -> Params:
     return replace(p, z=w, frame_mask=fm)
 
 
+def simulation_initialise(p: Params, dtype=np.float32) -> Params:
+    """Simulation.initialise models/core.py:59-129 as far as the parameters go: normalize_weights (:72), the loss-weight
+    normalisation (:73), then the eager forward whose returned simulation -- with normalize_weights applied AGAIN by
+    Simulation.forward (:131-163) -- replaces self.params (:97-98).  The stored frame weights are therefore
+    softmax(softmax(w_in)); OptaxOptimizer.initialise multiplies those by F (opt/optimiser.py:243)."""
+    q = normalize_weights(p, dtype)
+    q = replace(q, fw=normalize_masked_loss_scalingweights(np.asarray(q.fw, dtype), np.asarray(q.nlf, dtype)).astype(dtype))
+    return normalize_weights(q, dtype)
+
+
 def frame_average(x, w, dtype=np.float32):
     """utils/jax_fn.py:15-38: sum(x * w.reshape(1,-1), axis=-1) for ndim>1 leaves."""
     x = np.asarray(x)
@@ -577,3 +587,73 @@ def optimise(problem, params, cfg: OptConfig, n_steps, tolerance=1e-10, converge
             if h["losses"].val_losses[0] < best["losses"].val_losses[0]:
                 best = h
     return {"history": history, "loss_trace": loss_trace, "state": state, "best": best}
+
+
+def optimise_pure(problem, params, cfg: OptConfig, n_steps, tolerance=1e-10, convergence=(1e-3,), ema_alpha=0.5,
+                  min_steps_per_threshold=2, dtype=np.float32, learning_rate=None):
+    """_optimise_pure opt/run.py:141-232 = lax.while_loop over OptaxOptimizer._pure_step (opt/optimiser.py:494-579) with the
+    functional tracker update_convergence / check_and_advance_threshold (opt/track.py:40-125) -- the loop batch_optimise
+    vmaps (opt/batch.py:107-146).  Differences to the Python loop `optimise` above, all reproduced here:
+      * the state enters dense (_ensure_dense_state, run.py:89-118): losses evaluated at the initial parameters, gradients
+        = zeros (so the first grad-dot is 0, not |g|^2);
+      * previous_loss of step k is the loss stored by step k-1 (the initial loss for k = 0: first raw delta = 0);
+      * the EMA of the loss delta and of the parameters RESTARTS whenever steps_since_threshold_start == 0 (at the start and
+        after every threshold advance), track.py:53-68;  there is no gradient-oscillation reset;
+      * the threshold test uses the 1-based state.step: step + 1 > initial_steps (optimiser.py:545-551);
+      * cond_fn (run.py:202-211) stops on converged / step >= n_steps / non-finite or < tolerance loss OF THE PREVIOUS STEP;
+      * every step is written to the history: save_state.params (softmax weights AFTER the update) paired with the losses
+        evaluated BEFORE it (optimiser.py:555-567);  `learning_rate` overrides cfg.learning_rate (the vmapped hyper-parameter)
+        for the thresholds and the target rates."""
+    if learning_rate is not None:
+        cfg = replace(cfg, learning_rate=float(learning_rate))
+    state = optimizer_initialise(params, cfg, dtype)
+    losses0, _, _ = loss_and_grads(problem, state.params, dtype)
+    zero = Grads(np.zeros_like(np.asarray(state.params.z, dtype)), dtype(0), dtype(0))
+    state = replace(state, losses=losses0, gradients=zero)
+    thr = np.sort(np.atleast_1d(np.asarray(convergence, np.float32)))[::-1] * np.float32(cfg.learning_rate)  # track.py:12-21
+    ema_delta = np.float32(0.0)
+    ema_w = np.asarray(state.params.z, dtype).copy()  # initialise_convergence_carry(initial_params), track.py:24-32
+    steps_since, idx, converged = 0, 0, False
+    F = np.asarray(state.params.z).shape[0]
+    hist_w = np.zeros((n_steps, F), dtype)
+    hist_total = np.zeros(n_steps, dtype)
+    hist_val0 = np.zeros(n_steps, dtype)
+    hist_losses = []
+    write_idx = 0
+    alpha = np.float32(ema_alpha)
+    while True:
+        cur_prev = state.losses.total_train_loss
+        if converged or state.step >= n_steps or not np.isfinite(cur_prev) or cur_prev < np.float32(tolerance):
+            break
+        prev_loss = np.float32(state.losses.total_train_loss)
+        state, loss, save_w = step_with_rates(problem, state, cfg, dtype)
+        cur = np.float32(loss)
+        raw = np.abs(prev_loss - cur)
+        first = steps_since == 0
+        ema_delta = raw if first else np.float32(alpha * raw + (np.float32(1.0) - alpha) * ema_delta)
+        ema_w = save_w if first else (dtype(ema_alpha) * save_w + (dtype(1.0) - dtype(ema_alpha)) * ema_w).astype(dtype)
+        steps_since += 1
+        # check_and_advance_threshold
+        ti = min(idx, len(thr) - 1)
+        rel = np.float32(ema_delta / cur) if cur > 0 else np.float32(0.0)
+        met = steps_since >= min_steps_per_threshold and rel < thr[ti] and state.step > cfg.initial_steps
+        more = idx + 1 < len(thr)
+        if met and more:
+            idx += 1
+            steps_since = 0
+        elif met:
+            converged = True
+        hist_w[write_idx] = save_w
+        hist_total[write_idx] = state.losses.total_train_loss
+        hist_val0[write_idx] = state.losses.val_losses[0]
+        hist_losses.append(state.losses)
+        write_idx += 1
+    best_index = None
+    if write_idx:
+        best_index = write_idx - 1
+        for i in range(write_idx):  # OptimizationHistory._pick_best_state opt/base.py:180-189 over ALL steps (batch.py:158-180)
+            if hist_val0[i] < hist_val0[best_index]:
+                best_index = i
+    return {"state": state, "write_idx": write_idx, "converged": converged, "threshold_idx": idx, "steps_since": steps_since,
+            "ema_loss_delta": float(ema_delta), "ema_w": ema_w, "history_w": hist_w, "history_total_train": hist_total,
+            "history_val0": hist_val0, "history_losses": hist_losses, "best_index": best_index}
