@@ -137,10 +137,17 @@ class BvEngine:
         self.T = int(np.asarray(timepoints).reshape(-1).shape[0]) if self.uptake else 0
 
         with torch.cuda.device(self.device):
+            staged = None
             if isinstance(heavy, PackedFeatures) or hasattr(heavy, "packed"):
                 self.features = heavy
-            else:
+            elif getattr(self, "_batched", False) or feature_dtype != "f32":
                 self.features = self._pack(heavy, acceptor, feature_dtype)
+            else:
+                # host -> device copies of the feature arrays start now, on a side stream; the set-up work that does not need
+                # them (CSR conversion and upload of the peptide maps, prior normalisation, the peer-exchange handshake of a
+                # frame-sharded engine) overlaps the transfer, the pack kernel waits for it
+                staged = self._upload(heavy, acceptor)
+                self.features = self._alloc_packed(R, F, feature_dtype)
             self.packed = self.features.packed
             prob = L.BvProblem()
             prob.R, prob.T, prob.n_slots = R, self.T, len(slots)
@@ -209,12 +216,14 @@ class BvEngine:
                 self.exchange = "nccl"
                 if exchange in ("auto", "nvlink"):
                     try:
-                        self.peer = PeerExchange(self.lib, group, prob, self.device)
+                        self.peer = PeerExchange.acquire(self.lib, group, prob, self.device)
                         self.peer.attach(self.plan)
                         self.exchange = "nvlink"
                     except RuntimeError:
                         if exchange == "nvlink":
                             raise
+            if staged is not None:
+                self._pack_staged(staged, feature_dtype)
             self.fused = self.exchange == "nvlink"
             self.red = self._view(L.BUF_RED, torch.float64)
             self.klsum = self._view(L.BUF_KLSUM, torch.float64)
@@ -242,7 +251,10 @@ class BvEngine:
             self.lib.jaxent_bv_plan_destroy(self.plan)
             self.plan = None
         if peer is not None:
-            peer.close()
+            if barrier:
+                peer.release()  # the ranks have synchronised: the mapping goes back to the pool (PeerExchange.acquire)
+            else:
+                peer.in_use = True  # cannot prove the peers are done with it: never reuse, freed at process exit
             self.peer = None
 
     def __del__(self):
@@ -301,6 +313,31 @@ class BvEngine:
         torch.cuda.current_stream().synchronize()
         del h, a
         return PackedFeatures(packed, R, F, fmt)
+
+    def _upload(self, heavy, acceptor):
+        """starts the host -> device transfer of both (R,F) arrays on a side stream; -> (heavy_dev, acceptor_dev, event)"""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            h = self._to_dev_matrix(heavy)
+            a = self._to_dev_matrix(acceptor)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return h, a, ev, side
+
+    def _alloc_packed(self, R: int, F: int, feature_dtype: str) -> PackedFeatures:
+        nbytes = self.lib.jaxent_bv_packed_bytes(R, F)
+        return PackedFeatures(torch.empty(nbytes // 4, dtype=torch.float32, device=self.device), R, F, 0)
+
+    def _pack_staged(self, staged, feature_dtype: str) -> None:
+        h, a, ev, side = staged
+        torch.cuda.current_stream().wait_event(ev)
+        h.record_stream(torch.cuda.current_stream())
+        a.record_stream(torch.cuda.current_stream())
+        R, F = self.R, self.F
+        L.check(self.lib.jaxent_bv_pack_features_f32(h.data_ptr(), a.data_ptr(), R, F, F, 0, F, self.packed.data_ptr(), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        del h, a
 
     def _to_dev_matrix(self, x) -> torch.Tensor:
         if isinstance(x, torch.Tensor):
@@ -503,12 +540,19 @@ class BvEngine:
             raise RuntimeError("enable_tracking() has not been called")
         done = 0
         st = None
+        first = self.steps_done
         while done < n_steps:
             m = min(chunk, n_steps - done)
             self.step(m)
             done += m
             st = self.track_status()
+            # launches after the device-side stop are no-ops: the number of updates applied is the device's count
+            self.steps_done = int(st.steps_done)
             if st.stop:
                 break
         self.finish_record()
-        return st if st is not None else self.track_status()
+        if st is None:
+            st = self.track_status()
+            self.steps_done = int(st.steps_done)
+        assert self.steps_done >= first
+        return st

@@ -79,6 +79,57 @@ def _build_engine(simulation: Simulation, data_targets, loss_functions, indexes,
                     settings, prior=prior, device=simulation.device, average_first=getattr(simulation, "_average_first", True))
 
 
+_EVAL_CACHE_MAX = 4  # scratch engines kept per Simulation (each pins one per-frame workspace on the GPU)
+
+
+def _target_fingerprint(t):
+    """what the engine copied to the device at build time, as far as it can be told cheaply (this runs on EVERY optimiser
+    step, so nothing frame-sized is touched): shapes, storage addresses and the small target arrays' sums.  A new object at a
+    recycled id() or a re-assigned array does not hit a stale engine; in-place edits of a frame-sized prior are not detected."""
+    def addr(x):
+        if isinstance(x, torch.Tensor):
+            return x.data_ptr()
+        if isinstance(x, np.ndarray):
+            return x.__array_interface__["data"][0]
+        return id(x)
+
+    parts = []
+    for ds in (getattr(t, "train", None), getattr(t, "val", None)):
+        if ds is not None:
+            y = getattr(ds, "y_true", None)
+            if y is None:
+                parts.append(None)
+            else:
+                small = int(np.prod(np.shape(y))) <= 65536
+                parts.append((tuple(np.shape(y)), addr(y), float(np.asarray(to_numpy(y), np.float64).sum()) if small else 0.0))
+    fwts = getattr(t, "frame_weights", None)
+    if fwts is not None:
+        parts.append((tuple(np.shape(fwts)), addr(fwts)))
+    mps = getattr(t, "model_parameters", None)
+    if mps:
+        parts.append((scalar(mps[0].bv_bc), scalar(mps[0].bv_bh)))
+    return tuple(parts)
+
+
+def _cached_engine(cache: list, simulation, data_targets, loss_functions, indexes, settings, max_entries: int) -> BvEngine:
+    """Engine for (targets, losses, indexes): entries hold STRONG references to their targets and are matched by identity
+    (an id() can be recycled once a dataloader is freed, e.g. across cross-validation folds on one Simulation) plus a
+    content fingerprint; least recently used entries beyond `max_entries` are closed."""
+    names = tuple(getattr(f, "__name__", repr(f)) for f in loss_functions)
+    idx = tuple(indexes)
+    fps = tuple(_target_fingerprint(t) for t in data_targets)
+    for i, (tg, nm, ix, fp, eng) in enumerate(cache):
+        if nm == names and ix == idx and len(tg) == len(data_targets) and all(a is b for a, b in zip(tg, data_targets)) and fp == fps:
+            cache.append(cache.pop(i))
+            return eng
+    eng = _build_engine(simulation, data_targets, loss_functions, indexes, settings)
+    cache.append((tuple(data_targets), names, idx, fps, eng))
+    while len(cache) > max_entries:
+        old = cache.pop(0)
+        old[4].close(barrier=False)
+    return eng
+
+
 def _record_view(eng: BvEngine, step: int) -> torch.Tensor:
     """float32 view (on the device, no sync) of the loss record of `step`."""
     recs = eng._records.view(torch.float32)
@@ -107,12 +158,8 @@ def _outputs_of(eng: BvEngine):
 def compute_loss(simulation: Simulation, params: Simulation_Parameters, data_targets, indexes, loss_functions):
     """Forward + all losses at `params` (reference opt/optimiser.py:608-644) -> (LossComponents, updated sim).
     Runs the forward-only pass and the tail kernel on a scratch engine that shares the packed features."""
-    key = (tuple(id(t) for t in data_targets), tuple(getattr(f, "__name__", repr(f)) for f in loss_functions), tuple(indexes))
-    cache = simulation.__dict__.setdefault("_eval_engines", {})
-    eng = cache.get(key)
-    if eng is None:
-        eng = _build_engine(simulation, data_targets, loss_functions, indexes, OptSettings())
-        cache[key] = eng
+    eng = _cached_engine(simulation.__dict__.setdefault("_eval_engines", []), simulation, data_targets, loss_functions, indexes,
+                         OptSettings(), _EVAL_CACHE_MAX)
     mp = params.model_parameters[0]
     eng.init_state(to_device(params.frame_weights, simulation.device).reshape(-1), scalar(mp.bv_bc), scalar(mp.bv_bh),
                    to_numpy(params.forward_model_weights), to_numpy(params.forward_model_scaling))
@@ -210,9 +257,13 @@ class OptaxOptimizer:
         return OptimizationState(params=params, opt_state=B200OptState(self._engine, 0))
 
     def _ensure_engine(self, simulation, data_targets, loss_functions, indexes, params: Simulation_Parameters) -> BvEngine:
-        key = (tuple(id(t) for t in data_targets), tuple(getattr(f, "__name__", repr(f)) for f in loss_functions), tuple(indexes))
-        if self._engine is not None and self._engine_key == key:
+        key = (tuple(data_targets), tuple(getattr(f, "__name__", repr(f)) for f in loss_functions), tuple(indexes),
+               tuple(_target_fingerprint(t) for t in data_targets))  # strong references: compared by identity below
+        if self._engine is not None and self._engine_key is not None and self._engine_key[1:] == key[1:] and \
+                len(self._engine_key[0]) == len(key[0]) and all(a is b for a, b in zip(self._engine_key[0], key[0])):
             return self._engine
+        if self._engine is not None:
+            self._engine.close(barrier=False)
         eng = _build_engine(simulation, data_targets, loss_functions, indexes, self._settings())
         mp = params.model_parameters[0]
         eng.init_state(to_device(params.frame_weights, simulation.device).reshape(-1), scalar(mp.bv_bc), scalar(mp.bv_bh),

@@ -89,11 +89,45 @@ class PeerExchange:
     fused in-kernel all-reduce.  Set-up only; raises if any rank cannot map its peers (the caller then
     falls back to NCCL collectives on all ranks together)."""
 
+    # Exchange buffers belong to the process group, not to one engine: mapping them (cudaMalloc + IPC handle exchange +
+    # cudaIpcOpenMemHandle on every peer) costs tens of milliseconds, so a released buffer set is kept and handed to the next
+    # engine of the same group / device that fits.  Every rank constructs and releases its engines in the same order, so the
+    # pools stay identical across ranks (acquire / release are collective in that sense).
+    _pool: dict = {}
+
+    @classmethod
+    def acquire(cls, lib, group, problem, device: torch.device) -> "PeerExchange":
+        import ctypes as C
+
+        need = lib.jaxent_bv_exchange_bytes_for(C.byref(problem), dist.get_world_size(group))
+        key = (id(group), torch.device(device).index)
+        for px in cls._pool.get(key, []):
+            if not px.in_use and px.nbytes >= need:
+                px.in_use = True
+                return px
+        px = cls(lib, group, problem, device)
+        cls._pool.setdefault(key, []).append(px)
+        return px
+
+    def release(self) -> None:
+        """the owning engine is done (its ranks have synchronised): keep the mapping for the next engine"""
+        self.in_use = False
+
+    @classmethod
+    def purge(cls) -> None:
+        """unmap and free every pooled buffer set (collective: call on all ranks, after a barrier)"""
+        for lst in cls._pool.values():
+            for px in lst:
+                px.close()
+        cls._pool.clear()
+
     def __init__(self, lib, group, problem, device: torch.device):
         import ctypes as C
 
         from . import _lib as L
 
+        self.in_use = True
+        self.nbytes = 0
         self.lib, self.group = lib, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.own = None
@@ -102,6 +136,7 @@ class PeerExchange:
         if self.world > L.MAX_RANKS:
             raise RuntimeError(f"the fused exchange supports at most {L.MAX_RANKS} ranks")
         nbytes = lib.jaxent_bv_exchange_bytes_for(C.byref(problem), self.world)
+        self.nbytes = nbytes
         ok, err = 1, ""
         handle = C.create_string_buffer(L.IPC_HANDLE_BYTES)
         ptr = C.c_void_p()

@@ -55,6 +55,19 @@ def build_case(spec):
     return case
 
 
+def case_from_arrays(heavy, acc, small):
+    """the bench workload (bench.py: features + the small peptide problem) as an oracle-style case dict"""
+    from oracle import bv_oracle as O
+
+    F = heavy.shape[1]
+    prior = np.full(F, 1.0 / F, np.float32)
+    slots = [O.LossSlot(O.UPTAKE_EYE_MSE, small.S_train, small.y_train, small.S_val, small.y_val), O.LossSlot(O.MAXENT_CONVEX_KL, prior=prior)]
+    pb = O.Problem(heavy, acc, small.k_ints, small.timepoints, slots, True)
+    fw = O.normalize_masked_loss_scalingweights(np.array([1.0, 1.0]), np.ones(2))
+    par = O.Params(prior.copy(), np.ones(F, np.float32), 0.35, 2.0, fw, np.full(2, 1000.0, np.float32), np.ones(2, np.float32))
+    return {"problem": pb, "params": par, "prior": prior}
+
+
 def to_np(x):
     import torch
 
@@ -64,8 +77,11 @@ def to_np(x):
 class RefRun:
     """the reference's objects for one case"""
 
-    def __init__(self, case, spec, x64):
-        jax = refload.load(x64=x64)
+    def __init__(self, case, spec, x64, real_jax=False):
+        if real_jax:  # bench.py --impl reference on a box that has jax + optax and the reference package on sys.path
+            import jax
+        else:
+            jax = refload.load(x64=x64)
         import jax.numpy as jnp
         from jax.experimental import sparse
 
