@@ -503,7 +503,7 @@ def run_reference(args, wl):
 
 # ---------------------------------------------------------------------------------------------- our arm
 def eager_rate(eng, K, W, EV=8):
-    """W warm-up + K timed eager steps of a single-GPU engine (three PDL-chained launches per step); CUDA events around
+    """W warm-up + K timed eager steps of a single-GPU engine (two PDL-chained launches per step); CUDA events around
     every EV-th pass kernel.  -> (ms per step, ms per pass kernel)"""
     import torch
 
@@ -521,12 +521,11 @@ def eager_rate(eng, K, W, EV=8):
         L.check(eng.lib.jaxent_bv_pass(eng.plan, 1, sp))
         if k % EV == 0:
             ev[k // EV][1].record()
-        L.check(eng.lib.jaxent_bv_reduce(eng.plan, sp))
         L.check(eng.lib.jaxent_bv_tail(eng.plan, sp))
     e1.record()
     torch.cuda.synchronize()
     eng.steps_done += K
-    eng.launches += 3 * K
+    eng.launches += 2 * K
     return e0.elapsed_time(e1) / K, float(np.mean([a.elapsed_time(b) for a, b in ev]))
 
 
@@ -779,7 +778,6 @@ def run_ours(args, wl):
         L.check(eng.lib.jaxent_bv_pass(eng.plan, 1, sp))
         if timed:
             ev_pass[k // EV][1].record()
-        L.check(eng.lib.jaxent_bv_reduce(eng.plan, sp))
         if eng.sharded and not eng.fused:
             dist.all_reduce(eng.red, group=group)
         L.check(eng.lib.jaxent_bv_tail(eng.plan, sp))
@@ -790,7 +788,7 @@ def run_ours(args, wl):
     sampler.stop_flag = True
     sampler.join()
     eng.steps_done += K
-    eng.launches += 3 * K
+    eng.launches += 2 * K
     ms_total = e0.elapsed_time(e1)
     pass_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pass]))
     t = torch.tensor([ms_total, pass_ms], device=dev, dtype=torch.float64)
@@ -982,7 +980,7 @@ def run_ours(args, wl):
                          **({"special_function": sfu} if sfu else {})},
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": 3 * K,
+            "gpu_launches": 2 * K,
             "clocks": sampler.result(),
             "graph_ms_per_step": graph_ms,
             "check": check,

@@ -24,7 +24,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
   size_t off_w, off_kappa, off_kappa_lo, off_cc, off_ch, off_ck, off_logpf, off_uptake, off_avg, off_pfG;
-  size_t off_partials, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_ticket, off_records;
+  size_t off_cta_scal, off_fx, off_nmax, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_ticket, off_records;
   size_t off_cl_scratch;
   size_t off_blob[JAXENT_MAX_SLOTS];
   int blob_words[JAXENT_MAX_SLOTS];
@@ -64,7 +64,9 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_avg = take((size_t)2 * R * 4);
   L.off_pfG = take((size_t)(T > 0 ? T : 1) * R * 4);
   const int part_n = pass_part_n(R, T, pb->uptake);
-  L.off_partials = take((size_t)MAX_PASS_CTAS * part_n * sizeof(double));
+  L.off_cta_scal = take((size_t)MAX_PASS_CTAS * 4 * sizeof(double));
+  L.off_fx = take((size_t)FX_REP * (part_n - 4) * sizeof(unsigned long long));
+  L.off_nmax = take(sizeof(float));
   L.off_xchg = take(xchg_bytes(part_n, 1));  // single-rank exchange buffer (red / kl inbox of world = 1)
   L.off_klpart = take((size_t)MAX_TAIL_CTAS * KL_N * sizeof(double));
   L.off_ctl = take(2 * sizeof(Ctl));
@@ -88,7 +90,8 @@ static Layout make_layout(const JaxentBvProblem* pb) {
 
 __global__ void state_init_kernel(const float* __restrict__ z0, long long F, StateSets st, Ctl* ctl, Ctl init,
                                   unsigned* epoch, unsigned* counter, unsigned* ticket, unsigned long long* xchg_local,
-                                  long long xchg_words, JaxentLossRecord* records) {
+                                  long long xchg_words, JaxentLossRecord* records, unsigned long long* fx, long long fx_words,
+                                  unsigned* nmax_bits, unsigned nmax_init) {
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long f = i0; f < F; f += stride) {
@@ -99,16 +102,31 @@ __global__ void state_init_kernel(const float* __restrict__ z0, long long F, Sta
     st.g[1][f] = 0.f;
   }
   if (i0 == 0) {
-    ctl[0] = init;
+    ctl[0] = init;          // epoch_id 0: the current block
+    init.epoch_id = -1;
     ctl[1] = init;
     *epoch = 0u;
     *counter = 0u;
     *ticket = 0u;
+    *nmax_bits = nmax_init;
   }
+  for (long long i = i0; i < fx_words; i += stride) fx[i] = 0ull;
   // the local exchange buffer: inboxes, flags and the error word (peers only write here after every rank's state_init)
   for (long long i = i0; i < xchg_words; i += stride) xchg_local[i] = 0ull;
   for (long long i = i0; i < (long long)(JAXENT_RECORD_RING * sizeof(JaxentLossRecord) / 4); i += stride)
     reinterpret_cast<int*>(records)[i] = 0;
+}
+
+// max |x| over the packed fp32 features as a bit pattern (|x| bits compare like unsigned integers; inf and NaN rank above
+// every finite value, so a non-finite feature is seen): bounds the fixed-point row sums of the pass (fx_scale)
+__global__ void absmax_kernel(const uint4* __restrict__ x, long long n16, unsigned* out_bits) {
+  unsigned m = 0u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    m = max(max(m, v.x & 0x7fffffffu), max(max(v.y & 0x7fffffffu, v.z & 0x7fffffffu), v.w & 0x7fffffffu));
+  }
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out_bits, m);
 }
 
 __global__ void export_kernel(StateSets st, const Ctl* ctl, const unsigned* epoch, long long F, float* z, float* m,
@@ -351,7 +369,8 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   // CTA 0 runs the R x T tail; the per-frame MaxEnt work is spread over the others (one CTA does both when F is small)
   long long fctas = (problem->F + 4095) / 4096;
   if (fctas > device_sm_count - 1) fctas = device_sm_count - 1;
-  p->tail_ctas = (fctas <= 1) ? 1 : (int)fctas + 1;
+  if (fctas < 1) fctas = 1;
+  p->tail_ctas = (int)fctas + 1;
   memset(&p->x, 0, sizeof(p->x));
   p->x.world = 1;
   p->x.rank = 0;
@@ -415,9 +434,18 @@ extern "C" int jaxent_bv_state_init(JaxentPlan* p, const float* z0, float zmax, 
       z0, p->prob.F, p->st, ctl, c, reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch),
       reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter), reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket),
       reinterpret_cast<unsigned long long*>(p->x.local), (long long)(xchg_bytes(p->x.part_n, p->x.world) / 8),
-      reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records));
+      reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records), reinterpret_cast<unsigned long long*>(p->ws + p->lay.off_fx),
+      (long long)FX_REP * (p->x.part_n - 4), reinterpret_cast<unsigned*>(p->ws + p->lay.off_nmax),
+      p->prob.feature_format == 1 ? 0x437f0000u /* 255.0f: u8 features */ : 0u);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("state_init launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  if (p->prob.feature_format == 0) {
+    absmax_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(p->prob.packed),
+                                                         (long long)(jaxent_bv_packed_bytes(p->prob.R, p->prob.F) / 16),
+                                                         reinterpret_cast<unsigned*>(p->ws + p->lay.off_nmax));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("absmax launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  }
   BlobSet bs;
   for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
     bs.words[i] = p->lay.blob_words[i];
@@ -467,10 +495,13 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.cc = reinterpret_cast<const float*>(p->ws + p->lay.off_cc);
   a.ch = reinterpret_cast<const float*>(p->ws + p->lay.off_ch);
   a.ck = reinterpret_cast<const float*>(p->ws + p->lay.off_ck);
-  a.partials = reinterpret_cast<double*>(p->ws + p->lay.off_partials);
+  a.fx = reinterpret_cast<unsigned long long*>(p->ws + p->lay.off_fx);
+  a.cta_scal = reinterpret_cast<double*>(p->ws + p->lay.off_cta_scal);
+  a.nmax = reinterpret_cast<const float*>(p->ws + p->lay.off_nmax);
+  a.ticket = reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket);
   a.x = p->x;
   a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
-  a.epoch = reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch);
+  a.epoch = reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch);
   a.records = reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records);
   a.b1 = (float)p->cfg.b1;
   a.b2 = (float)p->cfg.b2;
@@ -482,20 +513,10 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   return launch_pass(a, p->pass_threads + 32, p->rpt, p->pass_ctas, p->pass_smem, (cudaStream_t)stream);
 }
 
-extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t stream) {
-  int rc = check_ready(p, "reduce");
-  if (rc) return rc;
-  ReduceArgs a;
-  a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
-  a.partials = reinterpret_cast<const double*>(p->ws + p->lay.off_partials);
-  a.x = p->x;
-  a.epoch = reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch);
-  a.ticket = reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket);
-  a.dbg = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
-  a.n_part = p->pass_ctas;
-  a.part_n = p->x.part_n;
-  return launch_reduce(a, (cudaStream_t)stream);
-}
+// The fixed-order reduction of the per-CTA partials used to be a kernel of its own; the pass now finishes its sums itself
+// (fixed-point accumulators folded by its last CTA, see pass_epilogue in bv_pass.cu).  Kept as a no-op for callers of the
+// three-phase ABI: JAXENT_BUF_RED is complete when the pass has finished.
+extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t) { return check_ready(p, "reduce"); }
 
 extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   int rc = check_ready(p, "tail");
@@ -508,7 +529,6 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.st = p->st;
   a.x = p->x;
   a.ctl = reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl);
-  a.epoch = reinterpret_cast<const unsigned*>(p->ws + p->lay.off_epoch);
   a.counter = reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter);
   a.w = reinterpret_cast<float*>(p->ws + p->lay.off_w);
   a.kappa = reinterpret_cast<float*>(p->ws + p->lay.off_kappa);
@@ -528,7 +548,7 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
     a.blobs.blob[i] = a.blobs.words[i] ? reinterpret_cast<int*>(p->ws + p->lay.off_blob[i]) : nullptr;
   }
   {
-    const long long fc = (p->tail_ctas == 1) ? 1 : p->tail_ctas - 1;
+    const long long fc = p->tail_ctas - 1;
     a.frames_per_cta = (p->prob.F + fc - 1) / fc;
   }
   a.cl_scratch = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
@@ -552,15 +572,11 @@ extern "C" int jaxent_bv_finish_record(JaxentPlan* p, jaxent_stream_t stream) {
 extern "C" int jaxent_bv_forward_init(JaxentPlan* p, jaxent_stream_t stream) {
   int rc = jaxent_bv_pass(p, 0, stream);
   if (rc) return rc;
-  rc = jaxent_bv_reduce(p, stream);
-  if (rc) return rc;
   return jaxent_bv_tail(p, stream);
 }
 
 extern "C" int jaxent_bv_step(JaxentPlan* p, jaxent_stream_t stream) {
   int rc = jaxent_bv_pass(p, 1, stream);
-  if (rc) return rc;
-  rc = jaxent_bv_reduce(p, stream);
   if (rc) return rc;
   return jaxent_bv_tail(p, stream);
 }

@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArg
   io.p_max_tr = a.p_max_tr;
   io.p_max_va = a.p_max_va;
   io.c_pieces = a.NS;
+  io.prof = nullptr;
   io.ck = nullptr;
   tail_body<GENERAL>(pb, a.blobs, first_data, tsm, acc0, acc1, S, bc, bh, s_c.fw, s_c.fs, io, s_red, s_fin, my_c, my_a, my_b, my_lp, gbc_reg,
                      gbh_reg);

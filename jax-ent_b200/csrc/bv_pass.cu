@@ -334,6 +334,82 @@ __device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, cons
   return gather_hbar(kl_words, a.x.world, a.x.local + xchg_err_off(a.x), ep, ctl, a.records, lane, finish);
 }
 
+
+// ------------------------------------------------------------------------------------------ fixed-point row sums
+// |row sum| <= (sum of the un-normalised weights) * max |feature|.  In a step the weights are exp(z' - lse) with
+// sum exp(z - lse) = 1 and |z' - z| <= (1 - b1) / sqrt(1 - b2) < 3.2 for optax adam (the update does not depend on the
+// learning rate, which pre-scales the gradient): sum e' < e^3.2 < 64.  In the init pass e = exp(z0 - max z0) <= 1 per frame.
+// scale = 2^(61 - e) with bound < 2^e, so a sum stays below 2^61 and carries >= 2^-61 of the bound as resolution
+// (the fp32 tile sums that enter are good to 2^-24).
+__device__ __forceinline__ double fx_scale(float nmax, int mode, long long F) {
+  const double bound = (mode ? 64.0 : (double)F) * (double)fmaxf(nmax, 1e-30f);
+  const int e = ((__double2hiint(bound) >> 20) & 0x7ff) - 1022;  // bound < 2^e
+  return __hiloint2double((61 - e + 1023) << 20, 0);
+}
+__device__ __forceinline__ void fx_add(unsigned long long* dst, float v, double scale) {
+  atomicAdd(dst, (unsigned long long)__double2ll_rn((double)v * scale));  // RED.ADD.64: fire and forget
+}
+
+// End of the pass: every CTA leaves its three scalars in cta_scal and takes a ticket; the last one to arrive folds the
+// replicas of the fixed-point accumulators (any order gives the same integer), converts them to doubles, sums the per-CTA
+// scalars in CTA order, publishes everything (red_publish: plain store on one rank, stamped 16-byte stores into every
+// rank's inbox when frame-sharded), clears the accumulators for the next pass and advances the epoch.  This replaces the
+// separate reduce kernel (one launch boundary and ~5 us of every step).
+__device__ __forceinline__ void pass_epilogue(const PassArgs& a, float nmax_bound, int* s_last) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const unsigned ep = __ldcg(a.epoch);  // before the ticket: the last CTA advances it (nothing is kept live across the sweep for this)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!*s_last) return;
+  __threadfence();
+  if (tid == 0) JPROF(a.dbg, 44);
+  const unsigned nep = ep + 1u;
+  const int n_rows = a.part_n - 4;
+  const float nmax = *a.nmax;
+  const double scale = fx_scale(nmax_bound > 0.f ? nmax_bound : nmax, a.mode, a.F);
+  // non-finite features cannot be carried by integers: hand the tail NaN sums, the loss becomes non-finite (reference: data, not an error)
+  const double inv = (nmax <= 3.0e38f) ? 1.0 / scale : __longlong_as_double(0x7ff8000000000000ll);
+  constexpr int CPT = 4;  // columns per thread and trip: CPT * FX_REP loads in flight (one trip covers 4R columns at R <= 544)
+  for (int c0 = tid; c0 < n_rows; c0 += CPT * nt) {
+    unsigned long long v[CPT][FX_REP];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k)
+#pragma unroll
+      for (int r = 0; r < FX_REP; ++r) v[k][r] = (c0 + k * nt < n_rows) ? __ldcg(a.fx + (size_t)r * n_rows + c0 + k * nt) : 0ull;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int col = c0 + k * nt;
+      if (col < n_rows) {
+        long long t = 0;
+#pragma unroll
+        for (int r = 0; r < FX_REP; ++r) {
+          t += (long long)v[k][r];
+          a.fx[(size_t)r * n_rows + col] = 0ull;
+        }
+        red_publish(a.x, nep, col, (double)t * inv);
+      }
+    }
+  }
+  {  // sum e' (A), sum e' (B), grad-dot over the CTAs in fixed order, one warp each (a CTA has at least two warps)
+    const int lane = tid & 31;
+    for (int j = tid >> 5; j < 3; j += nt >> 5) {
+      double t = 0.0;
+      for (int c = lane; c < (int)gridDim.x; c += 32) t += __ldcg(a.cta_scal + (size_t)c * 4 + j);
+      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) red_publish(a.x, nep, n_rows + j, t);
+    }
+    if (tid == 0) red_publish(a.x, nep, n_rows + 3, 0.0);
+  }
+  __syncthreads();
+  if (tid == 0) {  // the kernel boundary orders these stores for the tail; peers never read the epoch
+    *a.ticket = 0u;
+    *a.epoch = nep;
+    JPROF(a.dbg, 46);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ per-frame uptake mode
 // ForwardPass.average_first = False (reference models/core.py:302-304, BV_uptake_ForwardPass models/HDX/forward.py:57-74):
 // the uptake is evaluated per (time point, residue, frame) and THEN frame-averaged, so the pass carries the non-linearity:
@@ -367,7 +443,7 @@ __device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
 // four per-frame partials (one 16-byte store) and the Adam warp, which has time to spare, sums them.
 template <int TM>
 __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ring, uint64_t* bars, float4* s_rows, const float* s_e,
-                                             float4* s_tab, double* part, int n, int mode, float bc, float bh, int NTc, int nbar) {
+                                             float4* s_tab, int n, int mode, float bc, float bh, int NTc, int nbar) {
   constexpr int TP = TM / 2;
   const int R = a.R, T = a.pf_T;
   const int tid = threadIdx.x;
@@ -387,8 +463,6 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
       my_tab[tp * NTc] = make_float4(t0_ < T ? kr * a.pf_tp[t0_] : 0.f, t1_ < T ? kr * a.pf_tp[t1_] : 0.f, g2.x, g2.y);  // kt = -log2(e) k_r tau_t
     }
   }
-  if (ok)
-    for (int k = 0; k < 2 * T; ++k) part[(size_t)k * R + rc] = 0.0;
   float2 acc[2][TP];
 #pragma unroll
   for (int tp = 0; tp < TP; ++tp) acc[0][tp] = acc[1][tp] = make_float2(0.f, 0.f);
@@ -458,14 +532,17 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
     JCLK_TOC(clk_b, tb0);
   };
   auto flush = [&]() {
+    // the accumulated products are e' * exp(-k tau / PF) with the second factor in [0, 1]: bound = the sum of the weights
+    const double fxs = fx_scale(1.f, mode, a.F);
+    unsigned long long* fxp = a.fx + (size_t)(blockIdx.x % FX_REP) * (a.part_n - 4);
     if (ok) {
 #pragma unroll
       for (int br = 0; br < 2; ++br)
 #pragma unroll
         for (int tp = 0; tp < TP; ++tp) {
-          // single writer per address: deterministic
-          if (2 * tp < T) atomicAdd(&part[(size_t)(br * T + 2 * tp) * R + rc], (double)acc[br][tp].x);
-          if (2 * tp + 1 < T) atomicAdd(&part[(size_t)(br * T + 2 * tp + 1) * R + rc], (double)acc[br][tp].y);
+          // integer atomics: exact in any order
+          if (2 * tp < T) fx_add(fxp + (size_t)(br * T + 2 * tp) * R + rc, acc[br][tp].x, fxs);
+          if (2 * tp + 1 < T) fx_add(fxp + (size_t)(br * T + 2 * tp + 1) * R + rc, acc[br][tp].y, fxs);
           acc[br][tp] = make_float2(0.f, 0.f);
         }
     }
@@ -517,7 +594,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
   const long long t0 = s0 * S;          // first tile
   const int n = ns * S;                 // tiles of this CTA (frames past F are zero padding)
   const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
-  double* part = a.partials + (size_t)blockIdx.x * a.part_n;
+  __shared__ int s_last;
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -536,7 +613,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
   }
   if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 40);
   pdl_wait();               // everything the tail kernel wrote (ctl, cc/ch, w, kappa, klsum) is visible from here on
-  pdl_launch_dependents();  // lets the reduce kernel's launch overlap this kernel
+  pdl_launch_dependents();  // lets the tail kernel's launch and constant staging overlap this kernel
   if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 41);
 
   const unsigned ep = *a.epoch;
@@ -663,11 +740,12 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     }
     if (blockIdx.x == 0 && lane == 0) JPROF(a.dbg, 43);
     if (lane == 0) {
-      part[a.part_n - 4] = sumA;
-      part[a.part_n - 3] = sumB;
-      part[a.part_n - 2] = gdot;
-      part[a.part_n - 1] = 0.0;
+      double* sc = a.cta_scal + (size_t)blockIdx.x * 4;
+      sc[0] = sumA;
+      sc[1] = sumB;
+      sc[2] = gdot;
     }
+    pass_epilogue(a, 0.f, &s_last);
     return;
   }
 
@@ -684,12 +762,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     ccr[i] = (ok && mode) ? a.cc[rc] : 0.f;
     chr[i] = (ok && mode) ? a.ch[rc] : 0.f;
     nkr[i] = (ok && mode) ? -a.ck[rc] : 0.f;
-    if (ok) {
-      part[0 * R + rc] = 0.0;
-      part[1 * R + rc] = 0.0;
-      part[2 * R + rc] = 0.0;
-      part[3 * R + rc] = 0.0;
-    }
   }
   const uint32_t rstride = (uint32_t)R * (FMT == 0 ? 16u : 8u);
   const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -697,13 +769,15 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
 #pragma unroll
   for (int i = 0; i < RPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
-  auto flush = [&]() {
+  auto flush = [&]() {  // rare (every FLUSH_TILES tiles): scale and destination are re-derived here rather than kept in registers
+    const double fxs = fx_scale(*a.nmax, mode, a.F);
+    unsigned long long* fxp = a.fx + (size_t)(blockIdx.x % FX_REP) * (a.part_n - 4);
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       if (row[i] < R) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          atomicAdd(&part[k * R + row[i]], (double)acc[i][k]);  // single writer per address: deterministic
+          fx_add(fxp + k * R + row[i], acc[i][k], fxs);  // integer atomics: exact in any order
           acc[i][k] = 0.f;
         }
       }
@@ -763,6 +837,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     }
   }
   flush();
+  pass_epilogue(a, 0.f, &s_last);
 }
 
 // ------------------------------------------------------------------------------------------ per-frame mode: Adam warps, kernel
@@ -800,7 +875,7 @@ constexpr int BAR_ADAM = 5;  // the two Adam warps of the per-frame kernel, once
 // exponential instead of the IEEE sequences, and the per-frame state fetched 8 tiles ahead, one frame per lane.
 __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __restrict__ ctl, unsigned ep, int q, int lane, int NWc, int nbar,
                                              unsigned char* ring, uint64_t* bars, const float4* s_rows, float* s_e, double* s_x,
-                                             long long t0, long long s0, int ns, int n, double* part) {
+                                             long long t0, long long s0, int ns, int n) {
   const int mode = a.mode;
   const double hbar_d = mode ? pass_hbar(a, ep, ctl, lane, blockIdx.x == 0 && q == 0) : 0.0;
   const float hb_hi = (float)hbar_d, hb_lo = (float)(hbar_d - (double)hb_hi);  // see bv_pass_kernel's Adam warp
@@ -977,10 +1052,10 @@ __device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __res
   bar_sync(BAR_ADAM, 64);
   if (q == 0) {
     if (lane == 0) {
-      part[a.part_n - 4] = sumA + s_x[0];
-      part[a.part_n - 3] = sumB + s_x[1];
-      part[a.part_n - 2] = gdot + s_x[2];
-      part[a.part_n - 1] = 0.0;
+      double* sc = a.cta_scal + (size_t)blockIdx.x * 4;
+      sc[0] = sumA + s_x[0];
+      sc[1] = sumB + s_x[1];
+      sc[2] = gdot + s_x[2];
     }
   }
 }
@@ -1009,7 +1084,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
   const long long t0 = s0;
   const int n = ns;
   const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
-  double* part = a.partials + (size_t)blockIdx.x * a.part_n;
+  __shared__ int s_last;
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -1038,58 +1113,10 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
     }
     return;
   }
-  if (is_adam) {
-    pf_adam_warp(a, ctl, ep, q, lane, NWc, nbar, ring, bars, s_rows, s_e, s_x, t0, s0, ns, n, part);
-    return;
-  }
-  if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, part, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
-  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, part, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
-}
-
-// ------------------------------------------------------------------------------------------ reduce
-// sum_cta partials[cta][j] in CTA order (deterministic), stored into the red inbox of EVERY rank (slot = this rank);
-// the last block to finish advances the epoch.
-__global__ void __launch_bounds__(1024) reduce_kernel(const ReduceArgs a) {
-  // 32 columns x 32 partial-groups per block: every load is independent (latency overlapped) and
-  // the summation order is fixed (group-strided, then groups 0..31) -> bitwise reproducible.
-  __shared__ double sh[32][33];
-  if (blockIdx.x == 0 && threadIdx.x == 0) JPROF(a.dbg, 44);
-  pdl_wait();
-  pdl_launch_dependents();
-  if (blockIdx.x == 0 && threadIdx.x == 0) JPROF(a.dbg, 45);
-  const unsigned ep = *a.epoch;         // every block reads the epoch before the last one advances it (ticket below)
-  if (a.ctl[ep & 1u].trk_stop) return;  // on-device loop ended: keep the sums and the epoch as they are
-  const unsigned nep = ep + 1u;
-  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + lane;
-  double s = 0.0;
-  if (col < a.part_n) {
-    // at most 320 partial vectors: all (<= 10) loads of this thread are in flight together, summed in fixed order
-    double v[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      const int c = grp + 32 * k;
-      v[k] = (c < a.n_part) ? __ldcg(&a.partials[(size_t)c * a.part_n + col]) : 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < 10; ++k) s += v[k];
-  }
-  sh[grp][lane] = s;
-  __syncthreads();
-  if (grp == 0 && col < a.part_n) {
-    double t = 0.0;
-#pragma unroll
-    for (int g2 = 0; g2 < 32; ++g2) t += sh[g2][lane];
-    red_publish(a.x, nep, col, t);  // plain store (one rank) or stamped 16-byte stores into every rank's inbox
-  }
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(a.ticket, 1u);
-    if (ticket == gridDim.x - 1) {  // every block has read the old epoch by now
-      *a.ticket = 0u;
-      *a.epoch = nep;
-      JPROF(a.dbg, 46);
-    }
-  }
+  if (is_adam) pf_adam_warp(a, ctl, ep, q, lane, NWc, nbar, ring, bars, s_rows, s_e, s_x, t0, s0, ns, n);
+  else if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+  pass_epilogue(a, 1.f, &s_last);
 }
 
 __global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, const Xchg x, JaxentLossRecord* rec, int n_slots) {
@@ -1131,14 +1158,6 @@ int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, 
   }
   cudaError_t e = (le != cudaSuccess) ? le : cudaGetLastError();
   if (e != cudaSuccess) { set_error("bv_pass_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
-  return JAXENT_OK;
-}
-
-int launch_reduce(const ReduceArgs& a, cudaStream_t s) {
-  const int blocks = (a.part_n + 31) / 32;
-  cudaError_t e = launch_pdl(reduce_kernel, blocks, 1024, 0, s, a);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("reduce_kernel launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;
 }
 

@@ -50,16 +50,64 @@ struct StepScalars {
   double trk_prev_loss, trk_ema;
 };
 
-// The step scalars are derived in two parts by one warp each:
-//   derive_critical : everything the R x T tail and the per-frame terms wait for -- plateau branch d, S, the BV-parameter Adam
-//                     update (bc, bh), counters.  Runs before the block-wide barrier (1).
-//   derive_rest     : the learning rates / masks / bias corrections / log-sum-exp of the COMING update and the convergence
-//                     tracker.  In the tail CTA it is executed by the last warp while the (smaller) peptide-map phase keeps
-//                     only the first warps busy, i.e. off the critical path; the frame CTAs run it right after the critical part.
-// The powf / log evaluations run on separate lanes behind single call sites.
-__device__ __noinline__ void derive_critical(StepScalars* out, const Ctl* __restrict__ old, double SA, double SB, double gdot,
-                                             const JaxentOptConfig cfg) {
+// The step scalars are derived in three parts:
+//   derive_spec     : BEFORE the pass has finished (the tail is launched early, PDL): everything that only needs the previous
+//                     control block -- the BV-parameter Adam update for BOTH plateau branches (lane b takes branch b), bias
+//                     corrections, counters, masks.
+//   derive_critical : after the pass: the plateau decision from the reduced grad-dot, a select between the two prepared
+//                     updates, S.  A handful of instructions between the arrival of the sums and the block-wide barrier (1).
+//   derive_rest     : the learning rates / bias corrections / log-sum-exp of the COMING update and the convergence tracker.
+//                     Never on the R x T tail's path: a frame CTA (block 1) owns these fields of the new control block.
+struct SpecScalars {
+  float lr[2], mlr[2], bc[2], bh[2], mb0[2], mb1[2], vb0[2], vb1[2];
+  double dot_model;  // sum over (bc, bh) of prev * cur gradient: the BV-parameter part of the grad-dot
+};
+
+__device__ __noinline__ void derive_spec(SpecScalars* out, const Ctl* __restrict__ old, const JaxentOptConfig cfg) {
   const int lane = threadIdx.x & 31;
+  const int cm1 = old->count_model + (old->pending ? 1 : 0);
+  // lanes 0,1: b1^cm1, b2^cm1 (bias corrections of the BV-parameter Adam update)
+  float pw = 0.f;
+  if (lane < 2) pw = fpow((lane & 1) ? (float)cfg.b2 : (float)cfg.b1, (float)cm1);
+  const float pw0 = __shfl_sync(0xffffffffu, pw, 0), pw1 = __shfl_sync(0xffffffffu, pw, 1);
+  if (lane >= 2) return;
+  const int b = lane;  // plateau branch
+  const float g0 = old->gb[0], g1 = old->gb[1];
+  const float lr = b ? old->lrB : old->lrA, mlr = b ? old->mlrB : old->mlrA;
+  // optax adam + keep_params_nonnegative on (bc, bh) with the LR-pre-scaled gradients
+  const float b1 = (float)cfg.b1, b2 = (float)cfg.b2, eps = (float)cfg.eps, clip = cfg.clip_value;
+  const float om_b1 = (float)(1.0 - cfg.b1), om_b2 = (float)(1.0 - cfg.b2);
+  const float c1 = 1.0f - pw0, c2 = 1.0f - pw1;
+  float sg0 = g0 * mlr, sg1 = g1 * mlr;
+  if (clip > 0.f) {
+    sg0 = fminf(fmaxf(sg0, -clip), clip);
+    sg1 = fminf(fmaxf(sg1, -clip), clip);
+  }
+  const float mb0 = om_b1 * sg0 + b1 * old->mb[0];
+  const float mb1 = om_b1 * sg1 + b1 * old->mb[1];
+  const float vb0 = om_b2 * (sg0 * sg0) + b2 * old->vb[0];
+  const float vb1 = om_b2 * (sg1 * sg1) + b2 * old->vb[1];
+  float u0 = -((mb0 / c1) / (sqrtf(vb0 / c2) + eps));
+  float u1 = -((mb1 / c1) / (sqrtf(vb1 / c2) + eps));
+  if (old->bc + u0 < 0.f) u0 = -old->bc;  // optax.keep_params_nonnegative
+  if (old->bh + u1 < 0.f) u1 = -old->bh;
+  out->lr[b] = lr;
+  out->mlr[b] = mlr;
+  out->bc[b] = old->bc + u0;
+  out->bh[b] = old->bh + u1;
+  out->mb0[b] = mb0;
+  out->mb1[b] = mb1;
+  out->vb0[b] = vb0;
+  out->vb1[b] = vb1;
+  if (b == 0) {
+    const float p0 = old->have_prev ? old->gb_prev[0] : g0, p1 = old->have_prev ? old->gb_prev[1] : g1;
+    out->dot_model = (double)p0 * (double)g0 + (double)p1 * (double)g1;
+  }
+}
+
+// one thread
+__device__ __forceinline__ void derive_critical(StepScalars* out, const SpecScalars* __restrict__ sp, const Ctl* __restrict__ old, double SA,
+                                                double SB, double gdot, const JaxentOptConfig& cfg) {
   StepScalars s;
   s.pending = old->pending;
   s.step = old->step;
@@ -76,50 +124,34 @@ __device__ __noinline__ void derive_critical(StepScalars* out, const Ctl* __rest
   s.vb0 = old->vb[0];
   s.vb1 = old->vb[1];
   s.lse_old = old->lse;
-  const float g0 = old->gb[0], g1 = old->gb[1];
-  const float gp0 = old->gb_prev[0], gp1 = old->gb_prev[1];
-  const float olrA = old->lrA, olrB = old->lrB, omlrA = old->mlrA, omlrB = old->mlrB;
-  const int cm1 = s.cm + (s.pending ? 1 : 0), cf1 = s.cf + (s.pending ? 1 : 0);
-  // lanes 0,1: b1^cm1, b2^cm1 (bias corrections of the BV-parameter Adam update)
-  float pw = 0.f;
-  if (lane < 2) pw = fpow((lane & 1) ? (float)cfg.b2 : (float)cfg.b1, (float)cm1);
-  const float pw0 = __shfl_sync(0xffffffffu, pw, 0), pw1 = __shfl_sync(0xffffffffu, pw, 1);
-  if (lane != 0) return;
   s.d = 0;
   s.dot = 0.0;
   if (s.pending) {
-    const float p0 = s.have_prev ? gp0 : g0, p1 = s.have_prev ? gp1 : g1;
-    s.dot = gdot + (double)p0 * (double)g0 + (double)p1 * (double)g1;
-    s.d = ((float)s.dot < 0.f && s.step > 1) ? 1 : 0;  // opt/optimiser.py:403
-    s.lr = s.d ? olrB : olrA;
-    s.mlr = s.d ? omlrB : omlrA;
-    // optax adam + keep_params_nonnegative on (bc, bh) with the LR-pre-scaled gradients
-    const float b1 = (float)cfg.b1, b2 = (float)cfg.b2, eps = (float)cfg.eps, clip = cfg.clip_value;
-    const float om_b1 = (float)(1.0 - cfg.b1), om_b2 = (float)(1.0 - cfg.b2);
-    s.cm = cm1;
-    const float c1 = 1.0f - pw0, c2 = 1.0f - pw1;
-    float sg0 = g0 * s.mlr, sg1 = g1 * s.mlr;
-    if (clip > 0.f) {
-      sg0 = fminf(fmaxf(sg0, -clip), clip);
-      sg1 = fminf(fmaxf(sg1, -clip), clip);
-    }
-    s.mb0 = om_b1 * sg0 + b1 * s.mb0;
-    s.mb1 = om_b1 * sg1 + b1 * s.mb1;
-    s.vb0 = om_b2 * (sg0 * sg0) + b2 * s.vb0;
-    s.vb1 = om_b2 * (sg1 * sg1) + b2 * s.vb1;
-    float u0 = -((s.mb0 / c1) / (sqrtf(s.vb0 / c2) + eps));
-    float u1 = -((s.mb1 / c1) / (sqrtf(s.vb1 / c2) + eps));
-    if (s.bc + u0 < 0.f) u0 = -s.bc;  // optax.keep_params_nonnegative
-    if (s.bh + u1 < 0.f) u1 = -s.bh;
-    s.bc += u0;
-    s.bh += u1;
+    s.dot = gdot + sp->dot_model;
+    const int d = ((float)s.dot < 0.f && s.step > 1) ? 1 : 0;  // opt/optimiser.py:403
+    s.d = d;
+    s.lr = sp->lr[d];
+    s.mlr = sp->mlr[d];
+    s.bc = sp->bc[d];
+    s.bh = sp->bh[d];
+    s.mb0 = sp->mb0[d];
+    s.mb1 = sp->mb1[d];
+    s.vb0 = sp->vb0[d];
+    s.vb1 = sp->vb1[d];
+    s.cm += 1;
+    s.cf += 1;
     s.have_prev = 1;
-    s.cf = cf1;
     s.mask_idx = (s.step >= cfg.initial_steps) ? 1 : s.mask_idx;
     s.step += 1;
   }
   s.S = s.d ? SB : SA;
   s.loop_step = old->step;
+  // masks of the COMING update (state.step == step): opt/optimiser.py:365-381
+  {
+    const int mi = (s.step >= cfg.initial_steps) ? 1 : s.mask_idx;
+    s.mask_frame = (mi == 0) ? 1.f : (cfg.optimise_frame_weights ? 1.f : 0.f);
+    s.mask_model = (mi == 0) ? 0.f : (cfg.optimise_model_parameters ? 1.f : 0.f);
+  }
   // the fields of derive_rest start from their carried values
   s.trk_stop = old->trk_stop;
   s.snap_now = -1;
@@ -143,15 +175,12 @@ __device__ __noinline__ void derive_rest(StepScalars* sc, const Ctl* __restrict_
   if (lane != 0) return;
   // speculative rates of the NEXT update (state.step == step): opt/optimiser.py:365-381,403-413
   const bool switched = s.step >= cfg.initial_steps;
-  const int mi = switched ? 1 : s.mask_idx;
   const float base_lr = switched ? cfg.learning_rate : s.lr;
   const float base_mlr = switched ? cfg.learning_rate * cfg.model_parameters_lr_scale : s.mlr;
   s.lrA = base_lr;
   s.lrB = base_lr / cfg.plateau_denominator;
   s.mlrA = base_mlr;
   s.mlrB = base_mlr / cfg.plateau_denominator;
-  s.mask_frame = (mi == 0) ? 1.f : (cfg.optimise_frame_weights ? 1.f : 0.f);
-  s.mask_model = (mi == 0) ? 0.f : (cfg.optimise_model_parameters ? 1.f : 0.f);
   s.bc1 = 1.0f - pw2;
   s.bc2 = 1.0f - pw3;
   s.lse_new = (float)((double)s.lse_old + lgS);
@@ -228,6 +257,10 @@ __global__ void build_blobs_kernel(JaxentBvProblem pb, BlobSet bs) {
     const int* s = static_cast<const int*>(src);
     for (int i = tid; i < n; i += nt) dst[i] = s[i];
   };
+  auto cpd = [&](int* dst, const float* src, int n) {  // map values: float -> double (see blob_layout)
+    double* d = reinterpret_cast<double*>(dst);
+    for (int i = tid; i < n; i += nt) d[i] = (double)src[i];
+  };
   for (int i = 0; i < pb.n_slots; ++i) {
     const JaxentLossSlot& sl = pb.slots[i];
     if (sl.kind > JAXENT_LOSS_PF_L2 || bs.blob[i] == nullptr) continue;
@@ -245,13 +278,13 @@ __global__ void build_blobs_kernel(JaxentBvProblem pb, BlobSet bs) {
     cp(w + b.tr_col, sl.train.col, sl.train.nnz);
     cp(w + b.tr_tptr, sl.train.t_ptr, R + 1);
     cp(w + b.tr_trow, sl.train.t_row, sl.train.nnz);
-    cp(w + b.tr_val, sl.train.val, sl.train.nnz);
-    cp(w + b.tr_tval, sl.train.t_val, sl.train.nnz);
+    cpd(w + b.tr_val, sl.train.val, sl.train.nnz);
+    cpd(w + b.tr_tval, sl.train.t_val, sl.train.nnz);
     cp(w + b.tr_y, sl.train.y, sl.train.n_pep * Tm);
     if (sl.val.n_pep > 0) {
       cp(w + b.va_ptr, sl.val.row_ptr, sl.val.n_pep + 1);
       cp(w + b.va_col, sl.val.col, sl.val.nnz);
-      cp(w + b.va_val, sl.val.val, sl.val.nnz);
+      cpd(w + b.va_val, sl.val.val, sl.val.nnz);
       cp(w + b.va_y, sl.val.y, sl.val.n_pep * Tm);
     }
   }
@@ -265,10 +298,77 @@ int launch_build_blobs(const JaxentBvProblem& pb, const BlobSet& bs, cudaStream_
 }
 
 // ------------------------------------------------------------------------------------------ shared pieces
-// the new control block and the loss record, written by one warp (lane 0 the scalars, lanes 0..5 the slots)
-__device__ __forceinline__ void write_ctl_and_record(Ctl* __restrict__ neu, JaxentLossRecord* records, const StepScalars& sc,
-                                                     const Ctl& s_old, const double* s_fin, double gbc_reg, double gbh_reg,
-                                                     int n_slots, int lane, const TrackConfig& trk) {
+// The new control block has two writers with disjoint fields.  The R x T tail CTA (block 0) writes what it produces:
+// parameters, gradients, counters, masks, the loss record.  One warp; lane 0 the scalars, lanes 0..5 the slots.
+__device__ __forceinline__ void write_ctl_critical(Ctl* __restrict__ neu, JaxentLossRecord* records, const StepScalars& sc,
+                                                   const Ctl& s_old, const double* s_fin, double gbc_reg, double gbh_reg,
+                                                   int n_slots, int lane, unsigned ep) {
+  const float gb0 = (float)(s_fin[13] + gbc_reg) * sc.mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * sc.mask_model;
+  if (lane == 0) {
+    neu->step = sc.step;
+    neu->mask_idx = sc.mask_idx;
+    neu->branch = sc.d;
+    neu->pending = 1;
+    neu->have_prev = sc.have_prev;
+    neu->count_frame = sc.cf;
+    neu->count_model = sc.cm;
+    neu->kl_slot = s_old.kl_slot;
+    neu->lr = sc.lr;
+    neu->model_lr = sc.mlr;
+    neu->bc = sc.bc;
+    neu->bh = sc.bh;
+    neu->mb[0] = sc.mb0; neu->mb[1] = sc.mb1; neu->vb[0] = sc.vb0; neu->vb[1] = sc.vb1;
+    neu->gb_prev[0] = s_old.gb[0];
+    neu->gb_prev[1] = s_old.gb[1];
+    neu->gb[0] = gb0;
+    neu->gb[1] = gb1;
+    neu->mask_frame = sc.mask_frame;
+    neu->mask_model = sc.mask_model;
+    neu->kl_scale = s_old.kl_scale;
+    neu->last_dot = (float)sc.dot;
+    neu->last_lr = sc.lr;
+    neu->last_branch = sc.d;
+    neu->rec_idx = sc.step % JAXENT_RECORD_RING;
+    neu->hbar_data = s_fin[12];
+    neu->epoch_id = (int)ep;
+  }
+  if (lane < JAXENT_MAX_SLOTS) {
+    neu->fw[lane] = s_old.fw[lane];
+    neu->fs[lane] = s_old.fs[lane];
+  }
+  JaxentLossRecord* rec = records + (sc.step % JAXENT_RECORD_RING);
+  if (lane == 1) {
+    rec->step = sc.step;
+    rec->branch = sc.d;
+    rec->lr = sc.lr;
+    rec->grad_dot = (float)sc.dot;
+    rec->bc = sc.bc;
+    rec->bh = sc.bh;
+    rec->grad_bc = gb0;
+    rec->grad_bh = gb1;
+    rec->complete = 0;
+  }
+  if (lane < JAXENT_MAX_SLOTS) {
+    rec->train[lane] = (lane < n_slots) ? (float)s_fin[lane] : 0.f;
+    rec->val[lane] = (lane < n_slots) ? (float)s_fin[JAXENT_MAX_SLOTS + lane] : 0.f;
+  }
+  __syncwarp();
+  if (lane == 0 && s_old.kl_slot < 0) finish_record(neu, 0.0, records, n_slots);  // no MaxEnt slot: the record is complete here
+}
+
+// The first frame CTA (block 1) writes what derive_rest produced: the speculative learning rates, bias corrections and
+// log-sum-exp of the coming update, and the convergence tracker (+ the snapshot header).  Lanes 0 and 2 of one warp.
+__device__ __forceinline__ void write_ctl_rest(Ctl* __restrict__ neu, const JaxentLossRecord* records, const StepScalars& sc, int lane,
+                                               const TrackConfig& trk) {
+  if (lane == 0) {
+    neu->lrA = sc.lrA;
+    neu->lrB = sc.lrB;
+    neu->mlrA = sc.mlrA;
+    neu->mlrB = sc.mlrB;
+    neu->bc1 = sc.bc1;
+    neu->bc2 = sc.bc2;
+    neu->lse = sc.lse_new;
+  }
   if (lane == 2) {
     neu->trk_stop = sc.trk_stop;
     neu->trk_reason = sc.trk_reason;
@@ -295,63 +395,6 @@ __device__ __forceinline__ void write_ctl_and_record(Ctl* __restrict__ neu, Jaxe
       sn->losses = records[sc.loop_step % JAXENT_RECORD_RING];
     }
   }
-  const float gb0 = (float)(s_fin[13] + gbc_reg) * sc.mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * sc.mask_model;
-  if (lane == 0) {
-    neu->step = sc.step;
-    neu->mask_idx = sc.mask_idx;
-    neu->branch = sc.d;
-    neu->pending = 1;
-    neu->have_prev = sc.have_prev;
-    neu->count_frame = sc.cf;
-    neu->count_model = sc.cm;
-    neu->kl_slot = s_old.kl_slot;
-    neu->lr = sc.lr;
-    neu->model_lr = sc.mlr;
-    neu->bc = sc.bc;
-    neu->bh = sc.bh;
-    neu->mb[0] = sc.mb0; neu->mb[1] = sc.mb1; neu->vb[0] = sc.vb0; neu->vb[1] = sc.vb1;
-    neu->gb_prev[0] = s_old.gb[0];
-    neu->gb_prev[1] = s_old.gb[1];
-    neu->gb[0] = gb0;
-    neu->gb[1] = gb1;
-    neu->lrA = sc.lrA;
-    neu->lrB = sc.lrB;
-    neu->mlrA = sc.mlrA;
-    neu->mlrB = sc.mlrB;
-    neu->mask_frame = sc.mask_frame;
-    neu->mask_model = sc.mask_model;
-    neu->bc1 = sc.bc1;
-    neu->bc2 = sc.bc2;
-    neu->lse = sc.lse_new;
-    neu->kl_scale = s_old.kl_scale;
-    neu->last_dot = (float)sc.dot;
-    neu->last_lr = sc.lr;
-    neu->last_branch = sc.d;
-    neu->rec_idx = sc.step % JAXENT_RECORD_RING;
-    neu->hbar_data = s_fin[12];
-  }
-  if (lane < JAXENT_MAX_SLOTS) {
-    neu->fw[lane] = s_old.fw[lane];
-    neu->fs[lane] = s_old.fs[lane];
-  }
-  JaxentLossRecord* rec = records + (sc.step % JAXENT_RECORD_RING);
-  if (lane == 1) {
-    rec->step = sc.step;
-    rec->branch = sc.d;
-    rec->lr = sc.lr;
-    rec->grad_dot = (float)sc.dot;
-    rec->bc = sc.bc;
-    rec->bh = sc.bh;
-    rec->grad_bc = gb0;
-    rec->grad_bh = gb1;
-    rec->complete = 0;
-  }
-  if (lane < JAXENT_MAX_SLOTS) {
-    rec->train[lane] = (lane < n_slots) ? (float)s_fin[lane] : 0.f;
-    rec->val[lane] = (lane < n_slots) ? (float)s_fin[JAXENT_MAX_SLOTS + lane] : 0.f;
-  }
-  __syncwarp();
-  if (lane == 0 && s_old.kl_slot < 0) finish_record(neu, 0.0, records, n_slots);
 }
 
 // per-frame MaxEnt terms of frames [cta*frames_per_cta, ...): softmax weights, dKL/dw and the KL sums of this CTA
@@ -426,7 +469,7 @@ __device__ __forceinline__ void frame_terms(const TailArgs& a, const StepScalars
 // rank, stamped 16-byte stores into the kl inbox of every rank (slot = this rank) when frame-sharded
 __device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep, int* s_last) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned n_frame_ctas = gridDim.x > 1 ? gridDim.x - 1 : 1;
+  const unsigned n_frame_ctas = gridDim.x - 1;
   if (n_frame_ctas > 1) {
     if (tid < KL_N) __threadfence();
     __syncthreads();
@@ -459,60 +502,61 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   __shared__ double s_fin[16];
   __shared__ __align__(16) Ctl s_ctl2[2];  // both control blocks, fetched before the epoch is known
   __shared__ StepScalars s_sc;
+  __shared__ SpecScalars s_spec;
   __shared__ int s_last;
 
   const JaxentBvProblem& pb = a.prob;
-  const int R = pb.R, T = pb.uptake ? pb.T : 0, Tm = T > 0 ? T : 1;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  const bool tail_cta = blockIdx.x == 0;
-  const bool frame_cta = (gridDim.x == 1) || blockIdx.x > 0;
-  const float invR = 1.0f / (float)R, invTm = 1.0f / (float)Tm;
+  const int R = pb.R, T = pb.uptake ? pb.T : 0;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const bool tail_cta = blockIdx.x == 0;  // block 0: the R x T tail; blocks 1..: per-frame MaxEnt terms (the grid always has >= 2 blocks)
 
   const TailSmem tsm = carve_tail_smem(smem_raw, R, T, a.p_max_tr, a.p_max_va);
 
   TPROF(0); TPROF_F(0);
-  // ---- constant data first (peptide-map blob, rates, time points): independent of the previous kernel (PDL)
+  // ---- Everything that does not depend on the pass runs BEFORE the grid-dependency wait (the tail is launched while the
+  // pass streams, PDL): the peptide-map blob, rates and time points, BOTH control blocks (written by the previous tail, which
+  // had completed before the pass -- and hence this kernel -- could start), and the BV-parameter update for both plateau branches.
   int first_data = -1;
   if (tail_cta) first_data = stage_tail_constants(pb, a.blobs, tsm);
-  TPROF(1);
-  pdl_wait();               // the reduced partial sums and the previous control block are visible from here on
-  pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
-  TPROF(2); TPROF_F(1);
-  // ---- one global round trip: the epoch, BOTH control blocks (which of them is current depends on the epoch, so
-  // fetching both removes a dependent load) and the reduced sums are requested together
   {
     constexpr int CW = (int)(sizeof(Ctl) / 16);
     if (tid >= 64 && tid < 64 + 2 * CW) reinterpret_cast<int4*>(s_ctl2)[tid - 64] = __ldcg(reinterpret_cast<const int4*>(a.ctl) + (tid - 64));
+    if (tail_cta && lane < 16) s_red[warp][lane] = 0.0;
   }
-  const unsigned ep = __ldcg(a.epoch);
   __syncthreads();  // (0) control blocks staged
-  if (s_ctl2[ep & 1u].trk_stop) return;  // the on-device loop has ended (reduce did not advance the epoch): no-op
-  const Ctl& s_old = s_ctl2[(ep - 1u) & 1u];
-  Ctl* __restrict__ neu = a.ctl + (ep & 1u);
+  // the block that carries the larger epoch is the current one; this step's epoch follows from it (no load after the wait)
+  const int newest = ((int)(s_ctl2[1].epoch_id - s_ctl2[0].epoch_id) > 0) ? 1 : 0;
+  const Ctl& s_old = s_ctl2[newest];
+  if (s_old.trk_stop) return;  // the on-device loop has ended (the pass did not advance the epoch either): no-op
+  const unsigned ep = (unsigned)s_old.epoch_id + 1u;
+  Ctl* __restrict__ neu = a.ctl + (newest ^ 1);
   const int cur_set = ep & 1u;
+  if (warp == 0) derive_spec(&s_spec, &s_old, a.cfg);
+  TPROF(1);
+  pdl_wait();               // the reduced partial sums are visible from here on
+  pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
+  TPROF(2); TPROF_F(1);
 
+  // all loads of the reduced sums are issued together (one round trip); warp 0 then derives the scalars
+  const bool pfm = pb.uptake == 2;
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
+  if (tail_cta && tid < R && !pfm) {
+    accA0 = red_total(a.x, ep, 0 * R + tid);
+    accA1 = red_total(a.x, ep, 1 * R + tid);
+    accB0 = red_total(a.x, ep, 2 * R + tid);
+    accB1 = red_total(a.x, ep, 3 * R + tid);
+  }
   if (warp == 0) {
     const double SA = red_total(a.x, ep, a.part_n - 4), SB = red_total(a.x, ep, a.part_n - 3), gdot = red_total(a.x, ep, a.part_n - 2);
-    derive_critical(&s_sc, &s_old, SA, SB, gdot, a.cfg);
-    // the per-frame CTAs need the tracker's decisions (snapshot slot, EMA update) before their frame loop;
-    // the tail CTA defers this half to an otherwise idle warp of the peptide-map phase (see tail_body's `side`)
-    if (!tail_cta || gridDim.x == 1) {
+    __syncwarp();
+    if (lane == 0) derive_critical(&s_sc, &s_spec, &s_old, SA, SB, gdot, a.cfg);
+    // the per-frame CTAs need the tracker's decisions (snapshot slot, EMA update) before their frame loop
+    if (!tail_cta) {
       __syncwarp();
       derive_rest(&s_sc, &s_old, a.cfg, a.trk, a.records);
     }
   }
-  const bool pfm = pb.uptake == 2;
-  if (tail_cta) {
-    if (tid < R && !pfm) {
-      accA0 = red_total(a.x, ep, 0 * R + tid);
-      accA1 = red_total(a.x, ep, 1 * R + tid);
-      accB0 = red_total(a.x, ep, 2 * R + tid);
-      accB1 = red_total(a.x, ep, 3 * R + tid);
-    }
-    if (lane < 16) s_red[warp][lane] = 0.0;
-  }
-  __syncthreads();  // (1) everything staged, scalars broadcast
+  __syncthreads();  // (1) scalars broadcast
   TPROF(3); TPROF_F(2);
   const int d = s_sc.d;
   const double S = s_sc.S;
@@ -530,55 +574,53 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     io.p_max_tr = a.p_max_tr;
     io.p_max_va = a.p_max_va;
     io.c_pieces = 0;
+    io.prof = reinterpret_cast<long long*>(a.cl_scratch);
     io.ck = a.ck;
     if (pfm) {  // per-frame uptake mode: <u>[t,r] = 1 - acc[branch d][t][r] / S, acc = sum_f e'_f exp(-k tau / PF_f) from the pass
       const double invS = __drcp_rn(S);
 #pragma unroll 1
       for (int it = tid; it < R * T; it += nt) {
         const double uv = 1.0 - red_total(a.x, ep, d * T * R + it) * invS;
-        tsm.sU[it] = uv;
+        const int t = it / R, r = it - t * R;
+        tsm.sU[r * T + t] = uv;  // [r][t], as tail_body reads it
         a.uptake[it] = (float)uv;
       }
     }
-    const bool defer_rest = gridDim.x > 1;
-    auto side = [&]() {
-      if (defer_rest) derive_rest(&s_sc, &s_old, a.cfg, a.trk, a.records);
-    };
+#ifdef JX_ICACHE_TEST
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+      if (rep == 1) { __syncthreads(); if (lane < 16) s_red[warp][lane] = 0.0; __syncthreads(); TPROF(13); }
+#endif
     tail_body<GENERAL>(pb, a.blobs, first_data, tsm, d ? accB0 : accA0, d ? accB1 : accA1, S, bc, bh, s_old.fw, s_old.fs, io, s_red, s_fin,
-                       my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg, side);
-    if (defer_rest && first_data < 0) {  // no data slot: nothing called `side`
-      if (warp == 0) derive_rest(&s_sc, &s_old, a.cfg, a.trk, a.records);
-      __syncthreads();
+                       my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg);
+#ifdef JX_ICACHE_TEST
+      if (rep == 0) TPROF(14);
     }
+#endif
     if (tid < R && !pfm) {  // row coefficients of the next pass
       a.cc[tid] = (float)(my_c * bc);
       a.ch[tid] = (float)(my_c * bh);
     }
     TPROF(9);
-
-    if (tid < 32) write_ctl_and_record(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, lane, a.trk);
+    if (tid < 32) write_ctl_critical(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, lane, ep);
     TPROF(10);
+    return;
   }
 
-  // ================================================================== per-frame MaxEnt terms
-  // CTA 0 of a multi-CTA grid holds no frames and stays out of the fold: the last *frame* CTA publishes the sums,
-  // typically well before the R x T tail above has finished.
-  TPROF(11);
-  if (frame_cta) {
-    frame_terms(a, s_sc, s_old, cur_set, (gridDim.x == 1) ? 0 : (long long)blockIdx.x - 1, 0, s_red);
-    TPROF_F(3);
-    fold_kl_partials(a, ep, &s_last);
-    TPROF_F(4);
-  }
-  TPROF(12);
+  // ================================================================== per-frame MaxEnt terms (blocks 1..)
+  // The last frame CTA to finish publishes the MaxEnt sums, typically well before the R x T tail above has finished.
+  if (blockIdx.x == 1 && warp == 0) write_ctl_rest(neu, a.records, s_sc, lane, a.trk);
+  frame_terms(a, s_sc, s_old, cur_set, (long long)blockIdx.x - 1, 0, s_red);
+  TPROF_F(3);
+  fold_kl_partials(a, ep, &s_last);
+  TPROF_F(4);
 }
 
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va) {
   const size_t Tm = T > 0 ? T : 1;
-  const size_t dbl = (size_t)4 * R + (size_t)Tm * R + (size_t)T * R + 2 * (size_t)p_tr * Tm + (size_t)p_va * Tm + 4 * Tm;
-  const size_t f32 = (((size_t)R + 3) & ~(size_t)3) + ((Tm + 3) & ~(size_t)3);
+  const size_t dbl = (size_t)4 * R + (size_t)Tm * R + (size_t)T * R + 2 * (size_t)p_tr * Tm + (size_t)p_va * Tm + 4 * Tm + R + Tm;
   const BlobLayout b = blob_layout(R, (int)Tm, p_tr, nnz_tr, p_va, nnz_va);
-  return dbl * 8 + f32 * 4 + (size_t)b.words * 4 + 64;
+  return dbl * 8 + (size_t)b.words * 4 + 64;
 }
 
 int blob_words(int R, int T, int p_tr, int nnz_tr, int p_va, int nnz_va) {

@@ -8,6 +8,12 @@
 
 namespace jx {
 
+#ifdef JX_PROFILE
+#define BPROF(i) do { if (io.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) io.prof[i] = gtime(); } while (0)
+#else
+#define BPROF(i) do {} while (0)
+#endif
+
 // ---- code-size discipline: this kernel runs a long straight-line path once per launch, so its cost is
 // dominated by instruction fetch.  Heavy math lives behind single __noinline__ call sites.
 static __device__ __noinline__ double wsum(double v) {
@@ -17,6 +23,26 @@ static __device__ __noinline__ double wsum(double v) {
 static __device__ __noinline__ double dexp(double x) { return exp(x); }
 static __device__ __noinline__ double dlog(double x) { return log(x); }
 static __device__ __noinline__ float fpow(float a, float b) { return powf(a, b); }
+// Explicit shared-memory loads by 32-bit shared address.  The peptide-map loops select between the train and the validation
+// arrays at run time; the compiler then loses the address space and emits GENERIC loads, which cost ~500 cycles per dependent
+// iteration on sm_100 (measured: 7600 cycles for a 10-entry row) against ~30 for LDS.
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds_i(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_d(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_d(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 // floor(x / d) for 0 <= x < 2^21 with inv = 1/d (exact: the fraction is >= 0.5/d away from an integer)
 __device__ __forceinline__ int fdiv(int x, float inv) { return (int)(((float)x + 0.5f) * inv); }
 
@@ -30,11 +56,14 @@ __host__ __device__ inline BlobLayout blob_layout(int R, int Tm, int p_tr, int n
   b.tr_trow = o; o += nnz_tr;
   b.va_ptr = o;  o += p_va + 1;
   b.va_col = o;  o += nnz_va;
-  b.tr_val = o;  o += nnz_tr;
-  b.tr_tval = o; o += nnz_tr;
   b.tr_y = o;    o += p_tr * Tm;
-  b.va_val = o;  o += nnz_va;
   b.va_y = o;    o += p_va * Tm;
+  // the map values are kept as doubles (8-byte aligned): a float -> double conversion is a 16-lane/clk instruction on
+  // sm_100 and the loops that read them run on ONE SM
+  o = (o + 1) & ~1;
+  b.tr_val = o;  o += 2 * nnz_tr;
+  b.tr_tval = o; o += 2 * nnz_tr;
+  b.va_val = o;  o += 2 * nnz_va;
   b.words = (o + 3) & ~3;
   return b;
 }
@@ -47,7 +76,7 @@ extern __shared__ __align__(16) unsigned char jx_dyn_smem[];
 // shared-memory carve-up of the tail body
 struct TailSmem {
   double *slp, *sxe, *sc_rt, *sU, *res_tr, *gp_tr, *res_va, *smean;
-  float *s_k, *s_tp;
+  double *s_k, *s_tp;  // intrinsic rates and time points, as doubles (see blob_layout)
   int* s_blob;
 };
 __device__ __forceinline__ TailSmem carve_tail_smem(unsigned char* smem_raw, int R, int T, int p_max_tr, int p_max_va) {
@@ -61,9 +90,9 @@ __device__ __forceinline__ TailSmem carve_tail_smem(unsigned char* smem_raw, int
   m.gp_tr = m.res_tr + (size_t)p_max_tr * Tm;          // [P_tr * Tm] pred -> residual -> dL/dpred
   m.res_va = m.gp_tr + (size_t)p_max_tr * Tm;          // [P_va * Tm]
   m.smean = m.res_va + (size_t)p_max_va * Tm;          // [4 * Tm]
-  m.s_k = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(m.smean + 4 * Tm) + 15) & ~uintptr_t(15));
-  m.s_tp = m.s_k + ((R + 3) & ~3);
-  m.s_blob = reinterpret_cast<int*>(m.s_tp + ((Tm + 3) & ~3));  // 16-byte aligned blob image
+  m.s_k = m.smean + 4 * Tm;                            // [R]
+  m.s_tp = m.s_k + R;                                  // [Tm]
+  m.s_blob = reinterpret_cast<int*>(smem_raw + ((((size_t)(reinterpret_cast<unsigned char*>(m.s_tp + Tm) - smem_raw)) + 15) & ~(size_t)15));  // 16-byte aligned blob image
   return m;
 }
 
@@ -84,8 +113,8 @@ __device__ __forceinline__ int stage_tail_constants(const JaxentBvProblem& pb, c
   }
   if (T > 0) {
 #pragma unroll 1
-    for (int i = tid; i < R; i += nt) m.s_k[i] = pb.k_ints[i];
-    if (tid < T) m.s_tp[tid] = pb.timepoints[tid];
+    for (int i = tid; i < R; i += nt) m.s_k[i] = (double)pb.k_ints[i];
+    if (tid < T) m.s_tp[tid] = (double)pb.timepoints[tid];
   }
   return first_data;
 }
@@ -98,6 +127,7 @@ struct TailIO {
   int pf_mode;    // 1: per-frame uptake mode -- the caller has filled sm.sU with the frame-averaged uptake already
   int p_max_tr, p_max_va;  // carve-up parameters (carve_tail_smem)
   float* ck;      // [R] centring constants of the pass (see "centred column sums" in tail_body), or nullptr (batched GEMM path)
+  long long* prof; // JX_PROFILE builds: %globaltimer stamps of the phases (else unused)
   int c_pieces;   // how the sweep sees the row coefficients: 0 = rounded to fp32, n > 0 = the sum of n bf16 pieces (batched GEMM path)
 };
 
@@ -140,7 +170,7 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
   (void)sm;
   double *slp = smx.slp, *sxe = smx.sxe, *sc_rt = smx.sc_rt, *sU = smx.sU, *res_tr = smx.res_tr, *gp_tr = smx.gp_tr, *res_va = smx.res_va,
          *smean = smx.smean;
-  float *s_k = smx.s_k, *s_tp = smx.s_tp;
+  const double *s_k = smx.s_k, *s_tp = smx.s_tp;
   int* s_blob = smx.s_blob;
   {
     my_a = 0, my_b = 0, my_lp = 0, my_c = 0;
@@ -159,14 +189,15 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
     if (T > 0 && !pfm) {
       __syncthreads();  // exp(-lnPF) visible
 #pragma unroll 1
-      for (int it = tid; it < R * T; it += nt) {
-        const int t = fdiv(it, invR), r = it - t * R;
-        const double e = dexp(-((double)s_k[r] * (double)s_tp[t] * sxe[r]));
+      for (int it = tid; it < R * T; it += nt) {  // sU is [r][t] (time fastest): see the gathers of phase (a)
+        const int r = fdiv(it, invTm), t = it - r * T;
+        const double e = dexp(-(s_k[r] * s_tp[t] * sxe[r]));
         sU[it] = 1.0 - e;
-        io.uptake[it] = (float)(1.0 - e);
+        io.uptake[t * R + r] = (float)(1.0 - e);
       }
     }
     __syncthreads();  // (2) lnPF / uptake visible
+    BPROF(4);
 
     // ---- loss slots
     double gbc_reg = 0.0, gbh_reg = 0.0;
@@ -199,57 +230,50 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
       const bool sigma = GENERAL && kind == JAXENT_LOSS_UPTAKE_SIGMA_MSE;
       const double half = pf ? 1.0 : 0.5;
 
-      // (a) predictions of train and val peptides, one (peptide, chunk of 4 time points) item per thread: the row's
-      // indices / values are read once per 4 products and the 4 accumulation chains are independent.  The eye / PF
-      // kinds finish residual + loss here.
+      // (a) predictions of train and val peptides, one (peptide, time point) item per thread.  This phase is pure latency
+      // (a few hundred short dot products on one SM), so the loop is shaped for it: the 4 (index, value, x) triples of a
+      // block are loaded before the first product, and only the fused multiply-adds of one accumulator are dependent.
+      // The eye / PF kinds finish residual + loss here.
       {
-        if (i == first_data && warp == nw - 1) side();
-        const int nch = (Tm + 3) >> 2;
-        const float inv_nch = 1.0f / (float)nch;
-        const int items = (Ptr + Pva) * nch;
+        const int items = (Ptr + Pva) * Tm;
         double pl_tr = 0.0, pl_va = 0.0;
+        const uint32_t blob = sm_addr(s_blob);
+        const uint32_t xb = sm_addr(pf ? slp : sU);
+        BPROF(16);
 #pragma unroll 1
         for (int j = tid; j < items; j += nt) {
-          const int row = fdiv(j, inv_nch), t0 = (j - row * nch) << 2;
+          const int row = fdiv(j, invTm), t = j - row * Tm;
           const bool va = row >= Ptr;
           const int p = va ? row - Ptr : row;
-          const int* ptr = s_blob + (va ? bl.va_ptr : bl.tr_ptr);
-          const int* col = s_blob + (va ? bl.va_col : bl.tr_col);
-          const float* val = reinterpret_cast<const float*>(s_blob + (va ? bl.va_val : bl.tr_val));
-          const float* y = reinterpret_cast<const float*>(s_blob + (va ? bl.va_y : bl.tr_y));
-          double* out = va ? res_va : ((centre || sigma) ? res_tr : gp_tr);
-          // clamped time indices keep the loads in bounds; surplus lanes of the last chunk are discarded
-          const int t1 = min(t0 + 1, Tm - 1), t2 = min(t0 + 2, Tm - 1), t3 = min(t0 + 3, Tm - 1);
-          const double* x0 = pf ? slp : sU + (size_t)t0 * R;
-          const double* x1 = pf ? slp : sU + (size_t)t1 * R;
-          const double* x2 = pf ? slp : sU + (size_t)t2 * R;
-          const double* x3 = pf ? slp : sU + (size_t)t3 * R;
-          double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-          const int qe = ptr[p + 1];
-#pragma unroll 2
-          for (int q = ptr[p]; q < qe; ++q) {
-            const int c = col[q];
-            const double v = (double)val[q];
-            p0 += v * x0[c];
-            p1 += v * x1[c];
-            p2 += v * x2[c];
-            p3 += v * x3[c];
+          const uint32_t a_ptr = blob + 4u * (uint32_t)(va ? bl.va_ptr : bl.tr_ptr), a_col = blob + 4u * (uint32_t)(va ? bl.va_col : bl.tr_col);
+          const uint32_t a_val = blob + 4u * (uint32_t)(va ? bl.va_val : bl.tr_val), a_y = blob + 4u * (uint32_t)(va ? bl.va_y : bl.tr_y);
+          const uint32_t a_out = sm_addr(va ? res_va : ((centre || sigma) ? res_tr : gp_tr));
+          // x[c] = lnPF[c] (PF kind) or uptake[c][t]: the 8 lanes of a peptide read 8 consecutive doubles per entry
+          const uint32_t x = xb + (pf ? 0u : 8u * (uint32_t)t), xs = pf ? 8u : 8u * (uint32_t)T;
+          const int qb = lds_i(a_ptr + 4u * p), qe = lds_i(a_ptr + 4u * p + 4u);
+          const float yv = lds_f(a_y + 4u * (uint32_t)j - (va ? 4u * (uint32_t)(Ptr * Tm) : 0u));  // y[p * Tm + t]
+          double pred = 0.0;
+          int q = qb;
+#pragma unroll 1
+          for (; q + 4 <= qe; q += 4) {
+            const uint32_t c0 = lds_i(a_col + 4u * q), c1 = lds_i(a_col + 4u * q + 4u), c2 = lds_i(a_col + 4u * q + 8u), c3 = lds_i(a_col + 4u * q + 12u);
+            const double v0 = lds_d(a_val + 8u * q), v1 = lds_d(a_val + 8u * q + 8u), v2 = lds_d(a_val + 8u * q + 16u), v3 = lds_d(a_val + 8u * q + 24u);
+            const double x0 = lds_d(x + xs * c0), x1 = lds_d(x + xs * c1), x2 = lds_d(x + xs * c2), x3 = lds_d(x + xs * c3);
+            pred += v0 * x0;  // same order as a one-by-one loop
+            pred += v1 * x1;
+            pred += v2 * x2;
+            pred += v3 * x3;
           }
-          const double pr[4] = {p0, p1, p2, p3};
-          double pl = 0.0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (t0 + k < Tm) {
-              double pred = pr[k];
-              if (!(centre || sigma)) {
-                pred -= (double)y[p * Tm + t0 + k];
-                pl += half * pred * pred;
-              }
-              out[p * Tm + t0 + k] = pred;
-            }
+#pragma unroll 1
+          for (; q < qe; ++q) pred += lds_d(a_val + 8u * q) * lds_d(x + xs * (uint32_t)lds_i(a_col + 4u * q));
+          if (!(centre || sigma)) {
+            pred -= (double)yv;
+            const double pl = half * pred * pred;
+            if (va) pl_va += pl; else pl_tr += pl;
           }
-          if (va) pl_va += pl; else pl_tr += pl;
+          sts_d(a_out + 8u * (uint32_t)(p * Tm + t), pred);
         }
+        BPROF(17);
         if (!(centre || sigma)) {
           const double nrm_tr = (Ptr > 0) ? __drcp_rn(pf ? (double)Ptr : (double)T * (double)Ptr) : 0.0;
           const double nrm_va = (Pva > 0) ? __drcp_rn(pf ? (double)Pva : (double)T * (double)Pva) : 0.0;
@@ -260,6 +284,7 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
             s_red[warp][JAXENT_MAX_SLOTS + i] = pl_va;
           }
         }
+        BPROF(18);
       }
       if (GENERAL && (centre || sigma)) {
         const float* tr_y = reinterpret_cast<const float*>(s_blob + bl.tr_y);
@@ -341,48 +366,55 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
         }
       }
       __syncthreads();  // (3) dL/dpred visible
+      BPROF(5);
 
-      // (b) back-projection to dL/d lnPF, one (residue, chunk of 4 time points) item per thread
+      // (b) back-projection to dL/d lnPF, one (residue, time point) item per thread, shaped like (a)
       {
-        const int* tptr = s_blob + bl.tr_tptr;
-        const int* trow = s_blob + bl.tr_trow;
-        const float* tval = reinterpret_cast<const float*>(s_blob + bl.tr_tval);
+        const uint32_t blob = sm_addr(s_blob);
+        const uint32_t a_tptr = blob + 4u * (uint32_t)bl.tr_tptr, a_trow = blob + 4u * (uint32_t)bl.tr_trow, a_tval = blob + 4u * (uint32_t)bl.tr_tval;
+        const uint32_t a_gp = sm_addr(gp_tr);
         const double g = scale * (pf ? 2.0 : 1.0) * __drcp_rn(pf ? (double)Ptr : (double)T * (double)Ptr);
-        const int nch = (Tm + 3) >> 2;
-        const int items = R * nch;
+        const int items = R * Tm;
+        BPROF(19);
 #pragma unroll 1
         for (int it = tid; it < items; it += nt) {
-          const int ch = fdiv(it, invR), r = it - ch * R, t0 = ch << 2;
-          const int o1 = min(t0 + 1, Tm - 1) - t0, o2 = min(t0 + 2, Tm - 1) - t0, o3 = min(t0 + 3, Tm - 1) - t0;
-          double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, colsum = 0.0;
-          const int qe = tptr[r + 1];
-#pragma unroll 2
-          for (int q = tptr[r]; q < qe; ++q) {
-            const double v = (double)tval[q];
-            const double* gp = gp_tr + trow[q] * Tm + t0;
-            b0 += v * gp[0];
-            b1 += v * gp[o1];
-            b2 += v * gp[o2];
-            b3 += v * gp[o3];
+          const int r = fdiv(it, invTm), t = it - r * Tm;  // time fastest: the 8 lanes of a residue read 8 consecutive doubles per entry
+          const uint32_t gpt = a_gp + 8u * (uint32_t)t;
+          const uint32_t tm8 = 8u * (uint32_t)Tm;
+          const int qb = lds_i(a_tptr + 4u * r), qe = lds_i(a_tptr + 4u * r + 4u);
+          // (loads issued before the loop: they only depend on the item)
+          double xk = 0.0, uu = 0.0;
+          if (!pf && !pfm) {
+            xk = s_k[r] * s_tp[t] * sxe[r];
+            uu = sU[it];
+          }
+          double back = 0.0, colsum = 0.0;
+          int q = qb;
+#pragma unroll 1
+          for (; q + 4 <= qe; q += 4) {
+            const uint32_t r0 = lds_i(a_trow + 4u * q), r1 = lds_i(a_trow + 4u * q + 4u), r2 = lds_i(a_trow + 4u * q + 8u), r3 = lds_i(a_trow + 4u * q + 12u);
+            const double v0 = lds_d(a_tval + 8u * q), v1 = lds_d(a_tval + 8u * q + 8u), v2 = lds_d(a_tval + 8u * q + 16u), v3 = lds_d(a_tval + 8u * q + 24u);
+            const double g0 = lds_d(gpt + tm8 * r0), g1 = lds_d(gpt + tm8 * r1), g2 = lds_d(gpt + tm8 * r2), g3 = lds_d(gpt + tm8 * r3);
+            back += v0 * g0;
+            back += v1 * g1;
+            back += v2 * g2;
+            back += v3 * g3;
+            if (GENERAL) colsum += v0 + v1 + v2 + v3;
+          }
+#pragma unroll 1
+          for (; q < qe; ++q) {
+            const double v = lds_d(a_tval + 8u * q);
+            back += v * lds_d(gpt + tm8 * (uint32_t)lds_i(a_trow + 4u * q));
             if (GENERAL) colsum += v;
           }
-          const double bk[4] = {b0, b1, b2, b3};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int t = t0 + k;
-            if (t < Tm) {
-              double back = bk[k];
-              if (centre) back -= colsum * smean[2 * T + t];  // centred gradient: minus mean_p(gp) through the column
-              if (!pf && !pfm) {
-                const double x = (double)s_k[r] * (double)s_tp[t] * sxe[r];
-                back *= -x * (1.0 - sU[(size_t)t * R + r]);  // du/dlnPF = -x exp(-x)
-              }
-              sc_rt[(size_t)t * R + r] = g * back;
-            }
-          }
+          if (centre) back -= colsum * smean[2 * T + t];  // centred gradient: minus mean_p(gp) through the column
+          if (!pf && !pfm) back *= -xk * (1.0 - uu);      // du/dlnPF = -x exp(-x)
+          sc_rt[(size_t)t * R + r] = g * back;
         }
+        BPROF(20);
       }
       __syncthreads();  // (4) items visible
+      BPROF(7);
       if (tid < R) {
         if (pfm) {
           // per-frame mode: the items ARE G[t,r] = dL/d<uptake>[t,r]; accumulate them over the data slots in global memory
@@ -419,7 +451,7 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
           for (int t = 0; t < Tm; ++t) {
             const double gv = (double)io.pf_G[(size_t)t * R + tid];
             gsum += gv;
-            gu += gv * sU[(size_t)t * R + tid];
+            gu += gv * sU[(size_t)tid * Tm + t];
           }
           kd = gsum - gu;  // the pass forms fl(kd) - sum_t G exp(-k tau / PF_f) = sum_t G (u_f - <u>) per row
           v12 = (io.ck != nullptr) ? -(kd - (double)(float)kd) : gu;
@@ -443,11 +475,10 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
       }
     }
     __syncthreads();  // (5)
-    if (tid < 15) {
-      double t = 0.0;
-#pragma unroll 1
-      for (int w = 0; w < nw; ++w) t += s_red[w][tid];  // fixed order
-      s_fin[tid] = t;
+    BPROF(8);
+    if (warp < 15) {  // value `warp` over the per-warp partials: one load per lane + a fixed-shape shuffle tree
+      const double t = wsum(lane < nw ? s_red[lane][warp] : 0.0);
+      if (lane == 0) s_fin[warp] = t;
     }
     __syncthreads();  // (6)
 

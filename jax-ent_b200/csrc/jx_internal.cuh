@@ -14,6 +14,7 @@ constexpr int U8_SUB_TILES = 4; // u8 features: one bulk-copy stage carries 4 ti
 constexpr int PASS_THREADS_MAX = 512;
 constexpr int TAIL_THREADS = 1024;
 constexpr int KL_N = 4;         // MaxEnt partial sums: sum w*kappa, sum p(log p - log q), sum(q - p), sum w
+constexpr int FX_REP = 4;       // replicas of the fixed-point row-sum accumulators (CTA c adds into replica c % FX_REP)
 
 // Device-resident control block; two copies, indexed by (epoch & 1).  Written only by the tail
 // kernel (and state_init), read by the pass kernel that follows it.
@@ -48,7 +49,8 @@ struct alignas(16) Ctl {
   int trk_have_prev, trk_have_ema;
   int trk_steps_since, trk_idx, trk_nsnap;
   float trk_ema_bc, trk_ema_bh;
-  int trk_pad[2];
+  int epoch_id;                // the epoch this block belongs to: lets the tail pick the current block before the pass has finished
+  int trk_pad;
   double trk_prev_loss, trk_ema;
 };
 static_assert(sizeof(Ctl) % 16 == 0, "Ctl is staged to shared memory with 16-byte vector copies");
@@ -207,23 +209,19 @@ struct PassArgs {
   const float* pf_G;        // [T][R] dL/d<uptake>[t,r] from the tail
   const float* pf_k;        // [R] intrinsic rates
   const float* pf_tp;       // [T] time points
-  double* partials;
+  // Row sums of all CTAs meet in ONE set of 64-bit fixed-point accumulators (integer atomics: exact, hence independent of
+  // the order in which the CTAs arrive -> bitwise reproducible without a fixed-order reduction kernel).  The scale is a
+  // power of two derived from a bound on the sums (see fx_scale()).  The last CTA to arrive converts them to doubles and
+  // publishes them (plain store, or stamped stores into every rank's inbox), clears them and advances the epoch.
+  unsigned long long* fx;   // [FX_REP][part_n - 4]
+  double* cta_scal;         // [CTA][4]: sum e' (both branches), grad-dot -- summed in CTA order by the last CTA
+  const float* nmax;        // max |feature| of this rank's packed arrays (state_init)
+  unsigned* ticket;
   Xchg x;
   const Ctl* ctl;
-  const unsigned* epoch;
+  unsigned* epoch;
   JaxentLossRecord* records;
   float b1, b2, om_b1, om_b2, eps, clip;
-  double* dbg;
-};
-
-struct ReduceArgs {
-  const Ctl* ctl;
-  const double* partials;
-  Xchg x;
-  unsigned* epoch;
-  unsigned* ticket;
-  int n_part;
-  int part_n;
   double* dbg;
 };
 
@@ -250,7 +248,6 @@ struct TailArgs {
   StateSets st;
   Xchg x;
   Ctl* ctl;
-  const unsigned* epoch;
   unsigned* counter;
   float* w;
   float* kappa;
@@ -313,7 +310,6 @@ inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, c
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s);
 // number of doubles every pass CTA contributes: row sums (+ sum e for both branches, grad-dot, pad)
 __host__ __device__ inline int pass_part_n(int R, int T, int uptake_mode) { return uptake_mode == 2 ? 2 * T * R + 4 : 4 * R + 4; }
-int launch_reduce(const ReduceArgs& a, cudaStream_t s);
 int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
 int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const Xchg& x, JaxentLossRecord* rec, int n_slots, cudaStream_t s);
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va);

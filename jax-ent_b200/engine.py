@@ -409,14 +409,13 @@ class BvEngine:
 
     def _phase(self, mode: int) -> None:
         s = _stream_ptr()
-        L.check(self.lib.jaxent_bv_pass(self.plan, mode, s))
-        L.check(self.lib.jaxent_bv_reduce(self.plan, s))
+        L.check(self.lib.jaxent_bv_pass(self.plan, mode, s))  # its last CTA completes and publishes the partial sums
         if not self.fused:
             self.comm.sum_(self.red)
         L.check(self.lib.jaxent_bv_tail(self.plan, s))
         if not self.fused:
             self.comm.sum_(self.klsum)
-        self.launches += 3
+        self.launches += 2
 
     def step(self, n: int = 1) -> None:
         """n optimise steps, enqueued on the current stream without host synchronisation."""
@@ -446,7 +445,7 @@ class BvEngine:
         for _ in range(n_graphs):
             self._graph.replay()
         self.steps_done += n_graphs * self._graph_steps
-        self.launches += 3 * n_graphs * self._graph_steps
+        self.launches += 2 * n_graphs * self._graph_steps
 
     def exchange_error(self) -> int:
         """non-zero once a peer-flag wait of the fused exchange timed out (a peer never arrived)"""

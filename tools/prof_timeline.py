@@ -36,14 +36,15 @@ for trial in range(4):
     rows.append(dbg.cpu().numpy().copy())
 dist.barrier()
 names = {40: "pass.start", 41: "pass.pdl", 42: "pass.kl", 43: "pass.cta0end", 44: "red.start", 45: "red.pdl", 46: "red.end",
-         0: "tail.start", 1: "tail.staged", 2: "tail.pdl", 3: "tail.scalars", 4: "tail.lnpf", 5: "tail.pred", 7: "tail.back", 9: "tail.fin", 10: "tail.ctl", 11: "tail.frames", 12: "tail.end",
+         0: "tail.start", 1: "tail.staged", 2: "tail.pdl", 3: "tail.scalars", 4: "tail.lnpf", 5: "tail.pred", 7: "tail.back", 8: "tail.sums", 9: "tail.fin", 16: "a.begin", 17: "a.loop", 18: "a.wsum", 19: "b.begin", 20: "b.loop", 13: "rep1.start", 14: "rep0.end", 10: "tail.ctl", 11: "tail.frames", 12: "tail.end",
          32: "ftail.start", 33: "ftail.pdl", 34: "ftail.scalars", 35: "ftail.frames", 36: "ftail.end"}
 for r in range(world):
     if r == rank:
         for a in rows[1:]:
             # last step: pass(40..43) -> reduce(44..46) -> tail(0..12); everything relative to pass.pdl
             t0 = a[41]
-            order = [40, 41, 42, 43, 44, 45, 46, 0, 1, 2, 3, 4, 5, 7, 9, 10, 11, 12, 33, 34, 35, 36]
+            order = [40, 41, 42, 43, 44, 45, 46, 0, 1, 2, 3, 4, 16, 17, 18, 5, 19, 20, 7, 8, 9, 10, 11, 12, 33, 34, 35, 36]
+            print("cycles: qloop", a[21], "nnz", a[22], "epilogue", a[23])
             print(f"rank {rank}: " + " ".join(f"{names[i]}={(a[i]-t0)/1e3:.1f}" for i in order), flush=True)
     dist.barrier()
 dist.destroy_process_group()
