@@ -335,6 +335,21 @@ int jaxent_bg_track_status(JaxentBatchPlan* plan, JaxentTrackStatus* status, jax
 int jaxent_bg_ctl_sizeof(void);
 int jaxent_bg_ctl_offset(int32_t field); /* 0: double S, 1: float bc, 2: float bh, 3: int step, 4: float lse */
 
+/* ---- plan handles and workspace identity, for foreign-function layers (csrc/xla_ffi.cc, the jax.ffi custom calls of
+ * INTEGRATION.md; the reference has no FFI of its own).  A custom call cannot carry a typed pointer, and a raw
+ * pointer attribute would outlive its plan silently: handles are (generation, slot) pairs that jaxent_handle_lookup
+ * rejects once the plan has been destroyed.  The workspace a plan was built on is reported by *_plan_workspace so that a
+ * handler can compare it with the buffer the runtime hands it; jaxent_bv_plan_rebind_workspace moves a plan to a new copy
+ * of the same workspace contents (XLA copies an operand it cannot alias in place). */
+#define JAXENT_HANDLE_BV_PLAN 1
+#define JAXENT_HANDLE_BATCH_PLAN 2
+int64_t jaxent_handle_register(void* plan, int32_t kind); /* > 0, or 0 on error; idempotent per plan */
+void* jaxent_handle_lookup(int64_t handle, int32_t kind);  /* NULL (and jaxent_last_error) for stale / foreign handles */
+void jaxent_handle_release_ptr(void* plan);                /* called by the *_plan_destroy functions */
+int jaxent_bv_plan_workspace(const JaxentPlan* plan, void** ptr, size_t* bytes);
+int jaxent_bv_plan_rebind_workspace(JaxentPlan* plan, void* workspace, size_t workspace_bytes);
+int jaxent_bg_plan_workspace(const JaxentBatchPlan* plan, void** ptr, size_t* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,5 +85,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+FFI_TEST_LIB = os.path.join(ROOT, "tests", "ffi_stub", "libjaxent_ffi_test.so")
+
+
+def build_ffi_test(force: bool = False) -> str:
+    """csrc/xla_ffi.cc (the jax.ffi handlers) compiled against the stand-in header of tests/ffi_stub, plus the test driver,
+    linked against the in-tree library.  Test infrastructure: type-checks the handlers and lets the tests call them."""
+    stub = os.path.join(ROOT, "tests", "ffi_stub")
+    srcs = [os.path.join(CSRC, "xla_ffi.cc"), os.path.join(stub, "driver.cc")]
+    deps = srcs + [os.path.join(stub, "xla", "ffi", "api", "ffi.h"), os.path.join(ROOT, "include", "jaxent_b200.h")]
+    if not force and os.path.exists(FFI_TEST_LIB) and all(os.path.getmtime(FFI_TEST_LIB) >= os.path.getmtime(d) for d in deps):
+        return FFI_TEST_LIB
+    build()
+    tmp = f"{FFI_TEST_LIB}.tmp.{os.getpid()}"
+    cmd = [nvcc_path(), "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O2", "-x", "cu", "-I", os.path.join(ROOT, "include"), "-I", stub,
+           "-o", tmp] + srcs + ["-L", HERE, "-ljaxent_b200", "-Xlinker", "-rpath=$ORIGIN/../../jax-ent_b200"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on the FFI shim ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, FFI_TEST_LIB)
+    return FFI_TEST_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

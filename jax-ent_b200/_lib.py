@@ -181,6 +181,12 @@ SYMBOLS = {
     "jaxent_bg_track_status": (C.c_int, [_VP, _VP, _VP]),
     "jaxent_bg_ctl_sizeof": (C.c_int, []),
     "jaxent_bg_ctl_offset": (C.c_int, [_I32]),
+    "jaxent_handle_register": (_I64, [_VP, _I32]),
+    "jaxent_handle_lookup": (_VP, [_I64, _I32]),
+    "jaxent_handle_release_ptr": (None, [_VP]),
+    "jaxent_bv_plan_workspace": (C.c_int, [_VP, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "jaxent_bv_plan_rebind_workspace": (C.c_int, [_VP, _VP, _SZ]),
+    "jaxent_bg_plan_workspace": (C.c_int, [_VP, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "jaxent_bv_state_init": (C.c_int, [_VP, _VP, _F, _F, _F, C.POINTER(_F), C.POINTER(_F), _VP]),
     "jaxent_bv_pass": (C.c_int, [_VP, _I32, _VP]),
     "jaxent_bv_reduce": (C.c_int, [_VP, _VP]),

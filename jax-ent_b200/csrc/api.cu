@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "jx_internal.cuh"
@@ -383,7 +384,84 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
   return JAXENT_OK;
 }
 
-extern "C" void jaxent_bv_plan_destroy(JaxentPlan* plan) { delete plan; }
+extern "C" void jaxent_bv_plan_destroy(JaxentPlan* plan) {
+  jaxent_handle_release_ptr(plan);
+  delete plan;
+}
+
+// ---- plan handles for foreign-function layers (csrc/xla_ffi.cc): a custom call carries a small integer, not a raw
+// pointer, so a handle that outlives its plan is detected instead of dereferenced.  handle = generation << 16 | slot.
+namespace {
+constexpr int HANDLE_SLOTS = 1024;
+struct HandleSlot { void* ptr; int kind; unsigned gen; };
+HandleSlot g_slots[HANDLE_SLOTS];
+std::mutex g_slots_mu;
+}  // namespace
+
+extern "C" int64_t jaxent_handle_register(void* plan, int32_t kind) {
+  if (!plan || (kind != JAXENT_HANDLE_BV_PLAN && kind != JAXENT_HANDLE_BATCH_PLAN)) { set_error("handle_register: invalid argument"); return 0; }
+  std::lock_guard<std::mutex> lk(g_slots_mu);
+  for (int i = 1; i < HANDLE_SLOTS; ++i)
+    if (g_slots[i].ptr == plan) return ((int64_t)g_slots[i].gen << 16) | i;  // idempotent
+  for (int i = 1; i < HANDLE_SLOTS; ++i)
+    if (!g_slots[i].ptr) {
+      g_slots[i].ptr = plan;
+      g_slots[i].kind = kind;
+      g_slots[i].gen += 1;
+      return ((int64_t)g_slots[i].gen << 16) | i;
+    }
+  set_error("handle_register: more than %d live plans", HANDLE_SLOTS - 1);
+  return 0;
+}
+
+extern "C" void* jaxent_handle_lookup(int64_t handle, int32_t kind) {
+  const int i = (int)(handle & 0xffff);
+  const unsigned gen = (unsigned)(handle >> 16);
+  std::lock_guard<std::mutex> lk(g_slots_mu);
+  if (handle <= 0 || i <= 0 || i >= HANDLE_SLOTS || !g_slots[i].ptr || g_slots[i].gen != gen || g_slots[i].kind != kind) {
+    set_error("stale or unknown plan handle %lld", (long long)handle);
+    return nullptr;
+  }
+  return g_slots[i].ptr;
+}
+
+extern "C" void jaxent_handle_release_ptr(void* plan) {
+  if (!plan) return;
+  std::lock_guard<std::mutex> lk(g_slots_mu);
+  for (int i = 1; i < HANDLE_SLOTS; ++i)
+    if (g_slots[i].ptr == plan) g_slots[i].ptr = nullptr;  // the generation stays: an old handle no longer matches
+}
+
+extern "C" int jaxent_bv_plan_workspace(const JaxentPlan* p, void** ptr, size_t* bytes) {
+  if (!p || !ptr || !bytes) { set_error("plan_workspace: NULL argument"); return JAXENT_E_INVALID; }
+  *ptr = p->ws;
+  *bytes = p->lay.total;
+  return JAXENT_OK;
+}
+
+// The caller's allocator moved the workspace (XLA copies a buffer it could not alias in place): same contents at a new
+// address.  Every pointer the plan derived from the old base is re-derived; external buffers (features, prior, maps,
+// peer-mapped exchange buffers, tracker buffers) are untouched.
+extern "C" int jaxent_bv_plan_rebind_workspace(JaxentPlan* p, void* workspace, size_t workspace_bytes) {
+  if (!p) { set_error("rebind_workspace: plan is NULL"); return JAXENT_E_INVALID; }
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) { set_error("workspace must be a 256-byte aligned device pointer"); return JAXENT_E_INVALID; }
+  if (workspace_bytes < p->lay.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, p->lay.total); return JAXENT_E_WORKSPACE; }
+  const Layout& L = p->lay;
+  p->ws = static_cast<unsigned char*>(workspace);
+  for (int s = 0; s < 2; ++s)
+    for (int b = 0; b < 2; ++b) {
+      p->st.z[s][b] = reinterpret_cast<float*>(p->ws + L.off_z[s][b]);
+      p->st.m[s][b] = reinterpret_cast<float*>(p->ws + L.off_m[s][b]);
+      p->st.v[s][b] = reinterpret_cast<float*>(p->ws + L.off_v[s][b]);
+    }
+  p->st.g[0] = reinterpret_cast<float*>(p->ws + L.off_g[0]);
+  p->st.g[1] = reinterpret_cast<float*>(p->ws + L.off_g[1]);
+  if (p->x.world == 1) {  // the single-rank exchange buffer lives in the workspace
+    p->x.base[0] = p->ws + L.off_xchg;
+    p->x.local = p->x.base[0];
+  }
+  return JAXENT_OK;
+}
 
 extern "C" int jaxent_bv_plan_buffer(const JaxentPlan* p, int32_t which, void** ptr, size_t* bytes) {
   if (!p || !ptr || !bytes) { set_error("plan_buffer: NULL argument"); return JAXENT_E_INVALID; }

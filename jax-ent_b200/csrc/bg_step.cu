@@ -803,6 +803,7 @@ struct JaxentBatchPlan {
   bg::BatchArgs a;
   float conv[JAXENT_TRACK_MAX_THRESHOLDS];
   unsigned char* ws;
+  size_t ws_bytes;
   size_t off_ctl_init;
   size_t tail_smem;
   int general;
@@ -912,6 +913,7 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   memset(p, 0, sizeof(*p));
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   p->ws = ws;
+  p->ws_bytes = L.total;
   bg::BatchArgs& a = p->a;
   a.prob = *pb;
   a.cfg = *cfg;
@@ -983,7 +985,17 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   return JAXENT_OK;
 }
 
-extern "C" void jaxent_bg_plan_destroy(JaxentBatchPlan* p) { delete p; }
+extern "C" void jaxent_bg_plan_destroy(JaxentBatchPlan* p) {
+  jaxent_handle_release_ptr(p);
+  delete p;
+}
+
+extern "C" int jaxent_bg_plan_workspace(const JaxentBatchPlan* p, void** ptr, size_t* bytes) {
+  if (!p || !ptr || !bytes) { set_error("bg_plan_workspace: NULL argument"); return JAXENT_E_INVALID; }
+  *ptr = p->ws;
+  *bytes = p->ws_bytes;
+  return JAXENT_OK;
+}
 
 static int bg_err(const char* what) {
   cudaError_t e = cudaGetLastError();
