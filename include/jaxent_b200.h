@@ -298,6 +298,13 @@ int jaxent_bv_predict_frames(const float* packed, int32_t R, int64_t F, int32_t 
 size_t jaxent_bg_features_bytes(int32_t R, int64_t F);
 int jaxent_bg_pack_features(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld, void* out,
                             int32_t* exact_flag, jaxent_stream_t stream);
+/* The same, storing N[r,f] - row_offsets[a][r] (row_offsets: device float[2][Rp], Rp = n_residues padded to 128, integer-valued;
+ * typically the rounded row means).  Hard-cutoff counts minus an integer stay exact in bf16, and the column sums H_f of the
+ * backward GEMM shrink from R x mean to the fluctuation scale, which is what their fp32 accumulation can carry through the
+ * cancellation H_f - hbar at R = 500 (measured: gradient error 3e-4 -> below 2e-5).  Pass the same array to
+ * jaxent_bg_plan_set_row_offsets: the tail adds row_offsets * S back to the forward sums and centres hbar. */
+int jaxent_bg_pack_features_centred(const float* heavy, const float* acceptor, const float* row_offsets, int32_t n_residues, int64_t n_frames,
+                                    int64_t ld, void* out, int32_t* exact_flag, jaxent_stream_t stream);
 int jaxent_bg_gemm1(const void* features, const void* cc3, float* H, int32_t n_fb, int32_t n_rg, int32_t Bn, int32_t NS,
                     int32_t sm_count, jaxent_stream_t stream);
 int jaxent_bg_gemm2(const void* features, const void* e3, float* partials, int32_t n_fb, int32_t n_rg, int32_t Bn, int32_t NS,
@@ -319,9 +326,15 @@ size_t jaxent_bg_workspace_bytes(const JaxentBvProblem* problem, int32_t n_repli
 int jaxent_bg_plan_create(const JaxentBvProblem* problem, const JaxentOptConfig* cfg, int32_t n_replicas, int32_t n_pieces,
                           void* workspace, size_t workspace_bytes, int32_t sm_count, JaxentBatchPlan** plan);
 void jaxent_bg_plan_destroy(JaxentBatchPlan* plan);
+/* features packed by jaxent_bg_pack_features_centred: the same row_offsets (device float[2][Rp], kept alive by the caller); before state_init */
+int jaxent_bg_plan_set_row_offsets(JaxentBatchPlan* plan, const float* row_offsets);
 int jaxent_bg_state_init(JaxentBatchPlan* plan, const float* z0, float zmax, float bc, float bh, const float* fw_host,
                          const float* fs_host, const float* lr_host, jaxent_stream_t stream);
 int jaxent_bg_step(JaxentBatchPlan* plan, jaxent_stream_t stream);
+/* n steps in one call: between two of them the per-(frame, replica) MaxEnt kernel of step k runs on the plan's side stream
+ * beside the backward tensor-core product of step k + 1 (event fork / join, no host synchronisation); the last step stays on
+ * `stream`, so everything observable after the call is complete.  jaxent_bg_step(p, s) == jaxent_bg_steps(p, 1, s). */
+int jaxent_bg_steps(JaxentBatchPlan* plan, int32_t n, jaxent_stream_t stream);
 /* the four phases of jaxent_bg_step, for timing: 0 gemm1, 1 grad + decide + adam, 2 gemm2, 3 reduce + tails + MaxEnt terms */
 int jaxent_bg_step_phase(JaxentBatchPlan* plan, int32_t phase, jaxent_stream_t stream);
 int jaxent_bg_plan_buffer(const JaxentBatchPlan* plan, int32_t which, void** ptr, size_t* bytes);

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjaxent_b200.so")
 SOURCES = ["bv_pass.cu", "bv_tail.cu", "api.cu", "bg_gemm.cu", "bg_step.cu", "bv_contacts.cu"]
-HEADERS = [os.path.join(CSRC, "jx_internal.cuh"), os.path.join(CSRC, "bv_tail_body.cuh"), os.path.join(ROOT, "include", "jaxent_b200.h")]
+HEADERS = [os.path.join(CSRC, "jx_internal.cuh"), os.path.join(CSRC, "bv_tail_body.cuh"), os.path.join(CSRC, "bg_mma.cuh"), os.path.join(ROOT, "include", "jaxent_b200.h")]
 
 
 def nvcc_path() -> str:

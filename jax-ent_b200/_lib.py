@@ -168,6 +168,8 @@ SYMBOLS = {
     "jaxent_bv_predict_frames": (C.c_int, [_VP, _I32, _I64, _I32, _VP, _VP, _F, _F, _VP, _VP]),
     "jaxent_bg_features_bytes": (_SZ, [_I32, _I64]),
     "jaxent_bg_pack_features": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _VP, _VP, _VP]),
+    "jaxent_bg_pack_features_centred": (C.c_int, [_VP, _VP, _VP, _I32, _I64, _I64, _VP, _VP, _VP]),
+    "jaxent_bg_plan_set_row_offsets": (C.c_int, [_VP, _VP]),
     "jaxent_bg_gemm1": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "jaxent_bg_gemm2": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "jaxent_bg_workspace_bytes": (_SZ, [C.POINTER(BvProblem), _I32, _I32, _I32]),
@@ -175,6 +177,7 @@ SYMBOLS = {
     "jaxent_bg_plan_destroy": (None, [_VP]),
     "jaxent_bg_state_init": (C.c_int, [_VP, _VP, _F, _F, _F, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), _VP]),
     "jaxent_bg_step": (C.c_int, [_VP, _VP]),
+    "jaxent_bg_steps": (C.c_int, [_VP, _I32, _VP]),
     "jaxent_bg_step_phase": (C.c_int, [_VP, _I32, _VP]),
     "jaxent_bg_plan_buffer": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_SZ)]),
     "jaxent_bg_track_init": (C.c_int, [_VP, C.POINTER(_F), _I32, _F, _I32, _F, _VP, _VP, _VP, _VP]),

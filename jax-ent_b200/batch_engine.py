@@ -27,8 +27,9 @@ class GemmFeatures:
 
     format = 2  # JaxentBvProblem.feature_format of this layout
 
-    def __init__(self, packed: torch.Tensor, n_residues: int, n_frames: int, exact: bool):
+    def __init__(self, packed: torch.Tensor, n_residues: int, n_frames: int, exact: bool, row_off: Optional[torch.Tensor] = None):
         self.packed, self.R, self.F, self.exact = packed, int(n_residues), int(n_frames), bool(exact)
+        self.row_off = row_off  # float32 [2][Rp]: the integer row constants the stored values were centred with
 
     @property
     def nbytes(self) -> int:
@@ -50,12 +51,19 @@ def pack_gemm_features(heavy, acceptor, device, require_exact: bool = True) -> G
             raise ValueError("Input features have different shapes")  # reference models/core.py:61-62
         out = torch.empty(lib.jaxent_bg_features_bytes(R, F), dtype=torch.uint8, device=dev)
         flag = torch.ones(1, dtype=torch.int32, device=dev)
-        L.check(lib.jaxent_bg_pack_features(h.data_ptr(), a.data_ptr(), R, F, F, out.data_ptr(), flag.data_ptr(), _stream_ptr()))
+        # centred storage N - round(row mean): still exact in bf16 for integer counts, and the backward column sums shrink from
+        # R x mean to the fluctuation scale (jaxent_b200.h, jaxent_bg_pack_features_centred)
+        Rp = (R + 127) // 128 * 128
+        row_off = torch.zeros(2, Rp, dtype=torch.float32, device=dev)
+        row_off[0, :R] = torch.round(h.mean(dim=1))
+        row_off[1, :R] = torch.round(a.mean(dim=1))
+        L.check(lib.jaxent_bg_pack_features_centred(h.data_ptr(), a.data_ptr(), row_off.data_ptr(), R, F, F, out.data_ptr(), flag.data_ptr(),
+                                                    _stream_ptr()))
         exact = bool(flag.item())
     if require_exact and not exact:
         raise ValueError("the tensor-core sweep stores the features in bf16: values must be exactly representable "
                          "(hard-cutoff BV contact counts <= 256 are); use the sequential engine otherwise")
-    return GemmFeatures(out, R, F, exact)
+    return GemmFeatures(out, R, F, exact, row_off)
 
 
 class BatchedBvEngine(BvEngine):
@@ -86,6 +94,9 @@ class BatchedBvEngine(BvEngine):
         plan = C.c_void_p()
         L.check(self.lib.jaxent_bg_plan_create(C.byref(prob), C.byref(cfg), self.Bn, self.n_pieces, self.ws.data_ptr() + self._ws_off,
                                                nbytes, sm, C.byref(plan)))
+        feats = getattr(self, "features", None)
+        if feats is not None and getattr(feats, "row_off", None) is not None:
+            L.check(self.lib.jaxent_bg_plan_set_row_offsets(plan, feats.row_off.data_ptr()))
         return plan
 
     def __del__(self):
@@ -194,9 +205,7 @@ class BatchedBvEngine(BvEngine):
 
     def step(self, n: int = 1) -> None:
         with torch.cuda.device(self.device):
-            s = _stream_ptr()
-            for _ in range(n):
-                L.check(self.lib.jaxent_bg_step(self.plan, s))
+            L.check(self.lib.jaxent_bg_steps(self.plan, int(n), _stream_ptr()))  # one call: consecutive steps overlap (jaxent_b200.h)
         self.steps_done += n
         self.launches += 9 * n
 

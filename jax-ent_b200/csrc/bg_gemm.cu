@@ -27,7 +27,9 @@
 #include <cuda_bf16.h>
 
 #include <cstdio>
+#include <cstdlib>
 
+#include "bg_mma.cuh"
 #include "jx_internal.cuh"
 
 namespace jx {
@@ -38,68 +40,6 @@ constexpr int STAGE_K = 64;    // K elements per pipeline stage
 constexpr int A_STAGE_BYTES = 128 * STAGE_K * 2;  // 16 KB
 constexpr int N_STAGES = 2;
 constexpr int GEMM_THREADS = 192;  // 6 warps
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// shared-memory matrix descriptor, no swizzle: start address, leading / stride byte offsets (all >> 4), version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) |
-         (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct GemmArgs {
   const unsigned char* A;  // GF features
@@ -299,8 +239,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) bg_gemm_kernel(const GemmArgs
 }
 
 // (R,F) fp32 row-major -> GF bf16 layout; rows >= R and frames >= F are zero.  One thread per (row, 8-frame chunk).
-__global__ void pack_gf_kernel(const float* __restrict__ heavy, const float* __restrict__ acceptor, int R, long long F, long long ld,
-                               int n_rg, long long n_fb, unsigned char* __restrict__ out) {
+__global__ void pack_gf_kernel(const float* __restrict__ heavy, const float* __restrict__ acceptor, const float* __restrict__ row_off, int Rp,
+                               int R, long long F, long long ld, int n_rg, long long n_fb, unsigned char* __restrict__ out) {
   const long long n_items = n_fb * 2 * n_rg * 16 * 8;  // (fb, a, rg, fc, row-in-group)
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += (long long)gridDim.x * blockDim.x) {
     const int ri = (int)(it & 7);
@@ -313,24 +253,27 @@ __global__ void pack_gf_kernel(const float* __restrict__ heavy, const float* __r
     const int r = rg * 8 + ri;
     const long long f0 = fb * FB + fc * 8;
     const float* src = arr ? acceptor : heavy;
+    const float off = (row_off && r < R) ? row_off[arr * Rp + r] : 0.f;
     __nv_bfloat16 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const long long f = f0 + k;
-      v[k] = __float2bfloat16_rn((r < R && f < F) ? src[(long long)r * ld + f] : 0.f);
+      v[k] = __float2bfloat16_rn((r < R && f < F) ? src[(long long)r * ld + f] - off : 0.f);  // padding frames stay 0: they carry e' = 0
     }
     *reinterpret_cast<uint4*>(out + it * 16) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
 // flag <- 0 unless every value is exactly representable in bf16
-__global__ void fit_bf16_kernel(const float* __restrict__ x, long long n_rows, long long F, long long ld, int* flag) {
+__global__ void fit_bf16_kernel(const float* __restrict__ x, const float* __restrict__ off, long long n_rows, long long F, long long ld, int* flag) {
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   bool bad = false;
   for (long long i = i0; i < n_rows * F; i += stride) {
     const long long r = i / F, f = i - r * F;
-    const float v = x[r * ld + f];
-    bad = bad || !(__bfloat162float(__float2bfloat16_rn(v)) == v);
+    const float raw = x[r * ld + f];
+    const float v = raw - (off ? off[r] : 0.f);
+    // the stored value must be exact in bf16 AND the subtraction itself exact (raw == v + off in fp32)
+    bad = bad || !(__bfloat162float(__float2bfloat16_rn(v)) == v) || (off && v + off[r] != raw);
   }
   if (bad) *flag = 0;
 }
@@ -358,14 +301,20 @@ extern "C" size_t jaxent_bg_features_bytes(int32_t R, int64_t F) {
 
 extern "C" int jaxent_bg_pack_features(const float* heavy, const float* acceptor, int32_t R, int64_t F, int64_t ld, void* out,
                                        int32_t* exact_flag, jaxent_stream_t stream) {
+  return jaxent_bg_pack_features_centred(heavy, acceptor, nullptr, R, F, ld, out, exact_flag, stream);
+}
+
+extern "C" int jaxent_bg_pack_features_centred(const float* heavy, const float* acceptor, const float* row_offsets, int32_t R, int64_t F,
+                                               int64_t ld, void* out, int32_t* exact_flag, jaxent_stream_t stream) {
   if (!heavy || !acceptor || !out || R <= 0 || F <= 0 || ld < F) { set_error("bg_pack_features: invalid argument"); return JAXENT_E_INVALID; }
   const int n_rg = (R + 127) / 128 * 16;
+  const int Rp = n_rg * 8;
   const long long n_fb = (F + 127) / 128;
   if (exact_flag) {
-    bg::fit_bf16_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(heavy, R, F, ld, exact_flag);
-    bg::fit_bf16_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(acceptor, R, F, ld, exact_flag);
+    bg::fit_bf16_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(heavy, row_offsets, R, F, ld, exact_flag);
+    bg::fit_bf16_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(acceptor, row_offsets ? row_offsets + Rp : nullptr, R, F, ld, exact_flag);
   }
-  bg::pack_gf_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(heavy, acceptor, R, F, ld, n_rg, n_fb, static_cast<unsigned char*>(out));
+  bg::pack_gf_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(heavy, acceptor, row_offsets, Rp, R, F, ld, n_rg, n_fb, static_cast<unsigned char*>(out));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bg_pack_features launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
   return JAXENT_OK;

@@ -20,10 +20,12 @@
 #include <cuda_bf16.h>
 
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
+#include "bg_mma.cuh"
 #include "bv_tail_body.cuh"
 #include "jx_internal.cuh"
 
@@ -40,6 +42,7 @@ struct alignas(16) BCtl {
   float lrA, lrB, mlrA, mlrB, mask_frame, mask_model;
   float lr_eff, bc1, bc2, kl_scale, last_dot, pad0;
   double S, hbar_data, zp;  // zp = sum_f p_f z_f of the current logits
+  double lse_d, pad_d;      // log-sum-exp of the current logits, unrounded: (double)lse_old + log S (the MaxEnt loss needs more than fp32 here)
   double klsum[KL_N];
   float fw[JAXENT_MAX_SLOTS], fs[JAXENT_MAX_SLOTS];
   // ---- per-replica ConvergenceTracker (reference opt/track.py:128-197, opt/run.py:285-348); see derive_scalars (bv_tail.cu)
@@ -73,6 +76,7 @@ struct BatchArgs {
   float* avg;             // [Bn][2R]
   float* logpf;           // [Bn][R]
   float* uptake;          // [Bn][T*R]
+  const float* row_off;   // [2][Rp] integers the packed features were centred with (jaxent_bg_pack_features_centred), or nullptr
   float* pnorm;           // [F] normalised prior p_f = (|prior_f| + eps) / sum (fp32, as frame_terms forms it)
   double* kl_const;       // [2] sum_f p_f log p_f, sum_f p_f
   unsigned* gsel;         // which g buffer holds the current masked gradients
@@ -81,6 +85,7 @@ struct BatchArgs {
   int blob_words_max;     // words reserved for the blob image in the tail's shared memory
   int ew_blocks, fy;      // elementwise grid (2 blocks of 512 threads per SM) / frames per block iteration
   int adam_blocks;        // bt_adam keeps 128 registers per thread: one 512-thread block per SM, one wave
+  int dot_blocks;         // rows of part_dot written by the gradient kernel (bt_grad, or the fused tensor-core kernel)
   float eps_kl;
   // on-device loop (jaxent_bg_track_init)
   int trk_on, trk_n_thr, trk_min_steps;
@@ -124,6 +129,28 @@ __device__ __forceinline__ void weight_terms(float e, float invS, float p, bool 
     const float corr = fmaf(-r0, q, p) * rq;
     const double G_ = (1.0 - (double)r0) - (double)corr;
     kap = (w > 0.f) ? (double)lam * G_ : 0.0;
+  }
+}
+
+// The same kappa as weight_terms, as an unevaluated fp32 pair (kh + kl carries ~45 bits) and without a single fp64
+// instruction or conversion: float <-> double conversions run at 16 lanes/clk on sm_100, and the fused gradient kernel has
+// only its epilogue warps for this arithmetic.  1 - r0 is formed with its exact rounding error (2Sum), the product with
+// lambda with its exact FMA residual.
+__device__ __forceinline__ void weight_terms_pair(float e, float invS, float p, bool has_kl, float eps, float lam, float& w, float& kh, float& kl) {
+  w = e * invS;
+  kh = 0.f;
+  kl = 0.f;
+  if (has_kl && w > 0.f) {
+    const float q = fabsf(w) + eps;
+    const float rq = rcp_approx(q);
+    const float r0 = p * rq;
+    const float corr = fmaf(-r0, q, p) * rq;          // p/q = r0 + corr to ~1e-14
+    const float gh = 1.0f - r0;                         // 2Sum(1, -r0): gh + ge == 1 - r0 exactly
+    const float bb = gh - 1.0f;
+    const float ge = (1.0f - (gh - bb)) + (-r0 - bb);
+    const float gl = ge - corr;                         // G = 1 - p/q = gh + gl
+    kh = lam * gh;
+    kl = fmaf(lam, gh, -kh) + lam * gl;                 // lam * G = kh + kl
   }
 }
 
@@ -213,6 +240,244 @@ __global__ void __launch_bounds__(512) bt_grad_kernel(const BatchArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ fused gemm1 + gradient
+// H never leaves the chip: the backward product runs TRANSPOSED on the tensor cores,
+//     H^T[b, f] = sum_{a,r} c_a[r, b] * N_a[r, f]        M = 128 replicas, N = 256 frames, K = 2 Rp (x NS pieces of c)
+// so that a TMEM lane is a REPLICA and the columns are frames.  An epilogue thread then owns one replica: its constants
+// (1/S, lambda, mask, hbar) live in registers, its grad-dot is a plain register accumulation (no cross-lane reduction), and
+// for a given frame the 32 lanes of a warp touch 32 consecutive replicas of the [frame][replica] state arrays -- every
+// load and store is a coalesced 128-byte line.  The epilogue does what bt_grad did (weights, dKL/dw, masked gradient,
+// grad-dot partial) straight from tcgen05.ld, overlapped with the MMAs of the next tile (two TMEM accumulators).
+//   A operand  c pieces   global CC3 [s][a][kc][Bn][8]  -> smem [kc: 4][128 replicas][16 B]            K-major  (SBO 128, LBO 2048)
+//   B operand  features   global GF  [fb][a][rg][16 fc][8 r][8 f] -> smem [rg: 4][fc: 32][8 r][8 f]    MN-major (SBO 128, LBO 4096)
+//              (two frame blocks side by side: 32 chunks of 8 frames = N 256)
+// 5 stages of K = 32 (8 KB of features + NS x 8 KB of c pieces) cover the L2 latency; features cross L2 -> SM twice (one
+// tile per replica half), c pieces once per tile.  Used when Bn is a multiple of 128; otherwise gemm1 + bt_grad.
+constexpr int FG_STAGE_K = 32;
+constexpr int FG_STAGES = 5;
+constexpr int FG_B_BYTES = 256 * FG_STAGE_K * 2;  // 16 KB: features, 256 frames x 32 rows
+constexpr int FG_A_BYTES = 128 * FG_STAGE_K * 2;  // 8 KB per piece: 128 replicas x 32 rows
+constexpr int FG_EPI_WARPS = 16;                    // 4 per TMEM lane quarter: enough loads in flight to stream the state arrays
+constexpr int FG_THREADS = 64 + 32 * FG_EPI_WARPS;
+
+__global__ void __launch_bounds__(FG_THREADS, 1) bt_fused_grad_kernel(const BatchArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Bn = a.Bn, NS = a.NS;
+  const uint32_t stage_bytes = FG_B_BYTES + (uint32_t)NS * FG_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)FG_STAGES * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + FG_STAGES;
+  uint64_t* tfull = bars + 2 * FG_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  double* s_dot = reinterpret_cast<double*>(tmem_slot + 4);  // [FG_EPI_WARPS][32]
+
+  // tile = (pair of frame blocks, replica half); a CTA keeps ONE replica half (the grid is even when there are two)
+  const int halves = Bn >> 7;
+  const int n_fp = (a.n_fb + 1) >> 1;
+  const int h = (halves == 2) ? (int)(blockIdx.x & 1u) : 0;
+  const int fp0 = (halves == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int fp_step = (halves == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_stage = 2 * (a.n_rg / 4);  // both arrays, 32-row chunks
+
+  if (tid == 0) {
+    for (int s = 0; s < FG_STAGES; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull[s]), 1);
+      mbar_init(smem_u32(&tempty[s]), FG_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // two accumulators of 256 fp32 columns: all of tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t par = 0;
+      const unsigned char* gf = reinterpret_cast<const unsigned char*>(a.prob.packed);
+      for (int fp = fp0; fp < n_fp; fp += fp_step) {
+        const int fb0 = 2 * fp, fb1 = (2 * fp + 1 < a.n_fb) ? 2 * fp + 1 : fb0;  // odd tail: the second half repeats the first (ignored: f >= F)
+        for (int st = 0; st < n_stage; ++st) {
+          const int arr = st / (a.n_rg / 4), rg0 = (st - arr * (a.n_rg / 4)) * 4;
+          mbar_wait(smem_u32(&empty[slot]), par ^ 1u);
+          const uint32_t bar = smem_u32(&full[slot]);
+          unsigned char* dst = smem + (size_t)slot * stage_bytes;
+          mbar_expect_tx(bar, stage_bytes);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // features: 2 KB per (frame block, 8-row group) -> [rg][fc 0..15 | fc 16..31]
+            bulk_g2s(smem_u32(dst + g * 4096), gf + (((size_t)fb0 * 2 + arr) * a.n_rg + rg0 + g) * 2048, 2048, bar);
+            bulk_g2s(smem_u32(dst + g * 4096 + 2048), gf + (((size_t)fb1 * 2 + arr) * a.n_rg + rg0 + g) * 2048, 2048, bar);
+          }
+          for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)  // c pieces: 128 replicas x 16 B per k-chunk
+              bulk_g2s(smem_u32(dst + FG_B_BYTES + s * FG_A_BYTES + g * 2048),
+                       a.cc3 + ((((size_t)s * 2 + arr) * a.n_rg + rg0 + g) * Bn + (size_t)h * 128) * 16, 2048, bar);
+          if (++slot == FG_STAGES) {
+            slot = 0;
+            par ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      // D fp32, A / B bf16, A K-major, B MN-major (bit 16), N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+      int slot = 0, acc = 0;
+      uint32_t par = 0, tpar = 0;
+      for (int fp = fp0; fp < n_fp; fp += fp_step) {
+        mbar_wait(smem_u32(&tempty[acc]), tpar ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * 256);
+        uint32_t accumulate = 0;
+        for (int st = 0; st < n_stage; ++st) {
+          mbar_wait(smem_u32(&full[slot]), par);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)slot * stage_bytes);
+#pragma unroll
+          for (int j = 0; j < FG_STAGE_K / 16; ++j) {
+            const uint64_t bd = make_desc(sa + j * 2 * 4096, 4096, 128);
+            for (int s = 0; s < NS; ++s) {
+              const uint64_t ad = make_desc(sa + FG_B_BYTES + s * FG_A_BYTES + j * 2 * 2048, 2048, 128);
+              umma_bf16(d, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          tc_commit(smem_u32(&empty[slot]));
+          if (++slot == FG_STAGES) {
+            slot = 0;
+            par ^= 1u;
+          }
+        }
+        tc_commit(smem_u32(&tfull[acc]));
+        if (++acc == 2) {
+          acc = 0;
+          tpar ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue: one replica per thread
+    // 16 warps: warp (2 + w) reads TMEM lane quarter (2 + w) % 4 and takes the 16-frame column chunks j = (w / 4) mod 4 of a
+    // tile.  The state loads of the NEXT chunk are issued before the current one is evaluated (one chunk = 2 x 16 coalesced
+    // 128-byte lines per warp).
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
+    const int b = h * 128 + quarter * 32 + lane;
+    const BCtl* c = a.ctl + b;
+    const unsigned sel = *a.gsel;
+    const float* __restrict__ gprev = a.g[sel];
+    float* __restrict__ gout = a.g[sel ^ 1u];
+    const float* __restrict__ ep = a.e;
+    const float invS = (float)(1.0 / c->S), lam = c->kl_scale, maskf = c->mask_frame;
+    const double hbar = c->hbar_data + c->klsum[0];  // data part + MaxEnt part (see gather_hbar, bv_pass.cu)
+    const float hb_hi = (float)hbar, hb_lo = (float)(hbar - (double)hb_hi);
+    const bool have_prev = c->have_prev != 0, has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr, active = c->stop == 0;
+    const float* __restrict__ pn = a.pnorm;
+    const long long Fm1 = a.F - 1;
+    double dot = 0.0;
+    int acc = 0;
+    uint32_t tpar = 0;
+    float ev[16], gv[16], pv;
+    auto load_chunk = [&](long long f0) {  // lanes = consecutive replicas of one frame: coalesced lines; lane k also fetches p of frame k
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const long long f = f0 + k;
+        const size_t i = (size_t)(f < a.F ? f : Fm1) * Bn + b;
+        ev[k] = ep[i];
+        gv[k] = gprev[i];
+      }
+      const long long fl = f0 + (lane & 15);
+      pv = pn ? pn[fl < a.F ? fl : Fm1] : 0.f;
+    };
+    if (fp0 < n_fp) load_chunk((long long)fp0 * 256 + sub * 16);
+    for (int fp = fp0; fp < n_fp; fp += fp_step) {
+      mbar_wait(smem_u32(&tfull[acc]), tpar);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+      const long long fbase = (long long)fp * 256;
+#pragma unroll 1
+      for (int j = sub; j < 16; j += 4) {
+        const long long f0 = fbase + j * 16;
+        uint32_t hv[16];
+        tmem_ld16_issue(taddr + j * 16, hv);
+        float ec[16], gc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          ec[k] = ev[k];
+          gc[k] = gv[k];
+        }
+        const float pc = pv;
+        {  // next chunk of this warp: same tile, or the first one of the next tile
+          const bool more = j + 4 < 16;
+          const long long fn = more ? f0 + 64 : (long long)(fp + fp_step) * 256 + sub * 16;
+          if (more || fp + fp_step < n_fp) load_chunk(fn);
+        }
+        tmem_ld_wait();
+        float prod[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const long long f = f0 + k;
+          const float p = __shfl_sync(0xffffffffu, pc, k);
+          prod[k] = 0.f;
+          if (f < a.F) {
+            float w, kh, kl;
+            weight_terms_pair(ec[k], invS, p, has_kl, a.eps_kl, lam, w, kh, kl);
+            // (H + kappa) - hbar with kappa and hbar as fp32 pairs: the O(lambda) cancellation kh - hb_hi is exact (see bv_pass.cu)
+            const float gf = active ? maskf * (w * ((__uint_as_float(hv[k]) + (kh - hb_hi)) + (kl - hb_lo))) : 0.f;
+            prod[k] = (have_prev ? gc[k] : gf) * gf;
+            gout[(size_t)f * Bn + b] = gf;
+          }
+        }
+        // 16 products: fixed-shape fp32 tree, then one fp64 addition per chunk
+#pragma unroll
+        for (int st = 8; st; st >>= 1)
+#pragma unroll
+          for (int k = 0; k < st; ++k) prod[k] += prod[k + st];
+        dot += (double)prod[0];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+      if (++acc == 2) {
+        acc = 0;
+        tpar ^= 1u;
+      }
+    }
+    s_dot[(warp - 2) * 32 + lane] = dot;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp >= 2 && warp < 6) {  // this CTA's row of the grad-dot partials (fixed order over the 4 column sub-sets); zeros for the other half
+    const int quarter = warp & 3;
+    double t = 0.0;
+#pragma unroll
+    for (int sb = 0; sb < 4; ++sb) {
+      // the epilogue warp with lane quarter `quarter` and column sub-set sb is warp index 2 + w with (2 + w) % 4 == quarter, w / 4 == sb
+      const int w = ((quarter + 2) & 3) + 4 * sb;
+      t += s_dot[w * 32 + lane];
+    }
+    a.part_dot[(size_t)blockIdx.x * Bn + h * 128 + quarter * 32 + lane] = t;
+    if (halves == 2) a.part_dot[(size_t)blockIdx.x * Bn + (h ^ 1) * 128 + quarter * 32 + lane] = 0.0;
+  }
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------ bt_decide
 // one thread per replica: plateau rule, BV-parameter Adam (optax adam + keep_params_nonnegative), counters
 __global__ void bt_decide_kernel(const BatchArgs a) {
@@ -224,7 +489,7 @@ __global__ void bt_decide_kernel(const BatchArgs a) {
   if (c->stop) return;
   const JaxentOptConfig& cfg = a.cfg;
   double gdot = 0.0;
-  for (int k = lane; k < a.ew_blocks; k += 32) gdot += a.part_dot[(size_t)k * a.Bn + b];
+  for (int k = lane; k < a.dot_blocks; k += 32) gdot += a.part_dot[(size_t)k * a.Bn + b];
   gdot = wsum(gdot);
   if (lane != 0) return;
   const float g0 = c->gb[0], g1 = c->gb[1];
@@ -499,14 +764,20 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArg
     acc0 = a.red[(size_t)b * 2 * Rp + tid];
     acc1 = a.red[(size_t)b * 2 * Rp + Rp + tid];
   }
+  const double off0 = (a.row_off && tid < R) ? (double)a.row_off[tid] : 0.0, off1 = (a.row_off && tid < R) ? (double)a.row_off[Rp + tid] : 0.0;
   if (lane < 16) s_red[warp][lane] = 0.0;
   for (int i = tid; i < 2 * Rp; i += blockDim.x) s_cc[i] = 0.f;
   __syncthreads();
   if (s_c.stop) return;
   const double S = s_c.S;
+  // the GEMM swept centred features: sum_f e'_f (N[r,f] - off_r) = acc - off_r S
+  acc0 += off0 * S;
+  acc1 += off1 * S;
   const double bc = (double)s_c.bc, bh = (double)s_c.bh;
   double my_c, my_a, my_b, my_lp, gbc_reg, gbh_reg;
   TailIO io;
+  io.row_off = a.row_off;
+  io.row_off_stride = Rp;
   io.avg = a.avg + (size_t)b * 2 * R;
   io.logpf = a.logpf + (size_t)b * R;
   io.uptake = a.uptake + (size_t)b * (T > 0 ? T : 1) * R;
@@ -555,7 +826,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bt_tail_kernel(const BatchArg
     c->mlrB = base_mlr / cfg.plateau_denominator;
     c->mask_frame = (mi == 0) ? 1.f : (cfg.optimise_frame_weights ? 1.f : 0.f);
     c->mask_model = mask_model;
-    c->lse = (float)((double)s_c.lse + dlog(S));
+    const double lse_d = (double)s_c.lse + dlog(S);
+    c->lse_d = lse_d;
+    c->lse = (float)lse_d;
     c->hbar_data = s_fin[12];
     const float gb0 = (float)(s_fin[13] + gbc_reg) * mask_model, gb1 = (float)(s_fin[14] + gbh_reg) * mask_model;
     c->gb[0] = gb0;
@@ -730,7 +1003,8 @@ __global__ void __launch_bounds__(256) bt_klfold_kernel(const BatchArgs a, int n
     if (cw->kl_slot >= 0) {
       JaxentLossRecord* rec = a.records + (size_t)(cw->step % RB) * Bn + b;
       // kl[1] holds the rare-frame corrections sum p log1p(eps / w)
-      const double plogq = cw->zp - (double)cw->lse * a.kl_const[1] + kl[1];
+      // log w_f = z_f - (lse_old + log S) with the sum in double: the fp32 lse is 5e-7 off at lse ~ 11, which the loss scaling (x 1000) turns into 2e-4
+      const double plogq = cw->zp - cw->lse_d * a.kl_const[1] + kl[1];
       const float klv = (float)((a.kl_const[0] - plogq) + kl[2]);
       const int i = cw->kl_slot;
       rec->train[i] = klv;
@@ -808,6 +1082,9 @@ struct JaxentBatchPlan {
   size_t tail_smem;
   int general;
   int sm_count;
+  int fused_grad;  // phase 0 = bt_fused_grad_kernel (Bn a multiple of 128)
+  cudaStream_t side;        // jaxent_bg_steps: the MaxEnt terms of step k run here, beside the backward product of step k + 1
+  cudaEvent_t ev_tail, ev_kl;
   int initialised;
   long long steps;
 };
@@ -967,6 +1244,20 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   if (blocks < 1) blocks = 1;
   a.ew_blocks = (int)blocks;
   a.adam_blocks = a.ew_blocks < sm_count ? a.ew_blocks : sm_count;
+  // backward product: gemm1 + bt_grad; JAXENT_BG_FUSED=1 selects the single fused tensor-core kernel (whole 128-replica M tiles only)
+  {
+    const char* env = getenv("JAXENT_BG_FUSED");
+    p->fused_grad = (n_replicas % 128 == 0) && (env && env[0] == '1');  // opt-in: measured slower than gemm1 + bt_grad so far
+    a.dot_blocks = a.ew_blocks;
+    if (p->fused_grad) {
+      const int halves = n_replicas / 128;
+      const int n_tiles = ((a.n_fb + 1) / 2) * halves;
+      int grid = n_tiles < sm_count ? n_tiles : sm_count;
+      if (halves == 2) grid &= ~1;  // a CTA keeps one replica half
+      if (grid < halves) grid = halves;
+      a.dot_blocks = grid;
+    }
+  }
   {
     int nnz_tr = 1, nnz_va = 1;
     for (int i = 0; i < pb->n_slots; ++i)
@@ -981,13 +1272,41 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   if (p->tail_smem > 220 * 1024) { delete p; set_error("batched plan: tail needs %zu bytes of shared memory", p->tail_smem); return JAXENT_E_UNSUPPORTED; }
   p->general = general;
   p->sm_count = sm_count;
+  p->side = nullptr;
+  p->ev_tail = p->ev_kl = nullptr;
+  {  // side stream + fork / join events of jaxent_bg_steps (set-up time; JAXENT_BG_OVERLAP=0 keeps a step on one stream)
+    const char* env = getenv("JAXENT_BG_OVERLAP");
+    if (!(env && env[0] == '0')) {
+      cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_tail, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_kl, cudaEventDisableTiming);
+      if (e != cudaSuccess) {  // no device (CPU-side tests build plans without one) or out of resources: single-stream steps
+        (void)cudaGetLastError();
+        if (p->side) cudaStreamDestroy(p->side);
+        if (p->ev_tail) cudaEventDestroy(p->ev_tail);
+        p->side = nullptr;
+        p->ev_tail = p->ev_kl = nullptr;
+      }
+    }
+  }
   *out = p;
   return JAXENT_OK;
 }
 
 extern "C" void jaxent_bg_plan_destroy(JaxentBatchPlan* p) {
+  if (!p) return;
   jaxent_handle_release_ptr(p);
+  if (p->side) cudaStreamDestroy(p->side);
+  if (p->ev_tail) cudaEventDestroy(p->ev_tail);
+  if (p->ev_kl) cudaEventDestroy(p->ev_kl);
   delete p;
+}
+
+extern "C" int jaxent_bg_plan_set_row_offsets(JaxentBatchPlan* p, const float* row_offsets) {
+  if (!p) { set_error("bg_plan_set_row_offsets: plan is NULL"); return JAXENT_E_INVALID; }
+  p->a.row_off = row_offsets;
+  p->initialised = 0;  // the forward of jaxent_bg_state_init must follow
+  return JAXENT_OK;
 }
 
 extern "C" int jaxent_bg_plan_workspace(const JaxentBatchPlan* p, void** ptr, size_t* bytes) {
@@ -1008,7 +1327,9 @@ static int bg_gemm2_phase(JaxentBatchPlan* p, cudaStream_t s) {
   return jaxent_bg_gemm2(a.prob.packed, a.e3, a.P, a.n_fb, a.n_rg, a.Bn, a.NS, a.ksplit, s);
 }
 
-static int bg_tail_phase(JaxentBatchPlan* p, cudaStream_t s) {
+// reduce2 + per-replica tails on `s`; the MaxEnt kernel and its fold on `skl` (== s, or the plan's side stream between two
+// steps of one jaxent_bg_steps call: forked after the tails, joined by the caller on ev_kl)
+static int bg_tail_phase_split(JaxentBatchPlan* p, cudaStream_t s, cudaStream_t skl, bool fork) {
   const bg::BatchArgs& a = p->a;
   int rc;
   dim3 grid((2 * a.Rp + 31) / 32, (a.Bn + 31) / 32);
@@ -1032,11 +1353,25 @@ static int bg_tail_phase(JaxentBatchPlan* p, cudaStream_t s) {
       kl_configured = true;
     }
   }
-  bg::bt_kl_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)a.fy * KL_N * a.Bn * 8, s>>>(a);
+  if (fork) {
+    cudaError_t e = cudaEventRecord(p->ev_tail, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(skl, p->ev_tail, 0);
+    if (e != cudaSuccess) { set_error("bg_steps (fork): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  }
+  // beside the tensor-core kernel (197 KB of shared memory per SM) only ONE of these blocks fits on an SM: one block per SM then
+  const int kl_blocks = (fork && a.ew_blocks > p->sm_count) ? p->sm_count : a.ew_blocks;
+  bg::bt_kl_kernel<<<kl_blocks, (a.Bn / 4) * a.fy, (size_t)a.fy * KL_N * a.Bn * 8, skl>>>(a);
   if ((rc = bg_err("bt_kl"))) return rc;
-  bg::bt_klfold_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a, a.ew_blocks);
-  return bg_err("bt_klfold");
+  bg::bt_klfold_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, skl>>>(a, kl_blocks);
+  if ((rc = bg_err("bt_klfold"))) return rc;
+  if (fork) {
+    cudaError_t e = cudaEventRecord(p->ev_kl, skl);
+    if (e != cudaSuccess) { set_error("bg_steps (join): %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  }
+  return JAXENT_OK;
 }
+
+static int bg_tail_phase(JaxentBatchPlan* p, cudaStream_t s) { return bg_tail_phase_split(p, s, s, false); }
 
 static int bg_forward(JaxentBatchPlan* p, cudaStream_t s) {
   int rc = bg_gemm2_phase(p, s);
@@ -1044,16 +1379,35 @@ static int bg_forward(JaxentBatchPlan* p, cudaStream_t s) {
   return bg_tail_phase(p, s);
 }
 
+static size_t bg_fused_smem(int NS) {
+  return (size_t)bg::FG_STAGES * (bg::FG_B_BYTES + (size_t)NS * bg::FG_A_BYTES) + 256 + (size_t)bg::FG_EPI_WARPS * 32 * 8;
+}
+
+// phase 0: the backward product.  Bn a multiple of 128: one tensor-core kernel that also forms the masked gradients and the
+// grad-dot partials in its epilogue (H stays in tensor memory).  Otherwise: gemm1 -> H, and bt_grad in phase 1.
 static int bg_gemm1_phase(JaxentBatchPlan* p, cudaStream_t s) {
-  const bg::BatchArgs& a = p->a;
+  bg::BatchArgs& a = p->a;
+  if (p->fused_grad) {
+    const size_t smem = bg_fused_smem(a.NS);
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(bg::bt_fused_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("bt_fused_grad: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return JAXENT_E_UNSUPPORTED; }
+      configured = smem;
+    }
+    bg::bt_fused_grad_kernel<<<a.dot_blocks, bg::FG_THREADS, smem, s>>>(a);
+    return bg_err("bt_fused_grad");
+  }
   return jaxent_bg_gemm1(a.prob.packed, a.cc3, a.H, a.n_fb, a.n_rg, a.Bn, a.NS, p->sm_count, s);
 }
 
 static int bg_update_phase(JaxentBatchPlan* p, cudaStream_t s) {
   const bg::BatchArgs& a = p->a;
   int rc;
-  bg::bt_grad_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a);
-  if ((rc = bg_err("bt_grad"))) return rc;
+  if (!p->fused_grad) {
+    bg::bt_grad_kernel<<<a.ew_blocks, (a.Bn / 4) * a.fy, (size_t)a.fy * a.Bn * 8, s>>>(a);
+    if ((rc = bg_err("bt_grad"))) return rc;
+  }
   bg::bt_decide_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a);
   if ((rc = bg_err("bt_decide"))) return rc;
   bg::bt_adam_kernel<<<a.adam_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 1);
@@ -1127,12 +1481,34 @@ extern "C" int jaxent_bg_step_phase(JaxentBatchPlan* p, int32_t phase, jaxent_st
   }
 }
 
-extern "C" int jaxent_bg_step(JaxentBatchPlan* p, jaxent_stream_t stream) {
-  for (int ph = 0; ph < 4; ++ph) {
-    const int rc = jaxent_bg_step_phase(p, ph, stream);
-    if (rc) return rc;
+extern "C" int jaxent_bg_step(JaxentBatchPlan* p, jaxent_stream_t stream) { return jaxent_bg_steps(p, 1, stream); }
+
+// n steps in one call.  The per-(frame, replica) MaxEnt kernel of step k (bt_kl + its fold: memory / FMA bound) does not touch
+// anything the backward product of step k + 1 reads (features, c pieces), so between two steps of the same call it is
+// enqueued on the plan's side stream and joins the main stream just before bt_grad, which needs its sums: it then runs
+// under the tensor-core kernel instead of after it.  The last step of a call keeps everything on `stream`, so the state a
+// caller can observe after the call (loss records, control blocks, tracker snapshots) is complete -- same contract as n
+// calls of jaxent_bg_step.  Fork / join are events: no host synchronisation, capturable in a CUDA graph.
+extern "C" int jaxent_bg_steps(JaxentBatchPlan* p, int32_t n, jaxent_stream_t stream) {
+  if (!p || !p->initialised) { set_error("bg_step: jaxent_bg_state_init has not been called"); return JAXENT_E_INVALID; }
+  if (n < 1) { set_error("bg_steps: n must be >= 1"); return JAXENT_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  bool pending = false;
+  int rc;
+  for (int i = 0; i < n; ++i) {
+    if ((rc = bg_gemm1_phase(p, s))) return rc;
+    if (pending) {
+      cudaError_t e = cudaStreamWaitEvent(s, p->ev_kl, 0);
+      if (e != cudaSuccess) { set_error("bg_steps: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+      pending = false;
+    }
+    if ((rc = bg_update_phase(p, s))) return rc;
+    if ((rc = bg_gemm2_phase(p, s))) return rc;
+    const bool overlap = p->side != nullptr && i + 1 < n;
+    if ((rc = bg_tail_phase_split(p, s, overlap ? p->side : s, overlap))) return rc;
+    pending = overlap;
+    p->steps += 1;
   }
-  p->steps += 1;
   return JAXENT_OK;
 }
 

@@ -574,6 +574,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     io.p_max_tr = a.p_max_tr;
     io.p_max_va = a.p_max_va;
     io.c_pieces = 0;
+    io.row_off = nullptr;
+    io.row_off_stride = 0;
     io.prof = reinterpret_cast<long long*>(a.cl_scratch);
     io.ck = a.ck;
     if (pfm) {  // per-frame uptake mode: <u>[t,r] = 1 - acc[branch d][t][r] / S, acc = sum_f e'_f exp(-k tau / PF_f) from the pass

@@ -127,6 +127,8 @@ struct TailIO {
   int pf_mode;    // 1: per-frame uptake mode -- the caller has filled sm.sU with the frame-averaged uptake already
   int p_max_tr, p_max_va;  // carve-up parameters (carve_tail_smem)
   float* ck;      // [R] centring constants of the pass (see "centred column sums" in tail_body), or nullptr (batched GEMM path)
+  const float* row_off;  // batched tensor-core path: [2][Rp] per-row constants the stored features were centred with (or nullptr)
+  int row_off_stride;    // Rp
   long long* prof; // JX_PROFILE builds: %globaltimer stamps of the phases (else unused)
   int c_pieces;   // how the sweep sees the row coefficients: 0 = rounded to fp32, n > 0 = the sum of n bf16 pieces (batched GEMM path)
 };
@@ -456,7 +458,9 @@ __device__ __forceinline__ void tail_body(const JaxentBvProblem& pb, const BlobS
           kd = gsum - gu;  // the pass forms fl(kd) - sum_t G exp(-k tau / PF_f) = sum_t G (u_f - <u>) per row
           v12 = (io.ck != nullptr) ? -(kd - (double)(float)kd) : gu;
         } else {
-          kd = coeff_as_used(my_c * bc, io.c_pieces) * my_a + coeff_as_used(my_c * bh, io.c_pieces) * my_b;
+          // (the batched GEMM sweeps centred features N - off_r: its column sums, and hence hbar, are about <N>_r - off_r)
+          const double oa = io.row_off ? (double)io.row_off[tid] : 0.0, ob = io.row_off ? (double)io.row_off[io.row_off_stride + tid] : 0.0;
+          kd = coeff_as_used(my_c * bc, io.c_pieces) * (my_a - oa) + coeff_as_used(my_c * bh, io.c_pieces) * (my_b - ob);
           v12 = (io.ck != nullptr) ? kd - (double)(float)kd : kd;
         }
         if (io.ck != nullptr) io.ck[tid] = (float)kd;

@@ -130,3 +130,89 @@ def test_batched_rejects_fractional_features():
     x = torch.rand(8, 64, device="cuda") * 3.0 + 0.123456
     with pytest.raises(ValueError, match="bf16"):
         pack_gemm_features(x, x, "cuda:0")
+
+
+@pytest.mark.parametrize("B,F", [(128, 1100), (256, 2500)])
+def test_fused_gradient_kernel(B, F, monkeypatch):
+    """Bn a multiple of 128: the backward product and the gradient are ONE tensor-core kernel (H^T = c^T N with a replica per
+    TMEM lane, bt_fused_grad_kernel).  Against the two-kernel path (gemm1 + bt_grad) over several steps, and against the fp64
+    oracle's gradient for a few replicas.  F is chosen so that the number of 128-frame blocks is odd (a half-empty tile)."""
+    R, T = 53, 3
+    case = H.make_case(F, R, T, O.UPTAKE_EYE_MSE, extra=(O.PARAMS_L2,), seed=21, prior="random")
+    n = len(case["problem"].slots)
+    fw, fs, lr = _hparams(B, n, 13)
+    fs *= 10.0
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=True)
+    p = case["params"]
+    z0 = np.asarray(p.z, np.float32) * np.float32(F)
+    out = {}
+    for fused in ("1", "0"):  # the fused kernel is opt-in (JAXENT_BG_FUSED=1)
+        monkeypatch.setenv("JAXENT_BG_FUSED", fused)
+        eng = _batched(case, cfg, B)
+        eng.init_state(z0, p.bc, p.bh, fw, fs, lr)
+        eng.step(1)
+        torch.cuda.synchronize()
+        G1 = eng.gradients_all().cpu().numpy().copy()
+        eng.step(7)
+        torch.cuda.synchronize()
+        out[fused] = (G1, eng.gradients_all().cpu().numpy().copy(), [eng.records_at(k) for k in range(9)], eng.weights_all().cpu().numpy().copy())
+        eng.close() if hasattr(eng, "close") else None
+    (G1a, G8a, ra, Wa), (G1b, G8b, rb, Wb) = out["1"], out["0"]
+    scale = np.abs(G1b).max(axis=0, keepdims=True)
+    assert (np.abs(G1a - G1b) / scale).max() < 2e-6  # same arithmetic per element; only the tensor-core summation order differs
+    for k in range(9):
+        for b in range(B):
+            assert ra[k][b].branch == rb[k][b].branch and ra[k][b].complete == 1, (k, b)
+            np.testing.assert_allclose(ra[k][b].total_train, rb[k][b].total_train, rtol=2e-5)
+            np.testing.assert_allclose(ra[k][b].grad_dot, rb[k][b].grad_dot, rtol=1e-4, atol=1e-30)
+    np.testing.assert_allclose(Wa, Wb, atol=1e-4 / F, rtol=1e-3)
+    for b in (0, B // 2 - 1, B // 2, B - 1):  # both replica halves
+        par = O.Params(z0.astype(np.float64), p.frame_mask, p.bc, p.bh, fw[b], fs[b], p.nlf)
+        _, g, _ = O.loss_and_grads(case["problem"], par, np.float64)
+        gerr = np.abs(G1a[:, b] - g.z).max() / np.abs(g.z).max()
+        assert gerr < 2e-5, (b, gerr)
+
+
+def test_config5_size_against_oracle():
+    """BASELINE config 5 at full size -- 256 replicas (32 MaxEnt strengths x 8 ... here: one sweep of 256 strengths) on 100 000
+    frames x 500 residues x 8 time points, three bf16 pieces -- against the NumPy fp64 oracle: three teacher-forced steps of four
+    replicas (both ends and the middle of the sweep): loss of the state, masked gradient of the update, sum of the weights."""
+    F, R, T, B = 100_000, 500, 8, 256
+    case = H.make_case(F, R, T, O.UPTAKE_EYE_MSE, seed=5)
+    n = len(case["problem"].slots)
+    gam = np.logspace(0, 3, B).astype(np.float32)
+    fw = np.stack([gam / (gam + 1), 1 / (gam + 1)], 1).astype(np.float32)
+    fs = np.full((B, n), 1000.0, np.float32)
+    lr = np.full(B, 1.0, np.float32)
+    cfg = O.OptConfig(learning_rate=1.0, clip_value=None)
+    eng = _batched(case, cfg, B)
+    p = case["params"]
+    z0 = np.asarray(p.z, np.float32) * np.float32(F)
+    eng.init_state(z0, p.bc, p.bh, fw, fs, lr)
+    which = (0, 85, 170, 255)
+    errs = []
+    for k in range(3):
+        torch.cuda.synchronize()
+        zk = eng.z[:, list(which)].cpu().numpy().astype(np.float64)
+        eng.step(1)
+        torch.cuda.synchronize()
+        recs = eng.records_at(k)
+        G = eng.gradients_all()[:, list(which)].cpu().numpy()
+        for j, b in enumerate(which):
+            par = O.Params(zk[:, j], p.frame_mask, p.bc, p.bh, fw[b], fs[b], p.nlf)
+            losses, g, _ = O.loss_and_grads(case["problem"], par, np.float64)
+            np.testing.assert_allclose(recs[b].train[0], losses.train_losses[0], rtol=1e-5)
+            # The MaxEnt value is ~0 here (weights within a few steps of the uniform prior) and is multiplied by
+            # forward_model_scaling = 1000.  The batched path forms sum_f p_f log w_f from the logits (no logarithm per
+            # (frame, replica)): log w_f = z_f - lse - log S, exact up to the common relative error of the fp32 exponentials in
+            # S (a few 1e-8 when all logits are equal).  So: absolute 1e-7 on the KL value, i.e. 1e-7 * fw * fs on the total.
+            np.testing.assert_allclose(recs[b].train[1], losses.train_losses[1], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(recs[b].total_train, losses.total_train_loss, rtol=1e-5, atol=1e-7 * float(fw[b, 1] * fs[b, 1]))
+            gerr = np.abs(G[:, j] - g.z).max() / np.abs(g.z).max()
+            # three-piece bf16 split of c (6e-6 of the column scale, test_gpu_bgemm.py) on CENTRED features: without the centring
+            # the fp32 column sums H_f ~ 1e4 lose the cancellation H_f - hbar and this error is 3e-4 at R = 500 (measured)
+            errs.append((k, b, float(abs(recs[b].train[0] / losses.train_losses[0] - 1)), float(gerr)))
+            assert gerr < 2e-5, (k, b, gerr)
+    print("config-5 size: (step, replica, data-loss rel err, gradient rel err)", errs)
+    W = eng.weights_all()
+    assert float((W.double().sum(0) - 1.0).abs().max()) < 1e-5
