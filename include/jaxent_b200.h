@@ -277,6 +277,14 @@ int jaxent_bv_export_state(JaxentPlan* plan, float* z, float* m, float* v, float
 int jaxent_bv_contacts(const float* coords, int64_t F, int32_t A, const int32_t* target_idx, const int32_t* target_resid, int32_t Nt,
                        const int32_t* contact_idx, const int32_t* contact_resid, int32_t Nc, int32_t ignore_lo, int32_t ignore_hi,
                        float radius, int32_t use_switch, const float* box, float* out, jaxent_stream_t stream);
+/* The same with a general (triclinic) cell -- the reference passes `box=universe.dimensions` to MDAnalysis' distance_array
+ * (contacts.py:210-215), which applies the minimum image in whatever cell the trajectory has.  box_stride = 3: box is
+ * float[F][3] orthorhombic lengths (as above); box_stride = 6: float[F][6] = {a_x, b_x, b_y, c_x, c_y, c_z}, the non-zero
+ * elements of the lower-triangular cell matrix (MDAnalysis triclinic_vectors).  radius must be below half the smallest
+ * diagonal element (one image at most within the radius). */
+int jaxent_bv_contacts_cell(const float* coords, int64_t F, int32_t A, const int32_t* target_idx, const int32_t* target_resid, int32_t Nt,
+                            const int32_t* contact_idx, const int32_t* contact_resid, int32_t Nc, int32_t ignore_lo, int32_t ignore_hi,
+                            float radius, int32_t use_switch, const float* box, int32_t box_stride, float* out, jaxent_stream_t stream);
 
 /* ---- per-frame forward pass (Simulation.predict, models/core.py:181-208): the forward pass on the un-averaged features.
  * packed: fp32 tile layout (jaxent_bv_pack_features_f32).  T = 0: out = log_Pf float[R][F] (BV_ForwardPass);

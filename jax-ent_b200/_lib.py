@@ -165,6 +165,7 @@ SYMBOLS = {
     "jaxent_bv_plan_set_exchange": (C.c_int, [_VP, _I32, _I32, C.POINTER(_VP)]),
     "jaxent_bv_exchange_error": (C.c_int, [_VP, _VP, _VP]),
     "jaxent_bv_contacts": (C.c_int, [_VP, _I64, _I32, _VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _F, _I32, _VP, _VP, _VP]),
+    "jaxent_bv_contacts_cell": (C.c_int, [_VP, _I64, _I32, _VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _F, _I32, _VP, _I32, _VP, _VP]),
     "jaxent_bv_predict_frames": (C.c_int, [_VP, _I32, _I64, _I32, _VP, _VP, _F, _F, _VP, _VP]),
     "jaxent_bg_features_bytes": (_SZ, [_I32, _I64]),
     "jaxent_bg_pack_features": (C.c_int, [_VP, _VP, _I32, _I64, _I64, _VP, _VP, _VP]),

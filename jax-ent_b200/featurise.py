@@ -24,11 +24,25 @@ def _i32(x, dev):
     return torch.as_tensor(np.asarray(x), dtype=torch.int32).to(dev).contiguous()
 
 
+def _cell_rows(dimensions: np.ndarray) -> np.ndarray:
+    """(n, 6) [lx, ly, lz, alpha, beta, gamma] in degrees -> (n, 6) [a_x, b_x, b_y, c_x, c_y, c_z], the non-zero elements of the
+    lower-triangular cell matrix (rows a, b, c) in MDAnalysis' convention for `universe.dimensions`."""
+    lx, ly, lz = dimensions[:, 0], dimensions[:, 1], dimensions[:, 2]
+    ca, cb, cg = (np.cos(np.deg2rad(dimensions[:, k])) for k in (3, 4, 5))
+    sg = np.sin(np.deg2rad(dimensions[:, 5]))
+    cx, cy = lz * cb, lz * (ca - cb * cg) / sg
+    cz2 = lz * lz - cx * cx - cy * cy
+    if np.any(cz2 <= 0) or np.any(sg <= 0):
+        raise ValueError("box angles do not describe a cell")
+    return np.stack([lx, ly * cg, ly * sg, cx, cy, np.sqrt(cz2)], axis=1)
+
+
 def calc_BV_contacts(coords, target_idx: Sequence[int], target_resid: Sequence[int], contact_idx: Sequence[int],
                      contact_resid: Sequence[int], radius: float, residue_ignore=(-2, 2), switch: bool = False, box=None,
                      device: Optional[str] = None) -> torch.Tensor:
     """coords: (n_frames, n_atoms, 3) float32 positions; returns (n_targets, n_frames) float32 contacts on the device.
-    Same arguments as the reference function, with the AtomGroups replaced by (atom index, residue id) lists."""
+    Same arguments as the reference function, with the AtomGroups replaced by (atom index, residue id) lists.  box: None,
+    orthorhombic lengths (3,) / (n_frames, 3), or MDAnalysis `dimensions` (6,) / (n_frames, 6) for a general (triclinic) cell."""
     if not torch.cuda.is_available():
         raise RuntimeError("jaxent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     lib = L.load()
@@ -44,19 +58,31 @@ def calc_BV_contacts(coords, target_idx: Sequence[int], target_resid: Sequence[i
         raise ValueError("empty atom selection")
     if int(ti.max()) >= A or int(ci.max()) >= A or int(ti.min()) < 0 or int(ci.min()) < 0:
         raise ValueError("atom index outside the coordinate array")
-    bx = None
+    bx, stride = None, 3
     if box is not None:
-        bx = torch.as_tensor(np.asarray(box, np.float32)).to(dev).reshape(-1, 3)
+        b = np.asarray(box, np.float64)
+        if b.shape[-1] == 6:  # MDAnalysis `dimensions`: [lx, ly, lz, alpha, beta, gamma] (what the reference passes, contacts.py:210-215)
+            b = b.reshape(-1, 6)
+            if np.allclose(b[:, 3:], 90.0):
+                b = b[:, :3]
+            else:
+                b = _cell_rows(b)
+                stride = 6
+                if float(radius) >= 0.5 * float(b[:, [0, 2, 5]].min()):
+                    raise ValueError("radius must be below half the smallest diagonal element of the triclinic cell")
+        else:
+            b = b.reshape(-1, 3)
+        bx = torch.as_tensor(b.astype(np.float32)).to(dev)
         if bx.shape[0] == 1:
-            bx = bx.expand(F, 3)
+            bx = bx.expand(F, stride)
         bx = bx.contiguous()
         if bx.shape[0] != F:
-            raise ValueError("box must be (3,) or (n_frames, 3) orthorhombic lengths")
+            raise ValueError("box must be (3,) / (n_frames, 3) orthorhombic lengths or (6,) / (n_frames, 6) MDAnalysis dimensions")
     out = torch.empty((ti.numel(), F), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        L.check(lib.jaxent_bv_contacts(xyz.data_ptr(), F, A, ti.data_ptr(), tr.data_ptr(), ti.numel(), ci.data_ptr(), cr.data_ptr(),
-                                       ci.numel(), int(residue_ignore[0]), int(residue_ignore[1]), float(radius), int(bool(switch)),
-                                       bx.data_ptr() if bx is not None else None, out.data_ptr(), _stream_ptr()))
+        L.check(lib.jaxent_bv_contacts_cell(xyz.data_ptr(), F, A, ti.data_ptr(), tr.data_ptr(), ti.numel(), ci.data_ptr(), cr.data_ptr(),
+                                            ci.numel(), int(residue_ignore[0]), int(residue_ignore[1]), float(radius), int(bool(switch)),
+                                            bx.data_ptr() if bx is not None else None, stride, out.data_ptr(), _stream_ptr()))
     return out
 
 

@@ -259,6 +259,8 @@ def test_contacts_and_predict_argument_validation():
     assert call(radius=0.0) == L.E_INVALID
     assert call(lo=3, hi=2) == L.E_INVALID
     assert "bv_contacts" in lib.jaxent_last_error().decode()
+    assert lib.jaxent_bv_contacts_cell(0x1000, 4, 10, 0x2000, 0x3000, 2, 0x4000, 0x5000, 5, -2, 2, 6.5, 0, 0x7000, 4, 0x6000, None) == L.E_INVALID
+    assert "box_stride" in lib.jaxent_last_error().decode()
     assert lib.jaxent_bv_predict_frames(None, 4, 8, 0, None, None, 0.35, 2.0, 0x1000, None) == L.E_INVALID
     assert lib.jaxent_bv_predict_frames(0x1000, 4, 8, 3, None, None, 0.35, 2.0, 0x2000, None) == L.E_INVALID  # uptake needs k_ints / time points
     assert lib.jaxent_bv_predict_frames(0x1004, 4, 8, 0, None, None, 0.35, 2.0, 0x2000, None) == L.E_INVALID  # alignment

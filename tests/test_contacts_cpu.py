@@ -43,3 +43,30 @@ def test_minimum_image():
     a = CO.calc_bv_contacts(xyz, [0], [0], [1], [10], radius=1.0)
     b = CO.calc_bv_contacts(xyz, [0], [0], [1], [10], radius=1.0, box=[10.0, 10.0, 10.0])
     assert a[0, 0] == 0 and b[0, 0] == 1
+
+
+def test_triclinic_cell_matrix_and_minimum_image():
+    # MDAnalysis' convention: a along x, b in the xy plane; a cubic cell gives the diagonal matrix
+    np.testing.assert_allclose(CO.triclinic_vectors([10, 10, 10, 90, 90, 90]), np.diag([10.0, 10.0, 10.0]), atol=1e-12)
+    B = CO.triclinic_vectors([10, 12, 9, 70, 80, 65])
+    np.testing.assert_allclose(np.linalg.norm(B, axis=1), [10, 12, 9], rtol=1e-12)
+    cosang = lambda u, v: u @ v / np.linalg.norm(u) / np.linalg.norm(v)
+    np.testing.assert_allclose(np.rad2deg(np.arccos([cosang(B[1], B[2]), cosang(B[0], B[2]), cosang(B[0], B[1])])), [70, 80, 65], rtol=1e-12)
+    # a separation of (b + c) + (0.3, 0.2, 0.1) is 0.374 long through the periodic images
+    d = (B[1] + B[2] + np.array([0.3, 0.2, 0.1]))[None, :]
+    np.testing.assert_allclose(CO.minimum_image_triclinic(d, B), [[0.3, 0.2, 0.1]], atol=1e-12)
+    xyz = np.zeros((1, 2, 3), np.float32)
+    xyz[0, 1] = d[0]
+    a = CO.calc_bv_contacts(xyz, [0], [0], [1], [10], radius=1.0)
+    b = CO.calc_bv_contacts(xyz, [0], [0], [1], [10], radius=1.0, box=[10, 12, 9, 70, 80, 65])
+    assert a[0, 0] == 0 and b[0, 0] == 1
+    # brute force over a wide image range agrees with the 27-image search
+    rng = np.random.default_rng(0)
+    dd = rng.uniform(-30, 30, size=(200, 3))
+    best = None
+    for i in range(-5, 6):
+        for j in range(-5, 6):
+            for k in range(-5, 6):
+                r2 = ((dd + i * B[0] + j * B[1] + k * B[2]) ** 2).sum(-1)
+                best = r2 if best is None else np.minimum(best, r2)
+    np.testing.assert_allclose((CO.minimum_image_triclinic(dd, B) ** 2).sum(-1), best, rtol=1e-12)

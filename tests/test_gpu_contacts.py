@@ -39,6 +39,33 @@ def test_contacts_match_oracle(F, n_res, switch, box):
         assert ref.max() > 0
 
 
+@pytest.mark.parametrize("dims,switch", [((40.0, 44.0, 36.0, 70.0, 80.0, 65.0), False), ((30.0, 30.0, 30.0, 60.0, 60.0, 90.0), False),
+                                         ((38.0, 41.0, 35.0, 100.0, 95.0, 110.0), True), ((33.0, 35.0, 31.0, 90.0, 90.0, 90.0), False)])
+def test_contacts_triclinic_cell(dims, switch):
+    """general cells (`box=universe.dimensions`, contacts.py:210-215): truncated-octahedron-like, rhombic-dodecahedron-like
+    and obtuse angles; the chain spans several cell lengths so most pairs are seen through an image."""
+    from jaxent_b200.featurise import calc_BV_contacts
+
+    F, n_res = 4, 120
+    xyz, n_sel, h_sel, heavy, oxy = _protein_like(F, n_res, 11)
+    per_frame = np.tile(np.asarray(dims, np.float64), (F, 1))
+    per_frame[:, :3] *= (1.0 + 0.01 * np.arange(F))[:, None]  # NPT-like: the cell changes from frame to frame
+    for (tgt, con, radius) in ((n_sel, heavy, 6.5), (h_sel, oxy, 2.4)):
+        ref = CO.calc_bv_contacts(xyz, tgt[0], tgt[1], con[0], con[1], radius, switch=switch, box=per_frame)
+        free = CO.calc_bv_contacts(xyz, tgt[0], tgt[1], con[0], con[1], radius, switch=switch)
+        got = calc_BV_contacts(xyz, tgt[0], tgt[1], con[0], con[1], radius, switch=switch, box=per_frame, device="cuda:0").cpu().numpy()
+        if switch:
+            np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-5)
+        else:
+            # the cell is fp32 on the device, fp64 in the oracle: a pair within 1e-5 A of the cut-off may fall either way
+            assert np.abs(got - ref).max() <= 1 and (got != ref).mean() < 2e-3
+        if radius > 3:
+            assert (ref != free).any()  # the images matter in this case
+    if dims[3:] != (90.0, 90.0, 90.0):  # orthorhombic `dimensions` take the per-axis path, which has no radius limit
+        with pytest.raises(ValueError, match="half"):
+            calc_BV_contacts(xyz, n_sel[0], n_sel[1], heavy[0], heavy[1], 20.0, box=dims, device="cuda:0")
+
+
 def test_featurise_feeds_the_optimise_path():
     from jaxent_b200.featurise import featurise_BV
     from jaxent_b200.batch_engine import pack_gemm_features
