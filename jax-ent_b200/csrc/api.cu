@@ -25,14 +25,13 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
   size_t off_w, off_kappa, off_kappa_lo, off_cc, off_ch, off_ck, off_logpf, off_uptake, off_avg, off_pfG;
-  size_t off_cta_scal, off_fx, off_nmax, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_ticket, off_records;
+  size_t off_cta_scal, off_fx, off_nmax, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_records;
   size_t off_cl_scratch;
   size_t off_blob[JAXENT_MAX_SLOTS];
   int blob_words[JAXENT_MAX_SLOTS];
   size_t total;
 };
 
-constexpr int MAX_PASS_CTAS = 2 * 160;
 constexpr int MAX_TAIL_CTAS = 176;
 
 static Layout make_layout(const JaxentBvProblem* pb) {
@@ -66,16 +65,15 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_pfG = take((size_t)(T > 0 ? T : 1) * R * 4);
   const int part_n = pass_part_n(R, T, pb->uptake);
   L.off_cta_scal = take((size_t)MAX_PASS_CTAS * 4 * sizeof(double));
-  L.off_fx = take((size_t)FX_REP * (part_n - 4) * sizeof(unsigned long long));
+  L.off_fx = take((size_t)2 * FX_REP * (part_n - 4) * sizeof(unsigned long long));  // two parities, see PassArgs
   L.off_nmax = take(sizeof(float));
   L.off_xchg = take(xchg_bytes(part_n, 1));  // single-rank exchange buffer (red / kl inbox of world = 1)
   L.off_klpart = take((size_t)MAX_TAIL_CTAS * KL_N * sizeof(double));
   L.off_ctl = take(2 * sizeof(Ctl));
   L.off_epoch = take(sizeof(unsigned));
   L.off_counter = take(sizeof(unsigned));
-  L.off_ticket = take(sizeof(unsigned));
   L.off_records = take((size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord));
-  L.off_cl_scratch = take(64 * sizeof(double));
+  L.off_cl_scratch = take((64 + 4 * (size_t)MAX_PASS_CTAS) * sizeof(double));  // + per-CTA pass timestamps (JX_PROFILE builds)
   for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
     L.off_blob[i] = 0;
     L.blob_words[i] = 0;
@@ -90,7 +88,7 @@ static Layout make_layout(const JaxentBvProblem* pb) {
 }
 
 __global__ void state_init_kernel(const float* __restrict__ z0, long long F, StateSets st, Ctl* ctl, Ctl init,
-                                  unsigned* epoch, unsigned* counter, unsigned* ticket, unsigned long long* xchg_local,
+                                  unsigned* epoch, unsigned* counter, unsigned long long* xchg_local,
                                   long long xchg_words, JaxentLossRecord* records, unsigned long long* fx, long long fx_words,
                                   unsigned* nmax_bits, unsigned nmax_init) {
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,7 +106,6 @@ __global__ void state_init_kernel(const float* __restrict__ z0, long long F, Sta
     ctl[1] = init;
     *epoch = 0u;
     *counter = 0u;
-    *ticket = 0u;
     *nmax_bits = nmax_init;
   }
   for (long long i = i0; i < fx_words; i += stride) fx[i] = 0ull;
@@ -176,6 +173,7 @@ struct JaxentPlan {
   unsigned char* ws;
   jx::StateSets st;
   int pass_threads, rpt, pass_ctas, stages, tail_ctas, p_max_tr, p_max_va, nnz_max_tr, nnz_max_va;
+  int sums_folded;  // jaxent_bv_reduce ran after the last pass: the tail reads JAXENT_BUF_RED instead of completing the sums itself
   jx::Xchg x;
   uint32_t tile_bytes, stage_stride, subtile_bytes;
   int sub_tiles;
@@ -476,7 +474,7 @@ extern "C" int jaxent_bv_plan_buffer(const JaxentPlan* p, int32_t which, void** 
     case JAXENT_BUF_LOGPF: *ptr = p->ws + p->lay.off_logpf; *bytes = (size_t)R * 4; break;
     case JAXENT_BUF_UPTAKE: *ptr = p->ws + p->lay.off_uptake; *bytes = (size_t)T * R * 4; break;
     case JAXENT_BUF_AVG: *ptr = p->ws + p->lay.off_avg; *bytes = (size_t)2 * R * 4; break;
-    case 8: *ptr = p->ws + p->lay.off_cl_scratch; *bytes = 64 * 8; break;  // debug timestamps (JX_TAIL_PROFILE builds)
+    case 8: *ptr = p->ws + p->lay.off_cl_scratch; *bytes = (64 + 4 * (size_t)MAX_PASS_CTAS) * 8; break;  // debug timestamps (JX_PROFILE builds)
     default: set_error("plan_buffer: unknown buffer id %d", which); return JAXENT_E_INVALID;
   }
   return JAXENT_OK;
@@ -510,10 +508,10 @@ extern "C" int jaxent_bv_state_init(JaxentPlan* p, const float* z0, float zmax, 
   Ctl* ctl = reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl);
   state_init_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(
       z0, p->prob.F, p->st, ctl, c, reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch),
-      reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter), reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket),
+      reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter),
       reinterpret_cast<unsigned long long*>(p->x.local), (long long)(xchg_bytes(p->x.part_n, p->x.world) / 8),
       reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records), reinterpret_cast<unsigned long long*>(p->ws + p->lay.off_fx),
-      (long long)FX_REP * (p->x.part_n - 4), reinterpret_cast<unsigned*>(p->ws + p->lay.off_nmax),
+      (long long)2 * FX_REP * (p->x.part_n - 4), reinterpret_cast<unsigned*>(p->ws + p->lay.off_nmax),
       p->prob.feature_format == 1 ? 0x437f0000u /* 255.0f: u8 features */ : 0u);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("state_init launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
@@ -576,7 +574,6 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.fx = reinterpret_cast<unsigned long long*>(p->ws + p->lay.off_fx);
   a.cta_scal = reinterpret_cast<double*>(p->ws + p->lay.off_cta_scal);
   a.nmax = reinterpret_cast<const float*>(p->ws + p->lay.off_nmax);
-  a.ticket = reinterpret_cast<unsigned*>(p->ws + p->lay.off_ticket);
   a.x = p->x;
   a.ctl = reinterpret_cast<const Ctl*>(p->ws + p->lay.off_ctl);
   a.epoch = reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch);
@@ -588,18 +585,25 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.eps = (float)p->cfg.eps;
   a.clip = p->cfg.clip_value;
   a.dbg = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
+  p->sums_folded = 0;
   return launch_pass(a, p->pass_threads + 32, p->rpt, p->pass_ctas, p->pass_smem, (cudaStream_t)stream);
 }
 
-// The fixed-order reduction of the per-CTA partials used to be a kernel of its own; the pass now finishes its sums itself
-// (fixed-point accumulators folded by its last CTA, see pass_epilogue in bv_pass.cu).  Kept as a no-op for callers of the
-// three-phase ABI: JAXENT_BUF_RED is complete when the pass has finished.
-extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t) { return check_ready(p, "reduce"); }
-
-extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
-  int rc = check_ready(p, "tail");
+// The pass leaves raw sums (fixed-point accumulators + per-CTA scalars); the tail kernel normally completes them itself.
+// A caller that all-reduces JAXENT_BUF_RED between the phases (NCCL instead of the fused peer-memory exchange) calls
+// jaxent_bv_reduce after the pass: it writes the completed sums to JAXENT_BUF_RED and the tail then reads them from there.
+static void fill_tail_args(JaxentPlan* p, TailArgs& a);
+extern "C" int jaxent_bv_reduce(JaxentPlan* p, jaxent_stream_t stream) {
+  int rc = check_ready(p, "reduce");
   if (rc) return rc;
+  if (p->x.world != 1) { set_error("reduce: the fused exchange completes the sums in the tail kernel"); return JAXENT_E_INVALID; }
   TailArgs a;
+  fill_tail_args(p, a);
+  p->sums_folded = 1;
+  return launch_reduce_fold(a, (cudaStream_t)stream);
+}
+
+static void fill_tail_args(JaxentPlan* p, TailArgs& a) {
   memset(&a, 0, sizeof(a));
   a.prob = p->prob;
   a.trk = p->trk;
@@ -608,6 +612,12 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.x = p->x;
   a.ctl = reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl);
   a.counter = reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter);
+  a.epoch = reinterpret_cast<unsigned*>(p->ws + p->lay.off_epoch);
+  a.fx = reinterpret_cast<unsigned long long*>(p->ws + p->lay.off_fx);
+  a.cta_scal = reinterpret_cast<const double*>(p->ws + p->lay.off_cta_scal);
+  a.nmax = reinterpret_cast<const float*>(p->ws + p->lay.off_nmax);
+  a.pass_ctas = p->pass_ctas;
+  a.fold_here = p->sums_folded ? 0 : 1;
   a.w = reinterpret_cast<float*>(p->ws + p->lay.off_w);
   a.kappa = reinterpret_cast<float*>(p->ws + p->lay.off_kappa);
   a.kappa_lo = reinterpret_cast<float*>(p->ws + p->lay.off_kappa_lo);
@@ -635,6 +645,13 @@ extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
   a.nnz_max_tr = p->nnz_max_tr;
   a.nnz_max_va = p->nnz_max_va;
   a.eps_kl = (float)(1e-10 / (double)p->prob.F_total);
+}
+
+extern "C" int jaxent_bv_tail(JaxentPlan* p, jaxent_stream_t stream) {
+  int rc = check_ready(p, "tail");
+  if (rc) return rc;
+  TailArgs a;
+  fill_tail_args(p, a);
   return launch_tail(a, p->tail_ctas, p->tail_smem, (cudaStream_t)stream);
 }
 

@@ -312,7 +312,7 @@ __device__ __forceinline__ void phase_b(const TileRegs<RPT>& d, const float* s_e
 // the step those sums belong to.
 // (plain pointers instead of the Xchg struct: passing a kernel-parameter struct by reference forces a local-memory copy)
 static __device__ __noinline__ double gather_hbar(const unsigned char* kl_words, int world, unsigned char* err_word, unsigned ep,
-                                                 const Ctl* __restrict__ ctl, JaxentLossRecord* records, int lane, bool finish) {
+                                                 const Ctl* ctl, JaxentLossRecord* records, int lane, bool finish) {
   double v = 0.0;
   if (lane < world * KL_N) {
     if (world == 1) v = __ldcg(reinterpret_cast<const double*>(kl_words) + lane);
@@ -329,86 +329,18 @@ static __device__ __noinline__ double gather_hbar(const unsigned char* kl_words,
   if (finish && lane == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
   return ctl->hbar_data + kl[0];
 }
-__device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, const Ctl* __restrict__ ctl, int lane, bool finish) {
+__device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, const Ctl* ctl, int lane, bool finish) {
   const unsigned char* kl_words = a.x.local + (a.x.world == 1 ? xchg_plain_kl_off(a.x) : xchg_kl_off(a.x, (int)(ep & 1u), 0));
   return gather_hbar(kl_words, a.x.world, a.x.local + xchg_err_off(a.x), ep, ctl, a.records, lane, finish);
 }
 
 
 // ------------------------------------------------------------------------------------------ fixed-point row sums
-// |row sum| <= (sum of the un-normalised weights) * max |feature|.  In a step the weights are exp(z' - lse) with
-// sum exp(z - lse) = 1 and |z' - z| <= (1 - b1) / sqrt(1 - b2) < 3.2 for optax adam (the update does not depend on the
-// learning rate, which pre-scales the gradient): sum e' < e^3.2 < 64.  In the init pass e = exp(z0 - max z0) <= 1 per frame.
-// scale = 2^(61 - e) with bound < 2^e, so a sum stays below 2^61 and carries >= 2^-61 of the bound as resolution
-// (the fp32 tile sums that enter are good to 2^-24).
-__device__ __forceinline__ double fx_scale(float nmax, int mode, long long F) {
-  const double bound = (mode ? 64.0 : (double)F) * (double)fmaxf(nmax, 1e-30f);
-  const int e = ((__double2hiint(bound) >> 20) & 0x7ff) - 1022;  // bound < 2^e
-  return __hiloint2double((61 - e + 1023) << 20, 0);
-}
-__device__ __forceinline__ void fx_add(unsigned long long* dst, float v, double scale) {
-  atomicAdd(dst, (unsigned long long)__double2ll_rn((double)v * scale));  // RED.ADD.64: fire and forget
-}
-
-// End of the pass: every CTA leaves its three scalars in cta_scal and takes a ticket; the last one to arrive folds the
-// replicas of the fixed-point accumulators (any order gives the same integer), converts them to doubles, sums the per-CTA
-// scalars in CTA order, publishes everything (red_publish: plain store on one rank, stamped 16-byte stores into every
-// rank's inbox when frame-sharded), clears the accumulators for the next pass and advances the epoch.  This replaces the
-// separate reduce kernel (one launch boundary and ~5 us of every step).
-__device__ __forceinline__ void pass_epilogue(const PassArgs& a, float nmax_bound, int* s_last) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const unsigned ep = __ldcg(a.epoch);  // before the ticket: the last CTA advances it (nothing is kept live across the sweep for this)
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) *s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!*s_last) return;
-  __threadfence();
-  if (tid == 0) JPROF(a.dbg, 44);
-  const unsigned nep = ep + 1u;
-  const int n_rows = a.part_n - 4;
-  const float nmax = *a.nmax;
-  const double scale = fx_scale(nmax_bound > 0.f ? nmax_bound : nmax, a.mode, a.F);
-  // non-finite features cannot be carried by integers: hand the tail NaN sums, the loss becomes non-finite (reference: data, not an error)
-  const double inv = (nmax <= 3.0e38f) ? 1.0 / scale : __longlong_as_double(0x7ff8000000000000ll);
-  constexpr int CPT = 4;  // columns per thread and trip: CPT * FX_REP loads in flight (one trip covers 4R columns at R <= 544)
-  for (int c0 = tid; c0 < n_rows; c0 += CPT * nt) {
-    unsigned long long v[CPT][FX_REP];
-#pragma unroll
-    for (int k = 0; k < CPT; ++k)
-#pragma unroll
-      for (int r = 0; r < FX_REP; ++r) v[k][r] = (c0 + k * nt < n_rows) ? __ldcg(a.fx + (size_t)r * n_rows + c0 + k * nt) : 0ull;
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-      const int col = c0 + k * nt;
-      if (col < n_rows) {
-        long long t = 0;
-#pragma unroll
-        for (int r = 0; r < FX_REP; ++r) {
-          t += (long long)v[k][r];
-          a.fx[(size_t)r * n_rows + col] = 0ull;
-        }
-        red_publish(a.x, nep, col, (double)t * inv);
-      }
-    }
-  }
-  {  // sum e' (A), sum e' (B), grad-dot over the CTAs in fixed order, one warp each (a CTA has at least two warps)
-    const int lane = tid & 31;
-    for (int j = tid >> 5; j < 3; j += nt >> 5) {
-      double t = 0.0;
-      for (int c = lane; c < (int)gridDim.x; c += 32) t += __ldcg(a.cta_scal + (size_t)c * 4 + j);
-      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) red_publish(a.x, nep, n_rows + j, t);
-    }
-    if (tid == 0) red_publish(a.x, nep, n_rows + 3, 0.0);
-  }
-  __syncthreads();
-  if (tid == 0) {  // the kernel boundary orders these stores for the tail; peers never read the epoch
-    *a.ticket = 0u;
-    *a.epoch = nep;
-    JPROF(a.dbg, 46);
-  }
-}
+// fx_scale() / fx_add() live in jx_internal.cuh.  The pass only ACCUMULATES: every CTA adds its tile sums into the fixed-point
+// accumulators of this epoch's parity and leaves its three scalars (sum e' of both branches, grad-dot) in cta_scal.  The
+// sums are completed after the kernel boundary -- by the tail kernel (fx_fold_col / fold_scal: all CTAs in parallel, stamped
+// peer stores spread over several CTAs when frame-sharded) or, for the three-phase ABI, by jaxent_bv_reduce.  There is no
+// ticket, no last-CTA serial section and no epoch store at the end of the pass (the tail advances the epoch).
 
 // ------------------------------------------------------------------------------------------ per-frame uptake mode
 // ForwardPass.average_first = False (reference models/core.py:302-304, BV_uptake_ForwardPass models/HDX/forward.py:57-74):
@@ -443,7 +375,7 @@ __device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
 // four per-frame partials (one 16-byte store) and the Adam warp, which has time to spare, sums them.
 template <int TM>
 __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ring, uint64_t* bars, float4* s_rows, const float* s_e,
-                                             float4* s_tab, int n, int mode, float bc, float bh, int NTc, int nbar) {
+                                             float4* s_tab, int n, int mode, float bc, float bh, int NTc, int nbar, unsigned fx_par) {
   constexpr int TP = TM / 2;
   const int R = a.R, T = a.pf_T;
   const int tid = threadIdx.x;
@@ -452,14 +384,14 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
   const uint32_t rowoff = (uint32_t)rc * 16u, rstride = (uint32_t)R * 16u;
   float4* my_tab = s_tab + tid;  // [TP][NTc] {kt(2 tp), kt(2 tp + 1), G(2 tp), G(2 tp + 1)}
   // centred: the tail's k_r = fl(sum_t G[t,r] (1 - <u>[t,r])) replaces sum_t G[t,r], so the row partial is sum_t G (u_f - <u>)
-  const float Gsum = (ok && mode) ? a.ck[rc] : 0.f;
+  const float Gsum = (ok && mode) ? __ldcg(a.ck + rc) : 0.f;
   {
     const float kr = -1.4426950408889634f * a.pf_k[rc];
 #pragma unroll
     for (int tp = 0; tp < TP; ++tp) {
       const int t0_ = 2 * tp, t1_ = 2 * tp + 1;
-      const float2 g2 = make_float2((ok && mode && t0_ < T) ? a.pf_G[(size_t)t0_ * R + rc] : 0.f,
-                                    (ok && mode && t1_ < T) ? a.pf_G[(size_t)t1_ * R + rc] : 0.f);
+      const float2 g2 = make_float2((ok && mode && t0_ < T) ? __ldcg(a.pf_G + (size_t)t0_ * R + rc) : 0.f,
+                                    (ok && mode && t1_ < T) ? __ldcg(a.pf_G + (size_t)t1_ * R + rc) : 0.f);
       my_tab[tp * NTc] = make_float4(t0_ < T ? kr * a.pf_tp[t0_] : 0.f, t1_ < T ? kr * a.pf_tp[t1_] : 0.f, g2.x, g2.y);  // kt = -log2(e) k_r tau_t
     }
   }
@@ -534,7 +466,7 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
   auto flush = [&]() {
     // the accumulated products are e' * exp(-k tau / PF) with the second factor in [0, 1]: bound = the sum of the weights
     const double fxs = fx_scale(1.f, mode, a.F);
-    unsigned long long* fxp = a.fx + (size_t)(blockIdx.x % FX_REP) * (a.part_n - 4);
+    unsigned long long* fxp = a.fx + (size_t)(fx_par * FX_REP + blockIdx.x % FX_REP) * (a.part_n - 4);
     if (ok) {
 #pragma unroll
       for (int br = 0; br < 2; ++br)
@@ -594,7 +526,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
   const long long t0 = s0 * S;          // first tile
   const int n = ns * S;                 // tiles of this CTA (frames past F are zero padding)
   const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
-  __shared__ int s_last;
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -612,11 +543,13 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     }
   }
   if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 40);
+  if (tid == blockDim.x - 32) JPROF(a.dbg, 64 + 4 * blockIdx.x);
   pdl_wait();               // everything the tail kernel wrote (ctl, cc/ch, w, kappa, klsum) is visible from here on
   pdl_launch_dependents();  // lets the tail kernel's launch and constant staging overlap this kernel
-  if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 41);
-
   const unsigned ep = *a.epoch;
+  if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 41);
+  if (tid == blockDim.x - 32) JPROF(a.dbg, 64 + 4 * blockIdx.x + 1);
+
   if (a.ctl[ep & 1u].trk_stop) {
     // the on-device loop has ended: drain the prefetched tiles and leave everything untouched
     if (is_adam && lane == 0) {
@@ -628,7 +561,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
 
   if (is_adam) {
     // ================================================================== Adam warp
-    const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
+    const Ctl* ctl = a.ctl + (ep & 1u);
     // MaxEnt sums of the tail that preceded this pass (all ranks; spins on the peers' words when frame-sharded)
     // hbar as an unevaluated fp32 pair: h_f - hbar is evaluated as (H + (k_hi - hb_hi)) + (k_lo - hb_lo), which keeps the
     // O(lambda) cancellation between kappa_f and hbar exact (Sterbenz) without fp64 instructions or conversions on this warp
@@ -668,9 +601,9 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
         m_ = min_[f];
         v_ = vin[f];
         if (mode) {
-          w_ = a.w[f];
-          k_ = a.kappa[f];
-          kl_ = a.kappa_lo[f];
+          w_ = __ldcg(a.w + f);
+          k_ = __ldcg(a.kappa + f);
+          kl_ = __ldcg(a.kappa_lo + f);
           gp_ = gprev[f];
         }
       }
@@ -745,7 +678,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
       sc[1] = sumB;
       sc[2] = gdot;
     }
-    pass_epilogue(a, 0.f, &s_last);
     return;
   }
 
@@ -759,9 +691,9 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     const bool ok = row[i] < R;
     const int rc = ok ? row[i] : R - 1;  // clamp: finite data, zero coefficients, result never stored
     rowoff[i] = (uint32_t)rc * (FMT == 0 ? 16u : 8u);
-    ccr[i] = (ok && mode) ? a.cc[rc] : 0.f;
-    chr[i] = (ok && mode) ? a.ch[rc] : 0.f;
-    nkr[i] = (ok && mode) ? -a.ck[rc] : 0.f;
+    ccr[i] = (ok && mode) ? __ldcg(a.cc + rc) : 0.f;
+    chr[i] = (ok && mode) ? __ldcg(a.ch + rc) : 0.f;
+    nkr[i] = (ok && mode) ? -__ldcg(a.ck + rc) : 0.f;
   }
   const uint32_t rstride = (uint32_t)R * (FMT == 0 ? 16u : 8u);
   const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -771,7 +703,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
 
   auto flush = [&]() {  // rare (every FLUSH_TILES tiles): scale and destination are re-derived here rather than kept in registers
     const double fxs = fx_scale(*a.nmax, mode, a.F);
-    unsigned long long* fxp = a.fx + (size_t)(blockIdx.x % FX_REP) * (a.part_n - 4);
+    unsigned long long* fxp = a.fx + (size_t)((ep & 1u) * FX_REP + blockIdx.x % FX_REP) * (a.part_n - 4);
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       if (row[i] < R) {
@@ -837,7 +769,10 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     }
   }
   flush();
-  pass_epilogue(a, 0.f, &s_last);
+#ifdef JX_PROFILE
+  if (tid == 0) atomicMax(reinterpret_cast<long long*>(a.dbg) + 44, gtime());  // latest CTA end of the run so far
+  if (tid == 0) JPROF(a.dbg, 64 + 4 * blockIdx.x + 2);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ per-frame mode: Adam warps, kernel
@@ -873,7 +808,7 @@ constexpr int BAR_ADAM = 5;  // the two Adam warps of the per-frame kernel, once
 // (measured with clock64: it, not the special-function unit, bounded the first version of this mode).  A quad has to be
 // turned around in ~1150 cycles, so: two Adam warps (warp q owns quad q of every tile), 2-ulp reciprocal / square root /
 // exponential instead of the IEEE sequences, and the per-frame state fetched 8 tiles ahead, one frame per lane.
-__device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __restrict__ ctl, unsigned ep, int q, int lane, int NWc, int nbar,
+__device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* ctl, unsigned ep, int q, int lane, int NWc, int nbar,
                                              unsigned char* ring, uint64_t* bars, const float4* s_rows, float* s_e, double* s_x,
                                              long long t0, long long s0, int ns, int n) {
   const int mode = a.mode;
@@ -1084,7 +1019,6 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
   const long long t0 = s0;
   const int n = ns;
   const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
-  __shared__ int s_last;
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -1102,10 +1036,10 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
   if (blockIdx.x == 0 && tid == NTc) JPROF(a.dbg, 40);
   pdl_wait();
   pdl_launch_dependents();
+  const unsigned ep = *a.epoch;
   if (blockIdx.x == 0 && tid == NTc) JPROF(a.dbg, 41);
 
-  const unsigned ep = *a.epoch;
-  const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
+  const Ctl* ctl = a.ctl + (ep & 1u);
   if (ctl->trk_stop) {  // the on-device loop has ended: drain the prefetched tiles and leave everything untouched
     if (is_adam && q == 0 && lane == 0) {
       const int pre = ns < a.stages ? ns : a.stages;
@@ -1114,9 +1048,8 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
     return;
   }
   if (is_adam) pf_adam_warp(a, ctl, ep, q, lane, NWc, nbar, ring, bars, s_rows, s_e, s_x, t0, s0, ns, n);
-  else if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
-  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
-  pass_epilogue(a, 1.f, &s_last);
+  else if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar, ep & 1u);
+  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar, ep & 1u);
 }
 
 __global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, const Xchg x, JaxentLossRecord* rec, int n_slots) {

@@ -471,9 +471,9 @@ __device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned n_frame_ctas = gridDim.x - 1;
   if (n_frame_ctas > 1) {
-    if (tid < KL_N) __threadfence();
     __syncthreads();
     if (tid == 0) {
+      __threadfence();  // after the barrier: covers every thread's stores of this CTA (w, kappa, klpart, cleared accumulators)
       const unsigned ticket = atomicAdd(a.counter, 1u);
       *s_last = (ticket == n_frame_ctas - 1);
     }
@@ -481,15 +481,72 @@ __device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep,
     *s_last = 1;
   }
   __syncthreads();
-  if (*s_last && warp < KL_N) {
-    __threadfence();
-    double t = 0.0;
+  if (*s_last) {
+    if (warp < KL_N) {
+      __threadfence();
+      double t = 0.0;
 #pragma unroll 1
-    for (unsigned cc = lane; cc < n_frame_ctas; cc += 32) t += __ldcg(&a.klpart[(size_t)cc * KL_N + warp]);
-    t = wsum(t);
-    if (lane == 0) kl_publish(a.x, ep, warp, t);
-    if (tid == 0) *a.counter = 0u;
+      for (unsigned cc = lane; cc < n_frame_ctas; cc += 32) t += __ldcg(&a.klpart[(size_t)cc * KL_N + warp]);
+      t = wsum(t);
+      if (lane == 0) kl_publish(a.x, ep, warp, t);
+      if (tid == 0) *a.counter = 0u;
+    }
   }
+}
+
+// ------------------------------------------------------------------------------------------ completing the pass's sums
+// Frame-sharded: one frame CTA per destination rank converts this rank's sums and stores them into that rank's inbox as
+// stamped 16-byte words (slot = this rank; the own inbox is a destination like any other, so every rank adds the same words
+// in the same order).  world CTAs work in parallel -- a single publishing CTA was limited by the rate at which one SM can
+// post NVLink stores (16k words for 8 ranks: ~10 us at R = 500).
+__device__ __forceinline__ void publish_sums(const TailArgs& a, unsigned ep, int dest, const unsigned long long* fxb, int n_rows, double inv) {
+  unsigned char* base = a.x.base[0];
+#pragma unroll
+  for (int r = 1; r < JAXENT_MAX_RANKS; ++r)
+    if (r == dest) base = a.x.base[r];  // compile-time indices: no local-memory copy of the parameter struct
+  unsigned char* slot0 = base + xchg_red_off(a.x, (int)(ep & 1u), a.x.rank);
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  constexpr int CP = 4;  // columns per thread and trip: CP * FX_REP loads in flight
+  for (int c0 = tid; c0 < n_rows; c0 += CP * nt) {
+    double v[CP];
+#pragma unroll
+    for (int k = 0; k < CP; ++k) v[k] = (c0 + k * nt < n_rows) ? fx_fold_col(fxb, n_rows, c0 + k * nt, inv) : 0.0;
+#pragma unroll
+    for (int k = 0; k < CP; ++k)
+      if (c0 + k * nt < n_rows) ll_store(slot0 + (size_t)(c0 + k * nt) * 16, v[k], ep);
+  }
+  if (warp == nw - 1) {  // the three scalars: the last warp (the first ones carry the columns)
+    double t[3];
+    fold_scal3(a.cta_scal, a.pass_ctas, lane, t);
+    if (lane < 4) ll_store(slot0 + (size_t)(n_rows + lane) * 16, lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : 0.0, ep);
+  }
+}
+
+// Three-phase ABI (jaxent_bv_reduce): the sums as plain doubles in JAXENT_BUF_RED, for a caller that all-reduces them itself
+// (NCCL) between the pass and the tail.
+__global__ void __launch_bounds__(1024) reduce_fold_kernel(const unsigned long long* fx, const double* cta_scal, const float* nmax,
+                                                           const Ctl* ctl, const unsigned* epoch, int per_frame_mode, long long F,
+                                                           int n_rows, int pass_ctas, double* red) {
+  const unsigned ep = *epoch;  // the epoch the pass started in (the tail advances it)
+  const Ctl* c = ctl + (ep & 1u);
+  if (c->trk_stop) return;
+  const unsigned long long* fxb = fx + (size_t)(ep & 1u) * FX_REP * n_rows;
+  const double inv = fx_inv_scale(*nmax, per_frame_mode != 0, c->pending, F);
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int col = tid; col < n_rows; col += nt) red[col] = fx_fold_col(fxb, n_rows, col, inv);
+  if (warp == nw - 1) {
+    double t[3];
+    fold_scal3(cta_scal, pass_ctas, lane, t);
+    if (lane < 4) red[n_rows + lane] = lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : 0.0;
+  }
+}
+
+int launch_reduce_fold(const TailArgs& a, cudaStream_t s) {
+  reduce_fold_kernel<<<1, 1024, 0, s>>>(a.fx, a.cta_scal, a.nmax, a.ctl, a.epoch, a.prob.uptake == 2, a.prob.F, a.part_n - 4, a.pass_ctas,
+                                        reinterpret_cast<double*>(a.x.local + xchg_plain_red_off(a.x)));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("reduce_fold launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
 }
 
 // ------------------------------------------------------------------------------------------ the tail
@@ -537,17 +594,52 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   pdl_launch_dependents();  // lets the next pass kernel's launch + TMA prologue overlap this kernel
   TPROF(2); TPROF_F(1);
 
-  // all loads of the reduced sums are issued together (one round trip); warp 0 then derives the scalars
+  // ---- the pass's sums.  Single rank: every reader folds the fixed-point accumulators itself (all loads of a thread in
+  // flight at once, one L2 round trip; no publishing step in between).  Frame-sharded: the first `world` frame CTAs publish
+  // this rank's sums to the ranks' inboxes, then everybody gathers all ranks' words (red_total spins on late ones).
   const bool pfm = pb.uptake == 2;
+  const int n_rows = a.part_n - 4;
+  const bool direct = a.fold_here && a.x.world == 1;
+  const unsigned long long* fx_cur = a.fx + (size_t)((ep & 1u) ^ 1u) * FX_REP * n_rows;  // the pass started in epoch ep - 1
+  const double fx_inv = a.fold_here ? fx_inv_scale(__ldg(a.nmax), pfm, s_old.pending, pb.F) : 0.0;
+  if (a.fold_here && a.x.world > 1 && !tail_cta) {
+    const int nf = (int)gridDim.x - 1;
+    for (int dest = (int)blockIdx.x - 1; dest < a.x.world; dest += nf) publish_sums(a, ep, dest, fx_cur, n_rows, fx_inv);
+  }
+  auto sum_col = [&](int j) -> double { return direct ? fx_fold_col(fx_cur, n_rows, j, fx_inv) : red_total(a.x, ep, j); };
+  double* red_plain = reinterpret_cast<double*>(a.x.local + xchg_plain_red_off(a.x));  // JAXENT_BUF_RED (single rank)
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (tail_cta && tid < R && !pfm) {
-    accA0 = red_total(a.x, ep, 0 * R + tid);
-    accA1 = red_total(a.x, ep, 1 * R + tid);
-    accB0 = red_total(a.x, ep, 2 * R + tid);
-    accB1 = red_total(a.x, ep, 3 * R + tid);
+    accA0 = sum_col(0 * R + tid);
+    accA1 = sum_col(1 * R + tid);
+    accB0 = sum_col(2 * R + tid);
+    accB1 = sum_col(3 * R + tid);
+    if (direct) {
+      red_plain[0 * R + tid] = accA0;
+      red_plain[1 * R + tid] = accA1;
+      red_plain[2 * R + tid] = accB0;
+      red_plain[3 * R + tid] = accB1;
+    }
   }
   if (warp == 0) {
-    const double SA = red_total(a.x, ep, a.part_n - 4), SB = red_total(a.x, ep, a.part_n - 3), gdot = red_total(a.x, ep, a.part_n - 2);
+    double SA, SB, gdot;
+    if (direct) {
+      double t3[3];
+      fold_scal3(a.cta_scal, a.pass_ctas, lane, t3);
+      SA = t3[0];
+      SB = t3[1];
+      gdot = t3[2];
+      if (tail_cta && lane == 0) {
+        red_plain[n_rows + 0] = SA;
+        red_plain[n_rows + 1] = SB;
+        red_plain[n_rows + 2] = gdot;
+        red_plain[n_rows + 3] = 0.0;
+      }
+    } else {
+      SA = red_total(a.x, ep, n_rows + 0);
+      SB = red_total(a.x, ep, n_rows + 1);
+      gdot = red_total(a.x, ep, n_rows + 2);
+    }
     __syncwarp();
     if (lane == 0) derive_critical(&s_sc, &s_spec, &s_old, SA, SB, gdot, a.cfg);
     // the per-frame CTAs need the tracker's decisions (snapshot slot, EMA update) before their frame loop
@@ -582,7 +674,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       const double invS = __drcp_rn(S);
 #pragma unroll 1
       for (int it = tid; it < R * T; it += nt) {
-        const double uv = 1.0 - red_total(a.x, ep, d * T * R + it) * invS;
+        const double sv = sum_col(d * T * R + it);
+        if (direct) red_plain[d * T * R + it] = sv;
+        const double uv = 1.0 - sv * invS;
         const int t = it / R, r = it - t * R;
         tsm.sU[r * T + t] = uv;  // [r][t], as tail_body reads it
         a.uptake[it] = (float)uv;
@@ -605,6 +699,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
     }
     TPROF(9);
     if (tid < 32) write_ctl_critical(neu, a.records, s_sc, s_old, s_fin, gbc_reg, gbh_reg, pb.n_slots, lane, ep);
+    if (tid == 0) *a.epoch = ep;  // the next pass starts after this kernel has completed and reads the new control block
     TPROF(10);
     return;
   }
@@ -612,6 +707,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   // ================================================================== per-frame MaxEnt terms (blocks 1..)
   // The last frame CTA to finish publishes the MaxEnt sums, typically well before the R x T tail above has finished.
   if (blockIdx.x == 1 && warp == 0) write_ctl_rest(neu, a.records, s_sc, lane, a.trk);
+  {  // clear the accumulator set the NEXT pass adds into (last read by the previous tail; the next pass cannot flush into it
+     // before this kernel has completed)
+    unsigned long long* fx_next = a.fx + (size_t)(ep & 1u) * FX_REP * n_rows;
+    const int nf = (int)gridDim.x - 1, total = FX_REP * n_rows;
+    for (int i = ((int)blockIdx.x - 1) * nt + tid; i < total; i += nf * nt) fx_next[i] = 0ull;
+  }
   frame_terms(a, s_sc, s_old, cur_set, (long long)blockIdx.x - 1, 0, s_red);
   TPROF_F(3);
   fold_kl_partials(a, ep, &s_last);

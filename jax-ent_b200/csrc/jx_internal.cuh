@@ -176,6 +176,70 @@ __device__ __forceinline__ void kl_gather_warp(const Xchg& x, unsigned ep, int l
 }
 #endif
 
+#ifdef __CUDACC__
+// ---- fixed-point row sums of the pass
+// |row sum| <= (sum of the un-normalised weights) * max |feature|.  In a step the weights are exp(z' - lse) with
+// sum exp(z - lse) = 1 and |z' - z| <= (1 - b1) / sqrt(1 - b2) < 3.2 for optax adam (the update does not depend on the
+// learning rate, which pre-scales the gradient): sum e' < e^3.2 < 64.  In the init pass e = exp(z0 - max z0) <= 1 per frame.
+// scale = 2^(61 - e) with bound < 2^e, so a sum stays below 2^61 and carries >= 2^-61 of the bound as resolution
+// (the fp32 tile sums that enter are good to 2^-24).
+__device__ __forceinline__ double fx_scale(float nmax, int mode, long long F) {
+  const double bound = (mode ? 64.0 : (double)F) * (double)fmaxf(nmax, 1e-30f);
+  const int e = ((__double2hiint(bound) >> 20) & 0x7ff) - 1022;  // bound < 2^e
+  return __hiloint2double((61 - e + 1023) << 20, 0);
+}
+__device__ __forceinline__ void fx_add(unsigned long long* dst, float v, double scale) {
+  atomicAdd(dst, (unsigned long long)__double2ll_rn((double)v * scale));  // RED.ADD.64: fire and forget
+}
+// 1 / scale of the sums a pass of `mode` left behind (NaN when a feature is not finite: integers cannot carry it, the tail
+// then sees NaN sums and the loss becomes non-finite -- the reference treats that as data, not as an error)
+__device__ __forceinline__ double fx_inv_scale(float nmax, bool per_frame_mode, int mode, long long F) {
+  const double scale = fx_scale(per_frame_mode ? 1.f : nmax, mode, F);
+  return (nmax <= 3.0e38f) ? 1.0 / scale : __longlong_as_double(0x7ff8000000000000ll);
+}
+// one column of the accumulators: the FX_REP replicas are integers, any order of addition gives the same sum
+__device__ __forceinline__ double fx_fold_col(const unsigned long long* fxb, int n_rows, int col, double inv) {
+  unsigned long long v[FX_REP];
+#pragma unroll
+  for (int r = 0; r < FX_REP; ++r) v[r] = __ldcg(fxb + (size_t)r * n_rows + col);
+  long long t = 0;
+#pragma unroll
+  for (int r = 0; r < FX_REP; ++r) t += (long long)v[r];
+  return (double)t * inv;
+}
+// the per-CTA scalars (0 sum e' branch A, 1 branch B, 2 grad-dot) summed over the pass CTAs by ONE WARP in a fixed order
+// (lane-strided, then a butterfly): every warp that evaluates this gets the same bits.  All loads of a lane are issued
+// before the first addition (one L2 round trip for the whole fold).
+constexpr int MAX_PASS_CTAS = 2 * 160;
+__device__ __forceinline__ void fold_scal3(const double* cta_scal, int n_ctas, int lane, double (&out)[3]) {
+  constexpr int U = MAX_PASS_CTAS / 32;
+  double2 ab[U];
+  double g[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int c = lane + 32 * u;
+    const bool ok = c < n_ctas;
+    ab[u] = ok ? __ldcg(reinterpret_cast<const double2*>(cta_scal + (size_t)c * 4)) : make_double2(0.0, 0.0);
+    g[u] = ok ? __ldcg(cta_scal + (size_t)c * 4 + 2) : 0.0;
+  }
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    t0 += ab[u].x;
+    t1 += ab[u].y;
+    t2 += g[u];
+  }
+  for (int o = 16; o; o >>= 1) {
+    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+  }
+  out[0] = t0;
+  out[1] = t1;
+  out[2] = t2;
+}
+#endif
+
 struct StateSets {
   float* z[2][2];
   float* m[2][2];
@@ -211,12 +275,11 @@ struct PassArgs {
   const float* pf_tp;       // [T] time points
   // Row sums of all CTAs meet in ONE set of 64-bit fixed-point accumulators (integer atomics: exact, hence independent of
   // the order in which the CTAs arrive -> bitwise reproducible without a fixed-order reduction kernel).  The scale is a
-  // power of two derived from a bound on the sums (see fx_scale()).  The last CTA to arrive converts them to doubles and
-  // publishes them (plain store, or stamped stores into every rank's inbox), clears them and advances the epoch.
-  unsigned long long* fx;   // [FX_REP][part_n - 4]
-  double* cta_scal;         // [CTA][4]: sum e' (both branches), grad-dot -- summed in CTA order by the last CTA
+  // power of two derived from a bound on the sums (see fx_scale()).  Two sets, indexed by the parity of the epoch the pass
+  // starts in: the kernel that follows (tail / reduce) converts the set of this pass and clears the other one.
+  unsigned long long* fx;   // [2 parities][FX_REP][part_n - 4]
+  double* cta_scal;         // [CTA][4]: sum e' (both branches), grad-dot -- summed in a fixed order by the consumer (fold_scal)
   const float* nmax;        // max |feature| of this rank's packed arrays (state_init)
-  unsigned* ticket;
   Xchg x;
   const Ctl* ctl;
   unsigned* epoch;
@@ -249,6 +312,14 @@ struct TailArgs {
   Xchg x;
   Ctl* ctl;
   unsigned* counter;
+  unsigned* epoch;            // advanced by the tail (CTA 0) once the new control block is written
+  // the pass's raw sums (see PassArgs) and how they reach this kernel
+  unsigned long long* fx;     // [2 parities][FX_REP][part_n - 4]
+  const double* cta_scal;     // [pass CTA][4]
+  const float* nmax;
+  int pass_ctas;
+  int fold_here;              // 1: this kernel completes the sums (and publishes them to the peers when frame-sharded);
+                              // 0: jaxent_bv_reduce already wrote them to JAXENT_BUF_RED (three-phase ABI, NCCL in between)
   float* w;
   float* kappa;
   float* kappa_lo;
@@ -311,6 +382,7 @@ int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, 
 // number of doubles every pass CTA contributes: row sums (+ sum e for both branches, grad-dot, pad)
 __host__ __device__ inline int pass_part_n(int R, int T, int uptake_mode) { return uptake_mode == 2 ? 2 * T * R + 4 : 4 * R + 4; }
 int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);
+int launch_reduce_fold(const TailArgs& a, cudaStream_t s);
 int launch_finish_record(const Ctl* ctl, const unsigned* epoch, const Xchg& x, JaxentLossRecord* rec, int n_slots, cudaStream_t s);
 size_t tail_smem_bytes(int R, int T, int p_tr, int p_va, int nnz_tr, int nnz_va);
 int blob_words(int R, int T, int p_tr, int nnz_tr, int p_va, int nnz_va);

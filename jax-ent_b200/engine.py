@@ -409,11 +409,14 @@ class BvEngine:
 
     def _phase(self, mode: int) -> None:
         s = _stream_ptr()
-        L.check(self.lib.jaxent_bv_pass(self.plan, mode, s))  # its last CTA completes and publishes the partial sums
-        if not self.fused:
+        L.check(self.lib.jaxent_bv_pass(self.plan, mode, s))
+        if self.sharded and not self.fused:
+            # NCCL exchange: complete the sums into JAXENT_BUF_RED, all-reduce them, the tail reads them from there
+            L.check(self.lib.jaxent_bv_reduce(self.plan, s))
             self.comm.sum_(self.red)
+            self.launches += 1
         L.check(self.lib.jaxent_bv_tail(self.plan, s))
-        if not self.fused:
+        if self.sharded and not self.fused:
             self.comm.sum_(self.klsum)
         self.launches += 2
 
@@ -445,7 +448,7 @@ class BvEngine:
         for _ in range(n_graphs):
             self._graph.replay()
         self.steps_done += n_graphs * self._graph_steps
-        self.launches += 2 * n_graphs * self._graph_steps
+        self.launches += (3 if self.sharded and not self.fused else 2) * n_graphs * self._graph_steps
 
     def exchange_error(self) -> int:
         """non-zero once a peer-flag wait of the fused exchange timed out (a peer never arrived)"""
