@@ -65,7 +65,7 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_pfG = take((size_t)(T > 0 ? T : 1) * R * 4);
   const int part_n = pass_part_n(R, T, pb->uptake);
   L.off_cta_scal = take((size_t)MAX_PASS_CTAS * 4 * sizeof(double));
-  L.off_fx = take((size_t)2 * FX_REP * (part_n - 4) * sizeof(unsigned long long));  // two parities, see PassArgs
+  L.off_fx = take((size_t)FX_REP * (part_n - 4) * sizeof(unsigned long long));
   L.off_nmax = take(sizeof(float));
   L.off_xchg = take(xchg_bytes(part_n, 1));  // single-rank exchange buffer (red / kl inbox of world = 1)
   L.off_klpart = take((size_t)MAX_TAIL_CTAS * KL_N * sizeof(double));
@@ -511,7 +511,7 @@ extern "C" int jaxent_bv_state_init(JaxentPlan* p, const float* z0, float zmax, 
       reinterpret_cast<unsigned*>(p->ws + p->lay.off_counter),
       reinterpret_cast<unsigned long long*>(p->x.local), (long long)(xchg_bytes(p->x.part_n, p->x.world) / 8),
       reinterpret_cast<JaxentLossRecord*>(p->ws + p->lay.off_records), reinterpret_cast<unsigned long long*>(p->ws + p->lay.off_fx),
-      (long long)2 * FX_REP * (p->x.part_n - 4), reinterpret_cast<unsigned*>(p->ws + p->lay.off_nmax),
+      (long long)FX_REP * (p->x.part_n - 4), reinterpret_cast<unsigned*>(p->ws + p->lay.off_nmax),
       p->prob.feature_format == 1 ? 0x437f0000u /* 255.0f: u8 features */ : 0u);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("state_init launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }

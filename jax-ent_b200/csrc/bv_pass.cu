@@ -312,7 +312,7 @@ __device__ __forceinline__ void phase_b(const TileRegs<RPT>& d, const float* s_e
 // the step those sums belong to.
 // (plain pointers instead of the Xchg struct: passing a kernel-parameter struct by reference forces a local-memory copy)
 static __device__ __noinline__ double gather_hbar(const unsigned char* kl_words, int world, unsigned char* err_word, unsigned ep,
-                                                 const Ctl* ctl, JaxentLossRecord* records, int lane, bool finish) {
+                                                 const Ctl* __restrict__ ctl, JaxentLossRecord* records, int lane, bool finish) {
   double v = 0.0;
   if (lane < world * KL_N) {
     if (world == 1) v = __ldcg(reinterpret_cast<const double*>(kl_words) + lane);
@@ -329,7 +329,7 @@ static __device__ __noinline__ double gather_hbar(const unsigned char* kl_words,
   if (finish && lane == 0) finish_record(ctl, kl[1] + kl[2], records, JAXENT_MAX_SLOTS);
   return ctl->hbar_data + kl[0];
 }
-__device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, const Ctl* ctl, int lane, bool finish) {
+__device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, const Ctl* __restrict__ ctl, int lane, bool finish) {
   const unsigned char* kl_words = a.x.local + (a.x.world == 1 ? xchg_plain_kl_off(a.x) : xchg_kl_off(a.x, (int)(ep & 1u), 0));
   return gather_hbar(kl_words, a.x.world, a.x.local + xchg_err_off(a.x), ep, ctl, a.records, lane, finish);
 }
@@ -337,10 +337,11 @@ __device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, cons
 
 // ------------------------------------------------------------------------------------------ fixed-point row sums
 // fx_scale() / fx_add() live in jx_internal.cuh.  The pass only ACCUMULATES: every CTA adds its tile sums into the fixed-point
-// accumulators of this epoch's parity and leaves its three scalars (sum e' of both branches, grad-dot) in cta_scal.  The
-// sums are completed after the kernel boundary -- by the tail kernel (fx_fold_col / fold_scal: all CTAs in parallel, stamped
-// peer stores spread over several CTAs when frame-sharded) or, for the three-phase ABI, by jaxent_bv_reduce.  There is no
-// ticket, no last-CTA serial section and no epoch store at the end of the pass (the tail advances the epoch).
+// accumulators and leaves its three scalars (sum e' of both branches, grad-dot) in cta_scal.  The sums are completed -- and
+// the accumulators cleared, each column by its one reader -- after the kernel boundary: by the tail kernel (fx_take_col /
+// fold_scal3: all CTAs in parallel, stamped peer stores spread over several CTAs when frame-sharded) or, for the three-phase
+// ABI, by jaxent_bv_reduce.  There is no ticket, no last-CTA serial section and no epoch store at the end of the pass (the
+// tail advances the epoch).
 
 // ------------------------------------------------------------------------------------------ per-frame uptake mode
 // ForwardPass.average_first = False (reference models/core.py:302-304, BV_uptake_ForwardPass models/HDX/forward.py:57-74):
@@ -375,7 +376,7 @@ __device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
 // four per-frame partials (one 16-byte store) and the Adam warp, which has time to spare, sums them.
 template <int TM>
 __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ring, uint64_t* bars, float4* s_rows, const float* s_e,
-                                             float4* s_tab, int n, int mode, float bc, float bh, int NTc, int nbar, unsigned fx_par) {
+                                             float4* s_tab, int n, int mode, float bc, float bh, int NTc, int nbar) {
   constexpr int TP = TM / 2;
   const int R = a.R, T = a.pf_T;
   const int tid = threadIdx.x;
@@ -384,14 +385,14 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
   const uint32_t rowoff = (uint32_t)rc * 16u, rstride = (uint32_t)R * 16u;
   float4* my_tab = s_tab + tid;  // [TP][NTc] {kt(2 tp), kt(2 tp + 1), G(2 tp), G(2 tp + 1)}
   // centred: the tail's k_r = fl(sum_t G[t,r] (1 - <u>[t,r])) replaces sum_t G[t,r], so the row partial is sum_t G (u_f - <u>)
-  const float Gsum = (ok && mode) ? __ldcg(a.ck + rc) : 0.f;
+  const float Gsum = (ok && mode) ? a.ck[rc] : 0.f;
   {
     const float kr = -1.4426950408889634f * a.pf_k[rc];
 #pragma unroll
     for (int tp = 0; tp < TP; ++tp) {
       const int t0_ = 2 * tp, t1_ = 2 * tp + 1;
-      const float2 g2 = make_float2((ok && mode && t0_ < T) ? __ldcg(a.pf_G + (size_t)t0_ * R + rc) : 0.f,
-                                    (ok && mode && t1_ < T) ? __ldcg(a.pf_G + (size_t)t1_ * R + rc) : 0.f);
+      const float2 g2 = make_float2((ok && mode && t0_ < T) ? a.pf_G[(size_t)t0_ * R + rc] : 0.f,
+                                    (ok && mode && t1_ < T) ? a.pf_G[(size_t)t1_ * R + rc] : 0.f);
       my_tab[tp * NTc] = make_float4(t0_ < T ? kr * a.pf_tp[t0_] : 0.f, t1_ < T ? kr * a.pf_tp[t1_] : 0.f, g2.x, g2.y);  // kt = -log2(e) k_r tau_t
     }
   }
@@ -466,7 +467,7 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
   auto flush = [&]() {
     // the accumulated products are e' * exp(-k tau / PF) with the second factor in [0, 1]: bound = the sum of the weights
     const double fxs = fx_scale(1.f, mode, a.F);
-    unsigned long long* fxp = a.fx + (size_t)(fx_par * FX_REP + blockIdx.x % FX_REP) * (a.part_n - 4);
+    unsigned long long* fxp = a.fx + (size_t)(blockIdx.x % FX_REP) * (a.part_n - 4);
     if (ok) {
 #pragma unroll
       for (int br = 0; br < 2; ++br)
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
 
   if (is_adam) {
     // ================================================================== Adam warp
-    const Ctl* ctl = a.ctl + (ep & 1u);
+    const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
     // MaxEnt sums of the tail that preceded this pass (all ranks; spins on the peers' words when frame-sharded)
     // hbar as an unevaluated fp32 pair: h_f - hbar is evaluated as (H + (k_hi - hb_hi)) + (k_lo - hb_lo), which keeps the
     // O(lambda) cancellation between kappa_f and hbar exact (Sterbenz) without fp64 instructions or conversions on this warp
@@ -601,9 +602,9 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
         m_ = min_[f];
         v_ = vin[f];
         if (mode) {
-          w_ = __ldcg(a.w + f);
-          k_ = __ldcg(a.kappa + f);
-          kl_ = __ldcg(a.kappa_lo + f);
+          w_ = a.w[f];
+          k_ = a.kappa[f];
+          kl_ = a.kappa_lo[f];
           gp_ = gprev[f];
         }
       }
@@ -691,9 +692,9 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
     const bool ok = row[i] < R;
     const int rc = ok ? row[i] : R - 1;  // clamp: finite data, zero coefficients, result never stored
     rowoff[i] = (uint32_t)rc * (FMT == 0 ? 16u : 8u);
-    ccr[i] = (ok && mode) ? __ldcg(a.cc + rc) : 0.f;
-    chr[i] = (ok && mode) ? __ldcg(a.ch + rc) : 0.f;
-    nkr[i] = (ok && mode) ? -__ldcg(a.ck + rc) : 0.f;
+    ccr[i] = (ok && mode) ? a.cc[rc] : 0.f;
+    chr[i] = (ok && mode) ? a.ch[rc] : 0.f;
+    nkr[i] = (ok && mode) ? -a.ck[rc] : 0.f;
   }
   const uint32_t rstride = (uint32_t)R * (FMT == 0 ? 16u : 8u);
   const int jred = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
 
   auto flush = [&]() {  // rare (every FLUSH_TILES tiles): scale and destination are re-derived here rather than kept in registers
     const double fxs = fx_scale(*a.nmax, mode, a.F);
-    unsigned long long* fxp = a.fx + (size_t)((ep & 1u) * FX_REP + blockIdx.x % FX_REP) * (a.part_n - 4);
+    unsigned long long* fxp = a.fx + (size_t)(blockIdx.x % FX_REP) * (a.part_n - 4);
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       if (row[i] < R) {
@@ -808,7 +809,7 @@ constexpr int BAR_ADAM = 5;  // the two Adam warps of the per-frame kernel, once
 // (measured with clock64: it, not the special-function unit, bounded the first version of this mode).  A quad has to be
 // turned around in ~1150 cycles, so: two Adam warps (warp q owns quad q of every tile), 2-ulp reciprocal / square root /
 // exponential instead of the IEEE sequences, and the per-frame state fetched 8 tiles ahead, one frame per lane.
-__device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* ctl, unsigned ep, int q, int lane, int NWc, int nbar,
+__device__ __forceinline__ void pf_adam_warp(const PassArgs& a, const Ctl* __restrict__ ctl, unsigned ep, int q, int lane, int NWc, int nbar,
                                              unsigned char* ring, uint64_t* bars, const float4* s_rows, float* s_e, double* s_x,
                                              long long t0, long long s0, int ns, int n) {
   const int mode = a.mode;
@@ -1039,7 +1040,7 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
   const unsigned ep = *a.epoch;
   if (blockIdx.x == 0 && tid == NTc) JPROF(a.dbg, 41);
 
-  const Ctl* ctl = a.ctl + (ep & 1u);
+  const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
   if (ctl->trk_stop) {  // the on-device loop has ended: drain the prefetched tiles and leave everything untouched
     if (is_adam && q == 0 && lane == 0) {
       const int pre = ns < a.stages ? ns : a.stages;
@@ -1048,8 +1049,8 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
     return;
   }
   if (is_adam) pf_adam_warp(a, ctl, ep, q, lane, NWc, nbar, ring, bars, s_rows, s_e, s_x, t0, s0, ns, n);
-  else if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar, ep & 1u);
-  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar, ep & 1u);
+  else if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
 }
 
 __global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, const Xchg x, JaxentLossRecord* rec, int n_slots) {

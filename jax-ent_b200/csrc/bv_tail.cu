@@ -495,45 +495,56 @@ __device__ __forceinline__ void fold_kl_partials(const TailArgs& a, unsigned ep,
 }
 
 // ------------------------------------------------------------------------------------------ completing the pass's sums
-// Frame-sharded: one frame CTA per destination rank converts this rank's sums and stores them into that rank's inbox as
-// stamped 16-byte words (slot = this rank; the own inbox is a destination like any other, so every rank adds the same words
-// in the same order).  world CTAs work in parallel -- a single publishing CTA was limited by the rate at which one SM can
-// post NVLink stores (16k words for 8 ranks: ~10 us at R = 500).
-__device__ __forceinline__ void publish_sums(const TailArgs& a, unsigned ep, int dest, const unsigned long long* fxb, int n_rows, double inv) {
-  unsigned char* base = a.x.base[0];
-#pragma unroll
-  for (int r = 1; r < JAXENT_MAX_RANKS; ++r)
-    if (r == dest) base = a.x.base[r];  // compile-time indices: no local-memory copy of the parameter struct
-  unsigned char* slot0 = base + xchg_red_off(a.x, (int)(ep & 1u), a.x.rank);
+// Frame-sharded: the first `world` frame CTAs share the columns; each converts its slice of this rank's sums, clears it and
+// stores it into EVERY rank's inbox as stamped 16-byte words (slot = this rank; the own inbox is a destination like any
+// other, so every rank adds the same words in the same order).  The CTAs work in parallel -- a single publishing CTA was
+// limited by the rate at which one SM can post NVLink stores (16k words for 8 ranks: ~10 us at R = 500).
+__device__ __forceinline__ void publish_sums(const TailArgs& a, unsigned ep, int part, int n_parts, int n_rows, double inv) {
+  const size_t off = xchg_red_off(a.x, (int)(ep & 1u), a.x.rank);
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  constexpr int CP = 4;  // columns per thread and trip: CP * FX_REP loads in flight
-  for (int c0 = tid; c0 < n_rows; c0 += CP * nt) {
+  const int per = (n_rows + n_parts - 1) / n_parts, c_begin = part * per, c_end = min(n_rows, c_begin + per);
+  constexpr int CP = 2;  // columns per thread and trip: CP * FX_REP loads in flight
+  for (int c0 = c_begin + tid; c0 < c_end; c0 += CP * nt) {
     double v[CP];
 #pragma unroll
-    for (int k = 0; k < CP; ++k) v[k] = (c0 + k * nt < n_rows) ? fx_fold_col(fxb, n_rows, c0 + k * nt, inv) : 0.0;
+    for (int k = 0; k < CP; ++k) v[k] = (c0 + k * nt < c_end) ? (double)fx_load_col(a.fx, n_rows, c0 + k * nt) * inv : 0.0;
 #pragma unroll
-    for (int k = 0; k < CP; ++k)
-      if (c0 + k * nt < n_rows) ll_store(slot0 + (size_t)(c0 + k * nt) * 16, v[k], ep);
+    for (int k = 0; k < CP; ++k) {
+      const int col = c0 + k * nt;
+      if (col < c_end) {
+#pragma unroll
+        for (int r = 0; r < JAXENT_MAX_RANKS; ++r)  // compile-time indices: no local-memory copy of the parameter struct
+          if (r < a.x.world) ll_store(a.x.base[r] + off + (size_t)col * 16, v[k], ep);
+        fx_clear_col(a.fx, n_rows, col);
+      }
+    }
   }
-  if (warp == nw - 1) {  // the three scalars: the last warp (the first ones carry the columns)
+  if (part == 0 && warp == nw - 1) {  // the three scalars: the last warp of the first publisher
     double t[3];
     fold_scal3(a.cta_scal, a.pass_ctas, lane, t);
-    if (lane < 4) ll_store(slot0 + (size_t)(n_rows + lane) * 16, lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : 0.0, ep);
+    if (lane < 4) {
+      const double v = lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : 0.0;
+#pragma unroll
+      for (int r = 0; r < JAXENT_MAX_RANKS; ++r)
+        if (r < a.x.world) ll_store(a.x.base[r] + off + (size_t)(n_rows + lane) * 16, v, ep);
+    }
   }
 }
 
 // Three-phase ABI (jaxent_bv_reduce): the sums as plain doubles in JAXENT_BUF_RED, for a caller that all-reduces them itself
 // (NCCL) between the pass and the tail.
-__global__ void __launch_bounds__(1024) reduce_fold_kernel(const unsigned long long* fx, const double* cta_scal, const float* nmax,
+__global__ void __launch_bounds__(1024) reduce_fold_kernel(unsigned long long* fx, const double* cta_scal, const float* nmax,
                                                            const Ctl* ctl, const unsigned* epoch, int per_frame_mode, long long F,
                                                            int n_rows, int pass_ctas, double* red) {
   const unsigned ep = *epoch;  // the epoch the pass started in (the tail advances it)
   const Ctl* c = ctl + (ep & 1u);
   if (c->trk_stop) return;
-  const unsigned long long* fxb = fx + (size_t)(ep & 1u) * FX_REP * n_rows;
   const double inv = fx_inv_scale(*nmax, per_frame_mode != 0, c->pending, F);
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  for (int col = tid; col < n_rows; col += nt) red[col] = fx_fold_col(fxb, n_rows, col, inv);
+  for (int col = tid; col < n_rows; col += nt) {
+    red[col] = (double)fx_load_col(fx, n_rows, col) * inv;
+    fx_clear_col(fx, n_rows, col);
+  }
   if (warp == nw - 1) {
     double t[3];
     fold_scal3(cta_scal, pass_ctas, lane, t);
@@ -600,25 +611,39 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   const bool pfm = pb.uptake == 2;
   const int n_rows = a.part_n - 4;
   const bool direct = a.fold_here && a.x.world == 1;
-  const unsigned long long* fx_cur = a.fx + (size_t)((ep & 1u) ^ 1u) * FX_REP * n_rows;  // the pass started in epoch ep - 1
   const double fx_inv = a.fold_here ? fx_inv_scale(__ldg(a.nmax), pfm, s_old.pending, pb.F) : 0.0;
   if (a.fold_here && a.x.world > 1 && !tail_cta) {
-    const int nf = (int)gridDim.x - 1;
-    for (int dest = (int)blockIdx.x - 1; dest < a.x.world; dest += nf) publish_sums(a, ep, dest, fx_cur, n_rows, fx_inv);
+    const int nf = (int)gridDim.x - 1, n_parts = nf < a.x.world ? nf : a.x.world;
+    if ((int)blockIdx.x - 1 < n_parts) publish_sums(a, ep, (int)blockIdx.x - 1, n_parts, n_rows, fx_inv);
   }
-  auto sum_col = [&](int j) -> double { return direct ? fx_fold_col(fx_cur, n_rows, j, fx_inv) : red_total(a.x, ep, j); };
+  // single rank: the R x T tail CTA is the one reader of every column (it clears what it has read)
+  auto sum_col = [&](int j) -> double {
+    if (!direct) return red_total(a.x, ep, j);
+    const double v = (double)fx_load_col(a.fx, n_rows, j) * fx_inv;
+    fx_clear_col(a.fx, n_rows, j);
+    return v;
+  };
   double* red_plain = reinterpret_cast<double*>(a.x.local + xchg_plain_red_off(a.x));  // JAXENT_BUF_RED (single rank)
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
   if (tail_cta && tid < R && !pfm) {
-    accA0 = sum_col(0 * R + tid);
-    accA1 = sum_col(1 * R + tid);
-    accB0 = sum_col(2 * R + tid);
-    accB1 = sum_col(3 * R + tid);
-    if (direct) {
+    if (direct) {  // all 4 * FX_REP loads in flight, then the clears
+      const long long t0 = fx_load_col(a.fx, n_rows, 0 * R + tid), t1 = fx_load_col(a.fx, n_rows, 1 * R + tid);
+      const long long t2 = fx_load_col(a.fx, n_rows, 2 * R + tid), t3 = fx_load_col(a.fx, n_rows, 3 * R + tid);
+      accA0 = (double)t0 * fx_inv;
+      accA1 = (double)t1 * fx_inv;
+      accB0 = (double)t2 * fx_inv;
+      accB1 = (double)t3 * fx_inv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fx_clear_col(a.fx, n_rows, k * R + tid);
       red_plain[0 * R + tid] = accA0;
       red_plain[1 * R + tid] = accA1;
       red_plain[2 * R + tid] = accB0;
       red_plain[3 * R + tid] = accB1;
+    } else {
+      accA0 = red_total(a.x, ep, 0 * R + tid);
+      accA1 = red_total(a.x, ep, 1 * R + tid);
+      accB0 = red_total(a.x, ep, 2 * R + tid);
+      accB1 = red_total(a.x, ep, 3 * R + tid);
     }
   }
   if (warp == 0) {
@@ -675,7 +700,10 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
 #pragma unroll 1
       for (int it = tid; it < R * T; it += nt) {
         const double sv = sum_col(d * T * R + it);
-        if (direct) red_plain[d * T * R + it] = sv;
+        if (direct) {
+          red_plain[d * T * R + it] = sv;
+          fx_clear_col(a.fx, n_rows, (d ^ 1) * T * R + it);  // the branch not taken is read by nobody: cleared here
+        }
         const double uv = 1.0 - sv * invS;
         const int t = it / R, r = it - t * R;
         tsm.sU[r * T + t] = uv;  // [r][t], as tail_body reads it
@@ -707,12 +735,6 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   // ================================================================== per-frame MaxEnt terms (blocks 1..)
   // The last frame CTA to finish publishes the MaxEnt sums, typically well before the R x T tail above has finished.
   if (blockIdx.x == 1 && warp == 0) write_ctl_rest(neu, a.records, s_sc, lane, a.trk);
-  {  // clear the accumulator set the NEXT pass adds into (last read by the previous tail; the next pass cannot flush into it
-     // before this kernel has completed)
-    unsigned long long* fx_next = a.fx + (size_t)(ep & 1u) * FX_REP * n_rows;
-    const int nf = (int)gridDim.x - 1, total = FX_REP * n_rows;
-    for (int i = ((int)blockIdx.x - 1) * nt + tid; i < total; i += nf * nt) fx_next[i] = 0ull;
-  }
   frame_terms(a, s_sc, s_old, cur_set, (long long)blockIdx.x - 1, 0, s_red);
   TPROF_F(3);
   fold_kl_partials(a, ep, &s_last);

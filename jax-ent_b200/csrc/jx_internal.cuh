@@ -198,7 +198,7 @@ __device__ __forceinline__ double fx_scale(float nmax, int mode, long long F) {
   return __hiloint2double((61 - e + 1023) << 20, 0);
 }
 __device__ __forceinline__ void fx_add(unsigned long long* dst, float v, double scale) {
-  atomicAdd(dst, (unsigned long long)__double2ll_rn((double)v * scale));  // RED.ADD.64: fire and forget
+  atomicAdd(dst, (unsigned long long)__double2ll_rn((double)v * scale));  // REDG.ADD.64: fire and forget
 }
 // 1 / scale of the sums a pass of `mode` left behind (NaN when a feature is not finite: integers cannot carry it, the tail
 // then sees NaN sums and the loss becomes non-finite -- the reference treats that as data, not as an error)
@@ -206,15 +206,21 @@ __device__ __forceinline__ double fx_inv_scale(float nmax, bool per_frame_mode, 
   const double scale = fx_scale(per_frame_mode ? 1.f : nmax, mode, F);
   return (nmax <= 3.0e38f) ? 1.0 / scale : __longlong_as_double(0x7ff8000000000000ll);
 }
-// one column of the accumulators: the FX_REP replicas are integers, any order of addition gives the same sum
-__device__ __forceinline__ double fx_fold_col(const unsigned long long* fxb, int n_rows, int col, double inv) {
+// one column of the accumulators: the FX_REP replicas are integers, any order of addition gives the same sum.  Every
+// column has exactly ONE reader per step, which also clears it for the next pass (the next pass cannot add to it before the
+// reading kernel has completed).
+__device__ __forceinline__ long long fx_load_col(const unsigned long long* fx, int n_rows, int col) {
   unsigned long long v[FX_REP];
 #pragma unroll
-  for (int r = 0; r < FX_REP; ++r) v[r] = __ldcg(fxb + (size_t)r * n_rows + col);
+  for (int r = 0; r < FX_REP; ++r) v[r] = __ldcg(fx + (size_t)r * n_rows + col);
   long long t = 0;
 #pragma unroll
   for (int r = 0; r < FX_REP; ++r) t += (long long)v[r];
-  return (double)t * inv;
+  return t;
+}
+__device__ __forceinline__ void fx_clear_col(unsigned long long* fx, int n_rows, int col) {
+#pragma unroll
+  for (int r = 0; r < FX_REP; ++r) fx[(size_t)r * n_rows + col] = 0ull;
 }
 // the per-CTA scalars (0 sum e' branch A, 1 branch B, 2 grad-dot) summed over the pass CTAs by ONE WARP in a fixed order
 // (lane-strided, then a butterfly): every warp that evaluates this gets the same bits.  All loads of a lane are issued
@@ -284,9 +290,9 @@ struct PassArgs {
   const float* pf_tp;       // [T] time points
   // Row sums of all CTAs meet in ONE set of 64-bit fixed-point accumulators (integer atomics: exact, hence independent of
   // the order in which the CTAs arrive -> bitwise reproducible without a fixed-order reduction kernel).  The scale is a
-  // power of two derived from a bound on the sums (see fx_scale()).  Two sets, indexed by the parity of the epoch the pass
-  // starts in: the kernel that follows (tail / reduce) converts the set of this pass and clears the other one.
-  unsigned long long* fx;   // [2 parities][FX_REP][part_n - 4]
+  // power of two derived from a bound on the sums (see fx_scale()).  The kernel that follows (tail / reduce) converts and
+  // clears them.
+  unsigned long long* fx;   // [FX_REP][part_n - 4]
   double* cta_scal;         // [CTA][4]: sum e' (both branches), grad-dot -- summed in a fixed order by the consumer (fold_scal)
   const float* nmax;        // max |feature| of this rank's packed arrays (state_init)
   Xchg x;
@@ -323,7 +329,7 @@ struct TailArgs {
   unsigned* counter;
   unsigned* epoch;            // advanced by the tail (CTA 0) once the new control block is written
   // the pass's raw sums (see PassArgs) and how they reach this kernel
-  unsigned long long* fx;     // [2 parities][FX_REP][part_n - 4]
+  unsigned long long* fx;     // [FX_REP][part_n - 4]
   const double* cta_scal;     // [pass CTA][4]
   const float* nmax;
   int pass_ctas;

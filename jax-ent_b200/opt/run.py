@@ -84,10 +84,18 @@ def _optimise(_simulation: Simulation, data_to_fit: Sequence, n_steps: int, tole
 
 def run_optimise(simulation: Simulation, data_to_fit: Sequence, config: OptimiserSettings, forward_models: Sequence,
                  indexes: Sequence[int], loss_functions: list, optimizer: Optional[OptaxOptimizer] = None,
-                 optimisable_funcs=None, initialise: Optional[bool] = False, _opt_fn: Callable = _optimise,
+                 optimisable_funcs=None, initialise: Optional[bool] = False, _opt_fn: Optional[Callable] = None,
                  jit_update_step: bool = False, logger: Optional[logging.Logger] = None, silent: bool = False):
-    """Run the optimisation (reference opt/run.py:376-461) -> (simulation, OptimizationHistory)."""
+    """Run the optimisation (reference opt/run.py:376-461) -> (simulation, OptimizationHistory).
+
+    `_opt_fn` (reference default: `_optimise`, the Python loop): left at None, the loop runs on the device
+    (`_optimise_device`: tracker, EMA parameters, snapshots and the stop decision in the tail kernel, one status read per 32
+    steps) -- it returns the same history, EMA history and best state as the Python loop, bit for bit
+    (tests/test_gpu_api.py::test_on_device_loop_matches_host_loop), without its per-step host synchronisation.  The
+    Python loop is used when the logger is at DEBUG level (it logs every step) or when `_opt_fn=_optimise` is passed."""
     _logger = logger if logger is not None else LOGGER
+    if _opt_fn is None:
+        _opt_fn = _optimise if (not silent and _logger.isEnabledFor(logging.DEBUG)) else _optimise_device
     if initialise:
         if not simulation.initialise():
             raise ValueError("Failed to initialise simulation")

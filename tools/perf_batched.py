@@ -30,3 +30,21 @@ print(f"NS={NS}: batched step {ms*1e3:.1f} us for {B} replicas = {1e3/ms:.1f} st
 lib, plan = eng.lib, eng.plan
 r = eng.records_at(eng.steps_done)
 print("loss replica 0 / 255:", r[0].total_train, r[255].total_train)
+# per-phase timing (events between the four phases of a step; phases are serialised here, no side-stream overlap)
+import ctypes as C
+from jaxent_b200.engine import _stream_ptr
+K = 10
+evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+for k in range(K):
+    evs[k][0].record()
+    for ph in range(4):
+        L.check(lib.jaxent_bg_step_phase(plan, ph, _stream_ptr()))
+        evs[k][ph + 1].record()
+torch.cuda.synchronize()
+names = ["gemm1 (+fused grad)", "grad+decide+adam", "gemm2", "reduce2+tail+kl+klfold"]
+tot = 0.0
+for ph in range(4):
+    t = np.median([evs[k][ph].elapsed_time(evs[k][ph + 1]) for k in range(K)]) * 1e3
+    tot += t
+    print(f"  phase {ph} {names[ph]:28s} {t:7.1f} us")
+print(f"  sum of phases {tot:.1f} us")

@@ -39,6 +39,9 @@ for trial in range(4):
     if os.environ.get("COMPACT") and trial > 0:
         t0 = a[41]
         g = lambda i: (a[i] - t0) / 1e3
+        per = a[64:].reshape(-1, 4).astype(np.float64); per = per[per[:, 0] > 0]
+        pc = lambda v: "/".join(f"{x:.1f}" for x in np.percentile((v - t0) / 1e3, [0, 50, 100]))
+        print(f"[r{rank}] per-CTA start {pc(per[:,0])} released {pc(per[:,1])} end {pc(per[:,2])}")
         print(f"[r{rank}] period {period:.1f} | lastCTA {g(44):.1f} tail.pdl {g(2):.1f} scalars {g(3):.1f} fin {g(9):.1f} ctl written {g(10):.1f} -> release gap {period - g(10):.1f} | tail body {g(9)-g(3):.1f}", flush=True)
 dist.barrier()
 names = {40: "pass.start", 41: "pass.pdl", 42: "pass.kl", 43: "pass.cta0end", 44: "red.start", 45: "red.pdl", 46: "red.end",
