@@ -84,7 +84,7 @@ struct BatchArgs {
   int p_max_tr, p_max_va;
   int blob_words_max;     // words reserved for the blob image in the tail's shared memory
   int ew_blocks, fy;      // elementwise grid (2 blocks of 512 threads per SM) / frames per block iteration
-  int adam_blocks;        // bt_adam keeps 128 registers per thread: one 512-thread block per SM, one wave
+  int adam_blocks, adam_threads;  // bt_adam: one replica per thread (see the kernel)
   int dot_blocks;         // rows of part_dot written by the gradient kernel (bt_grad, or the fused tensor-core kernel)
   float eps_kl;
   // on-device loop (jaxent_bg_track_init)
@@ -594,110 +594,92 @@ __global__ void bt_decide_kernel(const BatchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ bt_adam
-// thread = (4 consecutive replicas, chunk lane cy); a chunk is 8 consecutive frames: z, m, v updated in place, e' written
-// (16-byte loads / stores), and the bf16 pieces of e' stored as 16-byte K-chunks of the gemm2 B operand.
-// update = 0: initial forward (no Adam).
-__global__ void __launch_bounds__(512) bt_adam_kernel(const BatchArgs a, int update) {
-  extern __shared__ double sh_d[];  // [2][cy][Bn]
-  const int Bn = a.Bn, Bq = Bn >> 2, bq = threadIdx.x % Bq, cy = threadIdx.x / Bq, ncy = blockDim.x / Bq, b0 = 4 * bq;
-  const float4* __restrict__ g4p = reinterpret_cast<const float4*>(a.g[*a.gsel]);
-  float4* __restrict__ z4p = reinterpret_cast<float4*>(a.z);
-  float4* __restrict__ m4p = reinterpret_cast<float4*>(a.m);
-  float4* __restrict__ v4p = reinterpret_cast<float4*>(a.v);
-  float4* __restrict__ e4p = reinterpret_cast<float4*>(a.e);
-  __shared__ float s_f[4][256];
-  __shared__ int s_i[256];
-  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {  // per-replica constants through shared memory (see bt_grad)
-    const BCtl* c = a.ctl + b;
-    s_f[0][b] = c->lr_eff;
-    s_f[1][b] = c->lse;
-    s_f[2][b] = 1.0f / c->bc1;  // bias corrections applied as reciprocal multiplies
-    s_f[3][b] = 1.0f / c->bc2;
-    s_i[b] = ((update && !c->stop) ? 1 : 0) | ((c->kl_slot >= 0 && a.prob.prior != nullptr) ? 2 : 0);
-  }
-  __syncthreads();
-  float lr[4], lse[4], ibc1[4], ibc2[4];
-  bool active[4], has_kl[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    lr[j] = s_f[0][b0 + j];
-    lse[j] = s_f[1][b0 + j];
-    ibc1[j] = s_f[2][b0 + j];
-    ibc2[j] = s_f[3][b0 + j];
-    active[j] = s_i[b0 + j] & 1;
-    has_kl[j] = s_i[b0 + j] & 2;
-  }
+// thread = (ONE replica b, chunk lane cy); a chunk is 8 consecutive frames: z, m, v updated in place, e' written, and the bf16
+// pieces of e' stored as 16-byte K-chunks of the gemm2 B operand.  All 32 loads of a chunk (4 arrays x 8 frames, each a
+// coalesced 128-byte line per warp: consecutive lanes are consecutive replicas) are issued before the arithmetic; ~64
+// registers per thread, four 256-thread blocks per SM.  (The first version gave a thread 4 replicas x 8 frames with 16-byte
+// accesses: 128 registers, one block per SM, 197 us for 870 MB.)  update = 0: initial forward (no Adam).
+__global__ void __launch_bounds__(512, 2) bt_adam_kernel(const BatchArgs a, int update) {
+  extern __shared__ double sh_d[];  // [2][ncy][Bn]
+  const int Bn = a.Bn, b = threadIdx.x % Bn, cy = threadIdx.x / Bn, ncy = blockDim.x / Bn;
+  const float* __restrict__ gp = a.g[*a.gsel];
+  float* __restrict__ zp_ = a.z;
+  float* __restrict__ mp = a.m;
+  float* __restrict__ vp = a.v;
+  float* __restrict__ ep = a.e;
+  const BCtl* c = a.ctl + b;
+  const float lr = c->lr_eff, lse = c->lse;
+  const float ibc1 = 1.0f / c->bc1, ibc2 = 1.0f / c->bc2;  // bias corrections applied as reciprocal multiplies
+  const bool active = update && !c->stop;
+  const bool has_kl = c->kl_slot >= 0 && a.prob.prior != nullptr;
   const float b1 = (float)a.cfg.b1, b2 = (float)a.cfg.b2, eps = (float)a.cfg.eps, clip = a.cfg.clip_value;
   const float om_b1 = (float)(1.0 - a.cfg.b1), om_b2 = (float)(1.0 - a.cfg.b2);
   const int NS = a.NS;
   const long long n_chunks = (long long)a.n_fb * 16;
-  double sum[4] = {0.0, 0.0, 0.0, 0.0}, zp[4] = {0.0, 0.0, 0.0, 0.0};  // sum_f e'_f and sum_f p_f z'_f (MaxEnt loss)
+  double sum = 0.0, zp = 0.0;  // sum_f e'_f and sum_f p_f z'_f (MaxEnt loss)
   for (long long ch = (long long)blockIdx.x * ncy + cy; ch < n_chunks; ch += (long long)gridDim.x * ncy) {
-    __nv_bfloat16 p0[4][8], p1[4][8], p2[4][8];
+    const long long f0 = ch * 8;
+    __nv_bfloat16 p0[8], p1[8], p2[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const long long f = ch * 8 + k;
-      float en[4] = {0.f, 0.f, 0.f, 0.f};
-      if (f < a.F) {
-        const size_t i = (size_t)f * Bq + bq;
-        const float4 zv = z4p[i];
-        float z_[4] = {zv.x, zv.y, zv.z, zv.w};
+    for (int h = 0; h < 2; ++h) {  // two halves of 4 frames: 16 loads in flight per thread, 64 registers
+      float z_[4], m_[4], v_[4], g_[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long f = f0 + 4 * h + k;
+        const bool ok = f < a.F;
+        const size_t i = (size_t)(ok ? f : 0) * Bn + b;
+        z_[k] = ok ? zp_[i] : 0.f;
         if (update) {
-          const float4 gv = g4p[i], mv = m4p[i], vv = v4p[i];
-          const float g_[4] = {gv.x, gv.y, gv.z, gv.w}, m_[4] = {mv.x, mv.y, mv.z, mv.w}, v_[4] = {vv.x, vv.y, vv.z, vv.w};
-          float mo[4], vo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mo[j] = m_[j];
-            vo[j] = v_[j];
-            if (active[j]) {
-              float sg = g_[j] * lr[j];
-              if (clip > 0.f) sg = fminf(fmaxf(sg, -clip), clip);
-              mo[j] = om_b1 * sg + b1 * m_[j];
-              vo[j] = om_b2 * (sg * sg) + b2 * v_[j];
-              z_[j] = z_[j] - (mo[j] * ibc1[j]) / (sqrtf(vo[j] * ibc2[j]) + eps);
-            }
-          }
-          z4p[i] = make_float4(z_[0], z_[1], z_[2], z_[3]);
-          m4p[i] = make_float4(mo[0], mo[1], mo[2], mo[3]);
-          v4p[i] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+          g_[k] = ok ? gp[i] : 0.f;
+          m_[k] = ok ? mp[i] : 0.f;
+          v_[k] = ok ? vp[i] : 0.f;
         }
-        const float pf = a.prob.prior != nullptr ? a.pnorm[f] : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          en[j] = __expf(z_[j] - lse[j]);
-          sum[j] += (double)en[j];
-          if (has_kl[j]) zp[j] += (double)pf * (double)z_[j];
-        }
-        e4p[i] = make_float4(en[0], en[1], en[2], en[3]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split3(en[j], NS, p0[j][k], p1[j][k], p2[j][k]);
+      for (int k = 0; k < 4; ++k) {
+        const long long f = f0 + 4 * h + k;
+        const size_t i = (size_t)f * Bn + b;
+        float en = 0.f;
+        if (f < a.F) {
+          if (update) {
+            float mo = m_[k], vo = v_[k];
+            if (active) {
+              float sg = g_[k] * lr;
+              if (clip > 0.f) sg = fminf(fmaxf(sg, -clip), clip);
+              mo = om_b1 * sg + b1 * m_[k];
+              vo = om_b2 * (sg * sg) + b2 * v_[k];
+              z_[k] = z_[k] - (mo * ibc1) / (sqrtf(vo * ibc2) + eps);
+            }
+            zp_[i] = z_[k];
+            mp[i] = mo;
+            vp[i] = vo;
+          }
+          en = __expf(z_[k] - lse);
+          sum += (double)en;
+          if (has_kl) zp += (double)a.pnorm[f] * (double)z_[k];
+          ep[i] = en;
+        }
+        split3(en, NS, p0[4 * h + k], p1[4 * h + k], p2[4 * h + k]);
+      }
     }
     const long long fb = ch >> 4;
     const int kc = (int)(ch & 15);
     uint4* dst = reinterpret_cast<uint4*>(a.e3);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dst[(((size_t)fb * NS + 0) * 16 + kc) * Bn + b0 + j] = *reinterpret_cast<const uint4*>(p0[j]);
-      if (NS > 1) dst[(((size_t)fb * NS + 1) * 16 + kc) * Bn + b0 + j] = *reinterpret_cast<const uint4*>(p1[j]);
-      if (NS > 2) dst[(((size_t)fb * NS + 2) * 16 + kc) * Bn + b0 + j] = *reinterpret_cast<const uint4*>(p2[j]);
-    }
+    dst[(((size_t)fb * NS + 0) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p0);
+    if (NS > 1) dst[(((size_t)fb * NS + 1) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p1);
+    if (NS > 2) dst[(((size_t)fb * NS + 2) * 16 + kc) * Bn + b] = *reinterpret_cast<const uint4*>(p2);
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sh_d[cy * Bn + b0 + j] = sum[j];
-    sh_d[(ncy + cy) * Bn + b0 + j] = zp[j];
-  }
+  sh_d[cy * Bn + b] = sum;
+  sh_d[(ncy + cy) * Bn + b] = zp;
   __syncthreads();
-  for (int b = threadIdx.x; b < Bn; b += blockDim.x) {
+  for (int bb = threadIdx.x; bb < Bn; bb += blockDim.x) {
     double t = 0.0, tz = 0.0;
     for (int k = 0; k < ncy; ++k) {
-      t += sh_d[k * Bn + b];
-      tz += sh_d[(ncy + k) * Bn + b];
+      t += sh_d[k * Bn + bb];
+      tz += sh_d[(ncy + k) * Bn + bb];
     }
-    a.part_s[(size_t)blockIdx.x * Bn + b] = t;
-    a.part_s[(size_t)(MAX_EW_BLOCKS + blockIdx.x) * Bn + b] = tz;
+    a.part_s[(size_t)blockIdx.x * Bn + bb] = t;
+    a.part_s[(size_t)(MAX_EW_BLOCKS + blockIdx.x) * Bn + bb] = tz;
   }
 }
 
@@ -1243,7 +1225,14 @@ extern "C" int jaxent_bg_plan_create(const JaxentBvProblem* pb, const JaxentOptC
   if (blocks > bg::MAX_EW_BLOCKS) blocks = bg::MAX_EW_BLOCKS;
   if (blocks < 1) blocks = 1;
   a.ew_blocks = (int)blocks;
-  a.adam_blocks = a.ew_blocks < sm_count ? a.ew_blocks : sm_count;
+  // bt_adam: one replica per thread, blocks of adam_threads = Bn x (chunks per block), four 256-thread blocks per SM
+  a.adam_threads = n_replicas * (n_replicas >= 256 ? 1 : 256 / n_replicas);
+  {
+    const long long n_chunks = (long long)a.n_fb * 16, per_block = a.adam_threads / n_replicas;
+    long long ab = (n_chunks + per_block - 1) / per_block;
+    const long long cap = (long long)sm_count * 4 < bg::MAX_EW_BLOCKS ? (long long)sm_count * 4 : bg::MAX_EW_BLOCKS;
+    a.adam_blocks = (int)(ab < cap ? ab : cap);
+  }
   // backward product: gemm1 + bt_grad; JAXENT_BG_FUSED=1 selects the single fused tensor-core kernel (whole 128-replica M tiles only)
   {
     const char* env = getenv("JAXENT_BG_FUSED");
@@ -1410,7 +1399,7 @@ static int bg_update_phase(JaxentBatchPlan* p, cudaStream_t s) {
   }
   bg::bt_decide_kernel<<<(a.Bn * 32 + 255) / 256, 256, 0, s>>>(a);
   if ((rc = bg_err("bt_decide"))) return rc;
-  bg::bt_adam_kernel<<<a.adam_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 1);
+  bg::bt_adam_kernel<<<a.adam_blocks, a.adam_threads, (size_t)2 * a.adam_threads * 8, s>>>(a, 1);
   return bg_err("bt_adam");
 }
 
@@ -1458,7 +1447,7 @@ extern "C" int jaxent_bg_state_init(JaxentBatchPlan* p, const float* z0, float z
     if ((rc = bg_err("bt_prior"))) return rc;
   }
   if ((rc = launch_build_blobs(a.prob, a.blobs, s))) return rc;
-  bg::bt_adam_kernel<<<a.adam_blocks, (a.Bn / 4) * a.fy, (size_t)2 * a.fy * a.Bn * 8, s>>>(a, 0);
+  bg::bt_adam_kernel<<<a.adam_blocks, a.adam_threads, (size_t)2 * a.adam_threads * 8, s>>>(a, 0);
   if ((rc = bg_err("bt_adam(init)"))) return rc;
   rc = bg_forward(p, s);
   if (rc) return rc;
