@@ -352,9 +352,21 @@ int jaxent_bg_plan_buffer(const JaxentBatchPlan* plan, int32_t which, void** ptr
  * float[n+1][F][Bn]; snaps: JaxentTrackSnapshot[n+1][Bn].  A replica whose loop has ended is frozen; the others continue. */
 int jaxent_bg_track_init(JaxentBatchPlan* plan, const float* convergence, int32_t n, float ema_alpha, int32_t min_steps_per_threshold,
                          float tolerance, float* ema_w, float* snap_w, float* snap_ema, JaxentTrackSnapshot* snaps);
+/* which loop the per-replica tracker follows; call between jaxent_bg_track_init and jaxent_bg_state_init.
+ *   0 (default)  the Python loop _optimise (opt/run.py:235-373): ConvergenceTracker (opt/track.py:128-197), gradient-oscillation
+ *                reset, one history snapshot per completed threshold (slots 0..n);
+ *   1            _optimise_pure (opt/run.py:141-232) = lax.while_loop over OptaxOptimizer._pure_step (opt/optimiser.py:494-579),
+ *                the loop batch_optimise vmaps (opt/batch.py:107-146): update_convergence / check_and_advance_threshold
+ *                (opt/track.py:40-125) in fp32 -- the EMAs restart with every threshold, no oscillation reset, the threshold test
+ *                uses the 1-based state.step, cond_fn stops on the loss of the previous iteration.  Every iteration is an entry of
+ *                the reference's dense history; here the per-step losses stay in the record ring (256 deep: drain it at least
+ *                that often) and snapshot slot 0 follows the entry get_best_state would pick (smallest val_losses[0], first
+ *                occurrence; JaxentTrackSnapshot.loop_step = its index, snap_w slot 0 = its post-update frame weights). */
+int jaxent_bg_track_mode(JaxentBatchPlan* plan, int32_t mode);
 int jaxent_bg_track_status(JaxentBatchPlan* plan, JaxentTrackStatus* status, jaxent_stream_t stream);
 int jaxent_bg_ctl_sizeof(void);
-int jaxent_bg_ctl_offset(int32_t field); /* 0: double S, 1: float bc, 2: float bh, 3: int step, 4: float lse */
+int jaxent_bg_ctl_offset(int32_t field); /* 0: double S, 1: float bc, 2: float bh, 3: int step, 4: float lse, 5: int steps_since_threshold_start,
+                                           6: int best_step, 7: float best_val (pure-loop tracker) */
 
 /* ---- plan handles and workspace identity, for foreign-function layers (csrc/xla_ffi.cc, the jax.ffi custom calls of
  * INTEGRATION.md; the reference has no FFI of its own).  A custom call cannot carry a typed pointer, and a raw

@@ -27,4 +27,4 @@ from .opt.losses import (  # noqa: E402,F401
 )
 from .opt.optimiser import OptaxOptimizer, compute_loss  # noqa: E402,F401
 from .opt.batch import BatchOptimisationResult, HParamBatch, batch_optimise  # noqa: E402,F401
-from .opt.run import _optimise, _optimise_device, run_optimise  # noqa: E402,F401
+from .opt.run import _optimise, _optimise_device, _optimise_pure, run_optimise  # noqa: E402,F401

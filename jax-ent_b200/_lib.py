@@ -182,6 +182,7 @@ SYMBOLS = {
     "jaxent_bg_step_phase": (C.c_int, [_VP, _I32, _VP]),
     "jaxent_bg_plan_buffer": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_SZ)]),
     "jaxent_bg_track_init": (C.c_int, [_VP, C.POINTER(_F), _I32, _F, _I32, _F, _VP, _VP, _VP, _VP]),
+    "jaxent_bg_track_mode": (C.c_int, [_VP, _I32]),
     "jaxent_bg_track_status": (C.c_int, [_VP, _VP, _VP]),
     "jaxent_bg_ctl_sizeof": (C.c_int, []),
     "jaxent_bg_ctl_offset": (C.c_int, [_I32]),

@@ -147,9 +147,15 @@ class BatchedBvEngine(BvEngine):
         self.uptake_b = self._bview(5, torch.float32).view(self.Bn, max(self.T, 1), self.R) if self.uptake else None
 
     # ------------------------------------------------------------------ on-device loop of every replica
-    def enable_tracking(self, convergence, ema_alpha: float = 0.5, min_steps_per_threshold: int = 2, tolerance: float = 1e-10) -> None:
-        """Arm the per-replica ConvergenceTracker (reference opt/track.py:128-197); call before init_state().  The
-        thresholds are sorted descending here and scaled by each replica's learning rate on the device side."""
+    def enable_tracking(self, convergence, ema_alpha: float = 0.5, min_steps_per_threshold: int = 2, tolerance: float = 1e-10,
+                        loop: str = "python") -> None:
+        """Arm the per-replica tracker; call before init_state().  The thresholds are sorted descending here and scaled by
+        each replica's learning rate on the device side.  loop="python": ConvergenceTracker of `_optimise`
+        (reference opt/track.py:128-197, opt/run.py:285-348), a snapshot per completed threshold.  loop="pure": the functional
+        tracker of `_optimise_pure` (opt/track.py:40-125, opt/run.py:141-232), the loop the reference's batch_optimise vmaps --
+        every step is a history entry, snapshot slot 0 follows the best one (jaxent_bg_track_mode, jaxent_b200.h)."""
+        if loop not in ("python", "pure"):
+            raise ValueError("loop must be 'python' or 'pure'")
         conv = np.sort(np.atleast_1d(np.asarray(convergence, np.float32)))[::-1].copy()
         n = int(conv.shape[0])
         if n < 1 or n > L.TRACK_MAX_THRESHOLDS:
@@ -164,7 +170,9 @@ class BatchedBvEngine(BvEngine):
         L.check(self.lib.jaxent_bg_track_init(self.plan, arr, n, float(ema_alpha), int(min_steps_per_threshold), float(tolerance),
                                               self._trk_ema.data_ptr(), self._trk_snap_w.data_ptr(), self._trk_snap_ema.data_ptr(),
                                               self._trk_snaps.data_ptr()))
+        L.check(self.lib.jaxent_bg_track_mode(self.plan, 1 if loop == "pure" else 0))
         self._trk_n = n
+        self._trk_loop = loop
         self.tracking = True
 
     def track_status(self):
@@ -187,21 +195,42 @@ class BatchedBvEngine(BvEngine):
             out.append((sn, self._trk_snap_w[i, :, b], self._trk_snap_ema[i, :, b] if sn.have_ema else None))
         return out
 
-    def run(self, n_steps: int, chunk: int = 32):
+    def run(self, n_steps: int, chunk: int = 32, keep_records: bool = False):
         """Up to n_steps steps; replicas whose loop has ended are frozen on the device, the host looks at the status every
-        `chunk` steps and stops when every replica has ended.  Returns [TrackStatus]."""
+        `chunk` steps and stops when every replica has ended.  Returns [TrackStatus].  keep_records: the loss records of
+        every step are drained from the device ring with each status read (one small copy per chunk) and kept in
+        `self.record_history`, a (steps + 1, Bn) array of LossRecord bytes: row k = the losses evaluated at optimiser step k
+        (the reference's per-step history_losses, opt/optimiser.py:555-567), valid for k <= the replica's steps_done."""
         if not getattr(self, "tracking", False):
             raise RuntimeError("enable_tracking() has not been called")
+        chunk = max(1, min(int(chunk), RECORD_RING - 1))
         done, st = 0, None
         self._trk_snaps_host = None
+        rows = [self._record_rows(0, 1)] if keep_records else []  # row 0: the initial forward (jaxent_bg_state_init)
         while done < n_steps:
             m = min(chunk, n_steps - done)
             self.step(m)
+            if keep_records:  # row k is written by the tail of step k - 1; rows beyond a frozen replica's steps_done are stale
+                rows.append(self._record_rows(done + 1, m))
             done += m
             st = self.track_status()
             if all(s.stop for s in st):
                 break
+        if keep_records:
+            sz = C.sizeof(L.LossRecord)
+            self.record_history = np.concatenate(rows, axis=0) if rows else np.zeros((0, self.Bn, sz), np.uint8)
         return st if st is not None else self.track_status()
+
+    def _record_rows(self, first: int, n: int) -> np.ndarray:
+        """(n, Bn, sizeof(LossRecord)) bytes: ring rows of optimiser steps first .. first + n - 1"""
+        sz = C.sizeof(L.LossRecord)
+        ring = self._brecords.view(RECORD_RING, self.Bn * sz)
+        idx = torch.arange(first, first + n, device=self.device) % RECORD_RING
+        return ring[idx].cpu().numpy().reshape(n, self.Bn, sz)
+
+    def record_of(self, step: int, b: int):
+        """LossRecord of replica b at optimiser step `step` from the history kept by run(keep_records=True)"""
+        return L.LossRecord.from_buffer_copy(self.record_history[step, b].tobytes())
 
     def step(self, n: int = 1) -> None:
         with torch.cuda.device(self.device):

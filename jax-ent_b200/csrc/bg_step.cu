@@ -50,7 +50,8 @@ struct alignas(16) BCtl {
                           // evaluated (snapshot of the post-update weights), then `stop` freezes the replica
   int trk_reason, trk_stop_step, trk_have_prev, trk_have_ema, trk_steps_since, trk_idx, trk_nsnap;
   int snap_now, ema_update, ema_first, loop_step;
-  float trk_ema_bc, trk_ema_bh, trk_pad[2];
+  int trk_have_best, trk_best_step, trk_pad_i[2];  // pure-loop mode: loop index whose validation loss is the best so far
+  float trk_ema_bc, trk_ema_bh, trk_best_val, trk_pad;
   float thr[JAXENT_TRACK_MAX_THRESHOLDS];  // descending, already multiplied by this replica's learning rate
   double trk_prev_loss, trk_ema;
 };
@@ -89,6 +90,7 @@ struct BatchArgs {
   float eps_kl;
   // on-device loop (jaxent_bg_track_init)
   int trk_on, trk_n_thr, trk_min_steps;
+  int trk_pure;  // 1: the functional tracker of _optimise_pure (opt/track.py:40-125), the loop batch_optimise vmaps; 0: ConvergenceTracker of the Python loop
   float trk_alpha, trk_tolerance;
   float* ema_w;                // [F][Bn] EMA of the softmax weights
   float* snap_w;               // [n_thr + 1][F][Bn]
@@ -492,6 +494,18 @@ __global__ void bt_decide_kernel(const BatchArgs a) {
   for (int k = lane; k < a.dot_blocks; k += 32) gdot += a.part_dot[(size_t)k * a.Bn + b];
   gdot = wsum(gdot);
   if (lane != 0) return;
+  if (a.trk_on && a.trk_pure && c->step == 0) {
+    // cond_fn of _optimise_pure (opt/run.py:202-211) looks at the loss of the dense initial state before the first iteration
+    const double l0 = (double)a.records[b].total_train;
+    if (l0 < (double)a.trk_tolerance || isnan(l0) || isinf(l0)) {
+      c->stop = 1;
+      c->trk_reason = 2;
+      c->trk_stop_step = 0;
+      c->snap_now = -1;
+      c->ema_update = 0;
+      return;
+    }
+  }
   const float g0 = c->gb[0], g1 = c->gb[1];
   const float p0 = c->have_prev ? c->gb_prev[0] : g0, p1 = c->have_prev ? c->gb_prev[1] : g1;
   const double dot = gdot + (double)p0 * (double)g0 + (double)p1 * (double)g1;
@@ -533,7 +547,69 @@ __global__ void bt_decide_kernel(const BatchArgs a) {
   c->snap_now = -1;
   c->ema_update = 0;
   c->ema_first = 0;
-  if (a.trk_on) {
+  if (a.trk_on && a.trk_pure) {
+    // update_convergence / check_and_advance_threshold (opt/track.py:40-125) inside OptaxOptimizer._pure_step
+    // (opt/optimiser.py:494-579), fp32 like the reference's carry.  k = state.step before this update.
+    const int k = c->step - 1;
+    c->loop_step = k;
+    const JaxentLossRecord& rk = a.records[(size_t)(k % RB) * a.Bn + b];
+    const float loss = rk.total_train;
+    const float alpha = a.trk_alpha;
+    // previous_loss = the loss stored by iteration k - 1; the dense initial state carries the loss at the initial parameters,
+    // which is also what iteration 0 evaluates: first raw delta = 0
+    const float prev = c->trk_have_prev ? (float)c->trk_prev_loss : loss;
+    const float raw = fabsf(prev - loss);
+    const bool first = c->trk_steps_since == 0;  // the EMAs restart at the start and after every threshold advance
+    const float ema = first ? raw : alpha * raw + (1.0f - alpha) * (float)c->trk_ema;
+    c->trk_ema = (double)ema;
+    c->trk_have_ema = 1;
+    c->ema_update = 1;
+    c->ema_first = first ? 1 : 0;
+    c->trk_ema_bc = first ? c->bc : alpha * c->bc + (1.0f - alpha) * c->trk_ema_bc;
+    c->trk_ema_bh = first ? c->bh : alpha * c->bh + (1.0f - alpha) * c->trk_ema_bh;
+    c->trk_steps_since += 1;
+    c->trk_prev_loss = (double)loss;
+    c->trk_have_prev = 1;
+    const int ti = c->trk_idx < a.trk_n_thr ? c->trk_idx : a.trk_n_thr - 1;
+    const float rel = loss > 0.f ? ema / loss : 0.f;
+    const bool met = c->trk_steps_since >= a.trk_min_steps && rel < c->thr[ti] && c->step > cfg.initial_steps;  // 1-based state.step
+    if (met && c->trk_idx + 1 < a.trk_n_thr) {
+      c->trk_idx += 1;
+      c->trk_steps_since = 0;
+    } else if (met) {
+      c->stopping = 1;
+      c->trk_reason = 1;
+      c->trk_stop_step = k;
+    }
+    if (!c->stopping && (loss < a.trk_tolerance || isnan(loss) || isinf(loss))) {  // cond_fn before iteration k + 1
+      c->stopping = 1;
+      c->trk_reason = 2;
+      c->trk_stop_step = k;
+    }
+    // every iteration enters the reference's dense history (save_state = post-update weights, losses of step k) and
+    // get_best_state takes the smallest first validation loss (opt/base.py:180-189 over all steps, opt/batch.py:158-180): slot 0
+    // of the snapshot buffers follows the running minimum (strictly smaller: the first step that reaches it)
+    const float val0 = rk.val[0];
+    if (!c->trk_have_best || val0 < c->trk_best_val) {
+      c->trk_have_best = 1;
+      c->trk_best_val = val0;
+      c->trk_best_step = k;
+      c->snap_now = 0;
+      c->trk_nsnap = 1;
+      if (a.snaps != nullptr) {
+        JaxentTrackSnapshot* sn = a.snaps + b;
+        sn->loop_step = k;
+        sn->state_step = c->step;
+        sn->have_ema = 0;
+        sn->threshold_idx = c->trk_idx;
+        sn->bc = c->bc;
+        sn->bh = c->bh;
+        sn->ema_bc = c->trk_ema_bc;
+        sn->ema_bh = c->trk_ema_bh;
+        sn->losses = rk;
+      }
+    }
+  } else if (a.trk_on) {
     const int k = c->step - 1;
     c->loop_step = k;
     const double loss = (double)a.records[(size_t)(k % RB) * a.Bn + b].total_train;
@@ -925,7 +1001,7 @@ __global__ void __launch_bounds__(512) bt_kl_kernel(const BatchArgs a) {
           if (ema_update[j]) {
             const float em = ema_first[j] ? w : a.trk_alpha * w + (1.0f - a.trk_alpha) * a.ema_w[i];
             a.ema_w[i] = em;
-            if (snap[j] >= 0) a.snap_ema[(size_t)snap[j] * a.F * Bn + i] = em;
+            if (snap[j] >= 0 && !a.trk_pure) a.snap_ema[(size_t)snap[j] * a.F * Bn + i] = em;
           }
           if (snap[j] >= 0) a.snap_w[(size_t)snap[j] * a.F * Bn + i] = w;
         }
@@ -1531,6 +1607,9 @@ extern "C" int jaxent_bg_ctl_offset(int32_t field) {
     case 2: return (int)offsetof(bg::BCtl, bh);
     case 3: return (int)offsetof(bg::BCtl, step);
     case 4: return (int)offsetof(bg::BCtl, lse);
+    case 5: return (int)offsetof(bg::BCtl, trk_steps_since);
+    case 6: return (int)offsetof(bg::BCtl, trk_best_step);
+    case 7: return (int)offsetof(bg::BCtl, trk_best_val);
     default: return -1;
   }
 }
@@ -1557,6 +1636,17 @@ extern "C" int jaxent_bg_track_init(JaxentBatchPlan* p, const float* convergence
   a.snap_ema = snap_ema;
   a.snaps = snaps;
   for (int i = 0; i < n; ++i) p->conv[i] = convergence[i];
+  p->initialised = 0;  // the tracker state lives in the control blocks: jaxent_bg_state_init must follow
+  return JAXENT_OK;
+}
+
+// which loop the tracker follows: 0 (default) the Python loop `_optimise` (opt/run.py:235-373: ConvergenceTracker, oscillation
+// reset, a snapshot per threshold), 1 `_optimise_pure` (opt/run.py:141-232, what batch_optimise vmaps: functional tracker,
+// EMAs restart with every threshold, every step is a history entry -> snapshot slot 0 follows the best validation loss)
+extern "C" int jaxent_bg_track_mode(JaxentBatchPlan* p, int32_t mode) {
+  if (!p) { set_error("bg_track_mode: plan is NULL"); return JAXENT_E_INVALID; }
+  if (mode != 0 && mode != 1) { set_error("bg_track_mode: mode must be 0 (Python loop) or 1 (pure loop)"); return JAXENT_E_INVALID; }
+  p->a.trk_pure = mode;
   p->initialised = 0;  // the tracker state lives in the control blocks: jaxent_bg_state_init must follow
   return JAXENT_OK;
 }

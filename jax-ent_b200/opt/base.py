@@ -21,6 +21,16 @@ class LossComponents(NamedTuple):
     total_val_loss: Any
 
 
+class ConvergenceCarry(NamedTuple):
+    """carry of the functional tracker (reference opt/base.py: ConvergenceCarry), scalars held as Python / NumPy fp32 values"""
+
+    ema_loss_delta: Any
+    ema_params: Any
+    steps_since_threshold_start: Any
+    current_threshold_idx: Any
+    converged: Any
+
+
 class OptimizationState(NamedTuple):
     params: Simulation_Parameters
     opt_state: Any

@@ -3,11 +3,13 @@ forward_model_scaling, learning_rate) that share the features, the data and the 
 
 The reference vmaps `_optimise_pure` over the hyper-parameter batch.  Here a batch of replicas is advanced by ONE fused
 step on the tensor cores (BatchedBvEngine: the two feature sweeps are tcgen05 GEMMs over all replicas, DESIGN.md
-section 6) with the per-replica ConvergenceTracker, history snapshots and stop decision evaluated on the device; replicas
-whose loop has ended are frozen while the others continue -- the semantics of a vmapped `lax.while_loop`.  The
+section 6) with the per-replica tracker of `_optimise_pure` (update_convergence / check_and_advance_threshold,
+opt/track.py:40-125), the best-state selection and the stop decision evaluated on the device; replicas whose loop has
+ended are frozen while the others continue -- the semantics of a vmapped `lax.while_loop`.  Every step is a history entry
+with its losses, as in the reference; frame weights are kept for the best and the last entry only.  The
 tensor-core path needs features that are exact in bf16 (hard-cutoff contact counts); otherwise (`engine="sequential"`,
-or "auto" on other features) every run uses the single-ensemble on-device loop (`_optimise_device`) on shared packed
-features, one replica after the other."""
+or "auto" on other features) every run goes through `_optimise_pure` (opt/run.py: the same loop semantics, driven from the
+host over the single-ensemble fused step) on shared packed features, one replica after the other."""
 from __future__ import annotations
 
 from typing import Optional, Sequence
@@ -21,7 +23,7 @@ from ..interfaces.simulation import Simulation_Parameters, _replace
 from ..models.core import Simulation
 from .base import BatchOptimisationResult, HParamBatch, OptimizationHistory, OptimizationState  # noqa: F401 (re-exported)
 from .optimiser import OptaxOptimizer
-from .run import _optimise_device
+from .run import _optimise_pure
 
 
 def _batch_optimise_gemm(simulation: Simulation, fw, fs, lrs, batch_size: int, data_to_fit, config: OptimiserSettings, indexes,
@@ -52,25 +54,48 @@ def _batch_optimise_gemm(simulation: Simulation, fw, fs, lrs, batch_size: int, d
         hi = min(lo + per, n_h)
         eng = BatchedBvEngine(feats, None, simulation._k_ints, simulation._timepoints, specs, simulation._uptake, optimizer._settings(),
                               hi - lo, prior=prior, device=simulation.device)
-        eng.enable_tracking(convergence, config.ema_alpha, config.min_steps_per_threshold, config.tolerance)
+        eng.enable_tracking(convergence, config.ema_alpha, config.min_steps_per_threshold, config.tolerance, loop="pure")
         lr = lrs[lo:hi] if lrs is not None else np.full(hi - lo, config.learning_rate, np.float32)
         eng.init_state(z0, scalar(mp.bv_bc), scalar(mp.bv_bh), fw[lo:hi], fs[lo:hi], lr)
-        status = eng.run(config.n_steps)
+        status = eng.run(config.n_steps, keep_records=True)
+        w_last = eng.weights_all()
+        norm = Simulation_Parameters.normalize_weights(params)
+
+        # the per-step loss records of all replicas, uploaded once: history entries are views into this tensor
+        recs = torch.from_numpy(eng.record_history.copy()).view(torch.float32).to(eng.device)  # (steps + 1, Bn, record floats)
+        val0_all = eng.record_history.view(np.float32)[:, :, 14]  # LossRecord.val[0]
+
+        def _state(b, i, weights):
+            # history entry i of the reference (opt/optimiser.py:555-567, opt/batch.py:158-172): the parameters AFTER update i
+            # (the BV parameters step i + 1 was evaluated at) paired with the losses evaluated BEFORE it; step = the history index
+            nxt = recs[i + 1, b]
+            mp_s = type(mp)(bv_bc=nxt[4:5], bv_bh=nxt[5:6], temperature=mp.temperature, timepoints=mp.timepoints)
+            sp = _replace(norm, frame_weights=weights, model_parameters=[mp_s],
+                          forward_model_weights=fw[lo + b].astype(np.float32), forward_model_scaling=fs[lo + b].astype(np.float32))
+            return OptimizationState(sp, B200OptState(None, i + 1), i, _losses_from_record(recs[i, b], n_l, copy=False), None)
+
         for b in range(hi - lo):
             st = status[b]
+            n_written = int(st.steps_done)  # write_idx of the reference carry
             hist = OptimizationHistory()
-            for sn, w, _ema in eng.track_snapshots(b, st.n_snapshots):
-                mp_s = type(mp)(bv_bc=torch.tensor([sn.bc], device=eng.device), bv_bh=torch.tensor([sn.bh], device=eng.device),
-                                temperature=mp.temperature, timepoints=mp.timepoints)
-                sp = _replace(Simulation_Parameters.normalize_weights(params), frame_weights=w.clone(), model_parameters=[mp_s],
-                              forward_model_weights=fw[lo + b].astype(np.float32), forward_model_scaling=fs[lo + b].astype(np.float32))
-                rec = torch.frombuffer(bytearray(bytes(sn.losses)), dtype=torch.float32).to(eng.device)
-                hist.add_state(OptimizationState(sp, B200OptState(None, sn.state_step), sn.state_step, _losses_from_record(rec, n_l), None))
-            if hist.states:
-                hist.best_state = hist.get_best_state()
+            if n_written:
+                sn, w_best, _ = eng.track_snapshots(b, 1)[0]
+                val0 = val0_all[:n_written, b]
+                # _pick_best_state (opt/base.py:180-189): the last entry unless an earlier one is strictly better, then the first
+                # entry that reaches the minimum -- which is the one the device followed
+                best_i = n_written - 1 if not (val0.min() < val0[-1]) else int(sn.loop_step)
+                for i in range(n_written):
+                    if i == n_written - 1:
+                        weights = w_last[:, b].clone()
+                    elif i == best_i:
+                        weights = w_best.clone()
+                    else:
+                        weights = None  # a dense [n_steps, F] history per replica is not kept on this path
+                    hist.states.append(_state(b, i, weights))
+                hist.best_state = hist.states[best_i]
             histories.append(hist)
             best_states.append(hist.best_state if hist.states else state0)
-            conv_steps.append(int(st.steps_done))
+            conv_steps.append(n_written)
         del eng
     return histories, best_states, conv_steps
 
@@ -127,12 +152,13 @@ def batch_optimise(simulation: Simulation, hparam_batch: HParamBatch, batch_size
         run_sim = simulation._shallow_copy()
         run_sim.params = _replace(base_params, forward_model_weights=fw[i].astype(np.float32), forward_model_scaling=fs[i].astype(np.float32))
         state = run_opt.initialise(run_sim, optimisable_funcs)
-        _, run_opt = _optimise_device(run_sim, data_to_fit, config.n_steps, config.tolerance, config.convergence, indexes,
-                                      loss_functions, state, run_opt, ema_alpha=config.ema_alpha,
-                                      min_steps_per_threshold=config.min_steps_per_threshold)
+        # the same loop semantics as the tensor-core path: _optimise_pure (the loop the reference vmaps), host-driven
+        _, run_opt = _optimise_pure(run_sim, data_to_fit, config.n_steps, config.tolerance, config.convergence, indexes,
+                                    loss_functions, state, run_opt, ema_alpha=config.ema_alpha,
+                                    min_steps_per_threshold=config.min_steps_per_threshold)
         hist = run_opt.history
         histories.append(hist)
         best_states.append(hist.best_state if hist.states else state)
-        conv_steps.append(int(run_opt._device_status.steps_done))
+        conv_steps.append(int(run_opt._pure_carry[1]))
     return BatchOptimisationResult(tuple(histories), tuple(best_states), np.asarray(conv_steps, np.int32),
                                    HParamBatch(hparam_batch.forward_model_weights, hparam_batch.forward_model_scaling, hparam_batch.learning_rate))

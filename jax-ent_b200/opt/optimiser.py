@@ -137,8 +137,9 @@ def _record_view(eng: BvEngine, step: int) -> torch.Tensor:
     return recs[i : i + _REC_FLOATS]
 
 
-def _losses_from_record(rec: torch.Tensor, n: int) -> LossComponents:
-    rec = rec.clone()  # the ring slot is reused after JAXENT_RECORD_RING steps
+def _losses_from_record(rec: torch.Tensor, n: int, copy: bool = True) -> LossComponents:
+    if copy:
+        rec = rec.clone()  # the ring slot is reused after JAXENT_RECORD_RING steps
     return LossComponents(
         train_losses=rec[8 : 8 + n],
         val_losses=rec[14 : 14 + n],

@@ -18,7 +18,8 @@ from ..interfaces.simulation import Simulation_Parameters, _replace
 from ..models.core import Simulation
 from .base import OptimizationHistory, OptimizationState
 from .optimiser import OptaxOptimizer
-from .track import ConvergenceTracker
+from .track import (ConvergenceTracker, check_and_advance_threshold, create_convergence_thresholds, initialise_convergence_carry,
+                    update_convergence)
 
 LOGGER = logging.getLogger("jaxent.opt")
 
@@ -79,6 +80,66 @@ def _optimise(_simulation: Simulation, data_to_fit: Sequence, n_steps: int, tole
     if not silent:
         dt = time.time() - t_start
         _logger.info("Optimisation finished: %d steps in %.3f s (%.1f it/s)", step + 1, dt, (step + 1) / max(dt, 1e-9))
+    return _simulation, optimizer
+
+
+def _optimise_pure(_simulation: Simulation, data_to_fit: Sequence, n_steps: int, tolerance: float, convergence, indexes: Sequence[int],
+                   loss_functions: Sequence, opt_state: OptimizationState, optimizer: OptaxOptimizer, ema_alpha: float = 0.5,
+                   min_steps_per_threshold: int = 2, learning_rate: Optional[float] = None, **_unused):
+    """The loop of the reference's `_optimise_pure` (opt/run.py:141-232: lax.while_loop over OptaxOptimizer._pure_step,
+    opt/optimiser.py:494-579) driven from the host over the fused CUDA step -- the semantics batch_optimise vmaps
+    (opt/batch.py:107-146), which differ from the Python loop `_optimise`:
+      * the state enters dense: previous_loss of the first iteration is the loss at the initial parameters (first delta 0);
+      * update_convergence / check_and_advance_threshold (opt/track.py:40-125): EMAs restart with every threshold, no
+        gradient-oscillation reset, the threshold test uses the 1-based step;
+      * cond_fn: stop when converged, after n_steps, or when the loss stored by the previous iteration is non-finite / below
+        the tolerance (checked on the initial loss before the first iteration);
+      * every iteration is a history entry: the parameters AFTER the update with the losses evaluated BEFORE it, step = the
+        history index; best state = smallest val_losses[0], the last entry on ties with it (opt/base.py:180-189).
+    Frame weights are kept for the best and the last entry (the others carry frame_weights=None): the reference's dense
+    [n_steps, n_frames] history does not fit at the ensemble sizes this path is built for.  Returns (simulation, optimizer);
+    optimizer.history holds the entries, optimizer._pure_carry the final ConvergenceCarry and write_idx."""
+    from .optimiser import compute_loss
+
+    if isinstance(convergence, float):
+        convergence = [convergence]
+    lr = optimizer.learning_rate if learning_rate is None else float(learning_rate)
+    thresholds = create_convergence_thresholds(convergence, lr)
+    data_targets, losses_t, idx_t = tuple(data_to_fit), tuple(loss_functions), tuple(indexes)
+    optimizer.history = OptimizationHistory()
+    carry = initialise_convergence_carry(None)  # EMA parameters are not part of the returned history (opt/batch.py:158-180)
+    initial_losses, _ = compute_loss(_simulation, opt_state.params, data_targets, idx_t, losses_t)  # _ensure_dense_state, run.py:89-118
+    prev_loss = float(initial_losses.total_train_loss)
+    best_i, best_val = None, None
+    write_idx = 0
+    while not (carry.converged or write_idx >= n_steps or not math.isfinite(prev_loss) or prev_loss < tolerance):
+        opt_state, _, save_state, _simulation = optimizer.step(
+            optimizer=optimizer, state=opt_state, simulation=_simulation, data_targets=data_targets, loss_functions=losses_t, indexes=idx_t)
+        rec = optimizer._engine.records(write_idx, 1)[0]  # one device->host read per iteration
+        loss_val, val0 = float(rec.total_train), float(rec.val[0])
+        carry, _ = update_convergence(carry, prev_loss, loss_val, None, ema_alpha)
+        carry = check_and_advance_threshold(carry, loss_val, write_idx + 1, thresholds, min_steps_per_threshold, optimizer.initial_steps)
+        prev_loss = loss_val
+        entry = OptimizationState(save_state.params, save_state.opt_state, write_idx, save_state.losses, None)
+        states = optimizer.history.states
+
+        def _strip(i):  # idempotent
+            states[i] = states[i]._replace(params=_replace(states[i].params, frame_weights=None))
+
+        if best_val is None or val0 < best_val:  # first strict minimum so far: this entry keeps its weights, the old best drops them
+            if best_i is not None:
+                _strip(best_i)
+            best_i, best_val = write_idx, val0
+        if states and (write_idx - 1) != best_i:  # the previous entry is no longer the last one
+            _strip(write_idx - 1)
+        optimizer.history.states.append(entry)
+        write_idx += 1
+    if optimizer.history.states:
+        last_val0 = float(optimizer.history.states[-1].losses.val_losses[0])
+        pick = write_idx - 1 if not (best_val < last_val0) else best_i
+        optimizer.history.best_state = optimizer.history.states[pick]
+        _simulation.params = optimizer.history.best_state.params
+    optimizer._pure_carry = (carry, write_idx)
     return _simulation, optimizer
 
 
