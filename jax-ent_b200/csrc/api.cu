@@ -26,7 +26,7 @@ struct Layout {
   size_t off_z[2][2], off_m[2][2], off_v[2][2], off_g[2];
   size_t off_w, off_kappa, off_kappa_lo, off_cc, off_ch, off_ck, off_logpf, off_uptake, off_avg, off_pfG;
   size_t off_cta_scal, off_fx, off_nmax, off_xchg, off_klpart, off_ctl, off_epoch, off_counter, off_records;
-  size_t off_cl_scratch;
+  size_t off_cl_scratch, off_pf_db;
   size_t off_blob[JAXENT_MAX_SLOTS];
   int blob_words[JAXENT_MAX_SLOTS];
   size_t total;
@@ -74,6 +74,7 @@ static Layout make_layout(const JaxentBvProblem* pb) {
   L.off_counter = take(sizeof(unsigned));
   L.off_records = take((size_t)JAXENT_RECORD_RING * sizeof(JaxentLossRecord));
   L.off_cl_scratch = take((64 + 4 * (size_t)MAX_PASS_CTAS) * sizeof(double));  // + per-CTA pass timestamps (JX_PROFILE builds)
+  L.off_pf_db = take((size_t)PF_DB_MAX_CTAS * 2 * sizeof(double));  // per-frame mode: CTA partials of d loss / d (bc, bh)
   for (int i = 0; i < JAXENT_MAX_SLOTS; ++i) {
     L.off_blob[i] = 0;
     L.blob_words[i] = 0;
@@ -291,9 +292,9 @@ extern "C" int jaxent_bv_plan_create(const JaxentBvProblem* problem, const Jaxen
     return JAXENT_E_INVALID;
   }
   const int R = problem->R, T = problem->uptake ? problem->T : 0;
-  if (problem->uptake == 2 && cfg->optimise_model_parameters) {
-    set_error("per-frame uptake mode (average_first=False) optimises the frame weights only: the BV-parameter gradient of step k "
-              "would be needed before the same sweep's forward half can start (set optimise_model_parameters = 0)");
+  if (problem->uptake == 2 && cfg->optimise_model_parameters && problem->F_total != problem->F) {
+    set_error("per-frame uptake mode (average_first=False) with optimised BV parameters runs on one GPU: their gradient is a frame "
+              "sum of its own that the frame-sharded exchange does not carry (set optimise_model_parameters = 0 or do not shard)");
     return JAXENT_E_UNSUPPORTED;
   }
   Layout L = make_layout(problem);
@@ -586,6 +587,18 @@ extern "C" int jaxent_bv_pass(JaxentPlan* p, int32_t mode, jaxent_stream_t strea
   a.clip = p->cfg.clip_value;
   a.dbg = reinterpret_cast<double*>(p->ws + p->lay.off_cl_scratch);
   p->sums_folded = 0;
+  if (p->prob.uptake == 2 && p->cfg.optimise_model_parameters) {
+    // per-frame mode with optimised BV parameters (reference models/core.py:298-305 places no restriction): their gradient is a
+    // frame sum of its own (pf_dbeta_kernel) that must be complete before the update this pass applies; the pass then evaluates
+    // its forward half at the updated parameters of both plateau branches
+    a.pf_db = 1;
+    a.cfg = p->cfg;
+    if (mode == 1) {
+      rc = launch_pf_dbeta(a, reinterpret_cast<double*>(p->ws + p->lay.off_pf_db), reinterpret_cast<Ctl*>(p->ws + p->lay.off_ctl), a.records,
+                           (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  }
   return launch_pass(a, p->pass_threads + 32, p->rpt, p->pass_ctas, p->pass_smem, (cudaStream_t)stream);
 }
 

@@ -374,9 +374,13 @@ __device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
 // memory (each thread reads back only what it wrote: no barrier).  The special-function unit shares its issue queue with
 // shared-memory and shuffle instructions, so the reduction of H_f over the rows is NOT done here: every thread stores its
 // four per-frame partials (one 16-byte store) and the Adam warp, which has time to spare, sums them.
-template <int TM>
+// DB (BV parameters optimised, mode 1): the forward half must see the UPDATED parameters, which differ between the two plateau
+// branches (bcn[br], bhn[br] from derive_spec).  Phase B then re-evaluates the exponentials from the features of the unit
+// (kept in registers instead of the uptake values): three exponential sweeps in this kernel instead of one.
+template <int TM, bool DB>
 __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ring, uint64_t* bars, float4* s_rows, const float* s_e,
-                                             float4* s_tab, int n, int mode, float bc, float bh, int NTc, int nbar) {
+                                             float4* s_tab, int n, int mode, float bc, float bh, int NTc, int nbar,
+                                             float bcnA = 0.f, float bhnA = 0.f, float bcnB = 0.f, float bhnB = 0.f) {
   constexpr int TP = TM / 2;
   const int R = a.R, T = a.pf_T;
   const int tid = threadIdx.x;
@@ -408,6 +412,8 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
   uint32_t parity = 0;
 
   // phase A of one quad: u[j][tp] = exp(-k tau / PF) = 1 - uptake; per-frame partial sums of G.(1 - u) to the Adam warp
+  const float nl2e_bcn[2] = {-1.4426950408889634f * bcnA, -1.4426950408889634f * bcnB};
+  const float nl2e_bhn[2] = {-1.4426950408889634f * bhnA, -1.4426950408889634f * bhnB};
   auto phase_a_pf = [&](int half, float2 (&u)[PF_FU][TP]) {
     JCLK_TIC(tm0);
     if (half == 0) mbar_wait(smem_u32(&bars[slot]), parity);
@@ -436,9 +442,13 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
       for (int j = 0; j < PF_FU; ++j) {
         const float2 x2 = __fmul2_rn(kt2, pinv[j]);
         const float2 e2 = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
-        u[j][tp] = e2;
+        if (!DB) u[j][tp] = e2;
         p2[j] = __ffma2_rn(G2, e2, p2[j]);
       }
+    }
+    if (DB) {  // the unit's features stand in for its uptake values: u[j][0] = (Nc, Nh) of frame j
+#pragma unroll
+      for (int j = 0; j < PF_FU; ++j) u[j][0] = make_float2(nc[j], nh[j]);
     }
     // per-row partials of H_f for the 4 frames: the Adam warp of this quad sums them over the rows
     s_rows[half * NTc + tid] = make_float4(Gsum - (p2[0].x + p2[0].y), Gsum - (p2[1].x + p2[1].y), Gsum - (p2[2].x + p2[2].y),
@@ -457,10 +467,26 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
     for (int br = 0; br < 2; ++br) {
       const float4 e = e4[br];
       const float2 ev[PF_FU] = {bcast2(e.x), bcast2(e.y), bcast2(e.z), bcast2(e.w)};
+      if (DB) {
+        float2 pinv[PF_FU];
 #pragma unroll
-      for (int tp = 0; tp < TP; ++tp)
+        for (int j = 0; j < PF_FU; ++j) pinv[j] = bcast2(ex2_approx(fmaf(nl2e_bcn[br], u[j][0].x, nl2e_bhn[br] * u[j][0].y)));
 #pragma unroll
-        for (int j = 0; j < PF_FU; ++j) acc[br][tp] = __ffma2_rn(ev[j], u[j][tp], acc[br][tp]);
+        for (int tp = 0; tp < TP; ++tp) {
+          const float4 kg = my_tab[tp * NTc];
+          const float2 kt2 = make_float2(kg.x, kg.y);
+#pragma unroll
+          for (int j = 0; j < PF_FU; ++j) {
+            const float2 x2 = __fmul2_rn(kt2, pinv[j]);
+            acc[br][tp] = __ffma2_rn(ev[j], make_float2(ex2_approx(x2.x), ex2_approx(x2.y)), acc[br][tp]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int tp = 0; tp < TP; ++tp)
+#pragma unroll
+          for (int j = 0; j < PF_FU; ++j) acc[br][tp] = __ffma2_rn(ev[j], u[j][tp], acc[br][tp]);
+      }
     }
     JCLK_TOC(clk_b, tb0);
   };
@@ -1048,9 +1074,147 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 64, 1) bv_pass_kernel_pf(co
     }
     return;
   }
+  const bool db = a.pf_db && a.mode;
+  __shared__ SpecScalars s_spec;
+  if (db) {  // the BV parameters after the update this sweep speculates on, for both plateau branches (what the tail will select from)
+    if (warp == 0) derive_spec(&s_spec, ctl, a.cfg);
+    __syncthreads();
+  }
   if (is_adam) pf_adam_warp(a, ctl, ep, q, lane, NWc, nbar, ring, bars, s_rows, s_e, s_x, t0, s0, ns, n);
-  else if (a.pf_T <= 4) pf_consumer<4>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
-  else pf_consumer<PF_TMAX>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+  else if (db) {
+    if (a.pf_T <= 4) pf_consumer<4, true>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar, s_spec.bc[0], s_spec.bh[0], s_spec.bc[1], s_spec.bh[1]);
+    else pf_consumer<PF_TMAX, true>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar, s_spec.bc[0], s_spec.bh[0], s_spec.bc[1], s_spec.bh[1]);
+  } else if (a.pf_T <= 4) pf_consumer<4, false>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+  else pf_consumer<PF_TMAX, false>(a, ring, bars, s_rows, s_e, s_tab, n, a.mode, ctl->bc, ctl->bh, NTc, nbar);
+}
+
+// ------------------------------------------------------------------------------------------ per-frame mode: d loss / d (bc, bh)
+// With average_first = False the BV parameters act inside the frame sum:
+//   d<u>[t,r]/d bc = sum_f w_f (-x e^{-x}) Nc[r,f],  x = k_r tau_t exp(-(bc Nc[r,f] + bh Nh[r,f]))      (oracle loss_and_grads)
+//   d loss / d bc  = sum_f w_f sum_r Nc[r,f] D[r,f],  D[r,f] = sum_t G[t,r] (-x e^{-x})
+// which needs G = dL/d<u> of the CURRENT state (the tail's output) and has to be complete before the update the next sweep
+// applies: a sweep of its own over the packed features, between the tail and the pass.  Thread = residue row, quads of 4
+// frames read straight from global memory (consecutive rows are consecutive 16-byte words); fp32 per-thread sums are folded
+// into fp64 every 32 quads; one (bc, bh) partial per CTA, summed in a fixed order by pf_dbeta_fold_kernel.
+constexpr int PF_DB_CTAS = PF_DB_MAX_CTAS;
+__device__ __forceinline__ double wsum_d(double v) {  // fixed-shape shuffle tree
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int TM>
+__global__ void __launch_bounds__(PASS_THREADS_MAX) pf_dbeta_kernel(const PassArgs a, double* __restrict__ part) {
+  __shared__ double s_red[2][PASS_THREADS_MAX / 32];
+  const int R = a.R, T = a.pf_T, tid = threadIdx.x;
+  const unsigned ep = *a.epoch;
+  const Ctl* __restrict__ ctl = a.ctl + (ep & 1u);
+  const bool ok = tid < R;
+  const int rc = ok ? tid : R - 1;
+  float kt[TM], G[TM];
+  {
+    const float kr = -1.4426950408889634f * a.pf_k[rc];
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+      kt[t] = t < T ? kr * a.pf_tp[t] : 0.f;
+      G[t] = (ok && t < T) ? a.pf_G[(size_t)t * R + rc] : 0.f;
+    }
+  }
+  const float nl2e_bc = -1.4426950408889634f * ctl->bc, nl2e_bh = -1.4426950408889634f * ctl->bh;
+  const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.packed);
+  const size_t rstride = (size_t)R * 16u, rowoff = (size_t)rc * 16u;
+  const long long n_quads = 2 * a.n_tiles;
+  double dc = 0.0, dh = 0.0;
+  float fc = 0.f, fh = 0.f;
+  int since = 0;
+  for (long long qd = blockIdx.x; qd < n_quads; qd += gridDim.x) {
+    const unsigned char* sub = gsrc + (size_t)(qd >> 1) * a.tile_bytes + ((qd & 1) ? 2 * rstride : 0) + rowoff;
+    const float4 c4 = *reinterpret_cast<const float4*>(sub), h4 = *reinterpret_cast<const float4*>(sub + rstride);
+    const long long f0 = qd * PF_FU;
+    float w[PF_FU];
+#pragma unroll
+    for (int j = 0; j < PF_FU; ++j) w[j] = (f0 + j < a.F) ? a.w[f0 + j] : 0.f;
+    const float nc[PF_FU] = {c4.x, c4.y, c4.z, c4.w}, nh[PF_FU] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+    for (int j = 0; j < PF_FU; ++j) {
+      const float pinv = ex2_approx(fmaf(nl2e_bc, nc[j], nl2e_bh * nh[j]));
+      float D = 0.f;
+#pragma unroll
+      for (int t = 0; t < TM; ++t) {
+        const float x2 = kt[t] * pinv;           // -log2(e) x
+        D = fmaf(G[t] * x2, ex2_approx(x2), D);  // G (-x e^{-x}) log2(e)
+      }
+      const float wd = w[j] * D;
+      fc = fmaf(wd, nc[j], fc);
+      fh = fmaf(wd, nh[j], fh);
+    }
+    if (++since == 32) {
+      since = 0;
+      dc += (double)fc;
+      dh += (double)fh;
+      fc = fh = 0.f;
+    }
+  }
+  dc += (double)fc;
+  dh += (double)fh;
+  if (!ok) dc = dh = 0.0;
+  dc = wsum_d(dc);
+  dh = wsum_d(dh);
+  if ((tid & 31) == 0) {
+    s_red[0][tid >> 5] = dc;
+    s_red[1][tid >> 5] = dh;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_red[tid][k];
+    part[(size_t)blockIdx.x * 2 + tid] = t * 0.6931471805599453;  // 1 / log2(e)
+  }
+}
+
+// fixed-order fold of the CTA partials into the current control block's masked gradients (+ the loss record of this step)
+__global__ void pf_dbeta_fold_kernel(const double* __restrict__ part, int n_part, Ctl* ctl, const unsigned* epoch, JaxentLossRecord* records) {
+  __shared__ double s_red[2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // 1024 threads
+  double c = 0.0, h = 0.0;
+  for (int k = tid; k < n_part; k += blockDim.x) {
+    c += part[(size_t)k * 2];
+    h += part[(size_t)k * 2 + 1];
+  }
+  c = wsum_d(c);
+  h = wsum_d(h);
+  if (lane == 0) {
+    s_red[0][warp] = c;
+    s_red[1][warp] = h;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    Ctl* cb = ctl + (*epoch & 1u);
+    if (cb->trk_stop) return;
+    double tc = 0.0, th = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+      tc += s_red[0][k];
+      th += s_red[1][k];
+    }
+    cb->gb[0] += (float)tc * cb->mask_model;
+    cb->gb[1] += (float)th * cb->mask_model;
+    JaxentLossRecord* rec = records + cb->rec_idx;
+    rec->grad_bc = cb->gb[0];
+    rec->grad_bh = cb->gb[1];
+  }
+}
+
+int launch_pf_dbeta(const PassArgs& a, double* part, Ctl* ctl, JaxentLossRecord* records, cudaStream_t s) {
+  const long long n_quads = 2 * a.n_tiles;
+  const int grid = (int)(n_quads < PF_DB_CTAS ? n_quads : PF_DB_CTAS);
+  const int threads = (a.R + 31) / 32 * 32;
+  if (a.pf_T <= 4) pf_dbeta_kernel<4><<<grid, threads, 0, s>>>(a, part);
+  else pf_dbeta_kernel<PF_TMAX><<<grid, threads, 0, s>>>(a, part);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    pf_dbeta_fold_kernel<<<1, 1024, 0, s>>>(part, grid, ctl, a.epoch, records);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) { set_error("pf_dbeta launch: %s", cudaGetErrorString(e)); return JAXENT_E_CUDA; }
+  return JAXENT_OK;
 }
 
 __global__ void finish_record_kernel(const Ctl* ctl, const unsigned* epoch, const Xchg x, JaxentLossRecord* rec, int n_slots) {

@@ -22,7 +22,7 @@ static __device__ __noinline__ double wsum(double v) {
 }
 static __device__ __noinline__ double dexp(double x) { return exp(x); }
 static __device__ __noinline__ double dlog(double x) { return log(x); }
-static __device__ __noinline__ float fpow(float a, float b) { return powf(a, b); }
+// fpow: jx_internal.cuh
 // Explicit shared-memory loads by 32-bit shared address.  The peptide-map loops select between the train and the validation
 // arrays at run time; the compiler then loses the address space and emits GENERIC loads, which cost ~500 cycles per dependent
 // iteration on sm_100 (measured: 7600 cycles for a 10-entry row) against ~30 for LDS.

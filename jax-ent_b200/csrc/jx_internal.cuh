@@ -301,7 +301,66 @@ struct PassArgs {
   JaxentLossRecord* records;
   float b1, b2, om_b1, om_b2, eps, clip;
   double* dbg;
+  // per-frame uptake mode with optimised BV parameters: the forward half of the sweep uses the UPDATED parameters of each
+  // plateau branch (derive_spec on the current control block), and a sweep of its own forms d loss / d (bc, bh) first
+  int pf_db;
+  JaxentOptConfig cfg;
 };
+
+// powf out of line: one copy per translation unit, the same instruction sequence wherever the bias corrections are formed
+static __device__ __noinline__ float fpow(float a, float b) { return powf(a, b); }
+
+// BV-parameter Adam update for BOTH plateau branches from the previous control block (lane b of the calling warp takes branch
+// b; all 32 lanes must call).  Used by the tail (before the pass has finished) and by the per-frame pass when the BV
+// parameters are optimised (its forward half needs the updated parameters of both branches): out of line, so both callers
+// execute the same instruction sequence and agree bit for bit.
+struct SpecScalars {
+  float lr[2], mlr[2], bc[2], bh[2], mb0[2], mb1[2], vb0[2], vb1[2];
+  double dot_model;  // sum over (bc, bh) of prev * cur gradient: the BV-parameter part of the grad-dot
+};
+
+static __device__ __noinline__ void derive_spec(SpecScalars* out, const Ctl* __restrict__ old, const JaxentOptConfig cfg) {
+  const int lane = threadIdx.x & 31;
+  const int cm1 = old->count_model + (old->pending ? 1 : 0);
+  // lanes 0,1: b1^cm1, b2^cm1 (bias corrections of the BV-parameter Adam update)
+  float pw = 0.f;
+  if (lane < 2) pw = fpow((lane & 1) ? (float)cfg.b2 : (float)cfg.b1, (float)cm1);
+  const float pw0 = __shfl_sync(0xffffffffu, pw, 0), pw1 = __shfl_sync(0xffffffffu, pw, 1);
+  if (lane >= 2) return;
+  const int b = lane;  // plateau branch
+  const float g0 = old->gb[0], g1 = old->gb[1];
+  const float lr = b ? old->lrB : old->lrA, mlr = b ? old->mlrB : old->mlrA;
+  // optax adam + keep_params_nonnegative on (bc, bh) with the LR-pre-scaled gradients
+  const float b1 = (float)cfg.b1, b2 = (float)cfg.b2, eps = (float)cfg.eps, clip = cfg.clip_value;
+  const float om_b1 = (float)(1.0 - cfg.b1), om_b2 = (float)(1.0 - cfg.b2);
+  const float c1 = 1.0f - pw0, c2 = 1.0f - pw1;
+  float sg0 = g0 * mlr, sg1 = g1 * mlr;
+  if (clip > 0.f) {
+    sg0 = fminf(fmaxf(sg0, -clip), clip);
+    sg1 = fminf(fmaxf(sg1, -clip), clip);
+  }
+  const float mb0 = om_b1 * sg0 + b1 * old->mb[0];
+  const float mb1 = om_b1 * sg1 + b1 * old->mb[1];
+  const float vb0 = om_b2 * (sg0 * sg0) + b2 * old->vb[0];
+  const float vb1 = om_b2 * (sg1 * sg1) + b2 * old->vb[1];
+  float u0 = -((mb0 / c1) / (sqrtf(vb0 / c2) + eps));
+  float u1 = -((mb1 / c1) / (sqrtf(vb1 / c2) + eps));
+  if (old->bc + u0 < 0.f) u0 = -old->bc;  // optax.keep_params_nonnegative
+  if (old->bh + u1 < 0.f) u1 = -old->bh;
+  out->lr[b] = lr;
+  out->mlr[b] = mlr;
+  out->bc[b] = old->bc + u0;
+  out->bh[b] = old->bh + u1;
+  out->mb0[b] = mb0;
+  out->mb1[b] = mb1;
+  out->vb0[b] = vb0;
+  out->vb1[b] = vb1;
+  if (b == 0) {
+    const float p0 = old->have_prev ? old->gb_prev[0] : g0, p1 = old->have_prev ? old->gb_prev[1] : g1;
+    out->dot_model = (double)p0 * (double)g0 + (double)p1 * (double)g1;
+  }
+}
+
 
 constexpr int TRK_MAX_THR = 8;
 // static configuration of the on-device loop (jaxent_bv_track_init)
@@ -394,6 +453,8 @@ inline cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, c
 }
 
 int launch_pass(const PassArgs& a, int threads, int rpt, int ctas, size_t smem, cudaStream_t s);
+constexpr int PF_DB_MAX_CTAS = 592;
+int launch_pf_dbeta(const PassArgs& a, double* part, Ctl* ctl, JaxentLossRecord* records, cudaStream_t s);
 // number of doubles every pass CTA contributes: row sums (+ sum e for both branches, grad-dot, pad)
 __host__ __device__ inline int pass_part_n(int R, int T, int uptake_mode) { return uptake_mode == 2 ? 2 * T * R + 4 : 4 * R + 4; }
 int launch_tail(const TailArgs& a, int ctas, size_t smem, cudaStream_t s);

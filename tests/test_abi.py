@@ -159,15 +159,20 @@ def test_product_path_never_imports_the_oracle():
 
 # ---------------------------------------------------------------------------------------- round-1 additions
 def test_per_frame_mode_validation():
-    """uptake = 2 (ForwardPass.average_first = False): frame weights only, fp32 features, <= 512 residues, <= 8 time points"""
+    """uptake = 2 (ForwardPass.average_first = False): fp32 features, <= 512 residues, <= 8 time points; optimised BV parameters on
+    an unsharded ensemble only (their gradient is a frame sum of its own that the exchange does not carry)"""
     lib = L.load()
     pb = _valid_problem(); pb.uptake = 2; pb.slots[0].kind = L.LOSS_PARAMS_L2
     rc, plan, _ = _create(pb)
     assert rc == 0
     lib.jaxent_bv_plan_destroy(plan)
     opt_model = L.OptConfig(1.0, 1.0, 0, 1.005, 1.0, -1.0, 1, 1, 0.9, 0.999, 1e-8)
+    rc, plan, msg = _create(pb, cfg=opt_model)
+    assert rc == 0, msg
+    lib.jaxent_bv_plan_destroy(plan)
+    pb.F_total = 4 * pb.F  # a frame shard
     rc, _, msg = _create(pb, cfg=opt_model)
-    assert rc == L.E_UNSUPPORTED and "frame weights only" in msg
+    assert rc == L.E_UNSUPPORTED and "one GPU" in msg
     pb = _valid_problem(); pb.uptake = 2; pb.T = 9
     assert _create(pb)[0] == L.E_UNSUPPORTED
     pb = _valid_problem(); pb.uptake = 2; pb.feature_format = 1

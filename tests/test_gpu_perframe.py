@@ -3,7 +3,8 @@ then the frame average -- reference models/core.py:302-304, models/HDX/forward.p
 
 The pass evaluates F*R*(T+1) exponentials per step with the fast special-function unit (ex2.approx + a series below
 x = 0.25), so the per-step tolerance is 5e-5 (loss) / 2e-4 (gradients, max-abs relative) against the fp64 oracle instead
-of the 1e-5 of the average-first path; frame weights after a long run still agree to 1e-4."""
+of the 1e-5 of the average-first path; frame weights after a long run still agree to 1e-4.  BV-parameter optimisation in
+this mode: a sweep of its own for d loss / d (bc, bh) + the forward half of the pass at the updated parameters."""
 import numpy as np
 import pytest
 import torch
@@ -74,10 +75,39 @@ def test_per_frame_weights_after_500_steps():
     np.testing.assert_allclose(eng.weights.cpu().numpy(), w_ref, atol=1e-4)
 
 
-def test_per_frame_rejects_model_parameter_optimisation():
-    from jaxent_b200 import _lib as L
+@pytest.mark.parametrize("kind,extra,F,R,T,clip,init_steps", [
+    (O.UPTAKE_EYE_MSE, (O.PARAMS_L2,), 777, 97, 5, None, 0),
+    (O.UPTAKE_MC_EYE_MSE, (O.PARAMS_L1,), 1000, 53, 3, 1.0, 2),
+    (O.UPTAKE_SIGMA_MSE, (), 515, 64, 8, None, 0),
+    (O.UPTAKE_EYE_MSE, (), 4099, 500, 8, None, 0),
+])
+def test_per_frame_step_parity_model_parameters(kind, extra, F, R, T, clip, init_steps):
+    """BV-parameter optimisation with average_first = False (reference models/core.py:298-305 places no restriction;
+    examples/common/optimization.py:267-296): d loss / d (bc, bh) = sum_f w_f sum_{t,r} G[t,r] du[t,r,f]/d(bc, bh) comes from a
+    frame sweep of its own (pf_dbeta_kernel), and the forward half of the pass runs at the UPDATED parameters of each plateau
+    branch.  Teacher-forced against the fp64 oracle: losses (evaluated at the updated bc, bh), frame gradients, grad_bc / grad_bh."""
+    case = _case(F, R, T, kind, gamma=2.0, prior="random", extra=extra)
+    cfg = O.OptConfig(learning_rate=0.2, initial_learning_rate=1.0, initial_steps=init_steps, clip_value=clip, optimise_model_parameters=True)
+    eng, wl, wg = _check_steps(case, cfg, 7, STEP_RTOL=2e-4)
+    assert wl < 5e-5, wl
+    recs = eng.records(0, 8)
+    assert recs[init_steps].grad_bc != 0.0 and recs[7].bc != recs[0].bc  # the BV parameters really move
+    if init_steps:
+        assert recs[0].grad_bc == 0.0 and recs[1].bc == recs[0].bc  # masked during the initial steps
 
-    case = _case(300, 32, 3)
-    cfg = O.OptConfig(learning_rate=0.5, clip_value=None, optimise_model_parameters=True)
-    with pytest.raises(L.JaxentError, match="frame weights only"):
-        H.make_engine(case, cfg)
+
+def test_per_frame_model_parameters_trajectory():
+    """free-running: 200 steps with the BV parameters optimised, against the fp64 oracle loop"""
+    case = _case(600, 53, 3, seed=9, extra=(O.PARAMS_L2,))
+    cfg = O.OptConfig(learning_rate=0.05, initial_learning_rate=1.0, initial_steps=2, clip_value=None, optimise_model_parameters=True)
+    eng = H.make_engine(case, cfg)
+    H.init_engine(eng, case)
+    eng.step(200)
+    torch.cuda.synchronize()
+    st = O.optimizer_initialise(case["params"], cfg, np.float64)
+    for _ in range(200):
+        st, _, _ = O.step_with_rates(case["problem"], st, cfg, np.float64)
+    np.testing.assert_allclose(eng.weights.cpu().numpy(), O.softmax(st.params.z, np.float64), atol=1e-4)
+    sc = eng.export_state(())[1]
+    np.testing.assert_allclose([sc["bc"], sc["bh"]], [st.params.bc, st.params.bh], rtol=1e-3)
+    assert abs(sc["bc"] - case["params"].bc) > 1e-3  # moved away from the start
