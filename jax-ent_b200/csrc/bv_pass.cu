@@ -362,6 +362,62 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ float uptake_of(float x) { return 1.f - ex2_approx(-1.4426950408889634f * x); }
 
+// 2^x on the FMA pipe: range reduction with the 1.5 * 2^23 trick, degree-6 near-minimax polynomial on [-0.5, 0.5] (Chebyshev
+// interpolation: 8e-8 max relative error, bias 1e-9 -- ex2.approx is specified to 2 ulp, and a frame AVERAGE of exponentials
+// keeps whatever bias the approximation has), exponent insertion with an integer shift-add.  The Adam warps of the per-frame
+// kernel use it for e' (their MUFU instructions would queue behind the consumers'); for the consumers themselves see PF_EXP.
+#define JX_E2_C1 0.6931471824645996f
+#define JX_E2_C2 0.24022650718688965f
+#define JX_E2_C3 0.05550327152013779f
+#define JX_E2_C4 0.009618056938052177f
+#define JX_E2_C5 0.0013400427997112274f
+#define JX_E2_C6 0.00015461444854736328f
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.f);
+  const float y = x + 12582912.f;
+  const float f = x - (y - 12582912.f);  // [-0.5, 0.5]
+  float p = JX_E2_C6;
+  p = fmaf(p, f, JX_E2_C5);
+  p = fmaf(p, f, JX_E2_C4);
+  p = fmaf(p, f, JX_E2_C3);
+  p = fmaf(p, f, JX_E2_C2);
+  p = fmaf(p, f, JX_E2_C1);
+  p = fmaf(p, f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
+}
+// two values at once: add / fma as packed f32x2 instructions
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), one = make_float2(1.f, 1.f), mone = make_float2(-1.f, -1.f);
+  const float2 y = __fadd2_rn(x, magic);
+  const float2 t = __ffma2_rn(magic, mone, y);  // y - magic (exact)
+  const float2 f = __ffma2_rn(t, mone, x);      // x - t     (exact)
+  float2 p = make_float2(JX_E2_C6, JX_E2_C6);
+  p = __ffma2_rn(p, f, make_float2(JX_E2_C5, JX_E2_C5));
+  p = __ffma2_rn(p, f, make_float2(JX_E2_C4, JX_E2_C4));
+  p = __ffma2_rn(p, f, make_float2(JX_E2_C3, JX_E2_C3));
+  p = __ffma2_rn(p, f, make_float2(JX_E2_C2, JX_E2_C2));
+  p = __ffma2_rn(p, f, make_float2(JX_E2_C1, JX_E2_C1));
+  p = __ffma2_rn(p, f, one);
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(y.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(y.y) << 23)));
+}
+// which unit evaluates the F*R*(T+1) exponentials of the per-frame mode: 0 MUFU (ex2.approx), 1 the FMA-pipe polynomial,
+// 2 both (first value of a time-point pair on the FMA pipe, second on MUFU).  Measured at config 4 (1M x 500 x 8, B200):
+// pass 1957 / 2986 / 2632 us for 0 / 1 / 2 -- the polynomial's integer and min/max instructions and its extra live registers
+// (72 instead of 56 bytes of spill stack) cost more than the MUFU queue saves -- and the same parity against the fp64 oracle
+// in all three (loss 1e-7, gradients 1e-6 relative): MUFU it is.
+#ifndef PF_EXP
+#define PF_EXP 0
+#endif
+__device__ __forceinline__ float pf_exp2(float x) { return PF_EXP == 0 ? ex2_approx(x) : exp2_fma(x); }
+__device__ __forceinline__ float2 pf_exp2_pair(float2 x) {
+  if (PF_EXP == 0) return make_float2(ex2_approx(x.x), ex2_approx(x.y));
+  if (PF_EXP == 2) return make_float2(exp2_fma(x.x), ex2_approx(x.y));
+  return exp2_fma2(x);
+}
+
 constexpr int PF_FU = 4;  // frames per unit of work in this mode: a tile is handled as its two quads (see pf_consumer)
 
 __device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
@@ -431,7 +487,7 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
     float2 pinv[PF_FU], p2[PF_FU];
 #pragma unroll
     for (int j = 0; j < PF_FU; ++j) {
-      pinv[j] = bcast2(ex2_approx(fmaf(nlog2e_bc, nc[j], nlog2e_bh * nh[j])));  // exp(-lnPF)
+      pinv[j] = bcast2(pf_exp2(fmaf(nlog2e_bc, nc[j], nlog2e_bh * nh[j])));  // exp(-lnPF)
       p2[j] = make_float2(0.f, 0.f);
     }
 #pragma unroll
@@ -441,7 +497,7 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
 #pragma unroll
       for (int j = 0; j < PF_FU; ++j) {
         const float2 x2 = __fmul2_rn(kt2, pinv[j]);
-        const float2 e2 = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
+        const float2 e2 = pf_exp2_pair(x2);
         if (!DB) u[j][tp] = e2;
         p2[j] = __ffma2_rn(G2, e2, p2[j]);
       }
@@ -470,7 +526,7 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
       if (DB) {
         float2 pinv[PF_FU];
 #pragma unroll
-        for (int j = 0; j < PF_FU; ++j) pinv[j] = bcast2(ex2_approx(fmaf(nl2e_bcn[br], u[j][0].x, nl2e_bhn[br] * u[j][0].y)));
+        for (int j = 0; j < PF_FU; ++j) pinv[j] = bcast2(pf_exp2(fmaf(nl2e_bcn[br], u[j][0].x, nl2e_bhn[br] * u[j][0].y)));
 #pragma unroll
         for (int tp = 0; tp < TP; ++tp) {
           const float4 kg = my_tab[tp * NTc];
@@ -478,7 +534,7 @@ __device__ __forceinline__ void pf_consumer(const PassArgs& a, unsigned char* ri
 #pragma unroll
           for (int j = 0; j < PF_FU; ++j) {
             const float2 x2 = __fmul2_rn(kt2, pinv[j]);
-            acc[br][tp] = __ffma2_rn(ev[j], make_float2(ex2_approx(x2.x), ex2_approx(x2.y)), acc[br][tp]);
+            acc[br][tp] = __ffma2_rn(ev[j], pf_exp2_pair(x2), acc[br][tp]);
           }
         }
       } else {
@@ -813,22 +869,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA pipe (range reduction with the 1.5 * 2^23 trick, degree-6 polynomial, exponent insertion): 2.4e-7 relative.
-// The Adam warps use it because their special-function instructions would queue behind the consumers' (the MUFU / shared-memory
-// issue queue of a sub-partition is kept full by design in this kernel) and e' is on the critical path of every quad.
-__device__ __forceinline__ float exp2_fma(float x) {
-  x = fmaxf(x, -126.f);
-  const float y = x + 12582912.f;
-  const float f = x - (y - 12582912.f);  // [-0.5, 0.5]
-  float p = 0.00015403530393381608f;
-  p = fmaf(p, f, 0.0013333558146428443f);
-  p = fmaf(p, f, 0.009618129107628477f);
-  p = fmaf(p, f, 0.05550410866482158f);
-  p = fmaf(p, f, 0.2402265069591007f);
-  p = fmaf(p, f, 0.6931471805599453f);
-  p = fmaf(p, f, 1.f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
-}
 constexpr int BAR_ADAM = 5;  // the two Adam warps of the per-frame kernel, once, at the end
 
 // One invocation of the Adam code is a ~1500-cycle dependent chain on a single warp whatever the number of frames it carries
@@ -1135,12 +1175,12 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX) pf_dbeta_kernel(const PassAr
     const float nc[PF_FU] = {c4.x, c4.y, c4.z, c4.w}, nh[PF_FU] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
     for (int j = 0; j < PF_FU; ++j) {
-      const float pinv = ex2_approx(fmaf(nl2e_bc, nc[j], nl2e_bh * nh[j]));
+      const float pinv = pf_exp2(fmaf(nl2e_bc, nc[j], nl2e_bh * nh[j]));
       float D = 0.f;
 #pragma unroll
       for (int t = 0; t < TM; ++t) {
-        const float x2 = kt[t] * pinv;           // -log2(e) x
-        D = fmaf(G[t] * x2, ex2_approx(x2), D);  // G (-x e^{-x}) log2(e)
+        const float x2 = kt[t] * pinv;        // -log2(e) x
+        D = fmaf(G[t] * x2, pf_exp2(x2), D);  // G (-x e^{-x}) log2(e)
       }
       const float wd = w[j] * D;
       fc = fmaf(wd, nc[j], fc);

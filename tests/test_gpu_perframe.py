@@ -1,10 +1,10 @@
 """Per-frame BV uptake mode (ForwardPass.average_first = False): uptake per (time point, residue, frame),
 then the frame average -- reference models/core.py:302-304, models/HDX/forward.py:57-74.
 
-The pass evaluates F*R*(T+1) exponentials per step with the fast special-function unit (ex2.approx + a series below
-x = 0.25), so the per-step tolerance is 5e-5 (loss) / 2e-4 (gradients, max-abs relative) against the fp64 oracle instead
-of the 1e-5 of the average-first path; frame weights after a long run still agree to 1e-4.  BV-parameter optimisation in
-this mode: a sweep of its own for d loss / d (bc, bh) + the forward half of the pass at the updated parameters."""
+The pass evaluates F*R*(T+1) exponentials per step on the special-function unit (ex2.approx).  Per-step tolerance against the
+fp64 oracle: 1e-5 on every loss component and on the gradients (north_star's bound, the same as the average-first path;
+measured 1.5e-7 / 9.5e-7), frame weights after a long run 1e-4.  BV-parameter optimisation in this mode: a sweep of its own
+for d loss / d (bc, bh) + the forward half of the pass at the updated parameters."""
 import numpy as np
 import pytest
 import torch
@@ -14,6 +14,8 @@ from oracle import bv_oracle as O
 from test_gpu_parity import _check_steps
 
 pytestmark = pytest.mark.gpu
+
+PF_RTOL = 1e-5
 
 
 def _case(F, R, T, kind=O.UPTAKE_EYE_MSE, seed=4, **kw):
@@ -31,8 +33,8 @@ def _case(F, R, T, kind=O.UPTAKE_EYE_MSE, seed=4, **kw):
 def test_per_frame_step_parity(kind, F, R, T, clip):
     case = _case(F, R, T, kind, gamma=2.0, prior="random")
     cfg = O.OptConfig(learning_rate=1.0, initial_learning_rate=1.0, initial_steps=0, clip_value=clip, optimise_model_parameters=False)
-    _, wl, wg = _check_steps(case, cfg, 6, STEP_RTOL=2e-4)
-    assert wl < 5e-5, wl
+    _, wl, wg = _check_steps(case, cfg, 6, STEP_RTOL=PF_RTOL)
+    assert wl < 1e-6 and wg < 5e-6, (wl, wg)
 
 
 def test_per_frame_collapsed_weights():
@@ -43,8 +45,8 @@ def test_per_frame_collapsed_weights():
     case["problem"].average_first = False
     assert frac > 0.5
     cfg = O.OptConfig(learning_rate=1.0, clip_value=None, optimise_model_parameters=False)
-    _, wl, wg = _check_steps(case, cfg, 6, STEP_RTOL=2e-4)
-    assert wl < 5e-5, wl
+    _, wl, wg = _check_steps(case, cfg, 6, STEP_RTOL=PF_RTOL, mirror_slack=True)
+    assert wl < 1e-5, wl
 
 
 def test_per_frame_forward_outputs_and_difference_to_average_first():
@@ -88,8 +90,8 @@ def test_per_frame_step_parity_model_parameters(kind, extra, F, R, T, clip, init
     branch.  Teacher-forced against the fp64 oracle: losses (evaluated at the updated bc, bh), frame gradients, grad_bc / grad_bh."""
     case = _case(F, R, T, kind, gamma=2.0, prior="random", extra=extra)
     cfg = O.OptConfig(learning_rate=0.2, initial_learning_rate=1.0, initial_steps=init_steps, clip_value=clip, optimise_model_parameters=True)
-    eng, wl, wg = _check_steps(case, cfg, 7, STEP_RTOL=2e-4)
-    assert wl < 5e-5, wl
+    eng, wl, wg = _check_steps(case, cfg, 7, STEP_RTOL=PF_RTOL)
+    assert wl < 1e-6 and wg < 5e-6, (wl, wg)
     recs = eng.records(0, 8)
     assert recs[init_steps].grad_bc != 0.0 and recs[7].bc != recs[0].bc  # the BV parameters really move
     if init_steps:
