@@ -567,6 +567,23 @@ def extra_results(args, dev, main_eng, small, slots, settings, peak):
         del pf
     except Exception as ex:  # pragma: no cover
         out["cfg4_per_frame"] = {"error": str(ex)[:200]}
+    # ---- the same mode with the BV parameters optimised too: a sweep of its own for d loss / d (bc, bh) and the forward half of
+    # the pass at the updated parameters of both plateau branches (4 exponential sweeps per step instead of 1)
+    try:
+        import dataclasses
+
+        st_m = dataclasses.replace(settings, optimise_model_parameters=True)
+        pf = BvEngine(main_eng.features, None, small.k_ints, small.timepoints, slots, True, st_m, prior=prior, device=dev, average_first=False)
+        pf.init_state(torch.ones(F, device=dev), 0.35, 2.0, [0.5, 0.5], [1000.0, 1000.0])
+        ms, pms = eager_rate(pf, 10, 3)
+        out["cfg4_per_frame_bv_params"] = {"value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "pass_kernel_ms": pms,
+                                           "special_function_frac": 4 * F * R * (T + 1) / (ms * 1e-3) / (16 * 148 * clk * 1e6),
+                                           "note": "average_first=False, optimise_model_parameters: 4*F*R*(T+1) ex2 per step (gradient sweep + "
+                                                   "pass with the forward half re-evaluated for both plateau branches)"}
+        pf.close()
+        del pf
+    except Exception as ex:  # pragma: no cover
+        out["cfg4_per_frame_bv_params"] = {"error": str(ex)[:200]}
     return out
 
 
