@@ -632,6 +632,13 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
   const unsigned ep = *a.epoch;
   if (blockIdx.x == 0 && tid == blockDim.x - 32) JPROF(a.dbg, 41);
   if (tid == blockDim.x - 32) JPROF(a.dbg, 64 + 4 * blockIdx.x + 1);
+#ifdef JX_PROFILE
+  if (tid == blockDim.x - 32) {  // which SM this CTA runs on (per-CTA timelines: is the end-of-pass straggle tied to the SM?)
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    reinterpret_cast<long long*>(a.dbg)[64 + 4 * blockIdx.x + 3] = (long long)smid;
+  }
+#endif
 
   if (a.ctl[ep & 1u].trk_stop) {
     // the on-device loop has ended: drain the prefetched tiles and leave everything untouched
