@@ -602,7 +602,11 @@ __global__ void __launch_bounds__(PASS_THREADS_MAX + 32, RPT == 1 ? 2 : 1) bv_pa
   const int mode = a.mode;
 
   // static, deterministic tile partition
+#ifdef JX_REVERSE_PARTITION  // experiment: does the straggle follow the CTA index or the feature region?
+  const long long G = gridDim.x, cta = gridDim.x - 1 - blockIdx.x;
+#else
   const long long G = gridDim.x, cta = blockIdx.x;
+#endif
   const int S = a.sub_tiles;  // 8-frame tiles per bulk-copy stage
   const long long s0 = a.n_stage_units * cta / G, s1 = a.n_stage_units * (cta + 1) / G;
   const int ns = (int)(s1 - s0);        // stages of this CTA
