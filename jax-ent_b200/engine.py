@@ -336,7 +336,8 @@ class BvEngine:
         a.record_stream(torch.cuda.current_stream())
         R, F = self.R, self.F
         L.check(self.lib.jaxent_bv_pack_features_f32(h.data_ptr(), a.data_ptr(), R, F, F, 0, F, self.packed.data_ptr(), _stream_ptr()))
-        torch.cuda.current_stream().synchronize()
+        # no host synchronisation here: the pack kernel is stream-ordered before everything that reads the packed features, the
+        # staging buffers are kept alive by record_stream, and the caller's host-side set-up keeps overlapping the transfer
         del h, a
 
     def _to_dev_matrix(self, x) -> torch.Tensor:

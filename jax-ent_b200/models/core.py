@@ -63,10 +63,6 @@ class Simulation:
             raise RuntimeError("jaxent_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if self.device is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        logits = self.params.frame_weights
-        self.params = Simulation_Parameters.normalize_weights(self.params)
-        self.params = Simulation_Parameters.normalize_masked_loss_scalingweights(self.params)
-
         feat = self.input_features[0]
         if tuple(np.shape(feat.heavy_contacts)) != tuple(np.shape(feat.acceptor_contacts)) or len(np.shape(feat.heavy_contacts)) != 2:
             raise ValueError("BV features must be two (n_residues, n_frames) arrays of equal shape")
@@ -86,6 +82,10 @@ class Simulation:
         except Exception as e:
             raise ValueError(f"Failed to apply forward models without JIT: {e}")
         self._features = self._fwd_engine.features
+        # the engine has started the host -> device transfer of the features (the one large input of a job); the host-side
+        # parameter normalisation runs while it is in flight
+        self.params = Simulation_Parameters.normalize_weights(self.params)
+        self.params = Simulation_Parameters.normalize_masked_loss_scalingweights(self.params)
         # the reference re-applies the softmax here (models/core.py:72,97-98): params end up softmax(softmax(w0))
         _sim, _outputs = Simulation.forward(self, self.params, mutate=False)
         self.params = _sim.params
