@@ -527,6 +527,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   __shared__ StepScalars s_sc;
   __shared__ SpecScalars s_spec;
   __shared__ int s_last;
+  // frame-sharded gather of the 4R row sums, spread over all warps (GATHER_ROWS_MAX rows; larger R keeps one thread per row)
+  constexpr int GATHER_ROWS_MAX = 512;
+  __shared__ double s_cols[4 * GATHER_ROWS_MAX];
 
   const JaxentBvProblem& pb = a.prob;
   const int R = pb.R, T = pb.uptake ? pb.T : 0;
@@ -580,6 +583,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
   };
   double* red_plain = reinterpret_cast<double*>(a.x.local + xchg_plain_red_off(a.x));  // JAXENT_BUF_RED (single rank)
   double accA0 = 0, accA1 = 0, accB0 = 0, accB1 = 0;
+  const bool spread_gather = tail_cta && !direct && !pfm && R <= GATHER_ROWS_MAX && nt > 32;
   if (tail_cta && tid < R && !pfm) {
     if (direct) {  // all 4 * FX_REP loads in flight, then the clears
       const long long t0 = fx_load_col(a.fx, n_rows, 0 * R + tid), t1 = fx_load_col(a.fx, n_rows, 1 * R + tid);
@@ -594,12 +598,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       red_plain[1 * R + tid] = accA1;
       red_plain[2 * R + tid] = accB0;
       red_plain[3 * R + tid] = accB1;
-    } else {
+    } else if (!spread_gather) {
       accA0 = red_total(a.x, ep, 0 * R + tid);
       accA1 = red_total(a.x, ep, 1 * R + tid);
       accB0 = red_total(a.x, ep, 2 * R + tid);
       accB1 = red_total(a.x, ep, 3 * R + tid);
     }
+  }
+  if (spread_gather && warp > 0) {
+    // one poll of a column = all ranks' words in flight, one L2 round trip once they have landed.  A thread per row did four of
+    // them one after the other and warp 0 three more for the scalars (7 round trips on the critical path of every sharded
+    // step); here the 4R columns are spread over warps 1..31 (2-3 each) while warp 0 polls the three scalars side by side.
+    for (int j = tid - 32; j < 4 * R; j += nt - 32) s_cols[j] = red_total(a.x, ep, j);
   }
   if (warp == 0) {
     double SA, SB, gdot;
@@ -615,10 +625,13 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
         red_plain[n_rows + 2] = gdot;
         red_plain[n_rows + 3] = 0.0;
       }
-    } else {
-      SA = red_total(a.x, ep, n_rows + 0);
-      SB = red_total(a.x, ep, n_rows + 1);
-      gdot = red_total(a.x, ep, n_rows + 2);
+    } else {  // lanes 0..2 poll one scalar each (they spin independently), then the warp shares them
+      double v = 0.0;
+      if (lane < 3) v = red_total(a.x, ep, n_rows + lane);
+      __syncwarp();
+      SA = __shfl_sync(0xffffffffu, v, 0);
+      SB = __shfl_sync(0xffffffffu, v, 1);
+      gdot = __shfl_sync(0xffffffffu, v, 2);
     }
     __syncwarp();
     if (lane == 0) derive_critical(&s_sc, &s_spec, &s_old, SA, SB, gdot, a.cfg);
@@ -628,10 +641,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) bv_tail_kernel(const TailArgs
       derive_rest(&s_sc, &s_old, a.cfg, a.trk, a.records);
     }
   }
-  __syncthreads();  // (1) scalars broadcast
+  __syncthreads();  // (1) scalars broadcast (and the gathered columns)
   TPROF(3); TPROF_F(2);
   const int d = s_sc.d;
   const double S = s_sc.S;
+  if (spread_gather && tid < R) {
+    accA0 = s_cols[0 * R + tid];
+    accA1 = s_cols[1 * R + tid];
+    accB0 = s_cols[2 * R + tid];
+    accB1 = s_cols[3 * R + tid];
+  }
 
   // ================================================================== the R x T tail (CTA 0)
   if (tail_cta) {
