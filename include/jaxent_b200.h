@@ -82,7 +82,8 @@ typedef struct {
   int32_t R;            /* residues */
   int32_t T;            /* time points (uptake mode) */
   int32_t uptake;       /* 1: BV_uptake_ForwardPass, 0: BV_ForwardPass (log_Pf), 2: BV_uptake_ForwardPass with
-                           average_first = False (uptake per frame, then frame-averaged; models/core.py:302-304) */
+                           average_first = False (uptake per frame, then frame-averaged; models/core.py:302-304): fp32 features,
+                           R <= 512, T <= 8; optimise_model_parameters only on an unsharded ensemble (F_total == F) */
   int32_t n_slots;
   int64_t F;            /* frames held by this rank */
   int64_t F_total;      /* frames of the whole ensemble (eps = 1e-10 / F_total, opt/losses.py:308) */

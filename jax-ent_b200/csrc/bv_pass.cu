@@ -349,8 +349,10 @@ __device__ __forceinline__ double pass_hbar(const PassArgs& a, unsigned ep, cons
 //   u[t,r,f] = 1 - exp(-k_r tau_t exp(-(bc Nc[r,f] + bh Nh[r,f])))
 //   phase A  H_f = sum_{t,r} G[t,r] u[t,r,f]            G = dL/d<uptake> from the tail
 //   phase B  acc[branch][t][r] += e'_f (1 - u[t,r,f])  (the tail forms <u> = 1 - acc / S in double precision)
-// F*R*(T+1) exponentials per step make this mode special-function bound rather than HBM bound.  The BV parameters are
-// frozen in this mode (their gradient would be needed before the same sweep's forward half could start).
+// F*R*(T+1) exponentials per step make this mode special-function bound rather than HBM bound.  With frozen BV parameters the
+// uptake values of a unit serve both phases.  With optimised BV parameters (PassArgs::pf_db) their gradient is a frame sum
+// of its own (pf_dbeta_kernel, below) and phase B re-evaluates the exponentials at the updated parameters of each plateau
+// branch (pf_consumer<TM, true>).
 constexpr int PF_TMAX = 8;
 
 // 1 - exp(-x) for x >= 0 on the special-function unit: ex2.approx is accurate to 2 ulp, so the absolute error is below
