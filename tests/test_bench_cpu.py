@@ -56,3 +56,21 @@ def test_reference_arm_uses_all_host_threads_under_torchrun_env_and_prints_our_c
 
     ours = bench.workload_config(argparse.Namespace(gpus=2, per_frame=False), bench.WORKLOADS["cfg2"])
     assert d["config"] == ours
+
+
+def test_gpu_local_affinity_always_restores_the_affinity():
+    """the pinned input buffers are allocated under a narrowed CPU affinity (GPU-local NUMA node); whatever happens inside --
+    no GPU here, so the lookup fails -- the process affinity is what it was, and the note says what was done"""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    before = os.sched_getaffinity(0)
+    with bench.gpu_local_affinity(0) as note:
+        assert isinstance(note, str) and note
+    assert os.sched_getaffinity(0) == before
+    # narrowed-and-restored path, driven by hand
+    ctx = bench.gpu_local_affinity(0)
+    ctx.saved = before
+    os.sched_setaffinity(0, {min(before)})
+    ctx.__exit__(None, None, None)
+    assert os.sched_getaffinity(0) == before
