@@ -121,6 +121,38 @@ def test_convergence_tracker_matches_oracle_tracker():
     np.testing.assert_allclose(a.ema_params, b.ema_params)
 
 
+def test_functional_tracker_differs_from_the_class_tracker_where_the_reference_does():
+    """opt/track.py:24-125 (the pure loop's carry) against the ConvergenceTracker class (:128-197) on one loss sequence: the
+    functional tracker starts its EMA at the FIRST iteration (raw delta 0 against the dense initial loss), restarts it after
+    every threshold advance, holds the EMA of the parameters the same way, and ends `converged` without advancing the index."""
+    from jaxent_b200.opt import track as T
+
+    losses = np.asarray([10.0, 6.0, 4.0, 3.5, 3.4, 3.39, 3.389, 3.3889], np.float32)
+    thr = T.create_convergence_thresholds([0.5, 0.05], 1.0)
+    carry = T.initialise_convergence_carry(np.zeros(3))
+    prev, trace = losses[0], []
+    for i, l in enumerate(losses):
+        before = carry
+        carry, raw = T.update_convergence(carry, prev, l, np.full(3, float(i)), 0.5)
+        if before.steps_since_threshold_start == 0:
+            assert carry.ema_loss_delta == raw and np.all(carry.ema_params == float(i))  # restart
+        else:
+            assert carry.ema_loss_delta == pytest.approx(0.5 * raw + 0.5 * before.ema_loss_delta)
+            np.testing.assert_allclose(carry.ema_params, 0.5 * i + 0.5 * before.ema_params)
+        carry = T.check_and_advance_threshold(carry, l, i + 1, thr, 2, 0)
+        trace.append((carry.current_threshold_idx, carry.steps_since_threshold_start, bool(carry.converged)))
+        prev = l
+        if carry.converged:
+            break
+    assert trace[0] == (0, 1, False)            # first iteration: raw = 0 -> relative convergence 0 < thr, but only 1 step
+    assert trace[1][0] == 1 and trace[1][1] == 0  # second iteration: min_steps reached with ema = 0.5*4 + 0.5*0 = 2, 2/6 < 0.5 -> advance
+    assert carry.converged and carry.current_threshold_idx == 1  # the last threshold ends the loop without advancing the index
+    # the class tracker on the same sequence has no EMA at all after its first update (previous_loss is None there)
+    c = ConvergenceTracker([0.5, 0.05], 1.0, 0.5, 2)
+    c.update(None, float(losses[0]), np.zeros(3))
+    assert c.ema_loss_delta is None and not c.is_threshold_met(float(losses[0]), 0, 0)
+
+
 def test_simulation_requires_cuda_and_valid_inputs():
     f = J.BV_input_features(np.zeros((5, 8), np.float32), np.zeros((5, 8), np.float32), np.ones(5, np.float32))
     p = J.Simulation_Parameters(np.full(8, 1 / 8, np.float32), np.ones(8, np.float32), [J.BV_Model_Parameters()],
