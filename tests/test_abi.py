@@ -226,6 +226,10 @@ def test_batched_plan_validation():
     rc, plan, _ = create(_batched_problem())
     assert rc == 0 and plan.value
     assert lib.jaxent_bg_step(plan, None) == L.E_INVALID  # state_init has not run
+    # tracker mode: 0 Python loop (ConvergenceTracker), 1 pure loop (_optimise_pure, what batch_optimise vmaps)
+    assert lib.jaxent_bg_track_mode(plan, 1) == 0 and lib.jaxent_bg_track_mode(plan, 0) == 0
+    assert lib.jaxent_bg_track_mode(plan, 2) == L.E_INVALID and "mode" in lib.jaxent_last_error().decode()
+    assert lib.jaxent_bg_track_mode(None, 1) == L.E_INVALID
     lib.jaxent_bg_plan_destroy(plan)
     assert create(_batched_problem(), B=15)[0] == L.E_INVALID  # replicas are padded to a multiple of 16 by the caller
     assert create(_batched_problem(), B=272)[0] == L.E_INVALID
@@ -247,7 +251,7 @@ def test_batched_plan_validation():
     assert lib.jaxent_bg_gemm1(0x1000, 0x2000, 0x3000, 4, 60, 64, 3, 148, None) == L.E_INVALID  # residues not padded to 128
     assert lib.jaxent_bg_gemm1(0x1000, 0x2000, 0x3000, 4, 64, 40, 3, 148, None) == L.E_INVALID  # Bn not a multiple of 16
     assert lib.jaxent_bg_gemm2(0x1000, 0x2000, 0x3000, 4, 64, 64, 3, 99, None) == L.E_INVALID  # more k-splits than half blocks
-    assert lib.jaxent_bg_ctl_sizeof() % 16 == 0 and lib.jaxent_bg_ctl_offset(0) % 8 == 0 and lib.jaxent_bg_ctl_offset(9) == -1
+    assert lib.jaxent_bg_ctl_sizeof() % 16 == 0 and lib.jaxent_bg_ctl_offset(0) % 8 == 0 and lib.jaxent_bg_ctl_offset(7) > 0 and lib.jaxent_bg_ctl_offset(9) == -1
 
 
 def test_contacts_and_predict_argument_validation():
