@@ -547,7 +547,7 @@ def graph_rate(eng, K):
 
 def extra_results(args, dev, main_eng, small, slots, settings, peak):
     """The other BASELINE configs measured in the same process (N = 1 only), so that they are driver-visible: config 3,
-    config 2 and config 1 shapes, the per-frame uptake mode at config 4 and the batched tensor-core sweep of config 5.  Compact dicts."""
+    config 1, the per-frame uptake mode at config 4 and the batched tensor-core sweep of config 5.  Compact dicts."""
     import torch
 
     from jaxent_b200 import _lib as L
@@ -597,7 +597,7 @@ def extra_small_configs(args, dev, peak):
 
     out = {}
     settings = OptSettings(learning_rate=1.0, initial_learning_rate=1.0, initial_steps=0, clip_value=None)
-    for key in ("cfg3", "cfg2", "cfg1"):
+    for key in ("cfg3", "cfg1"):
         try:
             w = WORKLOADS[key]
             F, R, T = w["F"], w["R"], w["T"]
