@@ -80,3 +80,26 @@ def test_tail_kernels_do_not_copy_their_parameters(resources):
     for k, r in resources.items():
         if "bv_tail_kernel" in k:
             assert r["stack"] <= 512, (k, r)
+
+
+def test_per_frame_bv_gradient_sweep(resources):
+    """pf_dbeta_kernel (d loss / d (bc, bh) of the per-frame mode): exponentials on the special-function unit, no spills, and
+    enough registers left for two 512-thread CTAs per SM; the fold is a single small kernel"""
+    for tm in ("ILi4E", "ILi8E"):
+        k = _one(resources, "pf_dbeta_kernel", tm)
+        assert resources[k]["stack"] == 0 and resources[k]["reg"] <= 64
+        ops = _sass(k)
+        assert sum(o.startswith("MUFU.EX2") for o in ops) >= (5 if tm == "ILi4E" else 9)  # (T + 1) per (row, frame)
+        assert any(o.startswith("LDG.E.128") for o in ops), "quads of 4 frames are read as 16-byte words"
+    k = _one(resources, "pf_dbeta_fold_kernel")
+    assert resources[k]["stack"] == 0
+
+
+def test_per_frame_pass_holds_both_forward_variants(resources):
+    """bv_pass_kernel_pf contains the frozen-parameter consumer (uptake values kept in registers across the phases) and the
+    variant that re-evaluates the exponentials at the updated BV parameters of both plateau branches: more than twice the
+    special-function instructions of the frozen path alone (72 = 2 quads x 4 frames x 9 exponentials, for T <= 8)"""
+    k = _one(resources, "bv_pass_kernel_pf")
+    ops = _sass(k)
+    assert sum(o.startswith("MUFU.EX2") for o in ops) >= 3 * 72
+    assert any(o.startswith("CALL") for o in ops), "derive_spec stays out of line (the tail executes the same instructions)"
