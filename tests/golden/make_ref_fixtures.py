@@ -43,6 +43,10 @@ CASES = {
                   opt_model=True, clip=None, lr=1.0, init_lr=1.0, init_steps=0, spread=0.0),
     "collapsed": dict(F=500, R=20, T=4, kind="hdx_uptake_eye_MSE_loss", extra=(), seed=35, gamma=1.0, scaling=1000.0, prior="uniform",
                       opt_model=False, clip=None, lr=1.0, init_lr=1.0, init_steps=0, spread=10.0),
+    # ForwardPass.average_first = False (models/core.py:302-304 + the 2-D branch of BV_uptake_ForwardPass, models/HDX/forward.py:57-74)
+    # with the BV parameters optimised: pins the per-frame closed forms of the oracle, d loss / d (bc, bh) included
+    "uptake_perframe": dict(F=220, R=18, T=3, kind="hdx_uptake_eye_MSE_loss", extra=("model_params_L2_loss",), seed=36, gamma=2.0, scaling=100.0,
+                            prior="random", opt_model=True, clip=None, lr=0.3, init_lr=1.0, init_steps=1, spread=0.0, per_frame=True),
 }
 N_STEPS = 12
 
@@ -52,6 +56,8 @@ def build_case(spec):
 
     case = H.make_case(spec["F"], spec["R"], max(spec["T"], 1), spec["kind"], extra=tuple(spec["extra"]), seed=spec["seed"], gamma=spec["gamma"],
                        scaling=spec["scaling"], prior=spec["prior"])
+    if spec.get("per_frame"):
+        case["problem"].average_first = False
     return case
 
 
@@ -106,6 +112,10 @@ class RefRun:
         tp = jnp.asarray(pb.timepoints if pb.uptake else np.array([0.167, 1.0, 10.0]), dtype=fdt)
         cfg = BV_model_Config(num_timepoints=int(tp.shape[0]), timepoints=tp) if pb.uptake else BV_model_Config()
         model = BV_model(cfg)  # .forwardpass follows the config key: BV_uptake_ForwardPass with time points, else BV_ForwardPass
+        if not getattr(pb, "average_first", True):
+            # what the examples' BV_uptake_ForwardPass_frames selects (examples/common/optimization.py:267-296): the forward pass on
+            # the un-averaged features, outputs frame-averaged afterwards -- the reference's own class with its flag flipped
+            model.forwardpass.average_first = False
         mp = BV_Model_Parameters(bv_bc=jnp.asarray([par.bc], dtype=fdt), bv_bh=jnp.asarray([par.bh], dtype=fdt), timepoints=tp)
         self.loss_fns, self.targets = [], []
         name2fn = {n: getattr(RL, n) for n in ("hdx_uptake_eye_MSE_loss", "hdx_uptake_mean_centred_eye_MSE_loss", "hdx_uptake_sigma_MSE_loss",
@@ -271,7 +281,10 @@ def run_loops(name, spec, x64):
 def main():
     if not refload.available():
         raise SystemExit("reference sources not available: fixtures can only be generated in the build container")
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         for x64 in (False, True):
             out = run_case(name, spec, x64)
             if name in ("uptake_eye", "pf_l2"):
