@@ -10,7 +10,13 @@ CUDA path at large F.
 
 Parity pinning status
 ---------------------
-* Forward model, losses, loss-weight normalisation: pinned against the reference's own
+* Against the reference's own code, executed: tests/golden/ref_*.npz are produced by running the UNMODIFIED reference
+  sources (/root/reference/jaxent/src) on the torch-backed jax / optax / chex stand-ins of oracle/refstub
+  (tests/golden/make_ref_fixtures.py); tests/test_oracle_ref.py compares this file against them: losses and masked
+  gradients teacher-forced at 1e-9 (fp64) on six cases incl. collapsed weights and the per-frame branch
+  (average_first = False) with optimised BV parameters, free-running trajectories, the Python-loop history and the
+  pure-loop carry (_optimise_pure).
+* Forward model, losses, loss-weight normalisation: also pinned against the reference's own
   known-answer tests (tests/golden/reference_known_answers.json, transcribed from
   jaxent/tests/unit/... -- see tests/golden/make_golden.py) and, for gradients, against
   torch.autograd in fp64 (tests/test_oracle.py).
