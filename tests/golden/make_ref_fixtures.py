@@ -16,6 +16,7 @@ Reference entry points executed (file:line in /root/reference/jaxent/src):
   compute_loss, OptaxOptimizer.initialise / _step_with_rates / _step / _pure_step                  opt/optimiser.py
   create_gradient_masks / mask_gradients                opt/gradients.py
   _optimise, _optimise_pure, ConvergenceTracker, update_convergence, check_and_advance_threshold  opt/run.py, opt/track.py
+  batch_optimise (vmap of _optimise_pure over the hyper-parameter batch), _pick_best_state        opt/batch.py, opt/base.py
 """
 from __future__ import annotations
 
@@ -278,10 +279,57 @@ def run_loops(name, spec, x64):
     return out
 
 
+BATCH = dict(fw=[[0.5, 0.5, 0.3], [0.8, 0.2, 0.1], [0.3, 0.7, 0.5]], fs=[[1000.0, 1000.0, 100.0], [500.0, 1000.0, 1000.0], [1000.0, 200.0, 10.0]],
+             lr=[1.0, 0.5, 0.2], n_steps=40, convergence=[1.0, 0.3], batch_size=2)  # the first n_slots columns of fw / fs are used
+
+
+def run_batch(name, spec, x64):
+    """the reference's batch_optimise (opt/batch.py:51-192: jax.vmap of _optimise_pure over (fw, fs, lr), lax.map over the
+    batches, padding of the last batch) on one case: what every replica ends with, and the selection it returns"""
+    case = build_case(spec)
+    rr = RefRun(case, spec, x64)  # installs the stand-ins: the reference imports below need them
+    from jaxent.src.custom_types.config import OptimiserSettings
+    from jaxent.src.opt.base import HParamBatch
+    from jaxent.src.opt.batch import batch_optimise
+
+    jnp = rr.jnp
+    fdt = jnp.float64 if x64 else jnp.float32
+    cfg = OptimiserSettings(name="batch", n_steps=BATCH["n_steps"], tolerance=1e-10, convergence=list(BATCH["convergence"]), learning_rate=spec["lr"])
+    n_slots = len(case["problem"].slots)
+    fw_b, fs_b = np.asarray(BATCH["fw"])[:, :n_slots], np.asarray(BATCH["fs"])[:, :n_slots]
+    hp = HParamBatch(jnp.asarray(fw_b, dtype=fdt), jnp.asarray(fs_b, dtype=fdt), jnp.asarray(BATCH["lr"], dtype=jnp.float32))
+    res = batch_optimise(rr.sim, hp, BATCH["batch_size"], tuple(rr.targets), cfg, list(rr.indexes), list(rr.loss_fns), optimizer=rr.optimizer)
+    n_h, n_steps = len(BATCH["lr"]), BATCH["n_steps"]
+    tot = np.full((n_h, n_steps), np.nan)
+    val0 = np.full((n_h, n_steps), np.nan)
+    for b, h in enumerate(res.histories):
+        for i, st in enumerate(h.states):
+            tot[b, i] = float(st.losses.total_train_loss)
+            val0[b, i] = float(to_np(st.losses.val_losses).reshape(-1)[0])
+    return {
+        "batch_conv_steps": to_np(res.convergence_steps).astype(np.int64),
+        "batch_n_states": np.asarray([len(h.states) for h in res.histories]),
+        "batch_best_step": np.asarray([int(b.step) for b in res.best_states]),
+        "batch_best_total_train": np.asarray([float(b.losses.total_train_loss) for b in res.best_states]),
+        "batch_best_w": np.asarray([to_np(b.params.frame_weights) for b in res.best_states]),
+        "batch_last_w": np.asarray([to_np(h.states[-1].params.frame_weights) for h in res.histories]),
+        "batch_best_bc": np.asarray([float(to_np(b.params.model_parameters[0].bv_bc).reshape(-1)[0]) for b in res.best_states]),
+        "batch_hist_total_train": tot, "batch_hist_val0": val0,
+        "batch_fw": fw_b, "batch_fs": fs_b, "batch_lr": np.asarray(BATCH["lr"]),
+    }
+
+
 def main():
     if not refload.available():
         raise SystemExit("reference sources not available: fixtures can only be generated in the build container")
-    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate ("batch": the batch_optimise fixtures)
+    if not only or "batch" in only:
+        for name in ("uptake_eye", "pf_l2"):
+            for x64 in (False, True):
+                out = run_batch(name, CASES[name], x64)
+                path = os.path.join(HERE, f"ref_batch_{name}_{'f64' if x64 else 'f32'}.npz")
+                np.savez_compressed(path, **out)
+                print(f"{path}: iterations {out['batch_conv_steps']}, best entries {out['batch_best_step']}")
     for name, spec in CASES.items():
         if only and name not in only:
             continue
