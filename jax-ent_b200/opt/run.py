@@ -112,6 +112,11 @@ def _optimise_pure(_simulation: Simulation, data_to_fit: Sequence, n_steps: int,
     prev_loss = float(initial_losses.total_train_loss)
     best_i, best_val = None, None
     write_idx = 0
+    states = optimizer.history.states
+
+    def _strip(i):  # drop the frame weights of entry i (idempotent)
+        states[i] = states[i]._replace(params=_replace(states[i].params, frame_weights=None))
+
     while not (carry.converged or write_idx >= n_steps or not math.isfinite(prev_loss) or prev_loss < tolerance):
         opt_state, _, save_state, _simulation = optimizer.step(
             optimizer=optimizer, state=opt_state, simulation=_simulation, data_targets=data_targets, loss_functions=losses_t, indexes=idx_t)
@@ -121,23 +126,18 @@ def _optimise_pure(_simulation: Simulation, data_to_fit: Sequence, n_steps: int,
         carry = check_and_advance_threshold(carry, loss_val, write_idx + 1, thresholds, min_steps_per_threshold, optimizer.initial_steps)
         prev_loss = loss_val
         entry = OptimizationState(save_state.params, save_state.opt_state, write_idx, save_state.losses, None)
-        states = optimizer.history.states
-
-        def _strip(i):  # idempotent
-            states[i] = states[i]._replace(params=_replace(states[i].params, frame_weights=None))
-
         if best_val is None or val0 < best_val:  # first strict minimum so far: this entry keeps its weights, the old best drops them
             if best_i is not None:
                 _strip(best_i)
             best_i, best_val = write_idx, val0
         if states and (write_idx - 1) != best_i:  # the previous entry is no longer the last one
             _strip(write_idx - 1)
-        optimizer.history.states.append(entry)
+        states.append(entry)
         write_idx += 1
-    if optimizer.history.states:
-        last_val0 = float(optimizer.history.states[-1].losses.val_losses[0])
+    if states:
+        last_val0 = float(states[-1].losses.val_losses[0])
         pick = write_idx - 1 if not (best_val < last_val0) else best_i
-        optimizer.history.best_state = optimizer.history.states[pick]
+        optimizer.history.best_state = states[pick]
         _simulation.params = optimizer.history.best_state.params
     optimizer._pure_carry = (carry, write_idx)
     return _simulation, optimizer

@@ -178,3 +178,75 @@ def test_dataloader_containers():
     assert dl.train is ds and dl.key == "unknown"
     with pytest.raises(NotImplementedError):
         J.ExpD_Dataloader(data=[1])
+
+
+def test_optimise_pure_host_loop_on_a_scripted_optimizer(monkeypatch):
+    """opt/run.py::_optimise_pure (the loop of the reference's _optimise_pure, opt/run.py:141-232, driven from the host) with the
+    fused step replaced by a scripted one: where the loop ends, which entry is returned (_pick_best_state: the last entry unless
+    an earlier one is strictly better, then the first that reaches the minimum), and that only the best and the last entry keep
+    their frame weights."""
+    import types
+
+    from jaxent_b200.opt import optimiser as OPT
+    from jaxent_b200.opt import run as RUN
+    from jaxent_b200.opt.base import LossComponents, OptimizationState
+
+    class P:  # stands in for Simulation_Parameters: only _replace(frame_weights=...) is used on it
+        def __init__(self, w):
+            self.frame_weights = w
+
+    monkeypatch.setattr(RUN, "_replace", lambda p, **kw: P(kw.get("frame_weights", p.frame_weights)))
+
+    def scripted(losses, val0):
+        def lc(i):
+            return LossComponents(np.array([losses[i]]), np.array([val0[i]]), np.array([losses[i]]), np.array([val0[i]]), losses[i], val0[i])
+
+        monkeypatch.setattr(OPT, "compute_loss", lambda sim, params, *a: (lc(0), sim))
+        opt = types.SimpleNamespace(learning_rate=1.0, initial_steps=0, history=None, calls=0)
+        opt._engine = types.SimpleNamespace(records=lambda k, n: [types.SimpleNamespace(total_train=losses[k], val=[val0[k]])])
+
+        def step(optimizer, state, simulation, data_targets, loss_functions, indexes):
+            k = optimizer.calls
+            optimizer.calls += 1
+            save = OptimizationState(P(("w", k)), None, k + 1, lc(k), None)
+            return OptimizationState(P(("z", k + 1)), None, k + 1, lc(k), None), losses[k], save, simulation
+
+        opt.step = step
+        sim = types.SimpleNamespace(params=None)
+        return sim, opt
+
+    # (1) converges: thresholds 0.5 / 0.05 (x lr = 1), min 2 steps per threshold
+    losses = [10.0, 6.0, 4.0, 3.5, 3.4, 3.39, 3.389, 3.3889, 3.3888, 3.3887]
+    val0 = [5.0, 4.0, 3.0, 2.5, 2.6, 2.7, 2.8, 2.9, 3.0, 3.1]
+    sim, opt = scripted(losses, val0)
+    sim2, opt2 = RUN._optimise_pure(sim, (None,), 10, 1e-10, [0.5, 0.05], (0,), (None,), OptimizationState(P("z0"), None), opt)
+    carry, n = opt2._pure_carry
+    ref_carry = initialise_and_replay(losses, [0.5, 0.05])
+    assert n == ref_carry[1] and carry.converged == ref_carry[0].converged and n < 10
+    h = opt2.history
+    assert [s.step for s in h.states] == list(range(n))
+    assert h.best_state is h.states[3] and sim2.params is h.best_state.params  # val0 is smallest at entry 3
+    kept = [i for i, s in enumerate(h.states) if s.params.frame_weights is not None]
+    assert kept == sorted({3, n - 1}) and h.states[3].params.frame_weights == ("w", 3)
+    # (2) n_steps ends the loop; the last entry ties with the minimum -> the last entry is returned
+    sim, opt = scripted([5.0, 4.0, 3.0, 2.0], [2.0, 1.0, 1.5, 1.0])
+    _, opt2 = RUN._optimise_pure(sim, (None,), 4, 1e-10, [1e-9], (0,), (None,), OptimizationState(P("z0"), None), opt)
+    assert opt2._pure_carry[1] == 4 and opt2.history.best_state is opt2.history.states[3]
+    assert [i for i, s in enumerate(opt2.history.states) if s.params.frame_weights is not None] == [1, 3]
+    # (3) cond_fn looks at the initial loss before the first iteration: below the tolerance -> no iteration at all
+    sim, opt = scripted([1e-12, 1.0], [1.0, 1.0])
+    _, opt2 = RUN._optimise_pure(sim, (None,), 5, 1e-10, [1e-3], (0,), (None,), OptimizationState(P("z0"), None), opt)
+    assert opt2._pure_carry[1] == 0 and opt2.history.states == [] and opt.calls == 0
+
+
+def initialise_and_replay(losses, convergence, lr=1.0, alpha=0.5, min_steps=2, initial_steps=0):
+    from jaxent_b200.opt import track as T
+
+    thr = T.create_convergence_thresholds(convergence, lr)
+    carry, prev, n = T.initialise_convergence_carry(None), losses[0], 0
+    while not carry.converged and n < len(losses):
+        carry, _ = T.update_convergence(carry, prev, losses[n], None, alpha)
+        carry = T.check_and_advance_threshold(carry, losses[n], n + 1, thr, min_steps, initial_steps)
+        prev = losses[n]
+        n += 1
+    return carry, n
